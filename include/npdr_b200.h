@@ -1,0 +1,213 @@
+/*
+ * npdr_b200.h -- C ABI of libnpdr_b200.so, the B200-native engine for NPDR's hot path
+ * (distances -> neighbour pairs -> per-attribute GLM on projected pair differences).
+ *
+ * The reference (insilico/npdr) has no FFI boundary: its operator API is a set of exported
+ * R closures (NAMESPACE:11-24,29-30).  Each entry point below replaces one of them and is
+ * what an R `.Call` shim binds (see INTEGRATION.md for the shim and the R wrapper):
+ *
+ *   npdrb_diff               <- npdrDiff            R/nearestNeighbors.R:15-40
+ *   npdrb_distances          <- npdrDistances       R/nearestNeighbors.R:63-101
+ *   npdrb_nearest_neighbors  <- nearestNeighbors    R/nearestNeighbors.R:153-285 (+ get_Ri_nearest :622-634,
+ *                                                    uniqueNeighbors :572-583, knnVec :603-607)
+ *   npdrb_knn_surf           <- knnSURF             R/utils.R:12-18
+ *   npdrb_regress            <- the regression loop + diffRegression   R/npdr.R:391-430, 18-71
+ *   npdrb_npdr               <- npdr() between argument parsing and order()/p.adjust()
+ *                                                    R/npdr.R:256-270, 299-345, 391-430
+ *   npdrb_unireg             <- uniReg's per-column fits   R/utils.R:66-157
+ *
+ * What stays on the R side (per BASELINE north_star): argument parsing, factor coding,
+ * pt()/pnorm() p-values, order(), p.adjust(), data-frame assembly.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success, non-zero on error;
+ *     npdrb_last_error() returns a thread-local message for the last failure.
+ *   - matrices are column-major doubles, exactly as R holds them; inputs are never written.
+ *   - instance indices in pair lists are 1-based int32 (R's Ri_idx / NN_idx).
+ *   - there is NO CPU fallback: every compute entry point fails with NPDRB_ENODEVICE
+ *     when no sm_100 device is usable.
+ *   - buffers returned through pointer-to-pointer arguments are malloc'ed by the library
+ *     and released with npdrb_free().
+ *
+ * The `npdrb_session_*` functions expose the same stages on DEVICE-resident data so a host
+ * (R with several GPUs, or the Python/torch.distributed harness in this repo) can shard the
+ * path: row blocks for distance+neighbours, attribute columns for the regression.
+ */
+#ifndef NPDR_B200_H
+#define NPDR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPDRB_OK 0
+#define NPDRB_EINVAL 1        /* bad argument / unsupported option combination */
+#define NPDRB_ENODEVICE 2     /* no usable CUDA device (never falls back to the CPU) */
+#define NPDRB_ECUDA 3         /* CUDA runtime error, see npdrb_last_error() */
+#define NPDRB_ENOMEM 4
+#define NPDRB_EDATA 5         /* NA/NaN/Inf in the input, single-level binomial outcome, ... */
+
+/* npdrDiff diff.type, R/nearestNeighbors.R:15 ("manhattan" == "numeric-abs") */
+enum { NPDRB_DIFF_NUMERIC_ABS = 0, NPDRB_DIFF_NUMERIC_SQR = 1, NPDRB_DIFF_ALLELE_SHARING = 2,
+       NPDRB_DIFF_MATCH_MISMATCH = 3, NPDRB_DIFF_RAW = 4 /* uniReg: the attribute itself */ };
+/* npdrDistances metric, R/nearestNeighbors.R:63-101; PRECOMPUTED: R/nearestNeighbors.R:171-176 */
+enum { NPDRB_METRIC_MANHATTAN = 0, NPDRB_METRIC_EUCLIDEAN = 1, NPDRB_METRIC_ALLELE_SHARING_MANHATTAN = 2,
+       NPDRB_METRIC_RELIEF_SCALED_MANHATTAN = 3, NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN = 4,
+       NPDRB_METRIC_PRECOMPUTED = 5 };
+/* nbd.method, R/nearestNeighbors.R:153-154 */
+enum { NPDRB_NBD_MULTISURF = 0, NPDRB_NBD_SURF = 1, NPDRB_NBD_RELIEFF = 2 };
+/* regression.type, R/npdr.R:152 */
+enum { NPDRB_REG_LM = 0, NPDRB_REG_BINOMIAL = 1 };
+
+#define NPDRB_MAX_COVARS 4
+
+/* per-attribute statistics, one row per attribute (8 doubles):
+ *   [0] beta_a   coefficient of the attribute diff       (coeffs[2,1], R/npdr.R:52)
+ *   [1] stat_a   beta_a / se (t for lm, z for binomial)  (coeffs[2,3], R/npdr.R:53)
+ *   [2] beta_0   intercept                                (coeffs[1,1], R/npdr.R:62)
+ *   [3] stat_0   intercept / se
+ *   [4] df_resid M - rank                                 (mod$df.residual, R/npdr.R:39)
+ *   [5] r_squared (lm, R/npdr.R:67) or residual deviance (binomial)
+ *   [6] iters    IRLS iterations (binomial), 0 for lm
+ *   [7] flags    bit0: attribute diff aliased (constant column); with covariates the row then holds the
+ *                first non-aliased covariate, as summary()$coefficients would;
+ *                bit1: IRLS did not converge in 25 iterations; bit2: non-finite deviance/coefficients.
+ * pt()/pnorm() of stat_a, stat_0 are formed by the caller. */
+#define NPDRB_STATS_PER_ATTR 8
+#define NPDRB_FLAG_ALIASED 1
+#define NPDRB_FLAG_NOT_CONVERGED 2
+#define NPDRB_FLAG_NONFINITE 4
+
+typedef struct {
+    int32_t regression_type;                       /* NPDRB_REG_* */
+    int32_t attr_diff_type;                        /* NPDRB_DIFF_* */
+    int32_t nbd_method;                            /* NPDRB_NBD_* */
+    int32_t nbd_metric;                            /* NPDRB_METRIC_* */
+    int64_t knn;                                   /* relieff k; 0 -> knnSURF(N, sd_frac) */
+    double  msurf_sd_frac;                         /* sd.frac, default 0.5 */
+    int32_t n_covars;                              /* number of covariate columns used (= length(covar.diff.type), R/npdr.R:321) */
+    int32_t covar_diff_type[NPDRB_MAX_COVARS];     /* NPDRB_DIFF_* per covariate */
+    int32_t neighbor_sampling_unique;              /* neighbor.sampling == "unique", R/npdr.R:271-277 */
+    int32_t fast_euclidean;                        /* 1: allow FMA contraction in the euclidean sum (<=1e-12 rel) */
+    int32_t return_pairs;                          /* 1: also return the (Ri, NN) list */
+    int32_t reserved[8];
+} npdrb_opts;
+
+typedef struct {
+    int64_t n_attr;
+    double *stats;                                 /* n_attr x NPDRB_STATS_PER_ATTR, row-major; npdrb_free() */
+    int64_t n_pairs;                               /* num.neighbor.pairs, R/npdr.R:266 (before unique sampling) */
+    int64_t n_unique_pairs;                        /* num.unique.neighbors, R/npdr.R:269 */
+    int64_t n_pairs_used;                          /* rows of the regression (differs when neighbor.sampling == "unique") */
+    double  k_ave_empirical;                       /* mean(knnVec(pairs)), R/npdr.R:267 */
+    int64_t n_empty;                               /* instances with an empty neighbourhood (skipped) */
+    int64_t knn_used;                              /* relieff k actually used */
+    int32_t *Ri, *NN;                              /* if requested: pair list, 1-based; npdrb_free() */
+    double  ms_h2d, ms_distance, ms_neighbors, ms_prepare, ms_regress, ms_total; /* stage times (CUDA events) */
+    int32_t irls_passes;                           /* binomial: number of full passes over the pair stream */
+    int32_t reserved[7];
+} npdrb_result;
+
+typedef struct npdrb_ctx npdrb_ctx;                /* one per device */
+typedef struct npdrb_session npdrb_session;        /* one NPDR problem resident on one device */
+
+const char *npdrb_version(void);
+const char *npdrb_last_error(void);
+void npdrb_free(void *p);
+void npdrb_opts_default(npdrb_opts *o);
+void npdrb_result_release(npdrb_result *r);        /* frees the buffers inside *r */
+
+int npdrb_create(int device, npdrb_ctx **ctx);     /* NPDRB_ENODEVICE if the device is absent or not sm_100 */
+void npdrb_destroy(npdrb_ctx *ctx);
+/* use a caller-owned CUDA stream (cudaStream_t as void*) for all subsequent work, e.g. torch's current stream */
+int npdrb_set_stream(npdrb_ctx *ctx, void *cuda_stream);
+int npdrb_synchronize(npdrb_ctx *ctx);
+/* measured FP64 issue peaks of this device (DFMA and DADD micro-kernels): TFLOP/s counting FMA = 2, add = 1 */
+int npdrb_measure_fp64_peak(npdrb_ctx *ctx, double *dfma_tflops, double *dadd_tflops);
+/* number of this library's kernel launches since the context was created (bench.py's gpu_launches) */
+int64_t npdrb_launch_count(npdrb_ctx *ctx);
+
+/* ---- host-buffer operator API (inputs/outputs in host memory; copies included) ---- */
+
+/* npdrDiff on vectors of length n */
+int npdrb_diff(npdrb_ctx *ctx, const double *a, const double *b, int64_t n, int32_t diff_type, double norm_fac,
+               double *out);
+/* N x N distance matrix (column-major, symmetric, zero diagonal) from N x p attributes */
+int npdrb_distances(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, int32_t metric, int32_t fast_euclidean,
+                    double *D_out);
+int64_t npdrb_knn_surf(int64_t m_samples, double sd_frac);
+/* nearestNeighbors: X is N x p attributes, or the N x N distance matrix when nbd_metric == PRECOMPUTED.
+ * sd_vec (length N) may be NULL.  radius_out (length N) may be NULL; filled for surf/multisurf. */
+int npdrb_nearest_neighbors(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, int32_t nbd_method,
+                            int32_t nbd_metric, const double *sd_vec, double sd_frac, int64_t k,
+                            int32_t unique_sampling, int32_t **Ri, int32_t **NN, int64_t *M,
+                            int64_t *n_unique, int64_t *n_empty, double *radius_out);
+/* regression loop over all p attributes for a given pair list.
+ * y: length N outcome (lm: numeric; binomial: class labels, any two distinct doubles); pheno diff is formed
+ * here as in R/npdr.R:299-308.  C: N x q covariates or NULL.  stats_out: p x 8 row-major. */
+int npdrb_regress(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const int32_t *Ri, const int32_t *NN,
+                  int64_t M, const double *y, const double *C, int32_t q, const int32_t *covar_diff_type,
+                  int32_t attr_diff_type, int32_t regression_type, double *stats_out);
+/* the whole path on one device */
+int npdrb_npdr(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
+               const npdrb_opts *opts, npdrb_result *res);
+/* uniReg: univariate lm/glm of y on each raw column (+ covariates C as additional regressors) */
+int npdrb_unireg(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
+                 int32_t q, int32_t regression_type, double *stats_out);
+
+/* ---- device-resident session API (sharding across GPUs; bench "value" with inputs already in HBM) ---- */
+
+int npdrb_session_create(npdrb_ctx *ctx, int64_t N, int64_t p, int32_t q, npdrb_session **s);
+void npdrb_session_destroy(npdrb_session *s);
+/* copy host inputs in (pinned staging + async copies on the context stream); C may be NULL when q == 0 */
+int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, const double *C);
+/* or adopt device buffers: dX column-major with leading dimension ldx >= N (ldx % 2 == 0), dy[N], dC N x q (ld N) */
+int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy,
+                                    const double *dC);
+/* rows [row0, row0+nrows) of the distance matrix against all N instances (nrows == N: symmetric mode) */
+int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
+/* adopt a precomputed distance block (device, nrows x N row-major = the columns Ri of a symmetric D) */
+int npdrb_session_set_device_distances(npdrb_session *s, const double *dD, int64_t ldd, int64_t row0, int64_t nrows);
+int npdrb_session_set_sd_vec(npdrb_session *s, const double *sd_vec_host);   /* user sd.vec, length N */
+/* neighbour lists for the owned rows; *M_local = number of pairs found */
+int npdrb_session_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local,
+                            int64_t *n_empty_local);
+/* SURF needs one global mean/sd (R/nearestNeighbors.R:234-241).  Partial moments of the owned rows:
+ * out4[0] = sum of all owned entries, out4[1] = sum over the owned part of the strict upper triangle,
+ * out4[2] = its count, out4[3] = sum over that part of (d - centre)^2.  Multi-rank hosts call it with
+ * centre = 0, combine to the global mean, call again with that mean, then set the radius
+ *   sum_all/(2*num.pair) - sd.frac*sqrt(sumsq/(count-1))   with npdrb_session_set_surf_radius(). */
+int npdrb_session_surf_partial(npdrb_session *s, double centre, double *out4);
+int npdrb_session_set_surf_radius(npdrb_session *s, double radius);
+/* device pointers to the local pair segment (int32, 1-based), valid until the next neighbours/import call */
+int npdrb_session_local_pairs(npdrb_session *s, const int32_t **dRi, const int32_t **dNN, int64_t *M_local);
+/* copy the local pair segment into caller-owned DEVICE buffers (e.g. torch tensors that NCCL will all-gather) */
+int npdrb_session_copy_local_pairs_device(npdrb_session *s, int32_t *dRi_dst, int32_t *dNN_dst);
+int npdrb_session_copy_radius(npdrb_session *s, double *radius_host);       /* owned rows */
+int npdrb_session_copy_distances(npdrb_session *s, double *D_host);         /* nrows x N, row-major */
+/* the full pair list the regression will use (device pointers, e.g. the all-gathered segments) */
+int npdrb_session_import_pairs(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64_t M);
+int npdrb_session_import_pairs_host(npdrb_session *s, const int32_t *Ri, const int32_t *NN, int64_t M);
+/* uniqueNeighbors on the imported list: count, and optionally replace the list by its unique subset */
+int npdrb_session_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_unique);
+/* regression over attribute columns [attr0, attr0+nattr); stats_out host, nattr x 8 row-major */
+int npdrb_session_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t regression_type,
+                          int32_t attr_diff_type, const int32_t *covar_diff_type, double *stats_out,
+                          int32_t *irls_passes);
+int npdrb_session_copy_pairs(npdrb_session *s, int32_t *Ri_host, int32_t *NN_host);  /* imported list */
+/* milliseconds of the last call of each stage on this session (CUDA events on the context stream) */
+int npdrb_session_stage_ms(npdrb_session *s, double *ms_distance, double *ms_neighbors, double *ms_prepare,
+                           double *ms_regress);
+
+/* kernel-level timings of the last session_regress call, measured with CUDA events on the launching stream:
+ * out[0] ms of the first pass kernel (lm: the only pass; binomial: the pass at the mustart weights),
+ * out[1] summed ms of the full IRLS pass kernels, out[2] their number, out[3] attribute x record evaluations
+ * they executed (active attribute tiles x 128 x records), out[4] records in the pair stream. */
+int npdrb_session_kernel_ms(npdrb_session *s, double *out5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPDR_B200_H */

@@ -1,0 +1,12 @@
+"""npdr_b200 -- B200-native engine for NPDR's hot path behind the reference's operator API.
+
+Host-side mirror of the reference's exported R functions (insilico/npdr, NAMESPACE:11-24,29-30)
+over the C ABI of libnpdr_b200.so.  No CPU fallback: compute calls raise if the CUDA library
+or an sm_100 device is missing.
+"""
+from ._lib import NpdrB200Error, Context, Session, context  # noqa: F401
+from .api import (npdr, npdrDiff, npdrDistances, nearestNeighbors, uniqueNeighbors, knnVec, knnSURF,  # noqa: F401
+                  diffRegression, uniReg)
+from . import rstats  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,312 @@
+"""ctypes binding of libnpdr_b200.so (the C ABI declared in include/npdr_b200.h).
+
+There is no CPU fallback: importing this module loads the CUDA shared library, and every
+compute call fails loudly (NpdrB200Error) if no sm_100 device is usable.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libnpdr_b200.so")
+
+STATS_PER_ATTR = 8
+MAX_COVARS = 4
+DIFF = {"numeric-abs": 0, "manhattan": 0, "numeric-sqr": 1, "allele-sharing": 2, "match-mismatch": 3, "raw": 4}
+METRIC = {"manhattan": 0, "euclidean": 1, "allele-sharing-manhattan": 2, "relief-scaled-manhattan": 3,
+          "relief-scaled-euclidean": 4, "precomputed": 5}
+NBD = {"multisurf": 0, "surf": 1, "relieff": 2}
+REG = {"lm": 0, "binomial": 1}
+ENODEVICE = 2
+
+
+class NpdrB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libnpdr_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Opts(C.Structure):
+    _fields_ = [("regression_type", C.c_int32), ("attr_diff_type", C.c_int32), ("nbd_method", C.c_int32),
+                ("nbd_metric", C.c_int32), ("knn", C.c_int64), ("msurf_sd_frac", C.c_double),
+                ("n_covars", C.c_int32), ("covar_diff_type", C.c_int32 * MAX_COVARS),
+                ("neighbor_sampling_unique", C.c_int32), ("fast_euclidean", C.c_int32),
+                ("return_pairs", C.c_int32), ("reserved", C.c_int32 * 8)]
+
+
+class Result(C.Structure):
+    _fields_ = [("n_attr", C.c_int64), ("stats", C.POINTER(C.c_double)), ("n_pairs", C.c_int64),
+                ("n_unique_pairs", C.c_int64), ("n_pairs_used", C.c_int64), ("k_ave_empirical", C.c_double),
+                ("n_empty", C.c_int64), ("knn_used", C.c_int64), ("Ri", C.POINTER(C.c_int32)),
+                ("NN", C.POINTER(C.c_int32)), ("ms_h2d", C.c_double), ("ms_distance", C.c_double),
+                ("ms_neighbors", C.c_double), ("ms_prepare", C.c_double), ("ms_regress", C.c_double),
+                ("ms_total", C.c_double), ("irls_passes", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+
+# name -> (restype, argtypes); every symbol include/npdr_b200.h declares
+SIGNATURES = {
+    "npdrb_version": (C.c_char_p, []),
+    "npdrb_last_error": (C.c_char_p, []),
+    "npdrb_free": (None, [_vp]),
+    "npdrb_opts_default": (None, [C.POINTER(Opts)]),
+    "npdrb_result_release": (None, [C.POINTER(Result)]),
+    "npdrb_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "npdrb_destroy": (None, [_vp]),
+    "npdrb_set_stream": (C.c_int, [_vp, _vp]),
+    "npdrb_synchronize": (C.c_int, [_vp]),
+    "npdrb_measure_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
+    "npdrb_launch_count": (_i64, [_vp]),
+    "npdrb_diff": (C.c_int, [_vp, _dp, _dp, _i64, _i32, C.c_double, _dp]),
+    "npdrb_distances": (C.c_int, [_vp, _dp, _i64, _i64, _i32, _i32, _dp]),
+    "npdrb_knn_surf": (_i64, [_i64, C.c_double]),
+    "npdrb_nearest_neighbors": (C.c_int, [_vp, _dp, _i64, _i64, _i32, _i32, _dp, C.c_double, _i64, _i32,
+                                          C.POINTER(_ip), C.POINTER(_ip), C.POINTER(_i64), C.POINTER(_i64),
+                                          C.POINTER(_i64), _dp]),
+    "npdrb_regress": (C.c_int, [_vp, _dp, _i64, _i64, _ip, _ip, _i64, _dp, _dp, _i32, _ip, _i32, _i32, _dp]),
+    "npdrb_npdr": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, C.POINTER(Opts), C.POINTER(Result)]),
+    "npdrb_unireg": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, _i32, _i32, _dp]),
+    "npdrb_session_create": (C.c_int, [_vp, _i64, _i64, _i32, C.POINTER(_vp)]),
+    "npdrb_session_destroy": (None, [_vp]),
+    "npdrb_session_upload": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "npdrb_session_set_device_inputs": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "npdrb_session_distances": (C.c_int, [_vp, _i32, _i32, _i64, _i64]),
+    "npdrb_session_set_device_distances": (C.c_int, [_vp, _vp, _i64, _i64, _i64]),
+    "npdrb_session_set_sd_vec": (C.c_int, [_vp, _dp]),
+    "npdrb_session_neighbors": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "npdrb_session_surf_partial": (C.c_int, [_vp, C.c_double, _dp]),
+    "npdrb_session_set_surf_radius": (C.c_int, [_vp, C.c_double]),
+    "npdrb_session_local_pairs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    "npdrb_session_copy_local_pairs_device": (C.c_int, [_vp, _vp, _vp]),
+    "npdrb_session_copy_radius": (C.c_int, [_vp, _dp]),
+    "npdrb_session_copy_distances": (C.c_int, [_vp, _dp]),
+    "npdrb_session_import_pairs": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "npdrb_session_import_pairs_host": (C.c_int, [_vp, _ip, _ip, _i64]),
+    "npdrb_session_unique_pairs": (C.c_int, [_vp, _i32, C.POINTER(_i64)]),
+    "npdrb_session_regress": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _ip, _dp, C.POINTER(_i32)]),
+    "npdrb_session_copy_pairs": (C.c_int, [_vp, _ip, _ip]),
+    "npdrb_session_stage_ms": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "npdrb_session_kernel_ms": (C.c_int, [_vp, _dp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libnpdr_b200.so (needs no GPU) and bind every declared symbol."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(SO_PATH):
+                raise ImportError(f"{SO_PATH} is missing: build it with ./build.sh or __graft_entry__.build(); "
+                                  "npdr_b200 has no CPU fallback")
+            L = C.CDLL(SO_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)            # AttributeError if the library does not export it
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+def last_error():
+    return load().npdrb_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc != 0:
+        raise NpdrB200Error(rc, last_error())
+
+
+def f64(a, order="F"):
+    return np.require(np.asarray(a, dtype=np.float64), dtype=np.float64,
+                      requirements=["F" if order == "F" else "C", "A"])
+
+
+def dptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def iptr(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+class Context:
+    """One per device (npdrb_ctx)."""
+
+    def __init__(self, device=0):
+        L = load()
+        h = _vp()
+        check(L.npdrb_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            load().npdrb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        check(load().npdrb_set_stream(self.handle, _vp(int(cuda_stream_ptr))))
+
+    def synchronize(self):
+        check(load().npdrb_synchronize(self.handle))
+
+    def launch_count(self):
+        return int(load().npdrb_launch_count(self.handle))
+
+    def fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        check(load().npdrb_measure_fp64_peak(self.handle, C.byref(a), C.byref(b)))
+        return {"dfma_tflops": a.value, "dadd_tflops": b.value}
+
+
+_contexts = {}
+
+
+def context(device=0):
+    """Process-wide context cache."""
+    ctx = _contexts.get(device)
+    if ctx is None or ctx.handle is None:
+        ctx = Context(device)
+        _contexts[device] = ctx
+    return ctx
+
+
+def take_int_array(ptr, n):
+    """Copy a library-malloc'ed int32 buffer into numpy and free it."""
+    if n > 0:
+        out = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+    else:
+        out = np.zeros(0, dtype=np.int32)
+    load().npdrb_free(C.cast(ptr, _vp))
+    return out
+
+
+class Session:
+    """One NPDR problem resident on one device (npdrb_session): the sharding building block."""
+
+    def __init__(self, ctx, N, p, q=0):
+        self.ctx, self.N, self.p, self.q = ctx, int(N), int(p), int(q)
+        h = _vp()
+        check(load().npdrb_session_create(ctx.handle, self.N, self.p, self.q, C.byref(h)))
+        self.handle = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "handle", None):
+            load().npdrb_session_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, X=None, y=None, C_=None):
+        Xa = f64(X) if X is not None else None
+        ya = f64(y) if y is not None else None
+        Ca = f64(C_) if C_ is not None else None
+        check(load().npdrb_session_upload(self.handle, dptr(Xa), dptr(ya), dptr(Ca)))
+
+    def set_device_inputs(self, dX=0, ldx=0, dy=0, dC=0):
+        check(load().npdrb_session_set_device_inputs(self.handle, _vp(dX or None), int(ldx), _vp(dy or None), _vp(dC or None)))
+
+    def distances(self, metric="manhattan", fast_euclidean=False, row0=0, nrows=None):
+        nrows = self.N if nrows is None else nrows
+        check(load().npdrb_session_distances(self.handle, METRIC[metric], int(bool(fast_euclidean)), int(row0), int(nrows)))
+        self.nrows = int(nrows)
+
+    def set_device_distances(self, dD, ldd, row0, nrows):
+        check(load().npdrb_session_set_device_distances(self.handle, _vp(dD), int(ldd), int(row0), int(nrows)))
+        self.nrows = int(nrows)
+
+    def set_sd_vec(self, sd_vec):
+        a = f64(sd_vec) if sd_vec is not None else None
+        check(load().npdrb_session_set_sd_vec(self.handle, dptr(a)))
+
+    def neighbors(self, method="multisurf", sd_frac=0.5, k=0):
+        M, ne = _i64(), _i64()
+        check(load().npdrb_session_neighbors(self.handle, NBD[method], float(sd_frac), int(k), C.byref(M), C.byref(ne)))
+        return M.value, ne.value
+
+    def surf_partial(self, centre=0.0):
+        out = np.zeros(4)
+        check(load().npdrb_session_surf_partial(self.handle, float(centre), dptr(out)))
+        return out
+
+    def set_surf_radius(self, r):
+        check(load().npdrb_session_set_surf_radius(self.handle, float(r)))
+
+    def local_pairs(self):
+        a, b, M = _vp(), _vp(), _i64()
+        check(load().npdrb_session_local_pairs(self.handle, C.byref(a), C.byref(b), C.byref(M)))
+        return a.value, b.value, M.value
+
+    def copy_local_pairs_device(self, dRi_dst, dNN_dst):
+        check(load().npdrb_session_copy_local_pairs_device(self.handle, _vp(dRi_dst), _vp(dNN_dst)))
+
+    def copy_radius(self):
+        out = np.empty(self.nrows)
+        check(load().npdrb_session_copy_radius(self.handle, dptr(out)))
+        return out
+
+    def copy_distances(self):
+        out = np.empty((self.nrows, self.N), order="C")
+        check(load().npdrb_session_copy_distances(self.handle, dptr(out)))
+        return out
+
+    def import_pairs(self, dRi, dNN, M):
+        check(load().npdrb_session_import_pairs(self.handle, _vp(dRi), _vp(dNN), int(M)))
+        self.M = int(M)
+
+    def import_pairs_host(self, Ri, NN):
+        Ri = np.ascontiguousarray(Ri, dtype=np.int32); NN = np.ascontiguousarray(NN, dtype=np.int32)
+        check(load().npdrb_session_import_pairs_host(self.handle, iptr(Ri), iptr(NN), Ri.size))
+        self.M = int(Ri.size)
+
+    def unique_pairs(self, keep_unique_only=False):
+        n = _i64()
+        check(load().npdrb_session_unique_pairs(self.handle, int(bool(keep_unique_only)), C.byref(n)))
+        return n.value
+
+    def regress(self, attr0=0, nattr=None, regression_type="binomial", attr_diff_type="numeric-abs", covar_diff_type=()):
+        nattr = self.p - attr0 if nattr is None else nattr
+        out = np.empty((nattr, STATS_PER_ATTR))
+        cdt = np.asarray([DIFF[t] for t in covar_diff_type] + [DIFF["match-mismatch"]] * MAX_COVARS, dtype=np.int32)[:MAX_COVARS]
+        passes = _i32()
+        check(load().npdrb_session_regress(self.handle, int(attr0), int(nattr), REG[regression_type], DIFF[attr_diff_type],
+                                           iptr(cdt), dptr(out), C.byref(passes)))
+        self.irls_passes = passes.value
+        return out
+
+    def copy_pairs(self, M):
+        Ri = np.empty(M, dtype=np.int32); NN = np.empty(M, dtype=np.int32)
+        if M:
+            check(load().npdrb_session_copy_pairs(self.handle, iptr(Ri), iptr(NN)))
+        return Ri, NN
+
+    def kernel_ms(self):
+        out = np.zeros(5)
+        check(load().npdrb_session_kernel_ms(self.handle, dptr(out)))
+        return dict(zip(("pass_first_ms", "pass_full_ms", "n_pass_full", "evals_pass_full", "records"), out.tolist()))
+
+    def stage_ms(self):
+        v = [C.c_double() for _ in range(4)]
+        check(load().npdrb_session_stage_ms(self.handle, *[C.byref(x) for x in v]))
+        return dict(zip(("distance", "neighbors", "prepare", "regress"), [x.value for x in v]))

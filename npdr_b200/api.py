@@ -1,0 +1,420 @@
+"""Host-side mirror of the reference's operator API for the NPDR hot path.
+
+Same function names, argument meaning (snake_case spellings of the R formals) and error behaviour
+as the exported R closures of insilico/npdr; all arithmetic runs in libnpdr_b200.so on the GPU,
+the p-value / ordering / p.adjust residue in `rstats` (it stays in R in the R deployment).
+
+  npdr               R/npdr.R:151-634 (default branch; glmnet / correlation-data / separate hit-miss: rejected)
+  npdrDiff           R/nearestNeighbors.R:15-40
+  npdrDistances      R/nearestNeighbors.R:63-101
+  nearestNeighbors   R/nearestNeighbors.R:153-285
+  uniqueNeighbors    R/nearestNeighbors.R:572-583
+  knnVec             R/nearestNeighbors.R:603-607
+  knnSURF            R/utils.R:12-18
+  diffRegression     R/npdr.R:18-71
+  uniReg             R/utils.R:66-157
+"""
+import ctypes as C
+import sys
+import time
+
+import numpy as np
+
+from . import _lib, rstats
+from ._lib import DIFF, METRIC, NBD, REG, STATS_PER_ATTR, check, context, dptr, f64, iptr
+
+try:  # pandas is only used for the data-frame shaped inputs/outputs the reference has
+    import pandas as pd
+except Exception:  # pragma: no cover
+    pd = None
+
+
+def _as_matrix(dataset):
+    """-> (float64 Fortran matrix, column names)."""
+    if pd is not None and isinstance(dataset, pd.DataFrame):
+        names = [str(c) for c in dataset.columns]
+        X = np.asfortranarray(dataset.to_numpy(dtype=np.float64))
+        return X, names
+    X = np.asarray(dataset, dtype=np.float64)
+    if X.ndim == 1:
+        X = X.reshape(-1, 1)
+    return np.asfortranarray(X), [str(i + 1) for i in range(X.shape[1])]
+
+
+def _code_outcome(pheno, regression_type):
+    """Phenotype -> float64 vector.  binomial: any two-level labels are mapped to their factor codes
+    (only equality matters for the hit/miss diff, R/npdr.R:305); lm: numeric."""
+    a = np.asarray(pheno)
+    if regression_type == "binomial" or a.dtype.kind in "OUSb":
+        _, inv = np.unique(a, return_inverse=True)
+        return inv.astype(np.float64)
+    return a.astype(np.float64)
+
+
+def _covars_matrix(covars, covar_diff_type):
+    """R/npdr.R:315-345: active iff length(covars) > 1; num.covs = length(covar.diff.type) (quirk 2)."""
+    if covars is None or (isinstance(covars, str) and covars == "none"):
+        return None, [], []
+    if isinstance(covar_diff_type, str):
+        covar_diff_type = [covar_diff_type]
+    names = None
+    if pd is not None and isinstance(covars, (pd.DataFrame, pd.Series)):
+        names = [str(c) for c in (covars.columns if isinstance(covars, pd.DataFrame) else [covars.name or "cov1"])]
+        covars = covars.to_numpy()
+    Cm = np.asarray(covars)
+    if Cm.ndim == 1:
+        Cm = Cm.reshape(-1, 1)
+    if Cm.dtype.kind in "OUS":
+        raise TypeError("covars must be numeric (as.matrix() on a mixed data.frame yields characters in R too); "
+                        "code factors as integers first")
+    ncov = len(covar_diff_type)
+    if ncov > Cm.shape[1]:
+        raise ValueError("covar_diff_type has more entries than covars has columns")
+    if ncov > _lib.MAX_COVARS:
+        raise ValueError(f"at most {_lib.MAX_COVARS} covariates are supported")
+    Cm = np.asfortranarray(Cm[:, :ncov].astype(np.float64))
+    if names is None:
+        names = [f"cov{i + 1}" for i in range(ncov)]
+    for t in covar_diff_type:
+        if t not in DIFF or t == "raw":
+            raise ValueError(f"unknown covar.diff.type {t!r}")
+    return Cm, list(covar_diff_type), names[:ncov]
+
+
+def knnSURF(m_samples, sd_frac=0.5):
+    """Theoretical expected number of neighbours (R/utils.R:12-18)."""
+    return int(_lib.load().npdrb_knn_surf(int(m_samples), float(sd_frac)))
+
+
+def npdrDiff(a, b, diff_type="manhattan", norm_fac=1, device=0):
+    """Projected difference of two value vectors (R/nearestNeighbors.R:15-40)."""
+    if diff_type is None:
+        diff_type = "numeric-abs"
+    if diff_type == "correlation-data":
+        raise NotImplementedError("npdrDiff(diff.type='correlation-data') is outside the accelerated path (DESIGN.md)")
+    if diff_type not in DIFF or diff_type == "raw":
+        raise ValueError(f"'arg' should be one of the npdrDiff diff types, got {diff_type!r}")   # match.arg error
+    a = f64(np.ravel(a)); b = f64(np.ravel(b))
+    if a.size != b.size:
+        raise ValueError("a and b must have the same length")
+    out = np.empty(a.size)
+    check(_lib.load().npdrb_diff(context(device).handle, dptr(a), dptr(b), a.size, DIFF[diff_type], float(norm_fac), dptr(out)))
+    return out
+
+
+def npdrDistances(attr_mat, metric="manhattan", fast_dist=False, device=0, fast_euclidean=False):
+    """m x m distance matrix (R/nearestNeighbors.R:63-101).  fast_dist is accepted for signature
+    compatibility (it selects wordspace::dist.matrix in the reference)."""
+    X, _ = _as_matrix(attr_mat)
+    if metric == "hamming":
+        raise NotImplementedError("metric='hamming' is outside the accelerated path this round (DESIGN.md)")
+    if metric not in METRIC or metric == "precomputed":
+        return None        # the reference falls through and returns NULL for unknown metrics (:97-100)
+    N, p = X.shape
+    D = np.empty((N, N), order="F")
+    check(_lib.load().npdrb_distances(context(device).handle, dptr(X), N, p, METRIC[metric], int(bool(fast_euclidean)), dptr(D)))
+    return D
+
+
+def _nearest(X, nbd_method, nbd_metric, sd_vec, sd_frac, k, unique, device):
+    if nbd_method not in NBD:
+        raise ValueError(f"unknown nbd.method {nbd_method!r}")
+    if nbd_metric not in METRIC:
+        raise ValueError(f"unknown nbd.metric {nbd_metric!r}")
+    X = f64(X)
+    N, p = X.shape
+    if nbd_metric == "precomputed" and N != p:
+        raise ValueError("precomputed distances must be a square matrix")
+    sv = f64(sd_vec) if sd_vec is not None else None
+    Ri = C.POINTER(C.c_int32)(); NN = C.POINTER(C.c_int32)()
+    M = C.c_int64(); nu = C.c_int64(); ne = C.c_int64()
+    radius = np.full(N, np.nan)
+    check(_lib.load().npdrb_nearest_neighbors(context(device).handle, dptr(X), N, p, NBD[nbd_method], METRIC[nbd_metric],
+                                              dptr(sv), float(sd_frac), int(k), int(bool(unique)), C.byref(Ri), C.byref(NN),
+                                              C.byref(M), C.byref(nu), C.byref(ne), dptr(radius)))
+    ri = _lib.take_int_array(Ri, M.value)
+    nn = _lib.take_int_array(NN, M.value)
+    return ri, nn, {"n_unique": nu.value, "n_empty": ne.value, "radius": radius}
+
+
+def nearestNeighbors(attr_mat, nbd_method="multisurf", nbd_metric="manhattan", sd_vec=None, sd_frac=0.5, k=0,
+                     neighbor_sampling="none", att_to_remove=(), fast_dist=False, dopar_nn=False, device=0,
+                     return_info=False):
+    """(Ri_idx, NN_idx) neighbour-pair list, 1-based (R/nearestNeighbors.R:153-285)."""
+    if nbd_metric != "precomputed" and att_to_remove is not None and len(att_to_remove):
+        if pd is not None and isinstance(attr_mat, pd.DataFrame):
+            try:
+                attr_mat = attr_mat.drop(columns=list(att_to_remove))
+            except KeyError:
+                pass       # the reference swallows this error too (tryCatch, :183-187)
+        else:
+            Xa = np.asarray(attr_mat)
+            keep = [c for c in range(Xa.shape[1]) if c not in set(att_to_remove)]
+            attr_mat = Xa[:, keep]
+    X, _ = _as_matrix(attr_mat)
+    ri, nn, info = _nearest(X, nbd_method, nbd_metric, sd_vec, sd_frac, k, neighbor_sampling == "unique", device)
+    if pd is not None:
+        out = pd.DataFrame({"Ri_idx": ri, "NN_idx": nn})
+    else:  # pragma: no cover
+        out = np.column_stack([ri, nn])
+    return (out, info) if return_info else out
+
+
+def _pairs_arrays(neighbor_pairs):
+    if pd is not None and isinstance(neighbor_pairs, pd.DataFrame):
+        a = neighbor_pairs.iloc[:, 0].to_numpy(); b = neighbor_pairs.iloc[:, 1].to_numpy()
+    else:
+        arr = np.asarray(neighbor_pairs)
+        a, b = arr[:, 0], arr[:, 1]
+    return np.ascontiguousarray(a, dtype=np.int32), np.ascontiguousarray(b, dtype=np.int32)
+
+
+def uniqueNeighbors(neighbor_pairs, device=0):
+    """Drop the second occurrence of every unordered pair (R/nearestNeighbors.R:572-583).
+    The list must be grouped by ascending Ri_idx, as nearestNeighbors() returns it."""
+    ri, nn = _pairs_arrays(neighbor_pairs)
+    if ri.size and np.any(np.diff(ri) < 0):
+        raise ValueError("uniqueNeighbors expects rows grouped by ascending Ri_idx")
+    N = int(max(ri.max(initial=1), nn.max(initial=1)))
+    s = _lib.Session(context(device), N, 1, 0)
+    try:
+        s.import_pairs_host(ri, nn)
+        nu = s.unique_pairs(keep_unique_only=True)
+        r2, n2 = s.copy_pairs(nu)
+    finally:
+        s.close()
+    if pd is not None:
+        return pd.DataFrame({"Ri_idx": r2, "NN_idx": n2})
+    return np.column_stack([r2, n2])
+
+
+def knnVec(neighbor_pairs_mat):
+    """Number of neighbours of each instance that appears as Ri (R/nearestNeighbors.R:603-607).
+    Pure bookkeeping on the pair list (dplyr::count in the reference)."""
+    ri, _ = _pairs_arrays(neighbor_pairs_mat)
+    if ri.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    cnt = np.bincount(ri)
+    return cnt[cnt > 0]
+
+
+def _pvalues(stats, regression_type, dof=0):
+    """stats (p x 8, see include/npdr_b200.h) -> pval.att, pval.0 as diffRegression forms them (R/npdr.R:55,63)."""
+    z_a, z_0, df = stats[:, 1], stats[:, 3], stats[:, 4]
+    res_df = df if not dof else np.full_like(df, float(dof))
+    pval_att = rstats.pt(z_a, res_df, lower_tail=False)               # one-sided, t even for the logistic z (quirk 5)
+    if regression_type == "lm":
+        pval_0 = 2.0 * rstats.pt(-np.abs(z_0), df, lower_tail=True)    # summary.lm: two-sided t
+    else:
+        pval_0 = 2.0 * rstats.pnorm(-np.abs(z_0))                      # summary.glm: two-sided normal
+    return pval_att, pval_0
+
+
+def diffRegression(design_matrix_df, regression_type="binomial", fast_reg=False, dof=0, device=0):
+    """One regression of pheno.diff.vec on attr.diff.vec (+ covariate diffs) (R/npdr.R:18-71).
+    Returns (pval.att, beta.raw.att, beta.Z.att, beta.0, pval.0[, R.sqr])."""
+    if pd is None or not isinstance(design_matrix_df, pd.DataFrame):
+        raise TypeError("design_matrix_df must be a pandas DataFrame with a 'pheno.diff.vec' column")
+    if "pheno.diff.vec" not in design_matrix_df.columns:
+        raise ValueError("design.matrix.df must have a column named 'pheno.diff.vec'")
+    if regression_type not in REG:
+        raise ValueError(f"unknown regression.type {regression_type!r}")
+    y = _code_outcome(design_matrix_df["pheno.diff.vec"].to_numpy(), regression_type)
+    preds = design_matrix_df.drop(columns=["pheno.diff.vec"])
+    P = np.asfortranarray(preds.to_numpy(dtype=np.float64))
+    M, kk = P.shape
+    if kk < 1:
+        raise ValueError("design.matrix.df needs at least the attribute diff column")
+    if kk - 1 > _lib.MAX_COVARS:
+        raise ValueError(f"at most {_lib.MAX_COVARS} covariates are supported")
+    X = np.asfortranarray(P[:, :1]); Cm = np.asfortranarray(P[:, 1:]) if kk > 1 else None
+    out = np.empty((1, STATS_PER_ATTR))
+    check(_lib.load().npdrb_unireg(context(device).handle, dptr(X), M, 1, dptr(f64(y)), dptr(Cm), kk - 1,
+                                   REG[regression_type], dptr(out)))
+    pa, p0 = _pvalues(out, regression_type, dof)
+    if int(out[0, 7]) & 1 and kk == 1:
+        print("Regression failure. Possible monomorphic SNP or variable with no variation.\n", file=sys.stderr)
+    vec = [pa[0], out[0, 0], out[0, 1], out[0, 2], p0[0]]
+    if regression_type == "lm":
+        vec.append(out[0, 5])
+    return np.array(vec)
+
+
+def uniReg(outcome, dataset, regression_type="lm", padj_method="fdr", covars="none", device=0):
+    """Univariate regression of the outcome on every raw attribute (R/utils.R:66-157):
+    columns beta, beta.Z.att, pval, p.adj; rounded with format(digits = 5); sorted by pval."""
+    X, names, pheno = _split_outcome(outcome, dataset)
+    if regression_type not in REG:
+        raise ValueError(f"unknown regression.type {regression_type!r}")
+    y = _code_outcome(pheno, regression_type)
+    Cm = None; q = 0
+    if not (isinstance(covars, str) and covars == "none") and covars is not None:
+        Cm = np.asarray(covars, dtype=np.float64)
+        if Cm.ndim == 1:
+            Cm = Cm.reshape(-1, 1)
+        Cm = np.asfortranarray(Cm); q = Cm.shape[1]
+    N, p = X.shape
+    out = np.empty((p, STATS_PER_ATTR))
+    check(_lib.load().npdrb_unireg(context(device).handle, dptr(X), N, p, dptr(f64(y)), dptr(Cm), q,
+                                   REG[regression_type], dptr(out)))
+    beta, stat, df = out[:, 0], out[:, 1], out[:, 4]
+    bad = (out[:, 7].astype(int) & 1) == 1                      # aliased attribute -> NA row (R/utils.R:91-95)
+    if regression_type == "lm":
+        pval = 2.0 * rstats.pt(-np.abs(stat), df)
+    else:
+        pval = 2.0 * rstats.pnorm(-np.abs(stat))
+    beta = np.where(bad, np.nan, beta); stat = np.where(bad, np.nan, stat); pval = np.where(bad, np.nan, pval)
+    padj = rstats.format_sci(rstats.p_adjust(pval, padj_method), 5)
+    betas = rstats.format_fixed(beta, 5)
+    stats_f = rstats.format_fixed(stat, 5)
+    pvals = rstats.format_sci(pval, 5)
+    o = rstats.order(pvals)
+    table = np.column_stack([betas, stats_f, pvals, padj])[o]
+    if pd is not None:
+        return pd.DataFrame(table, index=[names[i] for i in o], columns=["beta", "beta.Z.att", "pval", "p.adj"])
+    return table
+
+
+def _split_outcome(outcome, dataset):
+    """R/npdr.R:166-173 / R/utils.R:68-80: outcome = column name / 1-based index, or a separate vector."""
+    scalar = isinstance(outcome, (str, int, np.integer)) or (np.ndim(outcome) == 0)
+    if scalar:
+        if pd is not None and isinstance(dataset, pd.DataFrame):
+            col = outcome if isinstance(outcome, str) else dataset.columns[int(outcome) - 1]
+            pheno = dataset[col].to_numpy()
+            X, names = _as_matrix(dataset.drop(columns=[col]))
+        else:
+            arr = np.asarray(dataset)
+            j = int(outcome) - 1
+            pheno = arr[:, j]
+            X, names = _as_matrix(np.delete(arr, j, axis=1))
+            names = [str(i + 1) for i in range(arr.shape[1]) if i != j]
+    else:
+        pheno = np.asarray(outcome)
+        X, names = _as_matrix(dataset)
+    if len(pheno) != X.shape[0]:
+        raise ValueError("outcome and dataset have different numbers of instances")
+    return X, names, pheno
+
+
+def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-abs", nbd_method="multisurf",
+         nbd_metric="manhattan", knn=0, msurf_sd_frac=0.5, covars="none", covar_diff_type="match-mismatch",
+         padj_method="bonferroni", verbose=False, use_glmnet=False, glmnet_alpha=1, glmnet_lower=0,
+         glmnet_lam="lambda.1se", rm_attr_from_dist=(), neighbor_sampling="none", separate_hitmiss_nbds=False,
+         corr_attr_names=None, fast_reg=False, fast_dist=False, dopar_nn=False, dopar_reg=False, unique_dof=False,
+         external_dist=None, device=0, return_info=False, k=None):
+    """Nearest-neighbour Projected-Distance Regression (R/npdr.R:151-634), default (non-glmnet) branch.
+
+    Same formals as the reference (dots -> underscores); `k` is accepted as an alias of `knn` because R's
+    partial argument matching lets the reference's demo scripts pass it.
+    Returns a DataFrame with columns att, pval.adj, pval.att, beta.raw.att, beta.Z.att, beta.0, pval.0
+    (+ R.sqr for lm), sorted by pval.att exactly as R/npdr.R:484-508 does.
+    fast_reg / fast_dist / dopar_nn / dopar_reg select CPU libraries or fork pools in the reference; they are
+    accepted and ignored (the GPU path is always used).  Unsupported branches raise instead of falling back.
+    """
+    if k is not None:
+        knn = k
+    if use_glmnet:
+        raise NotImplementedError("use.glmnet=TRUE (npdrNET, R/npdr.R:513-632) is outside the accelerated path")
+    if attr_diff_type == "correlation-data":
+        raise NotImplementedError("attr.diff.type='correlation-data' (R/npdr.R:176-205) is outside the accelerated path")
+    if separate_hitmiss_nbds:
+        raise NotImplementedError("separate.hitmiss.nbds=TRUE (nearestNeighborsSeparateHitMiss) is a 'next' row (DESIGN.md)")
+    if regression_type not in REG:
+        raise ValueError(f"unknown regression.type {regression_type!r}")
+    if attr_diff_type not in DIFF or attr_diff_type == "raw":
+        raise ValueError(f"unknown attr.diff.type {attr_diff_type!r}")
+    if nbd_method not in NBD:
+        raise ValueError(f"unknown nbd.method {nbd_method!r}")
+    if nbd_metric not in METRIC:
+        raise ValueError(f"unknown nbd.metric {nbd_metric!r}")
+
+    X, att_names, pheno = _split_outcome(outcome, dataset)
+    y = _code_outcome(pheno, regression_type)
+    N, p = X.shape
+    Cm, cdt, _ = _covars_matrix(covars, covar_diff_type)
+    q = len(cdt)
+    _, class_counts = np.unique(np.asarray(pheno), return_counts=True)
+    balanced_theoretical_k = knnSURF(2 * int(class_counts.min()) - 1, 0.5)
+
+    L = _lib.load()
+    ctx = context(device)
+    t_start = time.time()
+    info = {}
+    simple = (nbd_metric != "precomputed") and not (rm_attr_from_dist is not None and len(rm_attr_from_dist))
+    if verbose:
+        print("Finding nearest neighbor pairs.")
+    if simple:
+        o = _lib.Opts()
+        L.npdrb_opts_default(C.byref(o))
+        o.regression_type = REG[regression_type]; o.attr_diff_type = DIFF[attr_diff_type]
+        o.nbd_method = NBD[nbd_method]; o.nbd_metric = METRIC[nbd_metric]
+        o.knn = int(knn); o.msurf_sd_frac = float(msurf_sd_frac); o.n_covars = q
+        for i, t in enumerate(cdt):
+            o.covar_diff_type[i] = DIFF[t]
+        o.neighbor_sampling_unique = int(neighbor_sampling == "unique")
+        o.return_pairs = int(bool(return_info))
+        res = _lib.Result()
+        check(L.npdrb_npdr(ctx.handle, dptr(X), N, p, dptr(f64(y)), dptr(Cm), C.byref(o), C.byref(res)))
+        stats = np.ctypeslib.as_array(res.stats, shape=(p, STATS_PER_ATTR)).copy()
+        num_pairs, num_unique, n_used = res.n_pairs, res.n_unique_pairs, res.n_pairs_used
+        k_ave = res.k_ave_empirical
+        info = {f: getattr(res, f) for f in ("n_pairs", "n_unique_pairs", "n_pairs_used", "k_ave_empirical", "n_empty",
+                                             "knn_used", "ms_h2d", "ms_distance", "ms_neighbors", "ms_prepare",
+                                             "ms_regress", "ms_total", "irls_passes")}
+        if return_info and res.n_pairs_used > 0:
+            info["Ri"] = np.ctypeslib.as_array(res.Ri, shape=(res.n_pairs_used,)).copy()
+            info["NN"] = np.ctypeslib.as_array(res.NN, shape=(res.n_pairs_used,)).copy()
+        L.npdrb_result_release(C.byref(res))
+    else:
+        # neighbours from a reduced attribute set or a user distance matrix, regression on all attributes
+        if nbd_metric == "precomputed":
+            if external_dist is None:
+                raise ValueError("nbd.metric='precomputed' needs external.dist")
+            src, _ = _as_matrix(external_dist)
+        else:
+            keep = [i for i, nm in enumerate(att_names) if nm not in set(map(str, rm_attr_from_dist))]
+            src = np.asfortranarray(X[:, keep])
+        ri, nn, ninfo = _nearest(src, nbd_method, nbd_metric, None, msurf_sd_frac, knn, False, device)
+        num_pairs = ri.size
+        num_unique = ninfo["n_unique"]
+        k_ave = float(np.mean(knnVec(np.column_stack([ri, nn])))) if ri.size else 0.0
+        if neighbor_sampling == "unique":
+            u = uniqueNeighbors(np.column_stack([ri, nn]), device=device)
+            ri, nn = _pairs_arrays(u)
+        n_used = ri.size
+        stats = np.empty((p, STATS_PER_ATTR))
+        cdt_arr = np.asarray([DIFF[t] for t in cdt] + [DIFF["match-mismatch"]] * _lib.MAX_COVARS, dtype=np.int32)
+        check(L.npdrb_regress(ctx.handle, dptr(X), N, p, iptr(ri), iptr(nn), n_used, dptr(f64(y)), dptr(Cm), q,
+                              iptr(cdt_arr), DIFF[attr_diff_type], REG[regression_type], dptr(stats)))
+        info = {"n_pairs": num_pairs, "n_unique_pairs": num_unique, "n_pairs_used": n_used, "k_ave_empirical": k_ave,
+                "n_empty": ninfo["n_empty"]}
+        if return_info:
+            info["Ri"], info["NN"] = ri, nn
+    if verbose:
+        print(f"Neighborhood calculation: {time.time() - t_start:.3f} secs")
+        print(f"{num_pairs} total neighbor pairs (possible repeats).")
+        print(f"{num_unique} unique neighbor pairs.")
+        print(f"Theoretical multiSURF average neighbors: {knnSURF(N, msurf_sd_frac)}.")
+        print(f"Theoretical best average neighbors for class imbalance: {balanced_theoretical_k}.")
+        print(f"Empirical (computed from neighborhood) average neighbors: {k_ave}.")
+        if neighbor_sampling == "unique":
+            print(f"{n_used} unique neighbor pairs.\n\nPerforming projected distance regression.")
+
+    dof = (num_unique - 2) if unique_dof else 0                       # R/npdr.R:419-423
+    pval_att, pval_0 = _pvalues(stats, regression_type, dof)
+    flags = stats[:, 7].astype(int)
+    if np.any((flags & 1) == 1) and q == 0:
+        print("Regression failure. Possible monomorphic SNP or variable with no variation.\n", file=sys.stderr)
+    o = rstats.order(pval_att)                                        # R/npdr.R:486
+    pval_adj = rstats.p_adjust(pval_att[o], padj_method)              # R/npdr.R:488
+    cols = {"att": [att_names[i] for i in o], "pval.adj": pval_adj, "pval.att": pval_att[o],
+            "beta.raw.att": stats[o, 0], "beta.Z.att": stats[o, 1], "beta.0": stats[o, 2], "pval.0": pval_0[o]}
+    if regression_type == "lm":
+        cols["R.sqr"] = stats[o, 5]
+    out = pd.DataFrame(cols) if pd is not None else cols
+    if return_info:
+        info["stats"] = stats
+        info["order"] = o
+        return out, info
+    return out

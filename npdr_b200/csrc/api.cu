@@ -1,0 +1,547 @@
+// api.cu -- the C ABI of libnpdr_b200.so (see include/npdr_b200.h): contexts, sessions and the
+// host-buffer operator entry points that replace the reference's exported R functions.
+#include <math.h>
+#include <stdarg.h>
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void npdrb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+__global__ void check_finite_kernel(const double *__restrict__ v, int64_t n, int *__restrict__ bad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int b = 0;
+    for (; i < n; i += (int64_t)gridDim.x * blockDim.x) b |= !isfinite(v[i]);
+    if (b) atomicOr(bad, 1);
+}
+
+// FP64 issue-rate micro-kernels: 8 independent chains per thread, 4096 x 8 ops each
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < 4096; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+__global__ void __launch_bounds__(256) dadd_peak_kernel(double *out, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < 4096; ++i) {
+        x0 = __dadd_rn(x0, b); x1 = __dadd_rn(x1, b); x2 = __dadd_rn(x2, b); x3 = __dadd_rn(x3, b);
+        x4 = __dadd_rn(x4, b); x5 = __dadd_rn(x5, b); x6 = __dadd_rn(x6, b); x7 = __dadd_rn(x7, b);
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what) {
+    int *d_bad = nullptr, h_bad = 0;
+    NB_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    NB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    int grid = (int)((n + 255) / 256);
+    if (grid > 4096) grid = 4096;
+    if (grid < 1) grid = 1;
+    check_finite_kernel<<<grid, 256, 0, ctx->stream>>>(d, n, d_bad);
+    NB_LAUNCH_CHECK(ctx);
+    NB_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bad);
+    if (h_bad) { npdrb_set_error("%s contains NA/NaN/Inf (rejected: SURVEY 8a quirk 8)", what); return NPDRB_EDATA; }
+    return NPDRB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *npdrb_version(void) { return "npdr_b200 0.1.0 (sm_100a)"; }
+const char *npdrb_last_error(void) { return g_err; }
+void npdrb_free(void *p) { free(p); }
+
+void npdrb_opts_default(npdrb_opts *o) {
+    memset(o, 0, sizeof(*o));
+    o->regression_type = NPDRB_REG_BINOMIAL;          // npdr() defaults, R/npdr.R:151-164
+    o->attr_diff_type = NPDRB_DIFF_NUMERIC_ABS;
+    o->nbd_method = NPDRB_NBD_MULTISURF;
+    o->nbd_metric = NPDRB_METRIC_MANHATTAN;
+    o->knn = 0;
+    o->msurf_sd_frac = 0.5;
+    o->n_covars = 0;
+    for (int c = 0; c < NPDRB_MAX_COVARS; ++c) o->covar_diff_type[c] = NPDRB_DIFF_MATCH_MISMATCH;
+}
+
+void npdrb_result_release(npdrb_result *r) {
+    if (!r) return;
+    free(r->stats); free(r->Ri); free(r->NN);
+    r->stats = nullptr; r->Ri = nullptr; r->NN = nullptr;
+}
+
+int64_t npdrb_knn_surf(int64_t m_samples, double sd_frac) {
+    // knnSURF, R/utils.R:12-18: floor((m - 1) * (1 - erf(sd.frac/sqrt(2))) / 2), erf(x) = 2*pnorm(x*sqrt(2)) - 1
+    double x = sd_frac / sqrt(2.0);
+    double z = x * sqrt(2.0);
+    double pn = 0.5 * erfc(-z / sqrt(2.0));
+    double erfv = 2.0 * pn - 1.0;
+    return (int64_t)floor((double)(m_samples - 1) * (1.0 - erfv) / 2.0);
+}
+
+int npdrb_create(int device, npdrb_ctx **out) {
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        npdrb_set_error("no CUDA device available (%s); libnpdr_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return NPDRB_ENODEVICE;
+    }
+    if (device < 0 || device >= n) { npdrb_set_error("device %d out of range (0..%d)", device, n - 1); return NPDRB_ENODEVICE; }
+    cudaDeviceProp prop;
+    NB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        npdrb_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return NPDRB_ENODEVICE;
+    }
+    NB_CUDA(cudaSetDevice(device));
+    npdrb_ctx *c = new npdrb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    NB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    *out = c;
+    return NPDRB_OK;
+}
+
+void npdrb_destroy(npdrb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int npdrb_set_stream(npdrb_ctx *ctx, void *cuda_stream) {
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return NPDRB_OK;
+}
+
+int npdrb_synchronize(npdrb_ctx *ctx) {
+    NB_CUDA(cudaSetDevice(ctx->device));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NPDRB_OK;
+}
+
+int64_t npdrb_launch_count(npdrb_ctx *ctx) { return ctx->launches; }
+
+int npdrb_measure_fp64_peak(npdrb_ctx *ctx, double *dfma_tflops, double *dadd_tflops) {
+    NB_CUDA(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    double *d_out = nullptr;
+    NB_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    NB_CUDA(cudaEventCreate(&e0)); NB_CUDA(cudaEventCreate(&e1));
+    double best[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        for (int rep = 0; rep < 5; ++rep) {
+            NB_CUDA(cudaEventRecord(e0, ctx->stream));
+            if (which == 0) dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, 1.0000001, 1e-9);
+            else dadd_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, 1e-9);
+            NB_LAUNCH_CHECK(ctx);
+            NB_CUDA(cudaEventRecord(e1, ctx->stream));
+            NB_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            NB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            const double ops = (double)blocks * threads * 4096.0 * 8.0;
+            const double rate = ops / (ms * 1e-3) / 1e12 * (which == 0 ? 2.0 : 1.0);
+            if (rep > 0 && rate > best[which]) best[which] = rate;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dadd_tflops) *dadd_tflops = best[1];
+    return NPDRB_OK;
+}
+
+// ------------------------------------------------------------------ sessions
+int npdrb_session_create(npdrb_ctx *ctx, int64_t N, int64_t p, int32_t q, npdrb_session **out) {
+    *out = nullptr;
+    if (!ctx) { npdrb_set_error("session: null context"); return NPDRB_EINVAL; }
+    if (N < 1 || p < 1) { npdrb_set_error("session: need N >= 1 and p >= 1"); return NPDRB_EINVAL; }
+    if (N >= (1ll << 31) - 256) { npdrb_set_error("session: N too large"); return NPDRB_EINVAL; }
+    if (q < 0 || q > NPDRB_MAX_COVARS) { npdrb_set_error("session: 0..%d covariates supported, got %d", NPDRB_MAX_COVARS, q); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(ctx->device));
+    npdrb_session *s = new npdrb_session();
+    s->ctx = ctx; s->N = N; s->p = p; s->q = q;
+    NB_CUDA(cudaEventCreate(&s->ev[0]));
+    NB_CUDA(cudaEventCreate(&s->ev[1]));
+    *out = s;
+    return NPDRB_OK;
+}
+
+void npdrb_session_destroy(npdrb_session *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->own_X) cudaFree(s->dX);
+    cudaFree(s->dXs);
+    if (s->own_y) cudaFree(s->dy);
+    if (s->own_C) cudaFree(s->dC);
+    if (s->own_D) cudaFree(s->dD);
+    cudaFree(s->d_sd_vec); cudaFree(s->d_radius);
+    cudaFree(s->dRiL); cudaFree(s->dNNL); cudaFree(s->d_rowptr);
+    if (s->own_pairs) { cudaFree(s->dRi); cudaFree(s->dNN); }
+    cudaFree(s->dXT);
+    nb_free_streams(s);
+    if (s->ev[0]) cudaEventDestroy(s->ev[0]);
+    if (s->ev[1]) cudaEventDestroy(s->ev[1]);
+    delete s;
+}
+
+int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, const double *C) {
+    npdrb_ctx *ctx = s->ctx;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t N = s->N, p = s->p;
+    if (X) {
+        if (!s->dX || !s->own_X) {
+            s->ldx = nb_round_up(N, 16);
+            NB_CUDA(cudaMalloc(&s->dX, sizeof(double) * (size_t)s->ldx * (size_t)p));
+            s->own_X = true;
+            if (s->ldx != N) NB_CUDA(cudaMemsetAsync(s->dX, 0, sizeof(double) * (size_t)s->ldx * (size_t)p, ctx->stream));
+        }
+        NB_CUDA(cudaMemcpy2DAsync(s->dX, sizeof(double) * (size_t)s->ldx, X, sizeof(double) * (size_t)N,
+                                  sizeof(double) * (size_t)N, (size_t)p, cudaMemcpyHostToDevice, ctx->stream));
+        s->xt_attr0 = -1; s->xt_nattr = 0;
+    }
+    if (y) {
+        if (!s->dy || !s->own_y) { NB_CUDA(cudaMalloc(&s->dy, sizeof(double) * (size_t)N)); s->own_y = true; }
+        NB_CUDA(cudaMemcpyAsync(s->dy, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        s->streams_valid = false;
+    }
+    if (C && s->q > 0) {
+        if (!s->dC || !s->own_C) { NB_CUDA(cudaMalloc(&s->dC, sizeof(double) * (size_t)N * s->q)); s->own_C = true; }
+        NB_CUDA(cudaMemcpyAsync(s->dC, C, sizeof(double) * (size_t)N * s->q, cudaMemcpyHostToDevice, ctx->stream));
+        s->streams_valid = false;
+    }
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (X) NB_CHECK(check_finite(ctx, s->dX, s->ldx * p, "the attribute matrix"));
+    if (y) NB_CHECK(check_finite(ctx, s->dy, N, "the outcome"));
+    if (C && s->q > 0) NB_CHECK(check_finite(ctx, s->dC, N * s->q, "the covariates"));
+    return NPDRB_OK;
+}
+
+int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy, const double *dC) {
+    if (dX) {
+        if (ldx < s->N || (ldx & 1)) { npdrb_set_error("set_device_inputs: ldx must be even and >= N"); return NPDRB_EINVAL; }
+        if (((uintptr_t)dX) & 15) { npdrb_set_error("set_device_inputs: dX must be 16-byte aligned"); return NPDRB_EINVAL; }
+        if (s->own_X) cudaFree(s->dX);
+        s->dX = const_cast<double *>(dX); s->ldx = ldx; s->own_X = false;
+        s->xt_attr0 = -1; s->xt_nattr = 0;
+    }
+    if (dy) { if (s->own_y) cudaFree(s->dy); s->dy = const_cast<double *>(dy); s->own_y = false; s->streams_valid = false; }
+    if (dC) { if (s->own_C) cudaFree(s->dC); s->dC = const_cast<double *>(dC); s->own_C = false; s->streams_valid = false; }
+    return NPDRB_OK;
+}
+
+int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_distances(s, metric, fast_euclidean, row0, nrows);
+}
+
+int npdrb_session_set_device_distances(npdrb_session *s, const double *dD, int64_t ldd, int64_t row0, int64_t nrows) {
+    if (ldd < s->N || row0 < 0 || nrows < 1 || row0 + nrows > s->N) { npdrb_set_error("set_device_distances: bad block"); return NPDRB_EINVAL; }
+    if (s->own_D) cudaFree(s->dD);
+    s->dD = const_cast<double *>(dD); s->ldd = ldd; s->row0 = row0; s->nrows = nrows; s->own_D = false;
+    return NPDRB_OK;
+}
+
+int npdrb_session_set_sd_vec(npdrb_session *s, const double *sd_vec_host) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    if (!sd_vec_host) { cudaFree(s->d_sd_vec); s->d_sd_vec = nullptr; return NPDRB_OK; }
+    if (!s->d_sd_vec) NB_CUDA(cudaMalloc(&s->d_sd_vec, sizeof(double) * (size_t)s->N));
+    NB_CUDA(cudaMemcpy(s->d_sd_vec, sd_vec_host, sizeof(double) * (size_t)s->N, cudaMemcpyHostToDevice));
+    return NPDRB_OK;
+}
+
+int npdrb_session_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local,
+                            int64_t *n_empty_local) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_neighbors(s, nbd_method, sd_frac, k, M_local, n_empty_local);
+}
+
+int npdrb_session_set_surf_radius(npdrb_session *s, double radius) {
+    s->surf_radius = radius; s->have_surf_radius = true;
+    return NPDRB_OK;
+}
+
+int npdrb_session_local_pairs(npdrb_session *s, const int32_t **dRi, const int32_t **dNN, int64_t *M_local) {
+    if (!s->dRiL) { npdrb_set_error("local_pairs: run neighbors first"); return NPDRB_EINVAL; }
+    *dRi = s->dRiL; *dNN = s->dNNL; *M_local = s->M_local;
+    return NPDRB_OK;
+}
+
+int npdrb_session_copy_local_pairs_device(npdrb_session *s, int32_t *dRi_dst, int32_t *dNN_dst) {
+    if (!s->dRiL) { npdrb_set_error("copy_local_pairs_device: run neighbors first"); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    if (s->M_local > 0) {
+        NB_CUDA(cudaMemcpyAsync(dRi_dst, s->dRiL, sizeof(int32_t) * (size_t)s->M_local, cudaMemcpyDeviceToDevice, s->ctx->stream));
+        NB_CUDA(cudaMemcpyAsync(dNN_dst, s->dNNL, sizeof(int32_t) * (size_t)s->M_local, cudaMemcpyDeviceToDevice, s->ctx->stream));
+    }
+    NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return NPDRB_OK;
+}
+
+int npdrb_session_copy_radius(npdrb_session *s, double *radius_host) {
+    if (!s->d_radius) { npdrb_set_error("copy_radius: no radii"); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    NB_CUDA(cudaMemcpyAsync(radius_host, s->d_radius, sizeof(double) * (size_t)s->nrows, cudaMemcpyDeviceToHost, s->ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return NPDRB_OK;
+}
+
+int npdrb_session_copy_distances(npdrb_session *s, double *D_host) {
+    if (!s->dD) { npdrb_set_error("copy_distances: no distances"); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    NB_CUDA(cudaMemcpy2DAsync(D_host, sizeof(double) * (size_t)s->N, s->dD, sizeof(double) * (size_t)s->ldd,
+                              sizeof(double) * (size_t)s->N, (size_t)s->nrows, cudaMemcpyDeviceToHost, s->ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return NPDRB_OK;
+}
+
+int npdrb_session_import_pairs(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64_t M) {
+    if (M < 0 || (M > 0 && (!dRi || !dNN))) { npdrb_set_error("import_pairs: bad arguments"); return NPDRB_EINVAL; }
+    if (s->own_pairs) { cudaFree(s->dRi); cudaFree(s->dNN); }
+    s->dRi = const_cast<int32_t *>(dRi); s->dNN = const_cast<int32_t *>(dNN); s->M = M; s->own_pairs = false;
+    s->streams_valid = false;
+    return NPDRB_OK;
+}
+
+int npdrb_session_import_pairs_host(npdrb_session *s, const int32_t *Ri, const int32_t *NN, int64_t M) {
+    if (M < 0 || (M > 0 && (!Ri || !NN))) { npdrb_set_error("import_pairs_host: bad arguments"); return NPDRB_EINVAL; }
+    for (int64_t m = 0; m < M; ++m) {
+        if (Ri[m] < 1 || Ri[m] > s->N || NN[m] < 1 || NN[m] > s->N) {
+            npdrb_set_error("import_pairs_host: pair %lld = (%d, %d) out of range 1..%lld", (long long)m, Ri[m], NN[m], (long long)s->N);
+            return NPDRB_EINVAL;
+        }
+    }
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    if (s->own_pairs) { cudaFree(s->dRi); cudaFree(s->dNN); }
+    s->dRi = nullptr; s->dNN = nullptr;
+    NB_CUDA(cudaMalloc(&s->dRi, sizeof(int32_t) * (size_t)(M > 0 ? M : 1)));
+    NB_CUDA(cudaMalloc(&s->dNN, sizeof(int32_t) * (size_t)(M > 0 ? M : 1)));
+    s->own_pairs = true; s->M = M; s->streams_valid = false;
+    NB_CUDA(cudaMemcpyAsync(s->dRi, Ri, sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, s->ctx->stream));
+    NB_CUDA(cudaMemcpyAsync(s->dNN, NN, sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, s->ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return NPDRB_OK;
+}
+
+int npdrb_session_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_unique) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_unique_pairs(s, keep_unique_only, n_unique);
+}
+
+int npdrb_session_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t regression_type, int32_t attr_diff_type,
+                          const int32_t *covar_diff_type, double *stats_out, int32_t *irls_passes) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_regress(s, attr0, nattr, regression_type, attr_diff_type, covar_diff_type, stats_out, irls_passes);
+}
+
+int npdrb_session_copy_pairs(npdrb_session *s, int32_t *Ri_host, int32_t *NN_host) {
+    if (!s->dRi && s->M > 0) { npdrb_set_error("copy_pairs: no pair list"); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    NB_CUDA(cudaMemcpyAsync(Ri_host, s->dRi, sizeof(int32_t) * (size_t)s->M, cudaMemcpyDeviceToHost, s->ctx->stream));
+    NB_CUDA(cudaMemcpyAsync(NN_host, s->dNN, sizeof(int32_t) * (size_t)s->M, cudaMemcpyDeviceToHost, s->ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return NPDRB_OK;
+}
+
+int npdrb_session_stage_ms(npdrb_session *s, double *ms_distance, double *ms_neighbors, double *ms_prepare, double *ms_regress) {
+    if (ms_distance) *ms_distance = s->ms_distance;
+    if (ms_neighbors) *ms_neighbors = s->ms_neighbors;
+    if (ms_prepare) *ms_prepare = s->ms_prepare;
+    if (ms_regress) *ms_regress = s->ms_regress;
+    return NPDRB_OK;
+}
+
+int npdrb_session_kernel_ms(npdrb_session *s, double *out5) {
+    out5[0] = s->ms_pass_first; out5[1] = s->ms_pass_full; out5[2] = (double)s->n_pass_full; out5[3] = s->evals_pass_full;
+    double rec = 0;
+    for (int i = 0; i < s->n_streams; ++i) rec += (double)s->streams[i].n_rec;
+    out5[4] = rec;
+    return NPDRB_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer operator API
+int npdrb_diff(npdrb_ctx *ctx, const double *a, const double *b, int64_t n, int32_t diff_type, double norm_fac, double *out) {
+    if (!ctx) { npdrb_set_error("npdrb_diff: null context (no device)"); return NPDRB_ENODEVICE; }
+    if (diff_type < 0 || diff_type > NPDRB_DIFF_RAW) { npdrb_set_error("npdrb_diff: unknown diff type %d", diff_type); return NPDRB_EINVAL; }
+    if (n <= 0) return NPDRB_OK;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    NB_CUDA(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
+    NB_CUDA(cudaMemcpyAsync(d, a, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    NB_CUDA(cudaMemcpyAsync(d + n, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = nb_diff_vectors(ctx, d, d + n, n, diff_type, norm_fac, d + 2 * n);
+    if (rc == NPDRB_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d + 2 * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { npdrb_set_error("npdrb_diff: %s", cudaGetErrorString(e)); rc = NPDRB_ECUDA; }
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int npdrb_distances(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, int32_t metric, int32_t fast_euclidean, double *D_out) {
+    if (!ctx) { npdrb_set_error("npdrb_distances: null context (no device)"); return NPDRB_ENODEVICE; }
+    npdrb_session *s = nullptr;
+    NB_CHECK(npdrb_session_create(ctx, N, p, 0, &s));
+    int rc = npdrb_session_upload(s, X, nullptr, nullptr);
+    if (!rc) rc = nb_distances(s, metric, fast_euclidean, 0, N);
+    if (!rc) rc = npdrb_session_copy_distances(s, D_out);     // symmetric: row-major block == column-major matrix
+    npdrb_session_destroy(s);
+    return rc;
+}
+
+static int pairs_to_host(npdrb_session *s, int32_t **Ri, int32_t **NN) {
+    const int64_t M = s->M;
+    *Ri = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
+    *NN = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
+    if (!*Ri || !*NN) { npdrb_set_error("out of host memory for %lld pairs", (long long)M); return NPDRB_ENOMEM; }
+    if (M > 0) NB_CHECK(npdrb_session_copy_pairs(s, *Ri, *NN));
+    return NPDRB_OK;
+}
+
+// distances (or adoption of a precomputed matrix) + neighbours on one device; leaves the list imported in s
+static int neighbors_stage(npdrb_session *s, const double *X_or_D_host, int32_t nbd_method, int32_t nbd_metric,
+                           const double *sd_vec, double sd_frac, int64_t k, int32_t fast_euclidean,
+                           int64_t *M, int64_t *n_empty) {
+    npdrb_ctx *ctx = s->ctx;
+    const int64_t N = s->N;
+    if (nbd_metric == NPDRB_METRIC_PRECOMPUTED) {
+        // attr.mat is the distance matrix (R/nearestNeighbors.R:171-176); column Ri of D is row Ri of the block
+        if (!X_or_D_host) { npdrb_set_error("precomputed metric needs the distance matrix"); return NPDRB_EINVAL; }
+        double *dD = nullptr;
+        NB_CUDA(cudaMalloc(&dD, sizeof(double) * (size_t)N * (size_t)N));
+        NB_CUDA(cudaMemcpyAsync(dD, X_or_D_host, sizeof(double) * (size_t)N * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+        int rc = check_finite(ctx, dD, N * N, "the distance matrix");
+        if (rc) { cudaFree(dD); return rc; }
+        if (s->own_D) cudaFree(s->dD);
+        s->dD = dD; s->ldd = N; s->row0 = 0; s->nrows = N; s->own_D = true;
+    } else {
+        NB_CHECK(nb_distances(s, nbd_metric, fast_euclidean, 0, N));
+    }
+    NB_CHECK(npdrb_session_set_sd_vec(s, sd_vec));
+    NB_CHECK(nb_neighbors(s, nbd_method, sd_frac, k, M, n_empty));
+    NB_CHECK(npdrb_session_import_pairs(s, s->dRiL, s->dNNL, s->M_local));
+    return NPDRB_OK;
+}
+
+int npdrb_nearest_neighbors(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, int32_t nbd_method, int32_t nbd_metric,
+                            const double *sd_vec, double sd_frac, int64_t k, int32_t unique_sampling, int32_t **Ri,
+                            int32_t **NN, int64_t *M, int64_t *n_unique, int64_t *n_empty, double *radius_out) {
+    if (!ctx) { npdrb_set_error("npdrb_nearest_neighbors: null context (no device)"); return NPDRB_ENODEVICE; }
+    npdrb_session *s = nullptr;
+    const bool pre = nbd_metric == NPDRB_METRIC_PRECOMPUTED;
+    NB_CHECK(npdrb_session_create(ctx, N, pre ? N : p, 0, &s));
+    int rc = pre ? NPDRB_OK : npdrb_session_upload(s, X, nullptr, nullptr);
+    int64_t Ml = 0, ne = 0, nu = 0;
+    if (!rc) rc = neighbors_stage(s, X, nbd_method, nbd_metric, sd_vec, sd_frac, k, 0, &Ml, &ne);
+    if (!rc && radius_out && nbd_method != NPDRB_NBD_RELIEFF) rc = npdrb_session_copy_radius(s, radius_out);
+    if (!rc) rc = nb_unique_pairs(s, unique_sampling, &nu);
+    if (!rc) rc = pairs_to_host(s, Ri, NN);
+    if (!rc) { *M = s->M; if (n_unique) *n_unique = nu; if (n_empty) *n_empty = ne; }
+    npdrb_session_destroy(s);
+    return rc;
+}
+
+int npdrb_regress(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const int32_t *Ri, const int32_t *NN, int64_t M,
+                  const double *y, const double *C, int32_t q, const int32_t *covar_diff_type, int32_t attr_diff_type,
+                  int32_t regression_type, double *stats_out) {
+    if (!ctx) { npdrb_set_error("npdrb_regress: null context (no device)"); return NPDRB_ENODEVICE; }
+    npdrb_session *s = nullptr;
+    NB_CHECK(npdrb_session_create(ctx, N, p, q, &s));
+    int rc = npdrb_session_upload(s, X, y, C);
+    if (!rc) rc = npdrb_session_import_pairs_host(s, Ri, NN, M);
+    if (!rc) rc = nb_regress(s, 0, p, regression_type, attr_diff_type, covar_diff_type, stats_out, nullptr);
+    npdrb_session_destroy(s);
+    return rc;
+}
+
+int npdrb_npdr(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
+               const npdrb_opts *o, npdrb_result *res) {
+    if (!ctx) { npdrb_set_error("npdrb_npdr: null context (no device)"); return NPDRB_ENODEVICE; }
+    if (!o || !res) { npdrb_set_error("npdrb_npdr: null opts/result"); return NPDRB_EINVAL; }
+    memset(res, 0, sizeof(*res));
+    if (o->nbd_metric == NPDRB_METRIC_PRECOMPUTED) {
+        npdrb_set_error("npdrb_npdr: precomputed distances go through npdrb_nearest_neighbors + npdrb_regress");
+        return NPDRB_EINVAL;
+    }
+    cudaEvent_t t0, t1, t2;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    NB_CUDA(cudaEventCreate(&t0)); NB_CUDA(cudaEventCreate(&t1)); NB_CUDA(cudaEventCreate(&t2));
+    NB_CUDA(cudaEventRecord(t0, ctx->stream));
+    npdrb_session *s = nullptr;
+    int rc = npdrb_session_create(ctx, N, p, o->n_covars, &s);
+    if (rc) return rc;
+    rc = npdrb_session_upload(s, X, y, C);
+    if (!rc) { cudaEventRecord(t1, ctx->stream); }
+    int64_t M = 0, ne = 0, nu = 0;
+    int64_t k = o->knn;
+    if (o->nbd_method == NPDRB_NBD_RELIEFF && k <= 0) k = npdrb_knn_surf(N, o->msurf_sd_frac);
+    if (!rc) rc = neighbors_stage(s, nullptr, o->nbd_method, o->nbd_metric, nullptr, o->msurf_sd_frac, k, o->fast_euclidean, &M, &ne);
+    if (!rc) rc = nb_unique_pairs(s, o->neighbor_sampling_unique, &nu);
+    if (!rc && s->M <= 0) { npdrb_set_error("npdr: no neighbour pairs found"); rc = NPDRB_EDATA; }
+    int32_t passes = 0;
+    if (!rc) {
+        res->stats = (double *)malloc(sizeof(double) * (size_t)p * NPDRB_STATS_PER_ATTR);
+        if (!res->stats) { npdrb_set_error("out of host memory"); rc = NPDRB_ENOMEM; }
+    }
+    if (!rc) rc = nb_regress(s, 0, p, o->regression_type, o->attr_diff_type, o->covar_diff_type, res->stats, &passes);
+    if (!rc && o->return_pairs) rc = pairs_to_host(s, &res->Ri, &res->NN);
+    if (!rc) {
+        cudaEventRecord(t2, ctx->stream);
+        cudaEventSynchronize(t2);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1); res->ms_h2d = ms;
+        cudaEventElapsedTime(&ms, t0, t2); res->ms_total = ms;
+        res->n_attr = p; res->n_pairs = M; res->n_unique_pairs = nu; res->n_pairs_used = s->M;
+        res->n_empty = ne; res->knn_used = (o->nbd_method == NPDRB_NBD_RELIEFF) ? k : 0;
+        res->k_ave_empirical = (N - ne) > 0 ? (double)M / (double)(N - ne) : 0.0;   // mean(knnVec()): only Ri that appear
+        res->ms_distance = s->ms_distance; res->ms_neighbors = s->ms_neighbors;
+        res->ms_prepare = s->ms_prepare; res->ms_regress = s->ms_regress; res->irls_passes = passes;
+    } else {
+        npdrb_result_release(res);
+    }
+    npdrb_session_destroy(s);
+    cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+    return rc;
+}
+
+int npdrb_unireg(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C, int32_t q,
+                 int32_t regression_type, double *stats_out) {
+    // uniReg (R/utils.R:66-157): the same per-column GLM on the N raw rows -- the identity pair list (i, i)
+    // with the RAW diff (the attribute value itself), outcome and covariates taken as they are.
+    if (!ctx) { npdrb_set_error("npdrb_unireg: null context (no device)"); return NPDRB_ENODEVICE; }
+    npdrb_session *s = nullptr;
+    NB_CHECK(npdrb_session_create(ctx, N, p, q, &s));
+    int rc = npdrb_session_upload(s, X, y, C);
+    std::vector<int32_t> id((size_t)N);
+    for (int64_t i = 0; i < N; ++i) id[(size_t)i] = (int32_t)(i + 1);
+    if (!rc) rc = npdrb_session_import_pairs_host(s, id.data(), id.data(), N);
+    if (!rc) rc = nb_regress(s, 0, p, regression_type, NPDRB_DIFF_RAW, nullptr, stats_out, nullptr);
+    npdrb_session_destroy(s);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// common.cuh -- shared plumbing of libnpdr_b200.so (context, session, error handling).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/npdr_b200.h"
+
+void npdrb_set_error(const char *fmt, ...);
+
+#define NB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            npdrb_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return NPDRB_ECUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define NB_CHECK(call)                 \
+    do {                               \
+        int _rc = (call);              \
+        if (_rc != NPDRB_OK) return _rc; \
+    } while (0)
+
+#define NB_LAUNCH_CHECK(ctx)                                                                   \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            npdrb_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return NPDRB_ECUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+static inline int64_t nb_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+static inline int64_t nb_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+struct npdrb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int64_t launches = 0;
+    size_t smem_optin = 0;
+};
+
+// One bucketed pair stream for the regression kernels (see regress.cu).
+struct nb_stream {
+    int64_t n_rec = 0;            // records in this stream
+    double weight = 1.0;          // multiplicity applied to every record's contribution
+    uint32_t *rec = nullptr;      // il | jl << 8 | ybit << 16, bucketed by (I-block, J-block) tile
+    double *yv = nullptr;         // lm: |y_i - y_j| per record
+    double *cd[NPDRB_MAX_COVARS] = {nullptr, nullptr, nullptr, nullptr};  // covariate diffs per record
+    int32_t n_tiles = 0;          // non-empty tiles
+    int64_t *tile_ptr = nullptr;  // [n_tiles + 1] record offsets
+    int32_t *tile_ib = nullptr, *tile_jb = nullptr;
+    int32_t n_chunks = 0;
+    int32_t *chunk_tile = nullptr;  // [n_chunks + 1] tile ranges per work chunk
+};
+
+struct npdrb_session {
+    npdrb_ctx *ctx = nullptr;
+    int64_t N = 0, p = 0;
+    int32_t q = 0;
+    // inputs
+    double *dX = nullptr; int64_t ldx = 0; bool own_X = false;          // column-major, N x p, leading dim ldx
+    double *dXs = nullptr;                                               // pre-scaled copy for scaled metrics
+    double *dy = nullptr; bool own_y = false;
+    double *dC = nullptr; bool own_C = false;                            // N x q, ld N
+    // distance block: nrows x N, row-major with leading dim ldd (row r = column row0+r of the symmetric D)
+    double *dD = nullptr; int64_t ldd = 0; int64_t row0 = 0, nrows = 0; bool own_D = false;
+    double *d_sd_vec = nullptr;                                          // optional user sd.vec (length N)
+    double *d_radius = nullptr;                                          // owned rows
+    bool have_surf_radius = false; double surf_radius = 0.0;
+    // local neighbour segment
+    int32_t *dRiL = nullptr, *dNNL = nullptr; int64_t M_local = 0; int64_t n_empty_local = 0;
+    int64_t *d_rowptr = nullptr;
+    // list used by the regression
+    int32_t *dRi = nullptr, *dNN = nullptr; int64_t M = 0; bool own_pairs = false;
+    // regression workspace
+    double *dXT = nullptr; int64_t ldt = 0; int64_t xt_attr0 = -1, xt_nattr = 0;
+    nb_stream streams[2]; int n_streams = 0;
+    int32_t streams_reg_type = -1; int32_t streams_cov_sig = -1; bool streams_valid = false;
+    // timing
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    double ms_distance = 0, ms_neighbors = 0, ms_prepare = 0, ms_regress = 0;
+    // kernel-level timings of the last regress call (CUDA events around the pass-kernel launches)
+    double ms_pass_first = 0;      // lm: the single pass; binomial: the pass at the mustart weights
+    double ms_pass_full = 0;       // binomial: sum over the full IRLS passes
+    int n_pass_full = 0;
+    double evals_pass_full = 0;    // attribute x record evaluations executed by those passes (active tiles only)
+};
+
+// stage implementations (one .cu each)
+int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
+int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local, int64_t *n_empty);
+int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_unique);
+int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t regression_type, int32_t attr_diff_type,
+               const int32_t *covar_diff_type, double *stats_out_host, int32_t *irls_passes);
+int nb_diff_vectors(npdrb_ctx *ctx, const double *da, const double *db, int64_t n, int32_t type, double norm_fac,
+                    double *dout);
+int nb_measure_fp64_peak(npdrb_ctx *ctx, double *dfma_tflops, double *dadd_tflops);
+void nb_free_streams(npdrb_session *s);
+
+// diff function shared by the pair kernels (npdrDiff, R/nearestNeighbors.R:15-40, norm.fac = 1)
+__device__ __forceinline__ double nb_diff1(double a, double b, int type) {
+    switch (type) {
+    case NPDRB_DIFF_NUMERIC_SQR: { double t = fabs(a - b); return t * t; }
+    case NPDRB_DIFF_ALLELE_SHARING: return fabs(a - b) * 0.5;
+    case NPDRB_DIFF_MATCH_MISMATCH: return (a == b) ? 0.0 : 1.0;
+    case NPDRB_DIFF_RAW: return a;
+    default: return fabs(a - b);
+    }
+}

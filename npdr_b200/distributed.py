@@ -1,0 +1,180 @@
+"""Sharding NPDR's hot path over the GPUs of one node (one process per GPU, torch.distributed).
+
+The path has two embarrassingly parallel stages joined by ONE exchange:
+  A+B  distances + neighbour lists : row-block sharded (rank g owns instances I_g, computes D[I_g, :]);
+       multiSURF radii are per-row, so no reduction is needed; SURF needs two scalar all-reduces.
+  X    all-gather of the variable-length (Ri, NN) segments -- concatenation in rank order IS the
+       reference's order, because segments are contiguous in Ri.
+  C    regression : attribute-column sharded, every rank holds the full pair list; statistics are
+       gathered to rank 0.  No data-path reduction -> results are identical for any world size.
+
+`Engine` is the per-rank compute interface; `GpuEngine` drives libnpdr_b200 sessions.  The collective
+plumbing below only sees torch tensors, so it is exercised on CPU with the gloo backend in tests/.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROW_ALIGN = 128          # distance tiles are 128 rows: row blocks start on tile boundaries
+
+
+def partition_rows(N, world, align=ROW_ALIGN):
+    """Contiguous, tile-aligned row blocks [(row0, nrows)] covering 0..N; trailing ranks may be empty."""
+    n_tiles = -(-N // align)
+    base, extra = divmod(n_tiles, world)
+    out, t0 = [], 0
+    for r in range(world):
+        nt = base + (1 if r < extra else 0)
+        row0 = min(t0 * align, N)
+        row1 = min((t0 + nt) * align, N)
+        out.append((row0, row1 - row0))
+        t0 += nt
+    return out
+
+
+def partition_attrs(p, world):
+    """Contiguous attribute blocks [(attr0, nattr)]."""
+    base, extra = divmod(p, world)
+    out, a0 = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((a0, n))
+        a0 += n
+    return out
+
+
+class Engine:
+    """Per-rank compute interface used by npdr_sharded()."""
+    device = torch.device("cpu")
+
+    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k):
+        """-> (Ri, NN) int32 tensors on self.device for the owned rows (1-based, reference order)."""
+        raise NotImplementedError
+
+    def surf_partial(self, row0, nrows, nbd_metric, centre):
+        """-> 4 partial moments (see npdrb_session_surf_partial)."""
+        raise NotImplementedError
+
+    def set_surf_radius(self, radius):
+        raise NotImplementedError
+
+    def regress_block(self, Ri, NN, attr0, nattr, regression_type, attr_diff_type, covar_diff_type, unique):
+        """-> (stats float64 [nattr, 8] numpy, n_unique, n_pairs_used)."""
+        raise NotImplementedError
+
+
+def all_gather_varlen(t, group=None):
+    """All-gather 1-D tensors of different lengths; returns the concatenation in rank order."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+    pad[: t.numel()] = t
+    bufs = [torch.empty(mx, dtype=t.dtype, device=t.device) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)]), counts
+
+
+def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numeric-abs", nbd_method="multisurf",
+                 nbd_metric="manhattan", knn=0, msurf_sd_frac=0.5, covar_diff_type=(), neighbor_sampling="none",
+                 group=None):
+    """Run the path sharded over the default process group.  Every rank returns
+    (stats [p, 8] on rank 0 else None, info dict)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    row0, nrows = partition_rows(N, world)[rank]
+    dev = engine.device
+
+    if nbd_method == "surf" and world > 1:
+        # one global mean / sd: two scalar all-reduces (R/nearestNeighbors.R:234-241)
+        m0 = torch.tensor(engine.surf_partial(row0, nrows, nbd_metric, 0.0) if nrows else [0.0] * 4, dtype=torch.float64, device=dev)
+        dist.all_reduce(m0, group=group)
+        mean_u = float(m0[1] / m0[2])
+        m1 = torch.tensor(engine.surf_partial(row0, nrows, nbd_metric, mean_u) if nrows else [0.0] * 4, dtype=torch.float64, device=dev)
+        dist.all_reduce(m1, group=group)
+        num_pair = N * (N - 1) / 2.0
+        radius = float(m0[0]) / (2.0 * num_pair) - msurf_sd_frac * float(torch.sqrt(m1[3] / (m1[2] - 1.0)))
+        engine.set_surf_radius(radius)
+
+    if nrows > 0:
+        ri, nn = engine.neighbors_block(row0, nrows, nbd_method, nbd_metric, msurf_sd_frac, knn)
+    else:
+        ri = torch.zeros(0, dtype=torch.int32, device=dev); nn = torch.zeros(0, dtype=torch.int32, device=dev)
+    if world > 1:
+        ri_all, counts = all_gather_varlen(ri, group)
+        nn_all, _ = all_gather_varlen(nn, group)
+    else:
+        ri_all, nn_all, counts = ri, nn, [ri.numel()]
+
+    attr0, nattr = partition_attrs(p, world)[rank]
+    if nattr > 0:
+        stats, n_unique, n_used = engine.regress_block(ri_all, nn_all, attr0, nattr, regression_type, attr_diff_type,
+                                                       covar_diff_type, neighbor_sampling == "unique")
+        st = torch.from_numpy(np.ascontiguousarray(stats, dtype=np.float64)).to(dev)
+    else:
+        st = torch.zeros((0, 8), dtype=torch.float64, device=dev); n_unique, n_used = -1, -1
+    info = {"n_pairs": int(sum(counts)), "pair_counts": counts, "n_unique_pairs": n_unique, "n_pairs_used": n_used,
+            "rows": (row0, nrows), "attrs": (attr0, nattr)}
+    if world == 1:
+        return st.cpu().numpy(), info
+    flat, fcounts = all_gather_varlen(st.reshape(-1), group)      # tiny: p x 8 doubles in total
+    out = flat.reshape(-1, 8).cpu().numpy() if rank == 0 else None
+    return out, info
+
+
+class GpuEngine(Engine):
+    """libnpdr_b200 session on this rank's GPU.  Inputs are uploaded once (or adopted from device tensors)."""
+
+    def __init__(self, X=None, y=None, C=None, device_index=0, dX=None, ldx=None, dy=None, dC=None, N=None, p=None, q=None):
+        from . import _lib
+        self._lib = _lib
+        self.device = torch.device("cuda", device_index)
+        self.ctx = _lib.context(device_index)
+        if X is not None:
+            N, p = X.shape
+            q = 0 if C is None else (1 if np.ndim(C) == 1 else np.shape(C)[1])
+        self.N, self.p, self.q = N, p, q
+        self.session = _lib.Session(self.ctx, N, p, q)
+        if X is not None:
+            self.session.upload(X, y, C)
+        else:
+            self._keep = (dX, dy, dC)
+            self.session.set_device_inputs(dX.data_ptr(), ldx, dy.data_ptr(), dC.data_ptr() if dC is not None else 0)
+        self._metric_done = None
+
+    def close(self):
+        self.session.close()
+
+    def _ensure_distances(self, row0, nrows, nbd_metric):
+        key = (row0, nrows, nbd_metric)
+        if self._metric_done != key:
+            self.session.distances(nbd_metric, False, row0, nrows)
+            self._metric_done = key
+
+    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k):
+        self._ensure_distances(row0, nrows, nbd_metric)
+        M, _ = self.session.neighbors(nbd_method, sd_frac, k)
+        ri = torch.empty(max(M, 1), dtype=torch.int32, device=self.device)[:M]
+        nn = torch.empty(max(M, 1), dtype=torch.int32, device=self.device)[:M]
+        if M:
+            self.session.copy_local_pairs_device(ri.data_ptr(), nn.data_ptr())
+        return ri, nn
+
+    def surf_partial(self, row0, nrows, nbd_metric, centre):
+        self._ensure_distances(row0, nrows, nbd_metric)
+        return self.session.surf_partial(centre).tolist()
+
+    def set_surf_radius(self, radius):
+        self.session.set_surf_radius(radius)
+
+    def regress_block(self, Ri, NN, attr0, nattr, regression_type, attr_diff_type, covar_diff_type, unique):
+        torch.cuda.synchronize(self.device)          # NCCL results complete before the library's stream reads them
+        self._pairs = (Ri.contiguous(), NN.contiguous())
+        self.session.import_pairs(self._pairs[0].data_ptr(), self._pairs[1].data_ptr(), Ri.numel())
+        n_unique = self.session.unique_pairs(keep_unique_only=unique)
+        stats = self.session.regress(attr0, nattr, regression_type, attr_diff_type, covar_diff_type)
+        n_used = n_unique if unique else Ri.numel()
+        return stats, n_unique, n_used

@@ -1,0 +1,373 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs.  Bars (BASELINE north_star): neighbour-pair lists bit-exact; distances <= 1e-12 rel (here:
+bit-exact for manhattan and the non-contracted euclidean); lm statistics <= 1e-8 rel; binomial IRLS
+<= 1e-6 rel; identical attribute ordering."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_case, oracle_run
+
+pytestmark = pytest.mark.gpu
+
+RTOL_LM = 1e-8
+RTOL_IRLS = 1e-6
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import npdr_b200
+    npdr_b200.context(0)          # raises loudly when the CUDA library / device is missing
+    return npdr_b200
+
+
+def _stats_close(got, exp, rtol, what=""):
+    """Columns beta_a, stat_a, beta_0, stat_0, r2|deviance to rtol; df, iters, flags exactly."""
+    for col in (0, 1, 2, 3, 5):
+        g, e = got[:, col], exp[:, col]
+        assert np.array_equal(np.isnan(g), np.isnan(e)), f"{what} NaN pattern differs in column {col}"
+        ok = ~np.isnan(e)
+        err = np.abs(g[ok] - e[ok]) / np.maximum(np.abs(e[ok]), 1e-300)
+        # |beta| can be arbitrarily close to 0 for null attributes: allow rtol relative to the column scale too
+        scale = np.abs(e[ok]).max() if ok.any() else 1.0
+        bad = (err > rtol) & (np.abs(g[ok] - e[ok]) > rtol * 1e-3 * scale)
+        assert not bad.any(), f"{what} column {col}: max rel err {err.max():.3e} at {np.argmax(err)}"
+    assert np.array_equal(got[:, 4], exp[:, 4]), f"{what} df_resid differs"
+    assert np.array_equal(got[:, 6], exp[:, 6]), f"{what} IRLS iteration counts differ"
+    assert np.array_equal(got[:, 7], exp[:, 7]), f"{what} flags differ"
+
+
+# ------------------------------------------------------------------ npdrDiff
+def test_npdrdiff_reference_kats(nb):
+    a = [0, 1, 0, 1]; b = [0, 1, 0, 4]; d = [2, 1, 0, 1]
+    assert np.array_equal(nb.npdrDiff(a, b), [0, 0, 0, 3])
+    assert np.array_equal(nb.npdrDiff(a, b, "numeric-sqr", 3), [0, 0, 0, 3])
+    assert np.array_equal(nb.npdrDiff(a, d, "allele-sharing"), [1, 0, 0, 0])
+    assert np.array_equal(nb.npdrDiff(a, d, "match-mismatch"), [1, 0, 0, 0])
+    assert np.array_equal(nb.npdrDiff(a, b, None), [0, 0, 0, 3])
+    assert nb.npdrDiff([], []).size == 0
+
+
+def test_npdrdiff_random(nb, oracle):
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=1000); b = rng.normal(size=1000); b[::7] = a[::7]
+    for t, nf in (("numeric-abs", 1.0), ("manhattan", 2.5), ("numeric-sqr", 3.0), ("allele-sharing", 1.0), ("match-mismatch", 1.0)):
+        assert np.array_equal(nb.npdrDiff(a, b, t, nf), oracle.diff(a, b, t, nf)), t
+
+
+# ------------------------------------------------------------------ distances
+@pytest.mark.parametrize("shape", [(100, 100), (157, 500), (10, 10), (3, 1), (129, 17), (256, 33), (300, 1000), (513, 70)])
+@pytest.mark.parametrize("metric", ["manhattan", "euclidean"])
+def test_distances_bit_exact(nb, oracle, shape, metric):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    X = np.asfortranarray(rng.normal(size=shape))
+    D = nb.npdrDistances(X, metric)
+    E = oracle.distances(X, metric)
+    assert D.shape == E.shape
+    assert np.array_equal(D, E), f"max abs diff {np.abs(D - E).max():.3e}"
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+
+
+def test_distances_fixtures_and_scaled_metrics(nb, oracle):
+    for name in ("cfg1", "cfg2", "cfg3"):
+        c = load_case(name)
+        assert np.array_equal(nb.npdrDistances(c["X"], c["nbd_metric"]), oracle.distances(c["X"], c["nbd_metric"])), name
+    rng = np.random.default_rng(5)
+    X = np.asfortranarray(rng.normal(size=(90, 45)))
+    for m in ("relief-scaled-manhattan", "relief-scaled-euclidean"):
+        assert np.array_equal(nb.npdrDistances(X, m), oracle.distances(X, m)), m
+    G = np.asfortranarray(rng.integers(0, 3, size=(70, 200)).astype(float))
+    assert np.array_equal(nb.npdrDistances(G, "allele-sharing-manhattan"), oracle.distances(G, "allele-sharing-manhattan"))
+    assert nb.npdrDistances(X, "no-such-metric") is None          # the reference returns NULL
+
+
+def test_distances_fast_euclidean_tolerance(nb, oracle):
+    rng = np.random.default_rng(6)
+    X = np.asfortranarray(rng.normal(size=(200, 300)))
+    D = nb.npdrDistances(X, "euclidean", fast_euclidean=True)
+    E = oracle.distances(X, "euclidean")
+    off = ~np.eye(200, dtype=bool)
+    assert np.max(np.abs(D[off] - E[off]) / E[off]) <= 1e-12       # north_star tolerance for the contracted form
+
+
+def test_simple_and_tma_kernels_agree(nb, oracle):
+    rng = np.random.default_rng(7)
+    X = np.asfortranarray(rng.normal(size=(260, 90)))
+    os.environ["NPDRB_DIST_KERNEL"] = "simple"
+    try:
+        Ds = nb.npdrDistances(X, "manhattan")
+    finally:
+        del os.environ["NPDRB_DIST_KERNEL"]
+    assert np.array_equal(Ds, nb.npdrDistances(X, "manhattan")) and np.array_equal(Ds, oracle.distances(X))
+
+
+# ------------------------------------------------------------------ neighbours
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_neighbors_fixtures_bit_exact(nb, name):
+    c = load_case(name)
+    exp = np.load(os.path.join(GOLDEN, f"expected_{name}.npz"))
+    out, info = nb.nearestNeighbors(c["X"], c["nbd_method"], c["nbd_metric"], return_info=True)
+    assert np.array_equal(out["Ri_idx"].to_numpy(), exp["Ri"]) and np.array_equal(out["NN_idx"].to_numpy(), exp["NN"])
+    assert info["n_unique"] == int(exp["n_unique"])
+    if c["nbd_method"] != "relieff":
+        assert np.array_equal(info["radius"], exp["radius"])      # x87 long-double sums reproduced bit for bit
+
+
+@pytest.mark.parametrize("method", ["multisurf", "surf", "relieff"])
+@pytest.mark.parametrize("kind", ["normal", "snp", "dups"])
+def test_neighbors_random_bit_exact(nb, oracle, method, kind):
+    rng = np.random.default_rng(hash((method, kind)) % 2**32)
+    N, p = (211, 40) if kind == "normal" else (150, 24)
+    if kind == "normal":
+        X = rng.normal(size=(N, p))
+    else:
+        X = rng.integers(0, 3, size=(N, p)).astype(float)          # exact ties everywhere
+    if kind == "dups":
+        X[5] = X[60]; X[61] = X[60]; X[149] = X[0]                  # zero distances: dropped by filter(> 0)
+    X = np.asfortranarray(X)
+    for k in ((0, 7, 1) if method == "relieff" else (0,)):
+        ri, nn, D, r = oracle.nearest_neighbors(X, method, "manhattan", 0.5, k)
+        out, info = nb.nearestNeighbors(X, method, "manhattan", sd_frac=0.5, k=k, return_info=True)
+        assert np.array_equal(out["Ri_idx"].to_numpy(), ri), (method, kind, k)
+        assert np.array_equal(out["NN_idx"].to_numpy(), nn), (method, kind, k)
+        if r is not None:
+            assert np.array_equal(info["radius"], r)
+        nu, keep = oracle.unique_neighbors(ri, nn, N)
+        assert info["n_unique"] == nu
+        u = nb.nearestNeighbors(X, method, "manhattan", sd_frac=0.5, k=k, neighbor_sampling="unique")
+        assert np.array_equal(u["Ri_idx"].to_numpy(), ri[keep]) and np.array_equal(u["NN_idx"].to_numpy(), nn[keep])
+        u2 = nb.uniqueNeighbors(out)
+        assert np.array_equal(u2.to_numpy(), u.to_numpy())
+        assert np.array_equal(nb.knnVec(out), oracle.knn_vec(ri, N))
+
+
+def test_neighbors_options(nb, oracle):
+    rng = np.random.default_rng(11)
+    X = np.asfortranarray(rng.normal(size=(120, 30)))
+    D = oracle.distances(X)
+    # user sd.vec, other sd.frac
+    sdv = rng.uniform(0.5, 2.0, size=120)
+    r, _ = oracle.radius_multisurf(D, 0.25, sdv)
+    ri, nn, _ = oracle.neighbors(D, "multisurf", radius=r)
+    out = nb.nearestNeighbors(X, "multisurf", sd_vec=sdv, sd_frac=0.25)
+    assert np.array_equal(out["Ri_idx"], ri) and np.array_equal(out["NN_idx"], nn)
+    # precomputed distances
+    out = nb.nearestNeighbors(D, "multisurf", "precomputed")
+    ri, nn, _, _ = oracle.nearest_neighbors(X)
+    assert np.array_equal(out["Ri_idx"], ri) and np.array_equal(out["NN_idx"], nn)
+    # att_to_remove
+    out = nb.nearestNeighbors(X, att_to_remove=[0, 3])
+    ri, nn, _, _ = oracle.nearest_neighbors(np.asfortranarray(X[:, [c for c in range(30) if c not in (0, 3)]]))
+    assert np.array_equal(out["Ri_idx"], ri) and np.array_equal(out["NN_idx"], nn)
+    # large sd.frac -> some instances have empty neighbourhoods: skipped, counted
+    out, info = nb.nearestNeighbors(X, "multisurf", sd_frac=3.0, return_info=True)
+    ri, nn, _, _ = oracle.nearest_neighbors(X, sd_frac=3.0)
+    assert np.array_equal(out["Ri_idx"], ri) and info["n_empty"] == 120 - np.unique(ri).size
+
+
+def test_surf_large_n_close(nb, oracle):
+    """N > 1024: the SURF radius comes from parallel moments (<= 1 ulp-level deviation)."""
+    rng = np.random.default_rng(12)
+    X = np.asfortranarray(rng.normal(size=(1100, 20)))
+    out, info = nb.nearestNeighbors(X, "surf", return_info=True)
+    ri, nn, D, r = oracle.nearest_neighbors(X, "surf")
+    assert abs(info["radius"][0] - r[0]) <= 4e-16 * r[0] * 4
+    assert np.array_equal(out["Ri_idx"], ri) and np.array_equal(out["NN_idx"], nn)
+
+
+# ------------------------------------------------------------------ regression
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_npdr_fixtures(nb, name):
+    c = load_case(name)
+    exp = np.load(os.path.join(GOLDEN, f"expected_{name}.npz"))
+    import pandas as pd
+    df = pd.DataFrame(c["X"], columns=c["names"])
+    covars = c["C"] if c["C"] is not None else "none"
+    out, info = nb.npdr(c["y"], df, c["regression_type"], "numeric-abs", c["nbd_method"], c["nbd_metric"],
+                        covars=covars, covar_diff_type=list(c["covar_diff_type"]) or "match-mismatch", return_info=True)
+    rtol = RTOL_LM if c["regression_type"] == "lm" else RTOL_IRLS
+    assert info["n_pairs"] == exp["Ri"].size and info["n_unique_pairs"] == int(exp["n_unique"])
+    assert np.array_equal(info["Ri"], exp["Ri"]) and np.array_equal(info["NN"], exp["NN"])
+    _stats_close(info["stats"], exp["stats"], rtol, name)
+    # identical attribute ordering and the reference's columns
+    from npdr_b200 import rstats
+    from npdr_b200.api import _pvalues
+    pe, _ = _pvalues(exp["stats"], c["regression_type"])
+    assert list(out["att"]) == [c["names"][i] for i in rstats.order(pe)]
+    want_cols = ["att", "pval.adj", "pval.att", "beta.raw.att", "beta.Z.att", "beta.0", "pval.0"]
+    assert list(out.columns) == want_cols + (["R.sqr"] if c["regression_type"] == "lm" else [])
+    assert abs(info["k_ave_empirical"] - exp["Ri"].size / np.unique(exp["Ri"]).size) < 1e-12
+
+
+@pytest.mark.parametrize("reg", ["lm", "binomial"])
+@pytest.mark.parametrize("q", [0, 1, 2, 4])
+@pytest.mark.parametrize("diff", ["numeric-abs", "numeric-sqr", "allele-sharing", "match-mismatch"])
+def test_regress_random(nb, oracle, reg, q, diff):
+    rng = np.random.default_rng(abs(hash((reg, q, diff))) % 2**32)
+    N, p = 140, 150                                               # p > 128: two attribute tiles, ragged
+    snp = diff in ("allele-sharing", "match-mismatch")
+    X = rng.integers(0, 3, size=(N, p)).astype(float) if snp else rng.normal(size=(N, p))
+    ycls = (rng.random(N) < 0.45).astype(float)
+    X[:, 0] += 1.5 * ycls                                          # one real effect
+    X[:, 7] = 1.0                                                  # constant attribute -> aliased
+    X = np.asfortranarray(X)
+    y = ycls if reg == "binomial" else rng.normal(size=N) + 0.8 * X[:, 0]
+    types = ["match-mismatch", "numeric-abs", "numeric-sqr", "numeric-abs"][:q]
+    C = None
+    if q:
+        C = np.asfortranarray(np.column_stack([rng.integers(0, 2, N).astype(float), rng.normal(40, 12, N).round(),
+                                               rng.normal(size=N), rng.normal(size=N)])[:, :q])
+    ri, nn, _, _ = oracle.nearest_neighbors(X)
+    yd = oracle.pair_diffs(y, ri, nn, "numeric-abs" if reg == "lm" else "match-mismatch")
+    cd = np.column_stack([oracle.pair_diffs(C[:, c], ri, nn, types[c]) for c in range(q)]) if q else None
+    exp = oracle.regress_attrs(X, ri, nn, yd, cd, diff, reg)
+    out, info = nb.npdr(y, X, reg, diff, covars=(C if q else "none"), covar_diff_type=(types if q else "match-mismatch"),
+                        return_info=True)
+    assert np.array_equal(info["Ri"], ri)
+    _stats_close(info["stats"], exp, RTOL_LM if reg == "lm" else RTOL_IRLS, f"{reg} q={q} {diff}")
+    assert int(info["stats"][7, 7]) & 1                            # the constant attribute is flagged
+
+
+def test_regress_user_pair_list_any_order(nb, oracle):
+    """npdrb_regress with a shuffled pair list (not grouped by Ri) gives the same statistics."""
+    from npdr_b200 import _lib
+    rng = np.random.default_rng(21)
+    N, p = 90, 40
+    X = np.asfortranarray(rng.normal(size=(N, p))); y = (rng.random(N) < 0.5).astype(float)
+    ri, nn, _, _ = oracle.nearest_neighbors(X)
+    exp = oracle.regress_attrs(X, ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"))
+    perm = rng.permutation(ri.size)
+    out = np.empty((p, 8))
+    ctx = _lib.context(0)
+    _lib.check(_lib.load().npdrb_regress(ctx.handle, _lib.dptr(X), N, p, _lib.iptr(np.ascontiguousarray(ri[perm])),
+                                        _lib.iptr(np.ascontiguousarray(nn[perm])), ri.size, _lib.dptr(y), None, 0, None, 0, 1,
+                                        _lib.dptr(out)))
+    _stats_close(out, exp, RTOL_IRLS, "shuffled")
+
+
+def test_diff_regression_and_unireg(nb, oracle):
+    import pandas as pd
+    rng = np.random.default_rng(22)
+    M = 700
+    d = np.abs(rng.normal(size=M)); c1 = rng.integers(0, 2, M).astype(float)
+    yb = (rng.random(M) < 1 / (1 + np.exp(-(0.8 * d - 0.5)))).astype(float)
+    design = np.asfortranarray(np.column_stack([np.ones(M), d, c1]))
+    coef, se, info = oracle.glm_binomial(design, yb)
+    got = nb.diffRegression(pd.DataFrame({"attr.diff.vec": d, "pheno.diff.vec": yb, "cov1": c1}), "binomial")
+    np.testing.assert_allclose(got[1:4], [coef[1], coef[1] / se[1], coef[0]], rtol=RTOL_IRLS)
+    yl = 0.3 + 0.5 * d + rng.normal(size=M)
+    coef, se, info = oracle.lm(design, yl)
+    got = nb.diffRegression(pd.DataFrame({"attr.diff.vec": d, "pheno.diff.vec": yl, "cov1": c1}), "lm")
+    np.testing.assert_allclose(got[1:4], [coef[1], coef[1] / se[1], coef[0]], rtol=RTOL_LM)
+    assert abs(got[5] - info["r_squared"]) <= RTOL_LM * info["r_squared"]
+    # uniReg on the case/control fixture (R/utils.R:58-64 example)
+    c = load_case("cfg1")
+    tab = nb.uniReg(c["y"], pd.DataFrame(c["X"], columns=c["names"]), "binomial")
+    assert list(tab.columns) == ["beta", "beta.Z.att", "pval", "p.adj"] and tab.shape == (100, 4)
+    j = c["names"].index(tab.index[0])
+    coef, se, _ = oracle.glm_binomial(np.asfortranarray(np.column_stack([np.ones(100), c["X"][:, j]])), c["y"])
+    assert abs(tab.iloc[0, 0] - coef[1]) <= 1e-4 * abs(coef[1]) and abs(tab.iloc[0, 1] - coef[1] / se[1]) <= 1e-4 * abs(coef[1] / se[1])
+    assert np.all(np.diff(tab["pval"].to_numpy()) >= 0)
+
+
+def test_error_behaviour(nb):
+    rng = np.random.default_rng(23)
+    X = rng.normal(size=(50, 8)); y = (rng.random(50) < 0.5).astype(float)
+    Xn = X.copy(); Xn[3, 2] = np.nan
+    with pytest.raises(nb.NpdrB200Error) as e:
+        nb.npdr(y, Xn)
+    assert e.value.code == 5
+    with pytest.raises(nb.NpdrB200Error) as e:                     # glm errors on a single-level response in R too
+        nb.npdr(np.zeros(50), X)
+    assert e.value.code == 5
+    with pytest.raises(nb.NpdrB200Error):
+        nb.npdr(y, X[:2], regression_type="binomial")              # N < 3
+
+
+def test_npdr_options(nb, oracle):
+    rng = np.random.default_rng(24)
+    N, p = 130, 20
+    X = np.asfortranarray(rng.normal(size=(N, p))); y = rng.normal(size=N)
+    # unique sampling + unique.dof + rm.attr.from.dist go through the two-step path
+    out, info = nb.npdr(y, X, "lm", neighbor_sampling="unique", unique_dof=True, return_info=True)
+    ri, nn, _, _ = oracle.nearest_neighbors(X)
+    nu, keep = oracle.unique_neighbors(ri, nn, N)
+    exp = oracle.regress_attrs(X, ri[keep], nn[keep], oracle.pair_diffs(y, ri[keep], nn[keep], "numeric-abs"), None, "numeric-abs", "lm")
+    _stats_close(info["stats"], exp, RTOL_LM, "unique")
+    assert info["n_pairs_used"] == nu and info["n_pairs"] == ri.size
+    out2, info2 = nb.npdr(y, X, "lm", rm_attr_from_dist=["1", "2"], return_info=True)
+    ri2, nn2, _, _ = oracle.nearest_neighbors(np.asfortranarray(X[:, 2:]))
+    assert np.array_equal(info2["Ri"], ri2) and np.array_equal(info2["NN"], nn2)
+    exp2 = oracle.regress_attrs(X, ri2, nn2, oracle.pair_diffs(y, ri2, nn2, "numeric-abs"), None, "numeric-abs", "lm")
+    _stats_close(info2["stats"], exp2, RTOL_LM, "rm.attr")
+    # k alias (R partial matching), relieff + euclidean + lm
+    out3, info3 = nb.npdr(y, X, "lm", nbd_method="relieff", nbd_metric="euclidean", k=9, return_info=True)
+    ri3, nn3, _, _ = oracle.nearest_neighbors(X, "relieff", "euclidean", 0.5, 9)
+    assert np.array_equal(info3["Ri"], ri3) and np.array_equal(info3["NN"], nn3)
+
+
+def test_session_row_blocks_equal_full(nb, oracle):
+    """Row-block sharded distance+neighbour stage (what each rank runs) concatenates to the full list."""
+    from npdr_b200 import _lib
+    rng = np.random.default_rng(25)
+    N, p = 300, 64
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    ri, nn, D, r = oracle.nearest_neighbors(X)
+    ctx = _lib.context(0)
+    got_ri, got_nn, got_r = [], [], []
+    for row0, nrows in ((0, 128), (128, 128), (256, 44)):
+        s = _lib.Session(ctx, N, p, 0)
+        s.upload(X)
+        s.distances("manhattan", False, row0, nrows)
+        assert np.array_equal(s.copy_distances(), D[row0:row0 + nrows, :])
+        M, _ = s.neighbors("multisurf", 0.5, 0)
+        a, b, m = s.local_pairs()
+        s.import_pairs(a, b, m)
+        x, y = s.copy_pairs(m)
+        got_ri.append(x); got_nn.append(y); got_r.append(s.copy_radius())
+        s.close()
+    assert np.array_equal(np.concatenate(got_ri), ri) and np.array_equal(np.concatenate(got_nn), nn)
+    assert np.array_equal(np.concatenate(got_r), r)
+
+
+def test_attribute_shards_equal_full(nb, oracle):
+    from npdr_b200 import _lib
+    rng = np.random.default_rng(26)
+    N, p = 100, 300
+    X = np.asfortranarray(rng.normal(size=(N, p))); y = (rng.random(N) < 0.5).astype(float)
+    ri, nn, _, _ = oracle.nearest_neighbors(X)
+    ctx = _lib.context(0)
+    s = _lib.Session(ctx, N, p, 0)
+    s.upload(X, y)
+    s.import_pairs_host(ri, nn)
+    full = s.regress(0, p, "binomial")
+    parts = [s.regress(a0, n, "binomial") for a0, n in ((0, 77), (77, 128), (205, 95))]
+    s.close()
+    assert np.array_equal(np.vstack(parts), full)                  # no cross-attribute arithmetic: bit-identical
+    exp = oracle.regress_attrs(X, ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"))
+    _stats_close(full, exp, RTOL_IRLS, "shards")
+
+
+def test_medium_scale_properties(nb, oracle):
+    """N=2000, p=600 (beyond what the oracle regresses in seconds for every attribute): full distance and
+    neighbour parity, regression parity on a 24-attribute slice, and size-independent invariants."""
+    rng = np.random.default_rng(27)
+    N, p = 2000, 600
+    f = rng.normal(size=(N, 1))
+    X = np.sqrt(0.8) * rng.normal(size=(N, p)) + np.sqrt(0.2) * f
+    y = (rng.random(N) < 0.5).astype(float)
+    X[:, :5] += 0.6 * y[:, None]
+    X = np.asfortranarray(X)
+    out, info = nb.npdr(y, X, return_info=True)
+    ri, nn, D, r = oracle.nearest_neighbors(X)
+    assert np.array_equal(info["Ri"], ri) and np.array_equal(info["NN"], nn)
+    sl = np.r_[0:8, 290:298, 592:600]
+    exp = oracle.regress_attrs(np.asfortranarray(X[:, sl]), ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"))
+    _stats_close(info["stats"][sl], exp, RTOL_IRLS, "medium")
+    # invariants: Ri != NN, grouped ascending, ascending NN within a group, threshold re-check
+    assert np.all(ri != nn) and np.all(np.diff(ri) >= 0)
+    same = np.diff(ri) == 0
+    assert np.all(np.diff(nn)[same] > 0)
+    assert np.all(D[nn - 1, ri - 1] < r[ri - 1]) and np.all(D[nn - 1, ri - 1] > 0)
+    assert set(out["att"][:5]) == {"1", "2", "3", "4", "5"}        # the planted effects rank first
