@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- NPDR hot-path benchmark (BASELINE.json metric: attr x neighbor-pair GLM evals/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg5|small] [--impl ours|reference]
+
+One "step" = one full pass of the hot path (distances -> multiSURF neighbour pairs -> per-attribute binomial
+IRLS) over one synthetic batch.  Workloads (BASELINE.json configs; synthetic stand-ins, seed 1618):
+  cfg4 (default)  4,000 instances x 20,000 attributes per GPU, binomial, multisurf, manhattan, q = 0.
+                  With --gpus N the attribute count grows to 20,000 x N (weak scaling: per-GPU work fixed).
+  cfg5            20,000 x 50,000, binomial, multisurf, manhattan, 2 covariates (strong scaling: total fixed).
+  small           1,024 x 2,048 (development).
+Sharding (N > 1, one process per GPU under torchrun): row blocks for distance+neighbours, one all-gather of
+the pair segments (NCCL), attribute columns for the regression, statistics gathered to rank 0.
+
+`value` is p*M / step time with inputs resident in HBM; `e2e` is the same metric through the host-buffer API
+(H2D of X, y inside the timed region, D2H of the statistics).  `roofline` describes the dominant kernel
+(the binomial IRLS pass kernel, FP64-issue bound) with CUDA-event launch durations; `cpu_baseline` /
+`--impl reference` time the CPU oracle (a restatement of the reference R algorithm; R itself cannot be installed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg4": dict(N=4000, p_per_gpu=20000, p_total=None, q=0, pct_signals=0.10, scaling="weak",
+                 desc="synthetic createSimulation2-style interaction data 4,000 x 20,000 per GPU: binomial, multisurf, manhattan"),
+    "cfg5": dict(N=20000, p_per_gpu=None, p_total=50000, q=2, pct_signals=0.01, scaling="strong",
+                 desc="synthetic 20,000 x 50,000: binomial, multisurf, manhattan, 2 covariates"),
+    "small": dict(N=1024, p_per_gpu=2048, p_total=None, q=0, pct_signals=0.05, scaling="weak",
+                  desc="development size 1,024 x 2,048 per GPU"),
+}
+SEED = 1618      # the package's convention (data-raw/fetch-data.R:10)
+
+
+def f_bin(q):
+    """Canonical FP64 flop count per attribute x pair x IRLS iteration: 68 for q=0, 92 for q=2."""
+    k = 2 + q
+    return 2 * ((k - 1) + k * (k + 1) // 2 + k) + (k - 1) + 7 + 48
+
+
+def gen_columns(gen, N, ncols, col0, p_total, n_func, f, g, sgn, device, dtype):
+    """Columns [col0, col0+ncols) of the stand-in data: x = sqrt(.8 - l^2) z + sqrt(.2) f + l * s * g  (l = 0 for
+    background attributes; for the n_func functional attributes the sign s flips between cases and controls on
+    half of them -> differential correlation, no main effect; createSimulation2 interactionErdos in spirit)."""
+    import torch
+    z = torch.randn((ncols, N), generator=gen, device=device, dtype=dtype)
+    idx = torch.arange(col0, col0 + ncols, device=device)
+    lam = torch.where(idx < n_func, 0.6, 0.0).to(dtype).unsqueeze(1)
+    flip = (idx >= n_func // 2) & (idx < n_func)
+    s = torch.where(flip.unsqueeze(1), sgn.unsqueeze(0), torch.ones_like(sgn).unsqueeze(0))
+    return torch.sqrt(0.8 - lam * lam) * z + np.sqrt(0.2) * f.unsqueeze(0) + lam * s * g.unsqueeze(0)
+
+
+def make_data(wl, world, device):
+    """-> dict with device tensors dX [p, ldx] (column-major N x p, ldx = N rounded up to 16), dy, dC."""
+    import torch
+    N, q = wl["N"], wl["q"]
+    p = wl["p_total"] or wl["p_per_gpu"] * world
+    ldx = (N + 15) // 16 * 16
+    gen = torch.Generator(device=device)
+    gen.manual_seed(SEED)
+    dt = torch.float64
+    perm = torch.randperm(N, generator=gen, device=device)
+    y = (perm < N // 2).to(dt)                                  # balanced classes
+    f = torch.randn(N, generator=gen, device=device, dtype=dt)
+    g = torch.randn(N, generator=gen, device=device, dtype=dt)
+    sgn = torch.where(y > 0, 1.0, -1.0).to(dt)
+    n_func = int(round(wl["pct_signals"] * p))
+    dX = torch.zeros((p, ldx), device=device, dtype=dt)
+    step = 2048
+    for c0 in range(0, p, step):
+        nc = min(step, p - c0)
+        dX[c0:c0 + nc, :N] = gen_columns(gen, N, nc, c0, p, n_func, f, g, sgn, device, dt)
+    dC = None
+    if q:
+        sex = (torch.rand(N, generator=gen, device=device, dtype=dt) < 0.5).to(dt)
+        age = torch.round(40.0 + 12.0 * torch.randn(N, generator=gen, device=device, dtype=dt))
+        dC = torch.stack([sex, age] + [torch.randn(N, generator=gen, device=device, dtype=dt) for _ in range(q - 2)])[:q].contiguous()
+    return dict(N=N, p=p, q=q, ldx=ldx, dX=dX, dy=y.contiguous(), dC=dC, n_func=n_func,
+                covar_diff_type=("match-mismatch", "numeric-abs")[:q])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_sample(wl_name, N_s, p_s, q):
+    """One pass of the hot path through the CPU oracle on a bounded sample (first N_s instances x p_s attributes of
+    the same synthetic recipe, numpy generator).  -> (evals, seconds, threads, M)."""
+    from oracle import oracle as O
+    O.build()
+    rng = np.random.default_rng(SEED)
+    f = rng.normal(size=(N_s, 1)); g = rng.normal(size=(N_s, 1))
+    y = (rng.permutation(N_s) < N_s // 2).astype(float)
+    sgn = np.where(y > 0, 1.0, -1.0)[:, None]
+    n_func = max(2, int(round(WORKLOADS[wl_name]["pct_signals"] * p_s)))
+    lam = np.where(np.arange(p_s) < n_func, 0.6, 0.0)[None, :]
+    flip = (np.arange(p_s) >= n_func // 2) & (np.arange(p_s) < n_func)
+    s = np.where(flip[None, :], sgn, 1.0)
+    X = np.asfortranarray(np.sqrt(0.8 - lam * lam) * rng.normal(size=(N_s, p_s)) + np.sqrt(0.2) * f + lam * s * g)
+    C = None
+    if q:
+        C = np.column_stack([(rng.random(N_s) < 0.5).astype(float), np.round(40 + 12 * rng.normal(size=N_s))])[:, :q]
+    t0 = time.perf_counter()
+    ri, nn, D, r = O.nearest_neighbors(X, "multisurf", "manhattan", 0.5)
+    yd = O.pair_diffs(y, ri, nn, "match-mismatch")
+    cd = None
+    if q:
+        types = ("match-mismatch", "numeric-abs")
+        cd = np.column_stack([O.pair_diffs(C[:, c], ri, nn, types[c]) for c in range(q)])
+    O.regress_attrs(X, ri, nn, yd, cd, "numeric-abs", "binomial")
+    dt = time.perf_counter() - t0
+    return float(p_s) * ri.size, dt, O.num_threads(), int(ri.size)
+
+
+def run_reference(args, wl_name, wl):
+    """--impl reference: the CPU restatement of the reference path on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N_s, p_s = (1000, 256) if wl_name != "small" else (512, 128)
+    vals, secs, M = [], [], 0
+    for it in range(args.warmup + args.steps):
+        ev, dt, thr, M = cpu_oracle_sample(wl_name, N_s, p_s, wl["q"])
+        if it >= args.warmup:
+            vals.append(ev / dt); secs.append(dt)
+    value = float(np.sum([v * s for v, s in zip(vals, secs)]) / np.sum(secs))
+    sample = (f"first {N_s} instances x {p_s} attributes of the {wl_name} recipe (M={M} pairs), all stages, "
+              f"OpenMP over attributes (the reference's dopar.reg analogue)")
+    line = {"impl": "reference", "metric": "npdr_attr_x_pair_glm_evals_per_s", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "description": wl["desc"], "regression": "binomial", "nbd": "multisurf",
+                       "metric": "manhattan", "covariates": wl["q"]},
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": thr, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU oracle = C restatement of the reference R algorithm (R cannot be installed here; the reference "
+                    "itself cannot allocate its dense M x p matrix at this workload, R/npdr.R:313)"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("NPDRB_BENCH_WORKLOAD", "cfg4"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl_name, wl = args.workload, WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl_name, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import npdr_b200 as nb
+    from npdr_b200.distributed import GpuEngine, npdr_sharded
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (npdr_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    ctx = nb.context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)      # library work and torch events share one stream
+
+    data = make_data(wl, world, device)
+    N, p, q = data["N"], data["p"], data["q"]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step_resident():
+        eng = GpuEngine(device_index=local_rank, dX=data["dX"], ldx=data["ldx"], dy=data["dy"], dC=data["dC"], N=N, p=p, q=q)
+        stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, data["covar_diff_type"])
+        km = eng.session.kernel_ms(); sm = eng.session.stage_ms(); passes = eng.session.irls_passes
+        eng.close()
+        return stats, info, km, sm, passes
+
+    # host copies for the end-to-end arm (pinned)
+    hX = hy = hC = None
+    if not args.no_e2e:
+        hXt = torch.empty((p, N), dtype=torch.float64, pin_memory=True)
+        hXt.copy_(data["dX"][:, :N])
+        hX = hXt.numpy().T                                       # (N, p) Fortran-ordered view of pinned memory
+        hy = data["dy"].cpu().numpy()
+        hC = np.asfortranarray(data["dC"].cpu().numpy().T) if q else None
+
+    def one_step_e2e():
+        eng = GpuEngine(X=hX, y=hy, C=hC, device_index=local_rank)     # H2D upload inside
+        stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, data["covar_diff_type"])
+        eng.close()
+        return stats, info                                              # stats are host numpy: D2H done
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = ctx.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        launches = torch.tensor([ctx.launch_count() - l0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        return float(ms.item()), int(launches.item()), out
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, launches, (stats, info, km, sm, passes) = timed(one_step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    M = info["n_pairs"]
+    ms_step = ms_total / args.steps
+    value = float(p) * M / (ms_step * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        e_steps = max(1, min(args.steps, 3))
+        ms_e, _, _ = timed(one_step_e2e, e_steps, 1)
+        ms_e /= e_steps
+        e2e = {"value": float(p) * M / (ms_e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e,
+               "h2d_bytes_per_step": int(world * (N * p * 8 + N * 8 + N * q * 8)), "d2h_bytes_per_step": int(p * 8 * 8),
+               "note": "host-buffer path: pinned X/y(/C) uploaded on every rank, statistics read back, every step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (IRLS pass kernel), rank 0's launches of the last step
+    peak = ctx.fp64_peak()
+    n_full = max(int(km["n_pass_full"]), 1)
+    flops = km["evals_pass_full"] * f_bin(q)
+    achieved = flops / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
+    hbm_peak = 6553.6
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    p_local = info["attrs"][1]
+    alg_bytes = n_full * (N * p_local * 8 + km["records"] * (4 + 8 * q) + p_local * 8 * 16)   # per pass: X slab once, record stream once, partials
+    roofline = {"kernel": "pass_kernel<IRLS_FULL> (binomial IRLS pass, npdr_b200/csrc/regress.cu)", "bound": "fp64",
+                "achieved": achieved, "peak": peak["dfma_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peak["dfma_tflops"] if peak["dfma_tflops"] else None, "traffic": None,
+                "peak_source": "measured live by npdrb_measure_fp64_peak (DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
+                "launches": n_full, "avg_launch_ms": km["pass_full_ms"] / n_full,
+                "flops_per_eval_iteration": f_bin(q), "evals_per_launch_avg": km["evals_pass_full"] / n_full,
+                "share_of_step": km["pass_full_ms"] / ms_step,
+                "hbm": {"achieved": alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9 if km["pass_full_ms"] > 0 else 0.0,
+                        "peak": hbm_peak, "unit": "GB/s",
+                        "frac": (alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9) / hbm_peak if km["pass_full_ms"] > 0 else None}}
+    dist_adds = float(p) * N * (N - 1)          # 2 DADD per element pair over the lower triangle (symmetric mode)
+    if world > 1:
+        dist_adds = 2.0 * float(p) * info["rows"][1] * N        # rectangle per rank
+    stage = {"distance_ms": sm["distance"], "neighbors_ms": sm["neighbors"], "prepare_ms": sm["prepare"], "regress_ms": sm["regress"],
+             "irls_full_passes": passes, "pass_first_ms": km["pass_first_ms"],
+             "distance_fp64_add_frac": (dist_adds / (sm["distance"] * 1e-3) / 1e12) / peak["dadd_tflops"] if sm["distance"] > 0 else None}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        N_s, p_s = (1500, 256) if wl_name != "small" else (512, 128)
+        ev, dt, thr, M_s = cpu_oracle_sample(wl_name, N_s, p_s, q)
+        cpu_baseline = {"value": ev / dt, "unit": "evals/s", "cores": thr, "kind": "port", "seconds": dt,
+                        "sample": f"first {N_s} instances x {p_s} attributes of the {wl_name} recipe (M={M_s} pairs), all stages, "
+                                  f"CPU oracle (C restatement of the reference R path), OpenMP over attributes"}
+
+    line = {"metric": "npdr_attr_x_pair_glm_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": wl["scaling"],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "description": wl["desc"], "N": N, "p": p, "q": q, "pairs_M": M,
+                       "regression": "binomial", "nbd": "multisurf", "metric": "manhattan", "seed": SEED,
+                       "parallelism": f"rows/{world} (distance+neighbours) -> all-gather pairs -> attrs/{world} (regression)",
+                       "l2": "inputs (X = %.0f MB per GPU) exceed the 126 MB L2; no flush needed" % (N * p * 8 / 1e6)},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "stages": stage, "fp64_peak_measured": peak}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

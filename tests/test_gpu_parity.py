@@ -282,7 +282,7 @@ def test_error_behaviour(nb):
         nb.npdr(np.zeros(50), X)
     assert e.value.code == 5
     with pytest.raises(nb.NpdrB200Error):
-        nb.npdr(y, X[:2], regression_type="binomial")              # N < 3
+        nb.npdr(np.array([0.0, 1.0]), X[:2], regression_type="binomial")   # N < 3
 
 
 def test_npdr_options(nb, oracle):
