@@ -126,6 +126,8 @@ int npdrb_set_stream(npdrb_ctx *ctx, void *cuda_stream);
 int npdrb_synchronize(npdrb_ctx *ctx);
 /* measured FP64 issue peaks of this device (DFMA and DADD micro-kernels): TFLOP/s counting FMA = 2, add = 1 */
 int npdrb_measure_fp64_peak(npdrb_ctx *ctx, double *dfma_tflops, double *dadd_tflops);
+/* return the library's cached device memory on this device to the driver (buffers are otherwise kept for reuse) */
+int npdrb_release_cache(npdrb_ctx *ctx);
 /* number of this library's kernel launches since the context was created (bench.py's gpu_launches) */
 int64_t npdrb_launch_count(npdrb_ctx *ctx);
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "npdrb_synchronize": (C.c_int, [_vp]),
     "npdrb_measure_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
     "npdrb_launch_count": (_i64, [_vp]),
+    "npdrb_release_cache": (C.c_int, [_vp]),
     "npdrb_diff": (C.c_int, [_vp, _dp, _dp, _i64, _i32, C.c_double, _dp]),
     "npdrb_distances": (C.c_int, [_vp, _dp, _i64, _i64, _i32, _i32, _dp]),
     "npdrb_knn_surf": (_i64, [_i64, C.c_double]),
@@ -165,6 +166,9 @@ class Context:
 
     def synchronize(self):
         check(load().npdrb_synchronize(self.handle))
+
+    def release_cache(self):
+        check(load().npdrb_release_cache(self.handle))
 
     def launch_count(self):
         return int(load().npdrb_launch_count(self.handle))

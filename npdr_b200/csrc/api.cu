@@ -2,6 +2,9 @@
 // host-buffer operator entry points that replace the reference's exported R functions.
 #include <math.h>
 #include <stdarg.h>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -11,6 +14,68 @@ void npdrb_set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ------------------------------------------------------------------ device-memory cache (see common.cuh)
+namespace {
+struct DevCache {
+    std::multimap<size_t, void *> free_blocks;          // size -> block
+    std::unordered_map<void *, size_t> live;            // blocks handed out
+    size_t cached_bytes = 0;
+};
+std::mutex g_cache_mu;
+DevCache g_cache[64];
+
+void cache_release_device(int dev) {
+    DevCache &c = g_cache[dev & 63];
+    for (auto &kv : c.free_blocks) (cudaFree)(kv.second);
+    c.free_blocks.clear();
+    c.cached_bytes = 0;
+}
+}  // namespace
+
+cudaError_t nb_cached_malloc(void **p, size_t bytes) {
+    *p = nullptr;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const size_t n = (bytes + 511) & ~(size_t)511;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    DevCache &c = g_cache[dev & 63];
+    auto it = c.free_blocks.lower_bound(n);
+    if (it != c.free_blocks.end() && it->first <= n + n / 8 + 4096) {       // close fit only: no silent bloat
+        *p = it->second;
+        c.live[*p] = it->first;
+        c.cached_bytes -= it->first;
+        c.free_blocks.erase(it);
+        return cudaSuccess;
+    }
+    e = (cudaMalloc)(p, n ? n : 512);
+    if (e != cudaSuccess) {                                                   // out of memory: drop the cache, retry once
+        cudaGetLastError();
+        cache_release_device(dev);
+        e = (cudaMalloc)(p, n ? n : 512);
+        if (e != cudaSuccess) return e;
+    }
+    c.live[*p] = n ? n : 512;
+    return cudaSuccess;
+}
+
+cudaError_t nb_cached_free(void *p) {
+    if (!p) return cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (int d = 0; d < 64; ++d) {                                            // usually found on the current device
+        DevCache &c = g_cache[(dev + d) & 63];
+        auto it = c.live.find(p);
+        if (it == c.live.end()) continue;
+        c.free_blocks.emplace(it->second, p);
+        c.cached_bytes += it->second;
+        c.live.erase(it);
+        return cudaSuccess;
+    }
+    return (cudaFree)(p);                                                     // not ours (should not happen)
 }
 
 namespace {
@@ -121,14 +186,29 @@ int npdrb_create(int device, npdrb_ctx **out) {
     return NPDRB_OK;
 }
 
+int npdrb_release_cache(npdrb_ctx *ctx) {
+    NB_CUDA(cudaSetDevice(ctx->device));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    cache_release_device(ctx->device);
+    return NPDRB_OK;
+}
+
 void npdrb_destroy(npdrb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        cache_release_device(ctx->device);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 int npdrb_set_stream(npdrb_ctx *ctx, void *cuda_stream) {
+    NB_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->stream) NB_CUDA(cudaStreamSynchronize(ctx->stream));      // the memory cache assumes one stream at a time
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
@@ -268,7 +348,8 @@ int npdrb_session_set_sd_vec(npdrb_session *s, const double *sd_vec_host) {
     NB_CUDA(cudaSetDevice(s->ctx->device));
     if (!sd_vec_host) { cudaFree(s->d_sd_vec); s->d_sd_vec = nullptr; return NPDRB_OK; }
     if (!s->d_sd_vec) NB_CUDA(cudaMalloc(&s->d_sd_vec, sizeof(double) * (size_t)s->N));
-    NB_CUDA(cudaMemcpy(s->d_sd_vec, sd_vec_host, sizeof(double) * (size_t)s->N, cudaMemcpyHostToDevice));
+    NB_CUDA(cudaMemcpyAsync(s->d_sd_vec, sd_vec_host, sizeof(double) * (size_t)s->N, cudaMemcpyHostToDevice, s->ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
     return NPDRB_OK;
 }
 

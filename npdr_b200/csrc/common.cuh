@@ -12,6 +12,16 @@
 
 void npdrb_set_error(const char *fmt, ...);
 
+// Device-memory cache (api.cu).  npdr() is called in loops (vwok's k grid, benchmarks) with identical buffer sizes;
+// raw cudaMalloc/cudaFree of multi-hundred-MB buffers cost ~100+ ms per call in page mapping and implicit device
+// synchronisation.  All library work on a device is issued to ONE stream, so a freed block may be handed out again
+// immediately: the next user is ordered after the previous one on that stream.  Every cudaMalloc/cudaFree in this
+// library goes through the cache; npdrb_release_cache() / npdrb_destroy() return the memory to the driver.
+cudaError_t nb_cached_malloc(void **p, size_t bytes);
+cudaError_t nb_cached_free(void *p);
+#define cudaMalloc(p, n) nb_cached_malloc((void **)(p), (n))
+#define cudaFree(p) nb_cached_free((void *)(p))
+
 #define NB_CUDA(call)                                                                              \
     do {                                                                                           \
         cudaError_t _e = (call);                                                                   \
@@ -58,6 +68,7 @@ struct nb_stream {
     double *cd[NPDRB_MAX_COVARS] = {nullptr, nullptr, nullptr, nullptr};  // covariate diffs per record
     int32_t n_tiles = 0;          // non-empty tiles
     int64_t *tile_ptr = nullptr;  // [n_tiles + 1] record offsets
+    int64_t *tile_mid = nullptr;  // [n_tiles] offset of the first miss (outcome bit 1) record of each tile
     int32_t *tile_ib = nullptr, *tile_jb = nullptr;
     int32_t n_chunks = 0;
     int32_t *chunk_tile = nullptr;  // [n_chunks + 1] tile ranges per work chunk

@@ -16,6 +16,7 @@
 // Bound: FP64 issue rate (binomial: ~52 FP64 instr per attribute x pair x pass at q = 2, exp/log via
 // dmath.cuh); staged bytes per evaluation are < 1 B, so HBM is far from binding.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include <math.h>
 #include "common.cuh"
 #include "dmath.cuh"
@@ -29,10 +30,12 @@ constexpr int RTHREADS = TA * NSLICE;  // 512
 constexpr int RCHUNK = 1024;           // records staged per step
 constexpr int KMAX = 2 + NPDRB_MAX_COVARS;
 
-enum { MODE_LM = 0, MODE_IRLS_INIT = 1, MODE_IRLS_FULL = 2 };
+// MODE_LM: moments with the outcome diff from the yv stream; MODE_SIGN: the same moments with the outcome
+// taken as s = +1 (miss) / -1 (hit) from the record bit (closed-form first IRLS pass); MODE_IRLS_FULL: one IRLS pass.
+enum { MODE_LM = 0, MODE_SIGN = 1, MODE_IRLS_FULL = 2 };
 
 __host__ __device__ constexpr int nacc_for(int mode, int q) {
-    return mode == MODE_LM ? (3 + q) : ((2 + q) * (3 + q) / 2 + (2 + q) + 1);
+    return mode != MODE_IRLS_FULL ? (3 + q) : ((2 + q) * (3 + q) / 2 + (2 + q) + 1);
 }
 
 // ------------------------------------------------------------------ layout helpers
@@ -52,11 +55,19 @@ __global__ void transpose_kernel(const double *__restrict__ X, int64_t ldx, int6
     }
 }
 
+// sort key = 2 * tile + outcome bit: inside every tile the hit records (bit 0) precede the miss records, so the
+// IRLS kernel runs each half with the outcome known at compile time.  ybits: 0 = lm (no bit), 1 = match-mismatch
+// of y over the pair, 2 = raw (uniReg: y of the instance itself)
 __global__ void tile_keys_kernel(const int32_t *__restrict__ Ri, const int32_t *__restrict__ NN, int64_t M, int n_jb,
-                                 uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+                                 const double *__restrict__ y, int ybits, uint32_t *__restrict__ keys,
+                                 uint32_t *__restrict__ idx) {
     int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
-    keys[m] = (uint32_t)((Ri[m] - 1) / BI) * (uint32_t)n_jb + (uint32_t)((NN[m] - 1) / BJ);
+    const int i = Ri[m] - 1, j = NN[m] - 1;
+    uint32_t bit = 0;
+    if (ybits == 1) bit = (y[i] != y[j]);
+    else if (ybits == 2) bit = (y[i] != 0.0);
+    keys[m] = 2u * ((uint32_t)(i / BI) * (uint32_t)n_jb + (uint32_t)(j / BJ)) + bit;
     idx[m] = (uint32_t)m;
 }
 
@@ -85,11 +96,13 @@ __global__ void gather_records_kernel(GatherArgs g) {
     if (t < g.M) {
         const int64_t m = g.perm[t];
         const int64_t i = g.Ri[m] - 1, j = g.NN[m] - 1;
-        uint32_t r = (uint32_t)(i % BI) | ((uint32_t)(j % BJ) << 8);
+        // record = byte offsets of the two instance rows inside a staged [64][128] double tile, plus the outcome bit:
+        // (il << 10) | (jl << 26) | y
+        uint32_t r = ((uint32_t)(i % BI) << 10) | ((uint32_t)(j % BJ) << 26);
         const double yi = g.y[i], yj = g.y[j];
         if (g.reg_type == NPDRB_REG_BINOMIAL) {
             miss = g.y_raw ? (yi != 0.0) : (yi != yj);     // match-mismatch: hit = 0, miss = 1
-            r |= (uint32_t)miss << 16;
+            r |= (uint32_t)miss;
         } else {
             g.yv[t] = g.y_raw ? yi : fabs(yi - yj);         // always numeric-abs (R/npdr.R:303)
         }
@@ -103,9 +116,42 @@ __global__ void gather_records_kernel(GatherArgs g) {
     if ((threadIdx.x & 31) == 0 && mask) atomicAdd(g.n_miss, (unsigned long long)__popc(mask));
 }
 
+// ---- mutual-pair folding -------------------------------------------------------------------------
+// Rows (i,j) and (j,i) of the pair list give the SAME regression row (same |x_i - x_j|, same phenotype and
+// covariate diffs), so every sufficient statistic is sum over unordered pairs of multiplicity x term.  The list
+// is split into a weight-1 stream (one-directional pairs) and a weight-2 stream (the i < j half of the mutual
+// pairs); the reverse halves are dropped.  Valid when no ordered pair is repeated (checked via popcount).
+__global__ void mark_bits_kernel(const int32_t *__restrict__ Ri, const int32_t *__restrict__ NN, int64_t M, int64_t N,
+                                 unsigned *__restrict__ bits) {
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    uint64_t b = (uint64_t)(Ri[m] - 1) * (uint64_t)N + (uint64_t)(NN[m] - 1);
+    atomicOr(&bits[b >> 5], 1u << (b & 31));
+}
+__global__ void popcount_kernel(const unsigned *__restrict__ bits, size_t words, unsigned long long *__restrict__ out) {
+    unsigned long long c = 0;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) c += __popc(bits[w]);
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+__global__ void classify_pairs_kernel(const int32_t *__restrict__ Ri, const int32_t *__restrict__ NN, int64_t M, int64_t N,
+                                      const unsigned *__restrict__ bits, unsigned char *__restrict__ f_single,
+                                      unsigned char *__restrict__ f_double) {
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int64_t i = Ri[m] - 1, j = NN[m] - 1;
+    int mutual = 0;
+    if (i != j) {
+        uint64_t b = (uint64_t)j * (uint64_t)N + (uint64_t)i;
+        mutual = (bits[b >> 5] >> (b & 31)) & 1u;
+    }
+    f_single[m] = (unsigned char)!mutual;
+    f_double[m] = (unsigned char)(mutual && i < j);
+}
+
 // shared (attribute-independent) lm moments of the record stream: M, Sy, Syy, Sc_r, Scy_r, Scc_rs
 constexpr int NSHARED_MAX = 3 + 2 * NPDRB_MAX_COVARS + NPDRB_MAX_COVARS * (NPDRB_MAX_COVARS + 1) / 2;
-struct SharedArgs { const double *yv; const double *cd[NPDRB_MAX_COVARS]; int64_t n; int q; double *out; };
+struct SharedArgs { const double *yv; const uint32_t *rec; const double *cd[NPDRB_MAX_COVARS]; int64_t n; int q; double *out; };
 __global__ void __launch_bounds__(256)
 shared_moments_kernel(SharedArgs a) {
     __shared__ double red[256];
@@ -113,7 +159,7 @@ shared_moments_kernel(SharedArgs a) {
     const int ns = 3 + 2 * a.q + a.q * (a.q + 1) / 2;
     for (int s = 0; s < NSHARED_MAX; ++s) acc[s] = 0.0;
     for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < a.n; t += (int64_t)gridDim.x * 256) {
-        const double y = a.yv[t];
+        const double y = a.yv ? a.yv[t] : ((a.rec[t] & 1u) ? 1.0 : -1.0);
         double c[NPDRB_MAX_COVARS];
         for (int r = 0; r < a.q; ++r) c[r] = a.cd[r][t];
         int s = 0;
@@ -135,7 +181,7 @@ shared_moments_kernel(SharedArgs a) {
 struct PassArgs {
     const double *XT; int64_t ldt; int64_t N; int nattr; int nattr_pad;
     const uint32_t *rec; const double *yv; const double *cd[NPDRB_MAX_COVARS];
-    const int64_t *tile_ptr; const int32_t *tile_ib; const int32_t *tile_jb; const int32_t *chunk_tile;
+    const int64_t *tile_ptr; const int64_t *tile_mid; const int32_t *tile_ib; const int32_t *tile_jb; const int32_t *chunk_tile;
     const double *beta;            // [KMAX][nattr_pad] current coefficients (IRLS_FULL)
     const unsigned char *tile_active;  // per attribute tile, or NULL
     double *partials;              // [n_chunks][NACC][nattr_pad]
@@ -153,7 +199,7 @@ template <int MODE, int Q, int DIFF>
 __global__ void __launch_bounds__(RTHREADS, 1)
 pass_kernel(PassArgs P) {
     constexpr int K = 2 + Q;
-    constexpr int NA = (MODE == MODE_LM) ? (3 + Q) : (K * (K + 1) / 2 + K + 1);
+    constexpr int NA = (MODE != MODE_IRLS_FULL) ? (3 + Q) : (K * (K + 1) / 2 + K + 1);
     extern __shared__ unsigned char smem_raw[];
     double *sXI = (double *)smem_raw;                   // [BI][TA]
     double *sXJ = sXI + BI * TA;                        // [BJ][TA]
@@ -218,29 +264,23 @@ pass_kernel(PassArgs P) {
 #pragma unroll 2
             for (int m = slice; m < n; m += NSLICE) {
                 const uint32_t r = sREC[m];
-                const double xi = sXI[(r & 0xFFu) * TA + al];
-                const double xj = sXJ[((r >> 8) & 0xFFu) * TA + al];
+                const double xi = sXI[((r >> 10) & 0x3Fu) * TA + al];
+                const double xj = sXJ[(r >> 26) * TA + al];
                 const double d = proj_diff<DIFF>(xi, xj, P.diff_type);
                 double c[Q > 0 ? Q : 1];
 #pragma unroll
                 for (int u = 0; u < Q; ++u) c[u] = sCD[u * RCHUNK + m];
-                if (MODE == MODE_LM) {
-                    const double yv = sCD[Q * RCHUNK + m];
+                if (MODE != MODE_IRLS_FULL) {
+                    const double yv = (MODE == MODE_LM) ? sCD[Q * RCHUNK + m] : ((r & 1u) ? 1.0 : -1.0);
                     acc[0] += d;
                     acc[1] = fma(d, d, acc[1]);
                     acc[2] = fma(d, yv, acc[2]);
 #pragma unroll
                     for (int u = 0; u < Q; ++u) acc[3 + u] = fma(d, c[u], acc[3 + u]);
                 } else {
-                    const bool yb = (r >> 16) & 1u;
+                    const bool yb = r & 1u;
                     double w, wz;
-                    if (MODE == MODE_IRLS_INIT) {
-                        // mustart = (y + 0.5)/2 -> mu = 0.75 / 0.25, eta = +-log 3, w = mu(1-mu) = 0.1875,
-                        // z = eta + (y - mu)/w  (base-R glm.fit + binomial()$initialize)
-                        const double z0 = 1.0986122886681098 + 0.25 / 0.1875;
-                        w = 0.1875;
-                        wz = yb ? (0.1875 * z0) : -(0.1875 * z0);
-                    } else {
+                    {
                         double eta = beta[0];
                         eta = fma(beta[1], d, eta);
 #pragma unroll
@@ -306,6 +346,400 @@ pass_kernel(PassArgs P) {
 #pragma unroll
         for (int sl = 1; sl < NSLICE; ++sl) s += red[(sl * NA + n) * TA + a];
         P.partials[((int64_t)chunk * NA + n) * P.nattr_pad + a0 + a] = s;
+    }
+}
+
+// ------------------------------------------------------------------ IRLS pass kernel, v2 (q <= 2)
+// Same arithmetic as pass_kernel<MODE_IRLS_FULL>, restructured for the FP64 issue port (ncu on v1: 94 warp
+// instructions per evaluation, only 38 of them FP64; 68 % issue-active, "wait" = dependency stalls on top):
+//   * each thread owns TWO adjacent attributes: one LDS.128 per instance row, one record fetch and one
+//     covariate fetch per pair for both, and two independent dependency chains the scheduler can interleave
+//     (the rare |eta| > 30 clamp is a single warp-level branch around the exp only, so the chains stay straight-line);
+//   * records are ordered hits-then-misses inside each tile (tile_mid), so y is a compile-time constant of the
+//     loop: no select, and w*z = w*eta - mu (hit) or w*eta + (1 - mu) (miss) costs one FMA;
+//   * record fields are pre-shifted into byte offsets when the chunk is staged;
+//   * polynomial coefficients come from constant memory (constant-bank operands, no IMAD.MOV/UMOV);
+//   * table indices are formed directly as byte offsets from the high word (2 integer ops each);
+//   * reciprocal: rcp.approx (2^-23) + ONE Newton step (2^-46 ~ 1.4e-14); exp / log are the trimmed
+//     nb_exp_fast / nb_log_ge1_fast recurrences (dmath.cuh carries the error budget and the host test).
+__constant__ double c_k[12] = {
+    NB_64_OVER_LN2, 6755399441055744.0, -NB_LN2_64_HI, -NB_LN2_64_LO,   // 0..3  exp range reduction
+    1.0 / 24.0, 1.0 / 6.0, 0.5,                                          // 4..6  exp polynomial
+    0.2, -0.25, 1.0 / 3.0, -0.5,                                         // 7..10 log polynomial
+    NB_LOG_INV_EPS                                                       // 11    log(1/DBL_EPSILON)
+};
+
+struct nb_tables2 {                 // shared-memory image used by v2
+    double exp_t[64];               // 2^(j/64)
+    double2 log_rl[128];            // (rc_i, -log rc_i)
+    double log_eln2_rot[64];        // entry (e - 1) & 63 holds e * ln2
+};
+
+constexpr int V2_TPS = TA / 2;      // threads per slice (64)
+// pair slices per CTA: 8 (512 threads, <= 128 registers) except the q = 2 IRLS pass, whose four interleaved
+// chains per thread need ~170 registers -> 6 slices (384 threads)
+__host__ __device__ constexpr int v2_nslice(int mode, int q) { return (mode == MODE_IRLS_FULL && q >= 2) ? 6 : 8; }
+constexpr int V2_RCHUNK = 512;      // records per staged chunk (two buffers)
+
+__device__ __forceinline__ double v2_exp_fast(double eta, uint32_t sT) {
+    const double tt = fma(eta, c_k[0], c_k[1]);
+    const int ki = __double2loint(tt);
+    const double kf = tt - c_k[1];
+    double r = fma(kf, c_k[2], eta);
+    r = fma(kf, c_k[3], r);
+    const double r2 = r * r;
+    double qq = fma(r, c_k[4], c_k[5]);
+    qq = fma(qq, r, c_k[6]);
+    qq = fma(qq, r2, r);
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x1F8)));
+    const double v = fma(tj, qq, tj);
+    return __hiloint2double(__double2hiint(v) + ((ki << 14) & 0xFFF00000), __double2loint(v));
+}
+// logit linkinv with R's clamps (stats family.c): eta < -30 -> DBL_EPSILON, eta > 30 -> 1/DBL_EPSILON
+__device__ __noinline__ double2 v2_exp_clamped(double eta, uint32_t sT) {      // -> (t, log t)
+    if (eta > 30.0) return make_double2(4503599627370496.0, c_k[11]);
+    if (eta < -30.0) return make_double2(2.220446049250313e-16, -c_k[11]);
+    return make_double2(v2_exp_fast(eta, sT), eta);
+}
+
+// everything after t = exp(eta): weights, deviance term, accumulation.  Y = outcome of this record range.
+template <int Q, int Y>
+__device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 ? Q : 1], const double eta, const double eta_dev,
+                                        const double t, double (&acc)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 1], const uint32_t sT) {
+    constexpr int K = 2 + Q;
+    constexpr int NA = K * (K + 1) / 2 + K + 1;
+    const double u1 = 1.0 + t;
+    double inv;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(u1));
+    inv = fma(inv, fma(-u1, inv, 1.0), inv);                    // 1/(1+t) = 1 - mu
+    const double mu = t * inv;
+    const double w = mu * inv;                                  // mu(1-mu) = mu.eta for the logit link
+    const int hi = __double2hiint(u1);
+    double rc, lrc, el;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lrc) : "r"(sT + 512u + (uint32_t)((hi >> 9) & 0x7F0)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(el) : "r"(sT + 512u + 2048u + (uint32_t)((hi >> 17) & 0x1F8)));
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u1));
+    const double f = fma(m, rc, -1.0);
+    double pp = fma(f, c_k[7], c_k[8]);
+    pp = fma(pp, f, c_k[9]);
+    pp = fma(pp, f, c_k[10]);
+    pp = fma(pp, f * f, f);
+    const double lg = (el + lrc) + pp;                          // log(1 + t) = -log(1 - mu)
+    // deviance residual / 2: -log(1 - mu) for a hit, -log(mu) = log(1 + t) - log(t) for a miss
+    // w * z = w * eta + (y - mu)
+    double wz;
+    if (Y == 0) { acc[NA - 1] += lg; wz = fma(w, eta, -mu); }
+    else { acc[NA - 1] += (lg - eta_dev); wz = fma(w, eta, inv); }
+    double wv[K];
+    wv[0] = w;
+    wv[1] = w * d;
+#pragma unroll
+    for (int u = 0; u < Q; ++u) wv[2 + u] = w * c[u];
+    int n_ = 0;
+#pragma unroll
+    for (int rr = 0; rr < K; ++rr) {
+#pragma unroll
+        for (int ss = rr; ss < K; ++ss) {
+            if (rr == 0) acc[n_] += wv[ss];
+            else acc[n_] = fma(wv[rr], (ss == 1) ? d : c[ss - 2 < 0 ? 0 : ss - 2], acc[n_]);
+            ++n_;
+        }
+    }
+    acc[n_] += wz;
+    acc[n_ + 1] = fma(wz, d, acc[n_ + 1]);
+#pragma unroll
+    for (int u = 0; u < Q; ++u) acc[n_ + 2 + u] = fma(wz, c[u], acc[n_ + 2 + u]);
+}
+
+// records [m_begin, m_end) of the staged chunk, this thread's slice, outcome Y.  Two records x two attributes are
+// in flight per thread: four independent exp -> reciprocal -> log chains (ncu on the two-chain version: FP64 pipe 63 %,
+// dominant stall = fixed-latency dependency wait with 1.35 eligible warps per cycle).
+template <int Q, int DIFF, int Y, int NSL>
+__device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint32_t sREC_addr, uint32_t sCD_addr,
+                                         uint32_t sXI_addr, uint32_t sXJ_addr, uint32_t sT, int diff_type,
+                                         const double (&beta0)[2 + Q], const double (&beta1)[2 + Q],
+                                         double (&acc0)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 1],
+                                         double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 1]) {
+    // each slice walks a CONTIGUOUS part of the range: records are in list order (grouped by Ri), so the I row
+    // repeats for several records in a row and stays in registers (halves the shared-memory tile traffic)
+    const int len = m_end - m_begin, per = (len + NSL - 1) / NSL;
+    const int m_lo = m_begin + slice * per, m_hi = (m_lo + per < m_end) ? (m_lo + per) : m_end;
+    uint32_t io_prev = 0xFFFFFFFFu;
+    double xa0 = 0.0, xa1 = 0.0;                                 // cached I row (two attributes)
+    int m = m_lo;
+    for (; m + 1 < m_hi; m += 2) {
+        uint32_t ra, rb;                                         // (il << 10) | (jl << 26) | y: byte offsets of the two rows
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ra) : "r"(sREC_addr + 4u * m));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rb) : "r"(sREC_addr + 4u * m + 4u));
+        const uint32_t ioa = ra & 0xFC00u, iob = rb & 0xFC00u;
+        if (ioa != io_prev) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xa0), "=d"(xa1) : "r"(sXI_addr + ioa));
+        double xb0 = xa0, xb1 = xa1;
+        if (iob != ioa) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xb0), "=d"(xb1) : "r"(sXI_addr + iob));
+        double ja0, ja1, jb0, jb1;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ja0), "=d"(ja1) : "r"(sXJ_addr + (ra >> 16)));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(jb0), "=d"(jb1) : "r"(sXJ_addr + (rb >> 16)));
+        double ca[Q > 0 ? Q : 1], cb[Q > 0 ? Q : 1];
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ca[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cb[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m) + 8u));
+        }
+        const double da0 = proj_diff<DIFF>(xa0, ja0, diff_type), da1 = proj_diff<DIFF>(xa1, ja1, diff_type);
+        const double db0 = proj_diff<DIFF>(xb0, jb0, diff_type), db1 = proj_diff<DIFF>(xb1, jb1, diff_type);
+        double ea0 = fma(beta0[1], da0, beta0[0]), ea1 = fma(beta1[1], da1, beta1[0]);
+        double eb0 = fma(beta0[1], db0, beta0[0]), eb1 = fma(beta1[1], db1, beta1[0]);
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+            ea0 = fma(beta0[2 + u], ca[u], ea0); ea1 = fma(beta1[2 + u], ca[u], ea1);
+            eb0 = fma(beta0[2 + u], cb[u], eb0); eb1 = fma(beta1[2 + u], cb[u], eb1);
+        }
+        const int hmax = max(max(__double2hiint(ea0) & 0x7fffffff, __double2hiint(ea1) & 0x7fffffff),
+                             max(__double2hiint(eb0) & 0x7fffffff, __double2hiint(eb1) & 0x7fffffff));
+        double ta0, ta1, tb0, tb1, la0 = ea0, la1 = ea1, lb0 = eb0, lb1 = eb1;
+        if (hmax < 0x403E0000) {                                 // |eta| < 30 for all four: straight-line
+            ta0 = v2_exp_fast(ea0, sT); ta1 = v2_exp_fast(ea1, sT);
+            tb0 = v2_exp_fast(eb0, sT); tb1 = v2_exp_fast(eb1, sT);
+        } else {
+            double2 v;
+            v = v2_exp_clamped(ea0, sT); ta0 = v.x; la0 = v.y;
+            v = v2_exp_clamped(ea1, sT); ta1 = v.x; la1 = v.y;
+            v = v2_exp_clamped(eb0, sT); tb0 = v.x; lb0 = v.y;
+            v = v2_exp_clamped(eb1, sT); tb1 = v.x; lb1 = v.y;
+        }
+        v2_tail<Q, Y>(da0, ca, ea0, la0, ta0, acc0, sT);
+        v2_tail<Q, Y>(da1, ca, ea1, la1, ta1, acc1, sT);
+        v2_tail<Q, Y>(db0, cb, eb0, lb0, tb0, acc0, sT);
+        v2_tail<Q, Y>(db1, cb, eb1, lb1, tb1, acc1, sT);
+        xa0 = xb0; xa1 = xb1; io_prev = iob;
+    }
+    if (m < m_hi) {                                              // odd tail: one record
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));
+        const uint32_t io = r & 0xFC00u;
+        if (io != io_prev) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xa0), "=d"(xa1) : "r"(sXI_addr + io));
+        double xj0, xj1;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj0), "=d"(xj1) : "r"(sXJ_addr + (r >> 16)));
+        double c[Q > 0 ? Q : 1];
+#pragma unroll
+        for (int u = 0; u < Q; ++u) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
+        const double d0 = proj_diff<DIFF>(xa0, xj0, diff_type), d1 = proj_diff<DIFF>(xa1, xj1, diff_type);
+        double eta0 = fma(beta0[1], d0, beta0[0]), eta1 = fma(beta1[1], d1, beta1[0]);
+#pragma unroll
+        for (int u = 0; u < Q; ++u) { eta0 = fma(beta0[2 + u], c[u], eta0); eta1 = fma(beta1[2 + u], c[u], eta1); }
+        const double2 a = v2_exp_clamped(eta0, sT), b = v2_exp_clamped(eta1, sT);
+        v2_tail<Q, Y>(d0, c, eta0, a.y, a.x, acc0, sT);
+        v2_tail<Q, Y>(d1, c, eta1, b.y, b.x, acc1, sT);
+    }
+}
+
+// Moment passes (lm pass / closed-form first IRLS pass).  MODE_LM: S(d), S(d^2), S(d*y), S(d*c_r) with y from the yv
+// stream.  MODE_SIGN: the outcome is s = -1 (hit) / +1 (miss); with hits-then-misses ordering it is enough to keep S(d)
+// of the hits and of the misses apart: S(d) = hits + misses, S(d*s) = misses - hits (one add + one FMA per evaluation).
+template <int MODE, int Q, int DIFF, int Y, int NSL>
+__device__ __forceinline__ void m2_range(int m_begin, int m_end, int slice, uint32_t sREC_addr, uint32_t sCD_addr,
+                                         uint32_t sXI_addr, uint32_t sXJ_addr, int diff_type,
+                                         double (&acc0)[3 + Q], double (&acc1)[3 + Q]) {
+    const int len = m_end - m_begin, per = (len + NSL - 1) / NSL;
+    const int m_lo = m_begin + slice * per, m_hi = (m_lo + per < m_end) ? (m_lo + per) : m_end;
+    uint32_t io_prev = 0xFFFFFFFFu;
+    double xi0 = 0.0, xi1 = 0.0;
+#pragma unroll 2
+    for (int m = m_lo; m < m_hi; ++m) {
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));
+        double xj0, xj1;
+        const uint32_t io = r & 0xFC00u;
+        if (io != io_prev) {
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi0), "=d"(xi1) : "r"(sXI_addr + io));
+            io_prev = io;
+        }
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj0), "=d"(xj1) : "r"(sXJ_addr + (r >> 16)));
+        const double d0 = proj_diff<DIFF>(xi0, xj0, diff_type);
+        const double d1 = proj_diff<DIFF>(xi1, xj1, diff_type);
+        if (MODE == MODE_LM) {
+            double yv;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(yv) : "r"(sCD_addr + 8u * (Q * V2_RCHUNK + m)));
+            acc0[0] += d0; acc1[0] += d1;
+            acc0[2] = fma(d0, yv, acc0[2]); acc1[2] = fma(d1, yv, acc1[2]);
+        } else if (Y == 0) {
+            acc0[0] += d0; acc1[0] += d1;
+        } else {
+            acc0[2] += d0; acc1[2] += d1;
+        }
+        acc0[1] = fma(d0, d0, acc0[1]); acc1[1] = fma(d1, d1, acc1[1]);
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+            double cu;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cu) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
+            acc0[3 + u] = fma(d0, cu, acc0[3 + u]); acc1[3 + u] = fma(d1, cu, acc1[3 + u]);
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One skeleton for the three v2 passes.  Shared memory: I tile [64][128], two J tiles (double buffered), two record
+// chunk buffers (records + covariate diffs (+ yv for lm)), the exp/log tables.  While tile t is being consumed the
+// J tile and the first record chunk of tile t+1 are in flight (cp.async), so the FP64 pipe does not idle on staging.
+template <int MODE, int Q>
+struct V2Layout {
+    static constexpr int NCD = (MODE == MODE_LM) ? (Q + 1) : (Q > 0 ? Q : 0);       // double streams per record
+    static constexpr int NA = (MODE != MODE_IRLS_FULL) ? (3 + Q) : ((2 + Q) * (3 + Q) / 2 + (2 + Q) + 1);
+    static constexpr uint32_t XI = 0;
+    static constexpr uint32_t XJ = BI * TA * 8;                                      // two buffers of BJ*TA*8
+    static constexpr uint32_t REC = XJ + 2 * BJ * TA * 8;                            // two buffers
+    static constexpr uint32_t REC_BYTES = V2_RCHUNK * 4;
+    static constexpr uint32_t CD = REC + 2 * REC_BYTES;                              // two buffers
+    static constexpr uint32_t CD_BYTES = (NCD > 0 ? NCD : 1) * V2_RCHUNK * 8;
+    static constexpr uint32_t TAB = CD + 2 * CD_BYTES;
+    static constexpr uint32_t TOTAL = TAB + sizeof(nb_tables2);
+    static constexpr int NSL = v2_nslice(MODE, Q);
+    static constexpr int THREADS = V2_TPS * NSL;
+    static constexpr uint32_t RED = NSL * NA * TA * 8;
+    static constexpr uint32_t SMEM = TOTAL > RED ? TOTAL : RED;
+};
+
+template <int MODE, int Q, int DIFF>
+__global__ void __launch_bounds__(V2Layout<MODE, Q>::THREADS, 1)
+pass2_kernel(PassArgs P) {
+    using L = V2Layout<MODE, Q>;
+    constexpr int K = 2 + Q;
+    constexpr int NA = L::NA;
+    constexpr int NSL = L::NSL;
+    constexpr int V2_THREADS = L::THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int tl = tid % V2_TPS, slice = tid / V2_TPS;
+    const int at = blockIdx.x, chunk = blockIdx.y;
+    if (MODE == MODE_IRLS_FULL && P.tile_active && !P.tile_active[at]) return;
+    const int64_t a0 = (int64_t)at * TA;
+
+    if (MODE == MODE_IRLS_FULL) {   // table image
+        nb_tables2 *sT = (nb_tables2 *)(smem_raw + L::TAB);
+        const nb_tables *g = P.tables;
+        for (int e = tid; e < 64; e += V2_THREADS) { sT->exp_t[e] = g->exp_t[e]; sT->log_eln2_rot[(e + 63) & 63] = g->log_eln2[e]; }
+        for (int e = tid; e < 128; e += V2_THREADS) sT->log_rl[e] = make_double2(g->log_rc[e], g->log_lrc[e]);
+    }
+    const uint32_t sT_addr = sbase + L::TAB;
+    const uint32_t sXI_addr = sbase + L::XI + (uint32_t)tl * 16u;
+
+    double beta0[K], beta1[K];
+    if (MODE == MODE_IRLS_FULL) {
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            beta0[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl];
+            beta1[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1];
+        }
+    }
+    double acc0[NA], acc1[NA];
+#pragma unroll
+    for (int n = 0; n < NA; ++n) { acc0[n] = 0.0; acc1[n] = 0.0; }
+
+    const int t_begin = P.chunk_tile[chunk], t_end = P.chunk_tile[chunk + 1];
+
+    // async stage of a [64][128] double tile (rows are TA contiguous doubles of XT, zero padded)
+    auto stage_tile = [&](uint32_t dst, int block) {
+        const double *g = P.XT + ((int64_t)block * 64) * P.ldt + a0;
+        for (int e = tid; e < 64 * TA / 2; e += V2_THREADS) {
+            const int row = e / (TA / 2), c2 = e % (TA / 2);
+            cp_async16(dst + (uint32_t)e * 16u, g + (int64_t)row * P.ldt + 2 * c2);
+        }
+    };
+    // async stage of records [rc, rc + n) (+ their covariate diffs / yv)
+    auto stage_records = [&](int buf, int64_t rc, int n) {
+        const uint32_t rdst = sbase + L::REC + buf * L::REC_BYTES, cdst = sbase + L::CD + buf * L::CD_BYTES;
+        for (int e = tid; e < n; e += V2_THREADS) {
+            cp_async4(rdst + 4u * e, P.rec + rc + e);
+#pragma unroll
+            for (int c = 0; c < Q; ++c) cp_async8(cdst + 8u * (c * V2_RCHUNK + e), P.cd[c] + rc + e);
+            if (MODE == MODE_LM) cp_async8(cdst + 8u * (Q * V2_RCHUNK + e), P.yv + rc + e);
+        }
+    };
+    auto first_chunk_len = [&](int t) -> int {
+        const int64_t len = P.tile_ptr[t + 1] - P.tile_ptr[t];
+        return (int)(len < V2_RCHUNK ? len : V2_RCHUNK);
+    };
+
+    int cur_ib = -1;
+    if (t_begin < t_end) {                                 // prologue: tile t_begin in flight
+        stage_tile(sbase + L::XJ, P.tile_jb[t_begin]);
+        stage_records(0, P.tile_ptr[t_begin], first_chunk_len(t_begin));
+        cp_async_commit();
+    }
+    for (int t = t_begin; t < t_end; ++t) {
+        const int buf = (t - t_begin) & 1;
+        const int ib = P.tile_ib[t];
+        const int64_t r0 = P.tile_ptr[t], r1 = P.tile_ptr[t + 1], rmid = P.tile_mid[t];
+        if (ib != cur_ib) {                                // new I block (once per row of tiles): nobody reads XI now? ->
+            __syncthreads();                               // all threads are done with the previous tile's compute
+            stage_tile(sbase + L::XI, ib);
+            cp_async_commit();
+            cur_ib = ib;
+        }
+        cp_async_wait_all();
+        __syncthreads();                                   // tile t staged; previous tile's buffers are free
+        if (t + 1 < t_end) {                               // prefetch tile t+1 into the other buffers
+            stage_tile(sbase + L::XJ + (buf ^ 1) * (BJ * TA * 8), P.tile_jb[t + 1]);
+            stage_records(buf ^ 1, P.tile_ptr[t + 1], first_chunk_len(t + 1));
+            cp_async_commit();
+        }
+        const uint32_t sXJ_addr = sbase + L::XJ + buf * (BJ * TA * 8) + (uint32_t)tl * 16u;
+        const uint32_t sREC_addr = sbase + L::REC + buf * L::REC_BYTES;
+        const uint32_t sCD_addr = sbase + L::CD + buf * L::CD_BYTES;
+        for (int64_t rc = r0; rc < r1; rc += V2_RCHUNK) {
+            const int n = (int)((r1 - rc < V2_RCHUNK) ? (r1 - rc) : V2_RCHUNK);
+            if (rc != r0) {                                // rare: more than one record chunk in this tile
+                __syncthreads();                           // previous chunk consumed
+                stage_records(buf, rc, n);
+                cp_async_commit();
+                cp_async_wait_all();                       // (also completes the prefetch; correctness only)
+                __syncthreads();
+            }
+            int ms = (int)(rmid - rc);                      // first miss record of this chunk
+            ms = ms < 0 ? 0 : (ms > n ? n : ms);
+            if constexpr (MODE == MODE_IRLS_FULL) {
+                v2_range<Q, DIFF, 0, NSL>(0, ms, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1);
+                v2_range<Q, DIFF, 1, NSL>(ms, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1);
+            } else if constexpr (MODE == MODE_LM) {
+                m2_range<MODE_LM, Q, DIFF, 0, NSL>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc0, acc1);
+            } else {
+                m2_range<MODE_SIGN, Q, DIFF, 0, NSL>(0, ms, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc0, acc1);
+                m2_range<MODE_SIGN, Q, DIFF, 1, NSL>(ms, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc0, acc1);
+            }
+        }
+    }
+    if (MODE == MODE_SIGN) {                               // (hits, misses) -> (S d, S d*s)
+        const double h0 = acc0[0], m0 = acc0[2], h1 = acc1[0], m1 = acc1[2];
+        acc0[0] = h0 + m0; acc0[2] = m0 - h0; acc1[0] = h1 + m1; acc1[2] = m1 - h1;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    double *red = (double *)smem_raw;                      // [NSL][NA][TA]
+#pragma unroll
+    for (int n = 0; n < NA; ++n) {
+        red[(slice * NA + n) * TA + 2 * tl] = acc0[n];
+        red[(slice * NA + n) * TA + 2 * tl + 1] = acc1[n];
+    }
+    __syncthreads();
+    for (int e = tid; e < NA * TA; e += V2_THREADS) {
+        const int n = e / TA, a = e % TA;
+        double sacc = red[(0 * NA + n) * TA + a];
+#pragma unroll
+        for (int sl = 1; sl < NSL; ++sl) sacc += red[(sl * NA + n) * TA + a];
+        P.partials[((int64_t)chunk * NA + n) * P.nattr_pad + a0 + a] = sacc;
     }
 }
 
@@ -486,6 +920,52 @@ __global__ void lm_finalize_kernel(SolveArgs S) {
     write_stats(S.stats + (int64_t)a * 8, beta, se, al, K, rdf, rsq, 0, 0);
 }
 
+// binomial, first solve: glm.fit starts from mustart = (y + 0.5)/2, i.e. mu = 0.75 / 0.25, eta = +-log 3, constant
+// weight w0 = mu(1-mu) = 3/16 and working response z = s * z0 (s = +1 miss, -1 hit).  X'WX and X'Wz are therefore
+// w0 times the plain moments the MODE_SIGN pass accumulated, and the deviance at mustart is M * 2 log(4/3).
+template <int Q>
+__global__ void irls_init_kernel(SolveArgs S) {
+    constexpr int K = 2 + Q, NA = 3 + Q;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= S.nattr) return;
+    double m[NA];
+    reduce_partials<NA>(S, a, m);
+    const double M = S.shared[0], Ss = S.shared[1];
+    const double *Sc = S.shared + 3, *Scs = S.shared + 3 + Q, *Scc = S.shared + 3 + 2 * Q;
+    const double w0 = 0.1875, z0 = 1.0986122886681098 + 0.25 / 0.1875;
+    double A[K][K], b[K];
+    A[0][0] = w0 * M; A[0][1] = A[1][0] = w0 * m[0]; A[1][1] = w0 * m[1];
+    b[0] = w0 * z0 * Ss; b[1] = w0 * z0 * m[2];
+    int cc = 0;
+    for (int r = 0; r < Q; ++r) {
+        A[0][2 + r] = A[2 + r][0] = w0 * Sc[r];
+        A[1][2 + r] = A[2 + r][1] = w0 * m[3 + r];
+        b[2 + r] = w0 * z0 * Scs[r];
+        for (int u = r; u < Q; ++u) { A[2 + r][2 + u] = A[2 + u][2 + r] = w0 * Scc[cc]; ++cc; }
+    }
+    S.dev_old[a] = M * (2.0 * 0.2876820724517809);         // sum of dev.resids at mustart: 2*log(4/3) each
+    double x[K], dinv[K];
+    bool al[K];
+    chol_solve<K>(A, b, 1e-13, x, dinv, al);
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+    bool ok = true;
+    for (int r = 0; r < K; ++r) ok = ok && isfinite(x[r]);
+    if (!ok) {
+        double beta[K], se[K];
+        for (int r = 0; r < K; ++r) { beta[r] = nanv; se[r] = nanv; al[r] = false; }
+        write_stats(S.stats + (int64_t)a * 8, beta, se, al, K, M - (double)K, nanv, 0, NPDRB_FLAG_NONFINITE);
+        S.active[a] = 0;
+        return;
+    }
+    for (int r = 0; r < K; ++r) {
+        S.beta[(int64_t)r * S.nattr_pad + a] = x[r];
+        S.se[(int64_t)r * S.nattr_pad + a] = al[r] ? nanv : sqrt(dinv[r]);
+    }
+    S.iters[a] = 1;
+    S.tile_active[a / TA] = 1;
+    atomicAdd(S.n_active, 1u);
+}
+
 // binomial: one IRLS bookkeeping step per attribute (glm.fit's loop body)
 template <int Q>
 __global__ void irls_step_kernel(SolveArgs S) {
@@ -502,9 +982,7 @@ __global__ void irls_step_kernel(SolveArgs S) {
     const double dev = 2.0 * m[NA - 1];
     bool finish = false;
     int flags = 0;
-    if (S.pass == 0) {
-        S.dev_old[a] = S.M * (2.0 * 0.2876820724517809);      // sum of dev.resids at mustart: 2*log(4/3) each
-    } else {
+    {
         const double devold = S.dev_old[a];
         if (!isfinite(dev)) { finish = true; flags |= NPDRB_FLAG_NONFINITE; }
         else if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) finish = true;      // glm.control(epsilon = 1e-8)
@@ -563,7 +1041,8 @@ int get_tables(npdrb_ctx *ctx, const nb_tables **out) {
         static const nb_tables host_tables = NB_TABLES_STATIC_INIT;
         nb_tables *d = nullptr;
         NB_CHECK(dmalloc(&d, 1));
-        NB_CUDA(cudaMemcpy(d, &host_tables, sizeof(nb_tables), cudaMemcpyHostToDevice));
+        NB_CUDA(cudaMemcpyAsync(d, &host_tables, sizeof(nb_tables), cudaMemcpyHostToDevice, ctx->stream));
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
         g_tables_dev[ctx->device & 63] = d;
     }
     *out = g_tables_dev[ctx->device & 63];
@@ -573,13 +1052,13 @@ int get_tables(npdrb_ctx *ctx, const nb_tables **out) {
 void free_stream(nb_stream &st) {
     cudaFree(st.rec); cudaFree(st.yv);
     for (int c = 0; c < NPDRB_MAX_COVARS; ++c) cudaFree(st.cd[c]);
-    cudaFree(st.tile_ptr); cudaFree(st.tile_ib); cudaFree(st.tile_jb); cudaFree(st.chunk_tile);
+    cudaFree(st.tile_ptr); cudaFree(st.tile_mid); cudaFree(st.tile_ib); cudaFree(st.tile_jb); cudaFree(st.chunk_tile);
     st = nb_stream();
 }
 
 // Build one bucketed stream from a pair list (device).  y_raw: uniReg mode.
 int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64_t M, int reg_type,
-                 const int32_t *cov_type, int y_raw, double weight, nb_stream &st, int64_t *n_miss_out) {
+                 const int32_t *cov_type, int y_raw, double weight, double work_share, nb_stream &st, int64_t *n_miss_out) {
     npdrb_ctx *ctx = s->ctx;
     const int64_t N = s->N;
     const int q = s->q;
@@ -593,14 +1072,15 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     void *tmp = nullptr;
     NB_CHECK(dmalloc(&keys, (size_t)M)); NB_CHECK(dmalloc(&idx, (size_t)M));
     NB_CHECK(dmalloc(&keys2, (size_t)M)); NB_CHECK(dmalloc(&perm, (size_t)M));
-    NB_CHECK(dmalloc(&hist, (size_t)n_tiles_all)); NB_CHECK(dmalloc(&d_miss, 1));
-    NB_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned) * (size_t)n_tiles_all, ctx->stream));
+    NB_CHECK(dmalloc(&hist, (size_t)2 * n_tiles_all)); NB_CHECK(dmalloc(&d_miss, 1));
+    NB_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned) * (size_t)2 * n_tiles_all, ctx->stream));
     NB_CUDA(cudaMemsetAsync(d_miss, 0, sizeof(unsigned long long), ctx->stream));
     const unsigned grid = (unsigned)nb_cdiv(M, 256);
-    tile_keys_kernel<<<grid, 256, 0, ctx->stream>>>(dRi, dNN, M, n_jb, keys, idx);
+    const int ybits = (reg_type == NPDRB_REG_BINOMIAL) ? (y_raw ? 2 : 1) : 0;
+    tile_keys_kernel<<<grid, 256, 0, ctx->stream>>>(dRi, dNN, M, n_jb, s->dy, ybits, keys, idx);
     NB_LAUNCH_CHECK(ctx);
     int end_bit = 1;
-    while ((1ll << end_bit) < n_tiles_all && end_bit < 32) ++end_bit;
+    while ((1ll << end_bit) < 2 * n_tiles_all && end_bit < 32) ++end_bit;
     size_t tmp_bytes = 0;
     NB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, perm, (int)M, 0, end_bit, ctx->stream));
     NB_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
@@ -619,26 +1099,28 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     gather_records_kernel<<<grid, 256, 0, ctx->stream>>>(g);
     NB_LAUNCH_CHECK(ctx);
 
-    std::vector<unsigned> h_hist((size_t)n_tiles_all);
+    std::vector<unsigned> h_hist((size_t)2 * n_tiles_all);
     unsigned long long h_miss = 0;
     NB_CUDA(cudaMemcpyAsync(h_hist.data(), hist, sizeof(unsigned) * h_hist.size(), cudaMemcpyDeviceToHost, ctx->stream));
     NB_CUDA(cudaMemcpyAsync(&h_miss, d_miss, sizeof(h_miss), cudaMemcpyDeviceToHost, ctx->stream));
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n_miss_out) *n_miss_out = (int64_t)h_miss;
 
-    std::vector<int64_t> tptr; std::vector<int32_t> tib, tjb;
+    std::vector<int64_t> tptr, tmid; std::vector<int32_t> tib, tjb;
     int64_t run = 0;
     for (int64_t t = 0; t < n_tiles_all; ++t) {
-        if (!h_hist[t]) continue;
-        tptr.push_back(run); tib.push_back((int32_t)(t / n_jb)); tjb.push_back((int32_t)(t % n_jb));
-        run += h_hist[t];
+        const int64_t n0 = h_hist[2 * t], n1 = h_hist[2 * t + 1];
+        if (!(n0 + n1)) continue;
+        tptr.push_back(run); tmid.push_back(run + n0);
+        tib.push_back((int32_t)(t / n_jb)); tjb.push_back((int32_t)(t % n_jb));
+        run += n0 + n1;
     }
     tptr.push_back(run);
     st.n_tiles = (int32_t)tib.size();
     // work chunks: contiguous tile ranges balanced by record count
     const int64_t n_at = nb_cdiv(s->xt_nattr > 0 ? s->xt_nattr : s->p, TA);
-    int64_t target = (int64_t)16 * ctx->sm_count;
-    int64_t C = nb_cdiv(target, n_at);
+    int64_t target = (int64_t)(16.0 * ctx->sm_count * work_share);
+    int64_t C = nb_cdiv(target > 1 ? target : 1, n_at);
     if (C < 1) C = 1;
     if (C > st.n_tiles) C = st.n_tiles;
     if (C < 1) C = 1;
@@ -654,10 +1136,12 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     }
     ctile.push_back(st.n_tiles);
     st.n_chunks = (int32_t)ctile.size() - 1;
-    NB_CHECK(dmalloc(&st.tile_ptr, tptr.size())); NB_CHECK(dmalloc(&st.tile_ib, tib.size() + 1));
+    NB_CHECK(dmalloc(&st.tile_ptr, tptr.size())); NB_CHECK(dmalloc(&st.tile_mid, tmid.size() + 1));
+    NB_CHECK(dmalloc(&st.tile_ib, tib.size() + 1));
     NB_CHECK(dmalloc(&st.tile_jb, tjb.size() + 1)); NB_CHECK(dmalloc(&st.chunk_tile, ctile.size()));
     NB_CUDA(cudaMemcpyAsync(st.tile_ptr, tptr.data(), sizeof(int64_t) * tptr.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!tib.empty()) {
+        NB_CUDA(cudaMemcpyAsync(st.tile_mid, tmid.data(), sizeof(int64_t) * tmid.size(), cudaMemcpyHostToDevice, ctx->stream));
         NB_CUDA(cudaMemcpyAsync(st.tile_ib, tib.data(), sizeof(int32_t) * tib.size(), cudaMemcpyHostToDevice, ctx->stream));
         NB_CUDA(cudaMemcpyAsync(st.tile_jb, tjb.data(), sizeof(int32_t) * tjb.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
@@ -688,6 +1172,33 @@ int launch_pass_q(npdrb_ctx *ctx, const PassArgs &P, int n_at, int n_chunks) {
     return P.diff_type == NPDRB_DIFF_NUMERIC_ABS ? launch_pass_t<MODE, Q, 0>(ctx, P, n_at, n_chunks)
                                                  : launch_pass_t<MODE, Q, 1>(ctx, P, n_at, n_chunks);
 }
+template <int MODE, int Q, int DIFF>
+int launch_pass2_t(npdrb_ctx *ctx, const PassArgs &P, int n_at, int n_chunks) {
+    const size_t smem = V2Layout<MODE, Q>::SMEM;
+    NB_CUDA(cudaFuncSetAttribute(pass2_kernel<MODE, Q, DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)n_at, (unsigned)n_chunks);
+    pass2_kernel<MODE, Q, DIFF><<<grid, V2Layout<MODE, Q>::THREADS, smem, ctx->stream>>>(P);
+    NB_LAUNCH_CHECK(ctx);
+    return NPDRB_OK;
+}
+// v2 covers q <= 2 (shared memory: I tile + two J tiles + record buffers <= 227 KB); larger q uses the v1 kernel
+template <int MODE>
+int launch_pass2(npdrb_ctx *ctx, int q, const PassArgs &P, int n_at, int n_chunks) {
+    const bool ad = P.diff_type == NPDRB_DIFF_NUMERIC_ABS;
+    switch (q) {
+    case 0: return ad ? launch_pass2_t<MODE, 0, 0>(ctx, P, n_at, n_chunks) : launch_pass2_t<MODE, 0, 1>(ctx, P, n_at, n_chunks);
+    case 1: return ad ? launch_pass2_t<MODE, 1, 0>(ctx, P, n_at, n_chunks) : launch_pass2_t<MODE, 1, 1>(ctx, P, n_at, n_chunks);
+    case 2: return ad ? launch_pass2_t<MODE, 2, 0>(ctx, P, n_at, n_chunks) : launch_pass2_t<MODE, 2, 1>(ctx, P, n_at, n_chunks);
+    }
+    npdrb_set_error("pass2: q > 2");
+    return NPDRB_EINVAL;
+}
+bool use_v1_only() {
+    const char *e = getenv("NPDRB_PASS_KERNEL");
+    return e && strcmp(e, "v1") == 0;
+}
+bool use_v2(int q) { return q <= 2 && !use_v1_only(); }
+
 template <int MODE>
 int launch_pass(npdrb_ctx *ctx, int q, const PassArgs &P, int n_at, int n_chunks) {
     switch (q) {
@@ -701,11 +1212,13 @@ int launch_pass(npdrb_ctx *ctx, int q, const PassArgs &P, int n_at, int n_chunks
     return NPDRB_EINVAL;
 }
 
-int launch_solve(npdrb_ctx *ctx, int q, bool lm, const SolveArgs &S) {
+enum { SOLVE_LM = 0, SOLVE_IRLS_INIT = 1, SOLVE_IRLS_STEP = 2 };
+int launch_solve(npdrb_ctx *ctx, int q, int kind, const SolveArgs &S) {
     const unsigned grid = (unsigned)nb_cdiv(S.nattr, 128);
 #define NB_SOLVE_CASE(QQ)                                                                  \
     case QQ:                                                                               \
-        if (lm) lm_finalize_kernel<QQ><<<grid, 128, 0, ctx->stream>>>(S);                  \
+        if (kind == SOLVE_LM) lm_finalize_kernel<QQ><<<grid, 128, 0, ctx->stream>>>(S);    \
+        else if (kind == SOLVE_IRLS_INIT) irls_init_kernel<QQ><<<grid, 128, 0, ctx->stream>>>(S); \
         else irls_step_kernel<QQ><<<grid, 128, 0, ctx->stream>>>(S);                       \
         break;
     switch (q) {
@@ -762,8 +1275,57 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     if (!s->streams_valid || s->streams_reg_type != reg_type || s->streams_cov_sig != sig) {
         nb_free_streams(s);
         int64_t n_miss = 0;
-        NB_CHECK(build_stream(s, s->dRi, s->dNN, s->M, reg_type, cov_type, y_raw, 1.0, s->streams[0], &n_miss));
-        s->n_streams = 1;
+        bool folded = false;
+        const char *nf = getenv("NPDRB_NO_FOLD");
+        if (!(nf && nf[0] == '1') && s->M >= 2) {
+            // classify: one-directional (weight 1) / mutual with i<j (weight 2) / mutual reverse (dropped)
+            const int64_t M = s->M;
+            const size_t words = ((size_t)N * (size_t)N + 31) / 32;
+            unsigned *d_bits = nullptr; unsigned char *d_f1 = nullptr, *d_f2 = nullptr; unsigned long long *d_cnt = nullptr;
+            int32_t *d_sel = nullptr; int *d_nsel = nullptr; void *d_tmp = nullptr;
+            NB_CHECK(dmalloc(&d_bits, words)); NB_CHECK(dmalloc(&d_f1, (size_t)M)); NB_CHECK(dmalloc(&d_f2, (size_t)M));
+            NB_CHECK(dmalloc(&d_cnt, 1)); NB_CHECK(dmalloc(&d_sel, (size_t)4 * M)); NB_CHECK(dmalloc(&d_nsel, 4));
+            NB_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned) * words, ctx->stream));
+            NB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
+            const unsigned grid = (unsigned)nb_cdiv(M, 256);
+            mark_bits_kernel<<<grid, 256, 0, ctx->stream>>>(s->dRi, s->dNN, M, N, d_bits);
+            NB_LAUNCH_CHECK(ctx);
+            popcount_kernel<<<1024, 256, 0, ctx->stream>>>(d_bits, words, d_cnt);
+            NB_LAUNCH_CHECK(ctx);
+            classify_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(s->dRi, s->dNN, M, N, d_bits, d_f1, d_f2);
+            NB_LAUNCH_CHECK(ctx);
+            size_t tmp_bytes = 0;
+            NB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, s->dRi, d_f1, d_sel, d_nsel, (int)M, ctx->stream));
+            NB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+            const int32_t *src[4] = {s->dRi, s->dNN, s->dRi, s->dNN};
+            const unsigned char *flg[4] = {d_f1, d_f1, d_f2, d_f2};
+            for (int k4 = 0; k4 < 4; ++k4)
+                NB_CUDA(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, src[k4], flg[k4], d_sel + (size_t)k4 * M, d_nsel + k4, (int)M, ctx->stream));
+            ctx->launches += 8;
+            unsigned long long h_cnt = 0; int h_nsel[4] = {0, 0, 0, 0};
+            NB_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
+            NB_CUDA(cudaMemcpyAsync(h_nsel, d_nsel, sizeof(h_nsel), cudaMemcpyDeviceToHost, ctx->stream));
+            NB_CUDA(cudaStreamSynchronize(ctx->stream));
+            const int64_t n1 = h_nsel[0], n2 = h_nsel[2];
+            int rc = NPDRB_OK;
+            if ((int64_t)h_cnt == M && n2 > 0 && n1 + 2 * n2 == M) {       // no repeated ordered pair: folding is exact
+                const double tot = (double)(n1 + n2);
+                int64_t miss1 = 0, miss2 = 0;
+                int ns = 0;
+                if (n1 > 0) { rc = build_stream(s, d_sel, d_sel + M, n1, reg_type, cov_type, y_raw, 1.0, n1 / tot, s->streams[ns], &miss1); ++ns; }
+                if (!rc) { rc = build_stream(s, d_sel + 2 * M, d_sel + 3 * M, n2, reg_type, cov_type, y_raw, 2.0, n2 / tot, s->streams[ns], &miss2); ++ns; }
+                s->n_streams = ns;
+                n_miss = miss1 + 2 * miss2;
+                folded = (rc == NPDRB_OK);
+            }
+            cudaFree(d_bits); cudaFree(d_f1); cudaFree(d_f2); cudaFree(d_cnt); cudaFree(d_sel); cudaFree(d_nsel); cudaFree(d_tmp);
+            if (rc) return rc;
+        }
+        if (!folded) {
+            nb_free_streams(s);
+            NB_CHECK(build_stream(s, s->dRi, s->dNN, s->M, reg_type, cov_type, y_raw, 1.0, 1.0, s->streams[0], &n_miss));
+            s->n_streams = 1;
+        }
         s->streams_reg_type = reg_type; s->streams_cov_sig = sig; s->streams_valid = true;
         if (reg_type == NPDRB_REG_BINOMIAL && (n_miss == 0 || n_miss == s->M)) {
             npdrb_set_error("binomial regression: the pair outcome has a single level (%lld of %lld pairs are misses)",
@@ -827,11 +1389,18 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             P.XT = s->dXT; P.ldt = s->ldt; P.N = N; P.nattr = (int)nattr; P.nattr_pad = (int)nattr_pad;
             P.rec = st.rec; P.yv = st.yv;
             for (int c = 0; c < NPDRB_MAX_COVARS; ++c) P.cd[c] = st.cd[c];
-            P.tile_ptr = st.tile_ptr; P.tile_ib = st.tile_ib; P.tile_jb = st.tile_jb; P.chunk_tile = st.chunk_tile;
+            P.tile_ptr = st.tile_ptr; P.tile_mid = st.tile_mid; P.tile_ib = st.tile_ib; P.tile_jb = st.tile_jb; P.chunk_tile = st.chunk_tile;
             P.beta = d_beta; P.tile_active = tile_active; P.partials = pp; P.tables = d_tab; P.diff_type = diff_type;
-            int rc = mode == MODE_LM ? launch_pass<MODE_LM>(ctx, q, P, (int)n_at, st.n_chunks)
-                   : mode == MODE_IRLS_INIT ? launch_pass<MODE_IRLS_INIT>(ctx, q, P, (int)n_at, st.n_chunks)
-                                            : launch_pass<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, st.n_chunks);
+            int rc;
+            if (use_v2(q)) {
+                rc = mode == MODE_LM ? launch_pass2<MODE_LM>(ctx, q, P, (int)n_at, st.n_chunks)
+                   : mode == MODE_SIGN ? launch_pass2<MODE_SIGN>(ctx, q, P, (int)n_at, st.n_chunks)
+                                       : launch_pass2<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, st.n_chunks);
+            } else {
+                rc = mode == MODE_LM ? launch_pass<MODE_LM>(ctx, q, P, (int)n_at, st.n_chunks)
+                   : mode == MODE_SIGN ? launch_pass<MODE_SIGN>(ctx, q, P, (int)n_at, st.n_chunks)
+                                       : launch_pass<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, st.n_chunks);
+            }
             if (rc) return rc;
             pp += part_stride[i];
         }
@@ -851,8 +1420,9 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     std::vector<double> pass_evals;
     double rec_total = 0;
     for (int i = 0; i < s->n_streams; ++i) rec_total += (double)s->streams[i].n_rec;
-    if (lm) {
-        // shared moments over all streams (weights applied on the host)
+    {
+        // attribute-independent moments of the record stream(s): M, S(y), S(y^2), S(c), S(c y), S(c c') with y the
+        // outcome diff (lm) or the sign s = +-1 of the hit/miss bit (binomial first pass); weights applied on the host
         const int nblk = 128;
         double *d_sh = nullptr;
         NB_CHECK(dmalloc(&d_sh, (size_t)nblk * NSHARED_MAX));
@@ -861,7 +1431,8 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         const int ns = 3 + 2 * q + q * (q + 1) / 2;
         for (int i = 0; i < s->n_streams; ++i) {
             SharedArgs a;
-            a.yv = s->streams[i].yv; a.n = s->streams[i].n_rec; a.q = q; a.out = d_sh;
+            a.yv = lm ? s->streams[i].yv : nullptr; a.rec = s->streams[i].rec;
+            a.n = s->streams[i].n_rec; a.q = q; a.out = d_sh;
             for (int c = 0; c < NPDRB_MAX_COVARS; ++c) a.cd[c] = s->streams[i].cd[c];
             NB_CUDA(cudaMemsetAsync(d_sh, 0, sizeof(double) * h.size(), ctx->stream));
             shared_moments_kernel<<<nblk, 256, 0, ctx->stream>>>(a);
@@ -873,35 +1444,40 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         }
         cudaFree(d_sh);
         for (int k = 0; k < NSHARED_MAX; ++k) S.shared[k] = (double)tot[k];
+    }
+    if (lm) {
         NB_CHECK(mark());
         NB_CHECK(run_pass(MODE_LM, nullptr));
         NB_CHECK(mark());
-        NB_CHECK(launch_solve(ctx, q, true, S));
+        NB_CHECK(launch_solve(ctx, q, SOLVE_LM, S));
         passes = 1;
     } else {
-        NB_CUDA(cudaMemsetAsync(d_tile_active, 1, (size_t)n_at, ctx->stream));
+        // pass 0: closed-form weights at mustart -> plain moments; then one full pass per IRLS iteration
+        NB_CUDA(cudaMemsetAsync(d_tile_active, 0, (size_t)n_at, ctx->stream));
+        NB_CUDA(cudaMemsetAsync(d_nactive, 0, sizeof(unsigned int), ctx->stream));
         NB_CHECK(mark());
-        NB_CHECK(run_pass(MODE_IRLS_INIT, nullptr));
+        NB_CHECK(run_pass(MODE_SIGN, nullptr));
         NB_CHECK(mark());
-        for (int pass = 0; pass <= 25; ++pass) {
-            if (pass > 0) {
-                int act = 0;
-                for (int64_t t = 0; t < n_at; ++t) act += h_tile_active[(size_t)t] ? 1 : 0;
-                pass_evals.push_back((double)act * TA * rec_total);
-                NB_CHECK(mark());
-                NB_CHECK(run_pass(MODE_IRLS_FULL, d_tile_active));
-                NB_CHECK(mark());
-                passes++;
-            }
-            NB_CUDA(cudaMemsetAsync(d_tile_active, 0, (size_t)n_at, ctx->stream));
-            NB_CUDA(cudaMemsetAsync(d_nactive, 0, sizeof(unsigned int), ctx->stream));
-            S.pass = pass;
-            NB_CHECK(launch_solve(ctx, q, false, S));
+        S.pass = 0;
+        NB_CHECK(launch_solve(ctx, q, SOLVE_IRLS_INIT, S));
+        for (int pass = 1; pass <= 25; ++pass) {
             unsigned int h_active = 0;
             NB_CUDA(cudaMemcpyAsync(&h_active, d_nactive, sizeof(h_active), cudaMemcpyDeviceToHost, ctx->stream));
             NB_CUDA(cudaMemcpyAsync(h_tile_active.data(), d_tile_active, (size_t)n_at, cudaMemcpyDeviceToHost, ctx->stream));
             NB_CUDA(cudaStreamSynchronize(ctx->stream));
             if (h_active == 0) break;
+            int act = 0;
+            for (int64_t t = 0; t < n_at; ++t) act += h_tile_active[(size_t)t] ? 1 : 0;
+            pass_evals.push_back((double)act * TA * rec_total);
+            NB_CHECK(mark());
+            NB_CHECK(run_pass(MODE_IRLS_FULL, d_tile_active));
+            NB_CHECK(mark());
+            passes++;
+            // the step kernel rebuilds the active flags; the pass above has consumed the old ones (stream order)
+            NB_CUDA(cudaMemsetAsync(d_tile_active, 0, (size_t)n_at, ctx->stream));
+            NB_CUDA(cudaMemsetAsync(d_nactive, 0, sizeof(unsigned int), ctx->stream));
+            S.pass = pass;
+            NB_CHECK(launch_solve(ctx, q, SOLVE_IRLS_STEP, S));
         }
     }
     NB_CUDA(cudaMemcpyAsync(stats_out_host, d_stats, sizeof(double) * (size_t)nattr * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -28,5 +28,19 @@ int main() {
         if (ab > max_abs_log) max_abs_log = ab;
     }
     printf("max_rel_exp=%.3e max_abs_log=%.3e max_rel_log=%.3e\n", max_rel_exp, max_abs_log, max_rel_log);
-    return !(max_rel_exp < 4e-16 && max_abs_log < 8e-15 && max_rel_log < 1e-15);
+    // trimmed variants used by the IRLS kernel
+    double fr_exp = 0, fa_log = 0;
+    for (int it = 0; it < 4000000; ++it) {
+        double eta = (it < 2000000) ? U(rng) : U(rng) / 30.0;
+        double t = nb_exp_fast(eta, T.exp_t);
+        long double te = expl((long double)eta);
+        double rel = (double)fabsl(((long double)t - te) / te);
+        if (rel > fr_exp) fr_exp = rel;
+        double u = 1.0 + (double)te;
+        double ab = (double)fabsl((long double)nb_log_ge1_fast(u, T.log_rc, T.log_lrc, T.log_eln2) - logl((long double)u));
+        double sc = (double)logl((long double)u); if (sc < 1.0) sc = 1.0;
+        if (ab / sc > fa_log) fa_log = ab / sc;
+    }
+    printf("fast: max_rel_exp=%.3e max_log_err(rel to max(1,log))=%.3e\n", fr_exp, fa_log);
+    return !(max_rel_exp < 4e-16 && max_abs_log < 8e-15 && max_rel_log < 1e-15 && fr_exp < 6e-14 && fa_log < 2e-15);
 }

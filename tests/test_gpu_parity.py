@@ -246,6 +246,25 @@ def test_regress_user_pair_list_any_order(nb, oracle):
     _stats_close(out, exp, RTOL_IRLS, "shuffled")
 
 
+@pytest.mark.parametrize("reg", ["lm", "binomial"])
+def test_mutual_pair_folding_is_exact(nb, reg):
+    """Folding (i,j)/(j,i) into one weight-2 record must not change the statistics beyond summation order."""
+    rng = np.random.default_rng(31)
+    N, p = 220, 130
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    y = (rng.random(N) < 0.5).astype(float) if reg == "binomial" else rng.normal(size=N)
+    C = np.asfortranarray(np.column_stack([rng.integers(0, 2, N).astype(float), rng.normal(40, 12, N).round()]))
+    kw = dict(covars=C, covar_diff_type=["match-mismatch", "numeric-abs"], return_info=True)
+    _, a = nb.npdr(y, X, reg, **kw)
+    os.environ["NPDRB_NO_FOLD"] = "1"
+    try:
+        _, b = nb.npdr(y, X, reg, **kw)
+    finally:
+        del os.environ["NPDRB_NO_FOLD"]
+    assert a["n_unique_pairs"] < a["n_pairs"]                      # there are mutual pairs to fold
+    _stats_close(a["stats"], b["stats"], 1e-11, "fold vs no fold")
+
+
 def test_diff_regression_and_unireg(nb, oracle):
     import pandas as pd
     rng = np.random.default_rng(22)
