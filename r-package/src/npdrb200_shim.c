@@ -1,0 +1,125 @@
+/*
+ * npdrb200_shim.c -- thin .Call shim between R and libnpdr_b200.so (include/npdr_b200.h).
+ *
+ * NOT compiled in the build container (no R headers there); it is the binding a maintainer adds to the
+ * reference package.  Plain R C API (no Rcpp dependency needed for five entry points).  Rules followed:
+ * inputs (SEXP payloads) are never written; native buffers are copied into R-allocated vectors and freed with
+ * npdrb_free(); errors are turned into Rf_error() only after native resources are released.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+#include "npdr_b200.h"
+
+static npdrb_ctx *g_ctx = NULL;
+
+static npdrb_ctx *ctx_get(void) {
+    if (!g_ctx && npdrb_create(0, &g_ctx) != NPDRB_OK) Rf_error("npdr_b200: %s", npdrb_last_error());
+    return g_ctx;
+}
+
+/* .Call("C_npdrb_distances", X, metric) -> N x N matrix           (npdrDistances, R/nearestNeighbors.R:63) */
+SEXP C_npdrb_distances(SEXP X, SEXP metric) {
+    SEXP dim = Rf_getAttrib(X, R_DimSymbol);
+    const R_xlen_t N = INTEGER(dim)[0], p = INTEGER(dim)[1];
+    SEXP D = PROTECT(Rf_allocMatrix(REALSXP, (int)N, (int)N));
+    int rc = npdrb_distances(ctx_get(), REAL(X), N, p, Rf_asInteger(metric), 0, REAL(D));
+    UNPROTECT(1);
+    if (rc) Rf_error("npdr_b200: %s", npdrb_last_error());
+    return D;
+}
+
+/* .Call("C_npdrb_nearest_neighbors", X, nbd.method, nbd.metric, sd.vec|NULL, sd.frac, k, unique)
+ *   -> list(Ri_idx, NN_idx, n_unique, n_empty, radius)             (nearestNeighbors, R/nearestNeighbors.R:153) */
+SEXP C_npdrb_nearest_neighbors(SEXP X, SEXP method, SEXP metric, SEXP sd_vec, SEXP sd_frac, SEXP k, SEXP uniq) {
+    SEXP dim = Rf_getAttrib(X, R_DimSymbol);
+    const R_xlen_t N = INTEGER(dim)[0], p = INTEGER(dim)[1];
+    int32_t *Ri = NULL, *NN = NULL;
+    int64_t M = 0, nu = 0, ne = 0;
+    SEXP radius = PROTECT(Rf_allocVector(REALSXP, N));
+    int rc = npdrb_nearest_neighbors(ctx_get(), REAL(X), N, p, Rf_asInteger(method), Rf_asInteger(metric),
+                                     Rf_isNull(sd_vec) ? NULL : REAL(sd_vec), Rf_asReal(sd_frac), (int64_t)Rf_asReal(k),
+                                     Rf_asLogical(uniq), &Ri, &NN, &M, &nu, &ne, REAL(radius));
+    if (rc) { UNPROTECT(1); Rf_error("npdr_b200: %s", npdrb_last_error()); }
+    SEXP ri = PROTECT(Rf_allocVector(INTSXP, M)), nn = PROTECT(Rf_allocVector(INTSXP, M));
+    if (M) { memcpy(INTEGER(ri), Ri, sizeof(int) * (size_t)M); memcpy(INTEGER(nn), NN, sizeof(int) * (size_t)M); }
+    npdrb_free(Ri); npdrb_free(NN);
+    const char *names[] = {"Ri_idx", "NN_idx", "n_unique", "n_empty", "radius", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, ri); SET_VECTOR_ELT(out, 1, nn);
+    SET_VECTOR_ELT(out, 2, Rf_ScalarReal((double)nu)); SET_VECTOR_ELT(out, 3, Rf_ScalarReal((double)ne));
+    SET_VECTOR_ELT(out, 4, radius);
+    UNPROTECT(4);
+    return out;
+}
+
+/* .Call("C_npdrb_npdr", X, y, C|NULL, opts(integer/real vector)) -> list(stats = p x 8 (row-major -> t()), counters)
+ * the whole path between argument parsing and order()/p.adjust()    (R/npdr.R:256-430) */
+SEXP C_npdrb_npdr(SEXP X, SEXP y, SEXP C, SEXP iopts, SEXP sd_frac) {
+    SEXP dim = Rf_getAttrib(X, R_DimSymbol);
+    const R_xlen_t N = INTEGER(dim)[0], p = INTEGER(dim)[1];
+    npdrb_opts o;
+    npdrb_opts_default(&o);
+    const int *io = INTEGER(iopts);     /* regression, attr diff, nbd method, nbd metric, knn, n_covars, unique, covar types... */
+    o.regression_type = io[0]; o.attr_diff_type = io[1]; o.nbd_method = io[2]; o.nbd_metric = io[3];
+    o.knn = io[4]; o.n_covars = io[5]; o.neighbor_sampling_unique = io[6];
+    for (int c = 0; c < o.n_covars && c < NPDRB_MAX_COVARS; ++c) o.covar_diff_type[c] = io[7 + c];
+    o.msurf_sd_frac = Rf_asReal(sd_frac);
+    npdrb_result res;
+    int rc = npdrb_npdr(ctx_get(), REAL(X), N, p, REAL(y), Rf_isNull(C) ? NULL : REAL(C), &o, &res);
+    if (rc) Rf_error("npdr_b200: %s", npdrb_last_error());
+    SEXP stats = PROTECT(Rf_allocMatrix(REALSXP, NPDRB_STATS_PER_ATTR, (int)p));     /* 8 x p, column = attribute */
+    memcpy(REAL(stats), res.stats, sizeof(double) * (size_t)p * NPDRB_STATS_PER_ATTR);
+    const char *names[] = {"stats", "n_pairs", "n_unique_pairs", "n_pairs_used", "k_ave_empirical", "n_empty", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, stats);
+    SET_VECTOR_ELT(out, 1, Rf_ScalarReal((double)res.n_pairs));
+    SET_VECTOR_ELT(out, 2, Rf_ScalarReal((double)res.n_unique_pairs));
+    SET_VECTOR_ELT(out, 3, Rf_ScalarReal((double)res.n_pairs_used));
+    SET_VECTOR_ELT(out, 4, Rf_ScalarReal(res.k_ave_empirical));
+    SET_VECTOR_ELT(out, 5, Rf_ScalarReal((double)res.n_empty));
+    npdrb_result_release(&res);
+    UNPROTECT(2);
+    return out;
+}
+
+/* .Call("C_npdrb_diff", a, b, type, norm.fac)                       (npdrDiff, R/nearestNeighbors.R:15) */
+SEXP C_npdrb_diff(SEXP a, SEXP b, SEXP type, SEXP norm_fac) {
+    const R_xlen_t n = XLENGTH(a);
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+    int rc = npdrb_diff(ctx_get(), REAL(a), REAL(b), n, Rf_asInteger(type), Rf_asReal(norm_fac), REAL(out));
+    UNPROTECT(1);
+    if (rc) Rf_error("npdr_b200: %s", npdrb_last_error());
+    return out;
+}
+
+/* .Call("C_npdrb_unireg", X, y, C|NULL, regression.type) -> 8 x p   (uniReg, R/utils.R:66) */
+SEXP C_npdrb_unireg(SEXP X, SEXP y, SEXP C, SEXP reg) {
+    SEXP dim = Rf_getAttrib(X, R_DimSymbol);
+    const R_xlen_t N = INTEGER(dim)[0], p = INTEGER(dim)[1];
+    int q = Rf_isNull(C) ? 0 : INTEGER(Rf_getAttrib(C, R_DimSymbol))[1];
+    SEXP stats = PROTECT(Rf_allocMatrix(REALSXP, NPDRB_STATS_PER_ATTR, (int)p));
+    int rc = npdrb_unireg(ctx_get(), REAL(X), N, p, REAL(y), q ? REAL(C) : NULL, q, Rf_asInteger(reg), REAL(stats));
+    UNPROTECT(1);
+    if (rc) Rf_error("npdr_b200: %s", npdrb_last_error());
+    return stats;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"C_npdrb_distances", (DL_FUNC)&C_npdrb_distances, 2},
+    {"C_npdrb_nearest_neighbors", (DL_FUNC)&C_npdrb_nearest_neighbors, 7},
+    {"C_npdrb_npdr", (DL_FUNC)&C_npdrb_npdr, 5},
+    {"C_npdrb_diff", (DL_FUNC)&C_npdrb_diff, 4},
+    {"C_npdrb_unireg", (DL_FUNC)&C_npdrb_unireg, 4},
+    {NULL, NULL, 0}};
+
+void R_init_npdrb200(DllInfo *dll) {
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}
+
+void R_unload_npdrb200(DllInfo *dll) {
+    (void)dll;
+    if (g_ctx) { npdrb_destroy(g_ctx); g_ctx = NULL; }
+}
