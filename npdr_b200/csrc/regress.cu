@@ -35,8 +35,14 @@ constexpr int KMAX = 2 + NPDRB_MAX_COVARS;
 enum { MODE_LM = 0, MODE_SIGN = 1, MODE_IRLS_FULL = 2 };
 
 __host__ __device__ constexpr int nacc_for(int mode, int q) {
-    return mode != MODE_IRLS_FULL ? (3 + q) : ((2 + q) * (3 + q) / 2 + (2 + q) + 1);
+    return mode != MODE_IRLS_FULL ? (3 + q) : ((2 + q) * (3 + q) / 2 + (2 + q) + 2);
 }
+// IRLS pass statistics per attribute (NA = K(K+1)/2 + K + 2, K = 2 + q):
+//   [0 .. K(K+1)/2)   X'WX upper triangle, row-major over r <= s, features v = [1, d, c_1..c_q], W = mu(1-mu)
+//   next K            score X'(y - mu)      (Newton form: beta_new = beta + (X'WX)^-1 X'(y - mu), identical to
+//                                            glm.fit's weighted least squares on z = eta + (y - mu)/mu.eta)
+//   NA-2              sum of log(1 + e^eta)                 } residual deviance = 2 * ([NA-2] - (ln2/64) * [NA-1])
+//   NA-1              sum over MISS records of eta * 64/ln2 }
 
 // ------------------------------------------------------------------ layout helpers
 // instance-major copy of X for attribute columns [attr0, attr0+nattr): XT[i * ldt + (a - attr0)]
@@ -199,7 +205,7 @@ template <int MODE, int Q, int DIFF>
 __global__ void __launch_bounds__(RTHREADS, 1)
 pass_kernel(PassArgs P) {
     constexpr int K = 2 + Q;
-    constexpr int NA = (MODE != MODE_IRLS_FULL) ? (3 + Q) : (K * (K + 1) / 2 + K + 1);
+    constexpr int NA = (MODE != MODE_IRLS_FULL) ? (3 + Q) : (K * (K + 1) / 2 + K + 2);
     extern __shared__ unsigned char smem_raw[];
     double *sXI = (double *)smem_raw;                   // [BI][TA]
     double *sXJ = sXI + BI * TA;                        // [BJ][TA]
@@ -307,8 +313,9 @@ pass_kernel(PassArgs P) {
                         const double lg = nb_log_ge1(u1, sT->log_rc, sT->log_lrc, sT->log_eln2);
                         // deviance residual / 2 = -log(mu) (y=1) or -log(1-mu) (y=0) = log(1+t) - y*log(t)
                         const double yd = yb ? 1.0 : 0.0;
-                        acc[NA - 1] += fma(-yd, eta_dev, lg);
-                        wz = fma(w, eta, yd - mu);          // w*z with z = eta + (y-mu)/mu.eta
+                        acc[NA - 2] += lg;
+                        if (yb) acc[NA - 1] = fma(eta_dev, NB_64_OVER_LN2, acc[NA - 1]);
+                        wz = yd - mu;                       // score weight (y - mu)
                     }
                     // X'WX upper triangle (row-major over r <= s), features v = [1, d, c...]
                     double wv[K];
@@ -362,11 +369,17 @@ pass_kernel(PassArgs P) {
 //   * table indices are formed directly as byte offsets from the high word (2 integer ops each);
 //   * reciprocal: rcp.approx (2^-23) + ONE Newton step (2^-46 ~ 1.4e-14); exp / log are the trimmed
 //     nb_exp_fast / nb_log_ge1_fast recurrences (dmath.cuh carries the error budget and the host test).
+// The v2 kernel carries the linear predictor in units of ln2/64: s = eta * 64/ln2 (the coefficients are pre-scaled
+// when they are loaded), so k = rint(s) and the reduced argument frac = s - k (exact) need no multiplication, and
+// exp(eta) = 2^(k/64) * exp(frac * ln2/64) with the ln2/64 powers folded into the polynomial coefficients.
+#define NB_C (0.6931471805599453 / 64.0)
 __constant__ double c_k[12] = {
-    NB_64_OVER_LN2, 6755399441055744.0, -NB_LN2_64_HI, -NB_LN2_64_LO,   // 0..3  exp range reduction
-    1.0 / 24.0, 1.0 / 6.0, 0.5,                                          // 4..6  exp polynomial
-    0.2, -0.25, 1.0 / 3.0, -0.5,                                         // 7..10 log polynomial
-    NB_LOG_INV_EPS                                                       // 11    log(1/DBL_EPSILON)
+    6755399441055744.0,                                                  // 0     1.5 * 2^52 (round-to-integer magic)
+    NB_C * NB_C * NB_C * NB_C / 24.0, NB_C * NB_C * NB_C / 6.0, NB_C * NB_C / 2.0, NB_C,   // 1..4  exp polynomial in frac
+    0.2, -0.25, 1.0 / 3.0, -0.5,                                         // 5..8  log polynomial
+    NB_LOG_INV_EPS * NB_64_OVER_LN2,                                     // 9     log(1/DBL_EPSILON) in units of ln2/64
+    30.0 * NB_64_OVER_LN2,                                               // 10    clamp threshold in the same units
+    NB_64_OVER_LN2                                                       // 11
 };
 
 struct nb_tables2 {                 // shared-memory image used by v2
@@ -381,34 +394,33 @@ constexpr int V2_TPS = TA / 2;      // threads per slice (64)
 __host__ __device__ constexpr int v2_nslice(int mode, int q) { return (mode == MODE_IRLS_FULL && q >= 2) ? 6 : 8; }
 constexpr int V2_RCHUNK = 512;      // records per staged chunk (two buffers)
 
-__device__ __forceinline__ double v2_exp_fast(double eta, uint32_t sT) {
-    const double tt = fma(eta, c_k[0], c_k[1]);
+__device__ __forceinline__ double v2_exp_fast(double sv, uint32_t sT) {            // sv = eta * 64/ln2, |eta| < 30
+    const double tt = sv + c_k[0];
     const int ki = __double2loint(tt);
-    const double kf = tt - c_k[1];
-    double r = fma(kf, c_k[2], eta);
-    r = fma(kf, c_k[3], r);
-    const double r2 = r * r;
-    double qq = fma(r, c_k[4], c_k[5]);
-    qq = fma(qq, r, c_k[6]);
-    qq = fma(qq, r2, r);
+    const double kf = tt - c_k[0];
+    const double fr = sv - kf;                                   // exact, |fr| <= 1/2
+    double qq = fma(fr, c_k[1], c_k[2]);
+    qq = fma(qq, fr, c_k[3]);
+    qq = fma(qq, fr, c_k[4]);
+    qq = qq * fr;                                                // exp(fr * ln2/64) - 1
     double tj;
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x1F8)));
     const double v = fma(tj, qq, tj);
     return __hiloint2double(__double2hiint(v) + ((ki << 14) & 0xFFF00000), __double2loint(v));
 }
 // logit linkinv with R's clamps (stats family.c): eta < -30 -> DBL_EPSILON, eta > 30 -> 1/DBL_EPSILON
-__device__ __noinline__ double2 v2_exp_clamped(double eta, uint32_t sT) {      // -> (t, log t)
-    if (eta > 30.0) return make_double2(4503599627370496.0, c_k[11]);
-    if (eta < -30.0) return make_double2(2.220446049250313e-16, -c_k[11]);
-    return make_double2(v2_exp_fast(eta, sT), eta);
+__device__ __noinline__ double2 v2_exp_clamped(double sv, uint32_t sT) {          // -> (t, log(t) * 64/ln2)
+    if (sv > c_k[10]) return make_double2(4503599627370496.0, c_k[9]);
+    if (sv < -c_k[10]) return make_double2(2.220446049250313e-16, -c_k[9]);
+    return make_double2(v2_exp_fast(sv, sT), sv);
 }
 
-// everything after t = exp(eta): weights, deviance term, accumulation.  Y = outcome of this record range.
+// everything after t = exp(eta): weights, deviance terms, accumulation.  Y = outcome of this record range.
 template <int Q, int Y>
-__device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 ? Q : 1], const double eta, const double eta_dev,
-                                        const double t, double (&acc)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 1], const uint32_t sT) {
+__device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 ? Q : 1], const double s_dev, const double t,
+                                        double (&acc)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], const uint32_t sT, const int k3ff) {
     constexpr int K = 2 + Q;
-    constexpr int NA = K * (K + 1) / 2 + K + 1;
+    constexpr int NA = K * (K + 1) / 2 + K + 2;
     const double u1 = 1.0 + t;
     double inv;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(u1));
@@ -419,18 +431,16 @@ __device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 
     double rc, lrc, el;
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lrc) : "r"(sT + 512u + (uint32_t)((hi >> 9) & 0x7F0)));
     asm("ld.shared.f64 %0, [%1];" : "=d"(el) : "r"(sT + 512u + 2048u + (uint32_t)((hi >> 17) & 0x1F8)));
-    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(u1));
+    int mhi;
+    asm("lop3.b32 %0, %1, 0x000FFFFF, %2, 0xEA;" : "=r"(mhi) : "r"(hi), "r"(k3ff));     // (hi & 0xFFFFF) | 0x3FF00000
+    const double m = __hiloint2double(mhi, __double2loint(u1));
     const double f = fma(m, rc, -1.0);
-    double pp = fma(f, c_k[7], c_k[8]);
-    pp = fma(pp, f, c_k[9]);
-    pp = fma(pp, f, c_k[10]);
+    double pp = fma(f, c_k[5], c_k[6]);
+    pp = fma(pp, f, c_k[7]);
+    pp = fma(pp, f, c_k[8]);
     pp = fma(pp, f * f, f);
-    const double lg = (el + lrc) + pp;                          // log(1 + t) = -log(1 - mu)
-    // deviance residual / 2: -log(1 - mu) for a hit, -log(mu) = log(1 + t) - log(t) for a miss
-    // w * z = w * eta + (y - mu)
-    double wz;
-    if (Y == 0) { acc[NA - 1] += lg; wz = fma(w, eta, -mu); }
-    else { acc[NA - 1] += (lg - eta_dev); wz = fma(w, eta, inv); }
+    acc[NA - 2] += (el + lrc) + pp;                             // log(1 + t) = -log(1 - mu)
+    if (Y == 1) acc[NA - 1] += s_dev;                           // misses: - log(t), summed in units of ln2/64
     double wv[K];
     wv[0] = w;
     wv[1] = w * d;
@@ -446,10 +456,18 @@ __device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 
             ++n_;
         }
     }
-    acc[n_] += wz;
-    acc[n_ + 1] = fma(wz, d, acc[n_ + 1]);
+    // score X'(y - mu): y - mu = -mu for a hit, 1 - mu = inv for a miss
+    if (Y == 0) {
+        acc[n_] -= mu;
+        acc[n_ + 1] = fma(-mu, d, acc[n_ + 1]);
 #pragma unroll
-    for (int u = 0; u < Q; ++u) acc[n_ + 2 + u] = fma(wz, c[u], acc[n_ + 2 + u]);
+        for (int u = 0; u < Q; ++u) acc[n_ + 2 + u] = fma(-mu, c[u], acc[n_ + 2 + u]);
+    } else {
+        acc[n_] += inv;
+        acc[n_ + 1] = fma(inv, d, acc[n_ + 1]);
+#pragma unroll
+        for (int u = 0; u < Q; ++u) acc[n_ + 2 + u] = fma(inv, c[u], acc[n_ + 2 + u]);
+    }
 }
 
 // records [m_begin, m_end) of the staged chunk, this thread's slice, outcome Y.  Two records x two attributes are
@@ -459,8 +477,9 @@ template <int Q, int DIFF, int Y, int NSL>
 __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint32_t sREC_addr, uint32_t sCD_addr,
                                          uint32_t sXI_addr, uint32_t sXJ_addr, uint32_t sT, int diff_type,
                                          const double (&beta0)[2 + Q], const double (&beta1)[2 + Q],
-                                         double (&acc0)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 1],
-                                         double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 1]) {
+                                         double (&acc0)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2],
+                                         double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2]) {
+    const int k3ff = 0x3FF00000;
     // each slice walks a CONTIGUOUS part of the range: records are in list order (grouped by Ri), so the I row
     // repeats for several records in a row and stays in registers (halves the shared-memory tile traffic)
     const int len = m_end - m_begin, per = (len + NSL - 1) / NSL;
@@ -497,7 +516,7 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         const int hmax = max(max(__double2hiint(ea0) & 0x7fffffff, __double2hiint(ea1) & 0x7fffffff),
                              max(__double2hiint(eb0) & 0x7fffffff, __double2hiint(eb1) & 0x7fffffff));
         double ta0, ta1, tb0, tb1, la0 = ea0, la1 = ea1, lb0 = eb0, lb1 = eb1;
-        if (hmax < 0x403E0000) {                                 // |eta| < 30 for all four: straight-line
+        if (hmax < 0x40A5A200) {                                 // |s| < 2769 < 30 * 64/ln2 (= 2769.97) for all four: straight-line
             ta0 = v2_exp_fast(ea0, sT); ta1 = v2_exp_fast(ea1, sT);
             tb0 = v2_exp_fast(eb0, sT); tb1 = v2_exp_fast(eb1, sT);
         } else {
@@ -507,10 +526,10 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
             v = v2_exp_clamped(eb0, sT); tb0 = v.x; lb0 = v.y;
             v = v2_exp_clamped(eb1, sT); tb1 = v.x; lb1 = v.y;
         }
-        v2_tail<Q, Y>(da0, ca, ea0, la0, ta0, acc0, sT);
-        v2_tail<Q, Y>(da1, ca, ea1, la1, ta1, acc1, sT);
-        v2_tail<Q, Y>(db0, cb, eb0, lb0, tb0, acc0, sT);
-        v2_tail<Q, Y>(db1, cb, eb1, lb1, tb1, acc1, sT);
+        v2_tail<Q, Y>(da0, ca, la0, ta0, acc0, sT, k3ff);
+        v2_tail<Q, Y>(da1, ca, la1, ta1, acc1, sT, k3ff);
+        v2_tail<Q, Y>(db0, cb, lb0, tb0, acc0, sT, k3ff);
+        v2_tail<Q, Y>(db1, cb, lb1, tb1, acc1, sT, k3ff);
         xa0 = xb0; xa1 = xb1; io_prev = iob;
     }
     if (m < m_hi) {                                              // odd tail: one record
@@ -528,8 +547,8 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
 #pragma unroll
         for (int u = 0; u < Q; ++u) { eta0 = fma(beta0[2 + u], c[u], eta0); eta1 = fma(beta1[2 + u], c[u], eta1); }
         const double2 a = v2_exp_clamped(eta0, sT), b = v2_exp_clamped(eta1, sT);
-        v2_tail<Q, Y>(d0, c, eta0, a.y, a.x, acc0, sT);
-        v2_tail<Q, Y>(d1, c, eta1, b.y, b.x, acc1, sT);
+        v2_tail<Q, Y>(d0, c, a.y, a.x, acc0, sT, k3ff);
+        v2_tail<Q, Y>(d1, c, b.y, b.x, acc1, sT, k3ff);
     }
 }
 
@@ -595,7 +614,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int MODE, int Q>
 struct V2Layout {
     static constexpr int NCD = (MODE == MODE_LM) ? (Q + 1) : (Q > 0 ? Q : 0);       // double streams per record
-    static constexpr int NA = (MODE != MODE_IRLS_FULL) ? (3 + Q) : ((2 + Q) * (3 + Q) / 2 + (2 + Q) + 1);
+    static constexpr int NA = (MODE != MODE_IRLS_FULL) ? (3 + Q) : ((2 + Q) * (3 + Q) / 2 + (2 + Q) + 2);
     static constexpr uint32_t XI = 0;
     static constexpr uint32_t XJ = BI * TA * 8;                                      // two buffers of BJ*TA*8
     static constexpr uint32_t REC = XJ + 2 * BJ * TA * 8;                            // two buffers
@@ -619,7 +638,8 @@ pass2_kernel(PassArgs P) {
     constexpr int NSL = L::NSL;
     constexpr int V2_THREADS = L::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    asm volatile("" : "+r"(sbase));                      // opaque: keep the window base in a register, not rematerialised
 
     const int tid = threadIdx.x;
     const int tl = tid % V2_TPS, slice = tid / V2_TPS;
@@ -640,8 +660,8 @@ pass2_kernel(PassArgs P) {
     if (MODE == MODE_IRLS_FULL) {
 #pragma unroll
         for (int r = 0; r < K; ++r) {
-            beta0[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl];
-            beta1[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1];
+            beta0[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl] * c_k[11];        // units of ln2/64
+            beta1[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1] * c_k[11];
         }
     }
     double acc0[NA], acc1[NA];
@@ -969,17 +989,18 @@ __global__ void irls_init_kernel(SolveArgs S) {
 // binomial: one IRLS bookkeeping step per attribute (glm.fit's loop body)
 template <int Q>
 __global__ void irls_step_kernel(SolveArgs S) {
-    constexpr int K = 2 + Q, NA = K * (K + 1) / 2 + K + 1;
+    constexpr int K = 2 + Q, NA = K * (K + 1) / 2 + K + 2;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= S.nattr) return;
     if (!S.active[a]) return;
     double m[NA];
     reduce_partials<NA>(S, a, m);
-    double A[K][K], b[K];
+    double A[K][K], b[K];                                   // X'WX and the score X'(y - mu)
     int n = 0;
     for (int r = 0; r < K; ++r) for (int c = r; c < K; ++c) { A[r][c] = A[c][r] = m[n]; ++n; }
     for (int r = 0; r < K; ++r) b[r] = m[n + r];
-    const double dev = 2.0 * m[NA - 1];
+    // residual deviance: 2 * sum[ log(1 + t) - y * log(t) ]; the miss part is accumulated in units of ln2/64
+    const double dev = 2.0 * (m[NA - 2] - (0.6931471805599453 / 64.0) * m[NA - 1]);
     bool finish = false;
     int flags = 0;
     {
@@ -1017,8 +1038,9 @@ __global__ void irls_step_kernel(SolveArgs S) {
         S.active[a] = 0;
         return;
     }
-    for (int r = 0; r < K; ++r) {
-        S.beta[(int64_t)r * S.nattr_pad + a] = x[r];
+    for (int r = 0; r < K; ++r) {                           // Newton / IRLS update: beta + (X'WX)^-1 X'(y - mu)
+        const double old = S.beta[(int64_t)r * S.nattr_pad + a];
+        S.beta[(int64_t)r * S.nattr_pad + a] = al[r] ? 0.0 : old + x[r];
         S.se[(int64_t)r * S.nattr_pad + a] = al[r] ? nanv : sqrt(dinv[r]);
     }
     S.iters[a] = S.pass + 1;
