@@ -25,6 +25,14 @@ struct nb_tables {
 
 #define NB_TABLES_STATIC_INIT { NB_EXP_TABLE_INIT, NB_LOG_RC_TABLE_INIT, NB_LOG_LRC_TABLE_INIT, NB_LOG_ELN2_TABLE_INIT }
 
+struct nb_tables256 {
+    double exp_t[256];     // 2^(j/256)
+    double log_rc[256];    // ~1/centre of mantissa bin i of width 1/256 (24 significant bits)
+    double log_lrc[256];   // -log(log_rc[i])
+    double log_eln2[64];   // e * ln2
+};
+#define NB_TABLES256_STATIC_INIT { NB_EXP256_TABLE_INIT, NB_LOG256_RC_TABLE_INIT, NB_LOG256_LRC_TABLE_INIT, NB_LOG_ELN2_TABLE_INIT }
+
 NB_HD uint64_t nb_d2u(double d) {
 #if defined(__CUDA_ARCH__)
     return (uint64_t)__double_as_longlong(d);
@@ -118,6 +126,40 @@ NB_HD double nb_log_ge1_fast(double u, const double* __restrict__ log_rc, const 
     p = nb_fma(p, f, -0.5);
     double f2 = f * f;
     p = nb_fma(p, f2, f);
+    return (log_eln2[e & 63] + log_lrc[i]) + p;
+}
+
+// ---- 256-entry variants (what pass2_kernel<IRLS_FULL> evaluates) -------------------------------
+// The linear predictor is carried in units of ln2/256 (sv = eta * 256/ln2): k = rint(sv), frac = sv - k is exact,
+// exp(eta) = 2^(k/256) * exp(frac * ln2/256) with a degree-3 polynomial (dropped term <= (ln2/512)^4/24 = 1.4e-13
+// relative); log(u), u >= 1: 256 mantissa bins, degree-4 log1p (dropped term <= 2^-45/5 = 5.7e-15 absolute).
+NB_HD double nb_exp_fast256(double sv, const double* __restrict__ exp_t) {
+    const double magic = 6755399441055744.0;
+    const double c = NB_LN2_256;
+    double tt = sv + magic;
+    int32_t ki = (int32_t)(uint32_t)nb_d2u(tt);
+    double kf = tt - magic;
+    double fr = sv - kf;
+    double qq = nb_fma(fr, c * c * c / 6.0, c * c / 2.0);
+    qq = nb_fma(qq, fr, c);
+    qq = qq * fr;
+    double tj = exp_t[ki & 255];
+    double v = nb_fma(tj, qq, tj);
+    uint64_t b = nb_d2u(v);
+    uint32_t hi = (uint32_t)(b >> 32) + (((uint32_t)ki & 0xFFFFFF00u) << 12);    // += (ki >> 8) << 20
+    return nb_u2d(((uint64_t)hi << 32) | (b & 0xFFFFFFFFull));
+}
+
+NB_HD double nb_log_ge1_fast256(double u, const double* __restrict__ log_rc, const double* __restrict__ log_lrc,
+                                const double* __restrict__ log_eln2) {
+    uint64_t b = nb_d2u(u);
+    int32_t e = (int32_t)(b >> 52) - 1023;
+    int32_t i = (int32_t)((b >> 44) & 255);
+    double m = nb_u2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    double f = nb_fma(m, log_rc[i], -1.0);
+    double p = nb_fma(f, -0.25, 1.0 / 3.0);
+    p = nb_fma(p, f, -0.5);
+    p = nb_fma(p, f * f, f);
     return (log_eln2[e & 63] + log_lrc[i]) + p;
 }
 

@@ -39,10 +39,13 @@ __host__ __device__ constexpr int nacc_for(int mode, int q) {
 }
 // IRLS pass statistics per attribute (NA = K(K+1)/2 + K + 2, K = 2 + q):
 //   [0 .. K(K+1)/2)   X'WX upper triangle, row-major over r <= s, features v = [1, d, c_1..c_q], W = mu(1-mu)
-//   next K            score X'(y - mu)      (Newton form: beta_new = beta + (X'WX)^-1 X'(y - mu), identical to
-//                                            glm.fit's weighted least squares on z = eta + (y - mu)/mu.eta)
-//   NA-2              sum of log(1 + e^eta)                 } residual deviance = 2 * ([NA-2] - (ln2/64) * [NA-1])
-//   NA-1              sum over MISS records of eta * 64/ln2 }
+//   next K            sum of (1 - mu) * v over ALL records.  The score X'(y - mu) = that minus the sum of v over the HIT
+//                     records (y - mu = (1 - mu) - 1 for a hit, 1 - mu for a miss); the hit moments are known from pass 0,
+//                     so the pass does not need to look at the outcome.  (Newton form: beta_new = beta +
+//                     (X'WX)^-1 X'(y - mu), identical to glm.fit's weighted least squares on z = eta + (y - mu)/mu.eta.)
+//   NA-2              sum of log(1 + e^eta)
+//   NA-1              clamp correction: sum over clamped MISS records of (log t - eta) (zero unless |eta| > 30)
+//   residual deviance = 2 * ([NA-2] - beta . (sum of v over the MISS records) - [NA-1])
 
 // ------------------------------------------------------------------ layout helpers
 // instance-major copy of X for attribute columns [attr0, attr0+nattr): XT[i * ldt + (a - attr0)]
@@ -191,7 +194,8 @@ struct PassArgs {
     const double *beta;            // [KMAX][nattr_pad] current coefficients (IRLS_FULL)
     const unsigned char *tile_active;  // per attribute tile, or NULL
     double *partials;              // [n_chunks][NACC][nattr_pad]
-    const nb_tables *tables;       // device copy of the exp/log tables
+    const nb_tables *tables;       // device copy of the exp/log tables (v1 kernel)
+    const nb_tables256 *tables256; // 256-entry tables (v2 kernel)
     int diff_type;
 };
 
@@ -312,10 +316,9 @@ pass_kernel(PassArgs P) {
                         w = mu * inv;                       // mu(1-mu) = mu.eta (logit)
                         const double lg = nb_log_ge1(u1, sT->log_rc, sT->log_lrc, sT->log_eln2);
                         // deviance residual / 2 = -log(mu) (y=1) or -log(1-mu) (y=0) = log(1+t) - y*log(t)
-                        const double yd = yb ? 1.0 : 0.0;
                         acc[NA - 2] += lg;
-                        if (yb) acc[NA - 1] = fma(eta_dev, NB_64_OVER_LN2, acc[NA - 1]);
-                        wz = yd - mu;                       // score weight (y - mu)
+                        if (yb && eta_dev != eta) acc[NA - 1] += (eta_dev - eta);
+                        wz = inv;                           // (1 - mu); the hit moments are subtracted in the solve
                     }
                     // X'WX upper triangle (row-major over r <= s), features v = [1, d, c...]
                     double wv[K];
@@ -369,22 +372,23 @@ pass_kernel(PassArgs P) {
 //   * table indices are formed directly as byte offsets from the high word (2 integer ops each);
 //   * reciprocal: rcp.approx (2^-23) + ONE Newton step (2^-46 ~ 1.4e-14); exp / log are the trimmed
 //     nb_exp_fast / nb_log_ge1_fast recurrences (dmath.cuh carries the error budget and the host test).
-// The v2 kernel carries the linear predictor in units of ln2/64: s = eta * 64/ln2 (the coefficients are pre-scaled
+// The v2 kernel carries the linear predictor in units of ln2/256: s = eta * 256/ln2 (the coefficients are pre-scaled
 // when they are loaded), so k = rint(s) and the reduced argument frac = s - k (exact) need no multiplication, and
-// exp(eta) = 2^(k/64) * exp(frac * ln2/64) with the ln2/64 powers folded into the polynomial coefficients.
-#define NB_C (0.6931471805599453 / 64.0)
-__constant__ double c_k[12] = {
+// exp(eta) = 2^(k/256) * exp(frac * ln2/256) with the ln2/256 powers folded into the polynomial coefficients
+// (nb_exp_fast256 / nb_log_ge1_fast256 in dmath.cuh are the host-tested statements of the same recurrences).
+#define NB_C NB_LN2_256
+__constant__ double c_k[10] = {
     6755399441055744.0,                                                  // 0     1.5 * 2^52 (round-to-integer magic)
-    NB_C * NB_C * NB_C * NB_C / 24.0, NB_C * NB_C * NB_C / 6.0, NB_C * NB_C / 2.0, NB_C,   // 1..4  exp polynomial in frac
-    0.2, -0.25, 1.0 / 3.0, -0.5,                                         // 5..8  log polynomial
-    NB_LOG_INV_EPS * NB_64_OVER_LN2,                                     // 9     log(1/DBL_EPSILON) in units of ln2/64
-    30.0 * NB_64_OVER_LN2,                                               // 10    clamp threshold in the same units
-    NB_64_OVER_LN2                                                       // 11
+    NB_C * NB_C * NB_C / 6.0, NB_C * NB_C / 2.0, NB_C,                   // 1..3  exp polynomial in frac
+    -0.25, 1.0 / 3.0, -0.5,                                              // 4..6  log polynomial
+    NB_LOG_INV_EPS * NB_256_OVER_LN2,                                    // 7     log(1/DBL_EPSILON) in units of ln2/256
+    30.0 * NB_256_OVER_LN2,                                              // 8     clamp threshold in the same units
+    NB_256_OVER_LN2                                                      // 9
 };
 
 struct nb_tables2 {                 // shared-memory image used by v2
-    double exp_t[64];               // 2^(j/64)
-    double2 log_rl[128];            // (rc_i, -log rc_i)
+    double exp_t[256];              // 2^(j/256)
+    double2 log_rl[256];            // (rc_i, -log rc_i)
     double log_eln2_rot[64];        // entry (e - 1) & 63 holds e * ln2
 };
 
@@ -394,30 +398,30 @@ constexpr int V2_TPS = TA / 2;      // threads per slice (64)
 __host__ __device__ constexpr int v2_nslice(int mode, int q) { return (mode == MODE_IRLS_FULL && q >= 2) ? 6 : 8; }
 constexpr int V2_RCHUNK = 512;      // records per staged chunk (two buffers)
 
-__device__ __forceinline__ double v2_exp_fast(double sv, uint32_t sT) {            // sv = eta * 64/ln2, |eta| < 30
+__device__ __forceinline__ double v2_exp_fast(double sv, uint32_t sT) {            // sv = eta * 256/ln2, |eta| < 30
     const double tt = sv + c_k[0];
     const int ki = __double2loint(tt);
     const double kf = tt - c_k[0];
     const double fr = sv - kf;                                   // exact, |fr| <= 1/2
     double qq = fma(fr, c_k[1], c_k[2]);
     qq = fma(qq, fr, c_k[3]);
-    qq = fma(qq, fr, c_k[4]);
-    qq = qq * fr;                                                // exp(fr * ln2/64) - 1
+    qq = qq * fr;                                                // exp(fr * ln2/256) - 1
     double tj;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x1F8)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x7F8)));
     const double v = fma(tj, qq, tj);
-    return __hiloint2double(__double2hiint(v) + ((ki << 14) & 0xFFF00000), __double2loint(v));
+    return __hiloint2double(__double2hiint(v) + ((ki & 0xFFFFFF00) << 12), __double2loint(v));   // * 2^(ki >> 8)
 }
-// logit linkinv with R's clamps (stats family.c): eta < -30 -> DBL_EPSILON, eta > 30 -> 1/DBL_EPSILON
-__device__ __noinline__ double2 v2_exp_clamped(double sv, uint32_t sT) {          // -> (t, log(t) * 64/ln2)
-    if (sv > c_k[10]) return make_double2(4503599627370496.0, c_k[9]);
-    if (sv < -c_k[10]) return make_double2(2.220446049250313e-16, -c_k[9]);
-    return make_double2(v2_exp_fast(sv, sT), sv);
+// logit linkinv with R's clamps (stats family.c): eta < -30 -> DBL_EPSILON, eta > 30 -> 1/DBL_EPSILON.
+// -> (t, log t - eta): the second component is the deviance correction of a clamped record (0 otherwise)
+__device__ __noinline__ double2 v2_exp_clamped(double sv, uint32_t sT) {
+    if (sv > c_k[8]) return make_double2(4503599627370496.0, (c_k[7] - sv) * NB_C);
+    if (sv < -c_k[8]) return make_double2(2.220446049250313e-16, (-c_k[7] - sv) * NB_C);
+    return make_double2(v2_exp_fast(sv, sT), 0.0);
 }
 
-// everything after t = exp(eta): weights, deviance terms, accumulation.  Y = outcome of this record range.
-template <int Q, int Y>
-__device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 ? Q : 1], const double s_dev, const double t,
+// everything after t = exp(eta): weight, log(1 + t), accumulation -- independent of the outcome
+template <int Q>
+__device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 ? Q : 1], const double t,
                                         double (&acc)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], const uint32_t sT, const int k3ff) {
     constexpr int K = 2 + Q;
     constexpr int NA = K * (K + 1) / 2 + K + 2;
@@ -425,22 +429,19 @@ __device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 
     double inv;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(u1));
     inv = fma(inv, fma(-u1, inv, 1.0), inv);                    // 1/(1+t) = 1 - mu
-    const double mu = t * inv;
-    const double w = mu * inv;                                  // mu(1-mu) = mu.eta for the logit link
+    const double w = fma(-inv, inv, inv);                       // mu(1-mu) = (1-mu) - (1-mu)^2 = mu.eta for the logit link
     const int hi = __double2hiint(u1);
     double rc, lrc, el;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lrc) : "r"(sT + 512u + (uint32_t)((hi >> 9) & 0x7F0)));
-    asm("ld.shared.f64 %0, [%1];" : "=d"(el) : "r"(sT + 512u + 2048u + (uint32_t)((hi >> 17) & 0x1F8)));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lrc) : "r"(sT + 2048u + (uint32_t)((hi >> 8) & 0xFF0)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(el) : "r"(sT + 2048u + 4096u + (uint32_t)((hi >> 17) & 0x1F8)));
     int mhi;
     asm("lop3.b32 %0, %1, 0x000FFFFF, %2, 0xEA;" : "=r"(mhi) : "r"(hi), "r"(k3ff));     // (hi & 0xFFFFF) | 0x3FF00000
     const double m = __hiloint2double(mhi, __double2loint(u1));
     const double f = fma(m, rc, -1.0);
-    double pp = fma(f, c_k[5], c_k[6]);
-    pp = fma(pp, f, c_k[7]);
-    pp = fma(pp, f, c_k[8]);
+    double pp = fma(f, c_k[4], c_k[5]);
+    pp = fma(pp, f, c_k[6]);
     pp = fma(pp, f * f, f);
     acc[NA - 2] += (el + lrc) + pp;                             // log(1 + t) = -log(1 - mu)
-    if (Y == 1) acc[NA - 1] += s_dev;                           // misses: - log(t), summed in units of ln2/64
     double wv[K];
     wv[0] = w;
     wv[1] = w * d;
@@ -456,56 +457,48 @@ __device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 
             ++n_;
         }
     }
-    // score X'(y - mu): y - mu = -mu for a hit, 1 - mu = inv for a miss
-    if (Y == 0) {
-        acc[n_] -= mu;
-        acc[n_ + 1] = fma(-mu, d, acc[n_ + 1]);
+    acc[n_] += inv;                                             // sum (1 - mu) v
+    acc[n_ + 1] = fma(inv, d, acc[n_ + 1]);
 #pragma unroll
-        for (int u = 0; u < Q; ++u) acc[n_ + 2 + u] = fma(-mu, c[u], acc[n_ + 2 + u]);
-    } else {
-        acc[n_] += inv;
-        acc[n_ + 1] = fma(inv, d, acc[n_ + 1]);
-#pragma unroll
-        for (int u = 0; u < Q; ++u) acc[n_ + 2 + u] = fma(inv, c[u], acc[n_ + 2 + u]);
-    }
+    for (int u = 0; u < Q; ++u) acc[n_ + 2 + u] = fma(inv, c[u], acc[n_ + 2 + u]);
 }
 
-// records [m_begin, m_end) of the staged chunk, this thread's slice, outcome Y.  Two records x two attributes are
-// in flight per thread: four independent exp -> reciprocal -> log chains (ncu on the two-chain version: FP64 pipe 63 %,
-// dominant stall = fixed-latency dependency wait with 1.35 eligible warps per cycle).
-template <int Q, int DIFF, int Y, int NSL>
+// records [m_begin, m_end) of the staged chunk, this thread's slice.  Two records x two attributes are in flight per
+// thread: four independent exp -> reciprocal -> log chains.
+template <int Q, int DIFF, int NSL>
 __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint32_t sREC_addr, uint32_t sCD_addr,
                                          uint32_t sXI_addr, uint32_t sXJ_addr, uint32_t sT, int diff_type,
                                          const double (&beta0)[2 + Q], const double (&beta1)[2 + Q],
                                          double (&acc0)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2],
                                          double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2]) {
+    constexpr int NA = (2 + Q) * (3 + Q) / 2 + (2 + Q) + 2;
     const int k3ff = 0x3FF00000;
     // each slice walks a CONTIGUOUS part of the range: records are in list order (grouped by Ri), so the I row
     // repeats for several records in a row and stays in registers (halves the shared-memory tile traffic)
     const int len = m_end - m_begin, per = (len + NSL - 1) / NSL;
     const int m_lo = m_begin + slice * per, m_hi = (m_lo + per < m_end) ? (m_lo + per) : m_end;
     uint32_t io_prev = 0xFFFFFFFFu;
-    double xa0 = 0.0, xa1 = 0.0;                                 // cached I row (two attributes)
+    double xi0 = 0.0, xi1 = 0.0;                                 // cached I row (two attributes)
     int m = m_lo;
     for (; m + 1 < m_hi; m += 2) {
         uint32_t ra, rb;                                         // (il << 10) | (jl << 26) | y: byte offsets of the two rows
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ra) : "r"(sREC_addr + 4u * m));
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rb) : "r"(sREC_addr + 4u * m + 4u));
         const uint32_t ioa = ra & 0xFC00u, iob = rb & 0xFC00u;
-        if (ioa != io_prev) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xa0), "=d"(xa1) : "r"(sXI_addr + ioa));
-        double xb0 = xa0, xb1 = xa1;
-        if (iob != ioa) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xb0), "=d"(xb1) : "r"(sXI_addr + iob));
         double ja0, ja1, jb0, jb1;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ja0), "=d"(ja1) : "r"(sXJ_addr + (ra >> 16)));
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(jb0), "=d"(jb1) : "r"(sXJ_addr + (rb >> 16)));
+        if (ioa != io_prev) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi0), "=d"(xi1) : "r"(sXI_addr + ioa));
+        const double da0 = proj_diff<DIFF>(xi0, ja0, diff_type), da1 = proj_diff<DIFF>(xi1, ja1, diff_type);
+        if (iob != ioa) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi0), "=d"(xi1) : "r"(sXI_addr + iob));
+        const double db0 = proj_diff<DIFF>(xi0, jb0, diff_type), db1 = proj_diff<DIFF>(xi1, jb1, diff_type);
+        io_prev = iob;
         double ca[Q > 0 ? Q : 1], cb[Q > 0 ? Q : 1];
 #pragma unroll
         for (int u = 0; u < Q; ++u) {
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ca[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cb[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m) + 8u));
         }
-        const double da0 = proj_diff<DIFF>(xa0, ja0, diff_type), da1 = proj_diff<DIFF>(xa1, ja1, diff_type);
-        const double db0 = proj_diff<DIFF>(xb0, jb0, diff_type), db1 = proj_diff<DIFF>(xb1, jb1, diff_type);
         double ea0 = fma(beta0[1], da0, beta0[0]), ea1 = fma(beta1[1], da1, beta1[0]);
         double eb0 = fma(beta0[1], db0, beta0[0]), eb1 = fma(beta1[1], db1, beta1[0]);
 #pragma unroll
@@ -515,40 +508,40 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         }
         const int hmax = max(max(__double2hiint(ea0) & 0x7fffffff, __double2hiint(ea1) & 0x7fffffff),
                              max(__double2hiint(eb0) & 0x7fffffff, __double2hiint(eb1) & 0x7fffffff));
-        double ta0, ta1, tb0, tb1, la0 = ea0, la1 = ea1, lb0 = eb0, lb1 = eb1;
-        if (hmax < 0x40A5A200) {                                 // |s| < 2769 < 30 * 64/ln2 (= 2769.97) for all four: straight-line
+        double ta0, ta1, tb0, tb1;
+        if (hmax < 0x40C5A380) {                                 // |s| < 11079 < 30 * 256/ln2 (= 11079.9) for all four
             ta0 = v2_exp_fast(ea0, sT); ta1 = v2_exp_fast(ea1, sT);
             tb0 = v2_exp_fast(eb0, sT); tb1 = v2_exp_fast(eb1, sT);
-        } else {
+        } else {                                                 // rare: R's eta clamps; misses carry a deviance correction
             double2 v;
-            v = v2_exp_clamped(ea0, sT); ta0 = v.x; la0 = v.y;
-            v = v2_exp_clamped(ea1, sT); ta1 = v.x; la1 = v.y;
-            v = v2_exp_clamped(eb0, sT); tb0 = v.x; lb0 = v.y;
-            v = v2_exp_clamped(eb1, sT); tb1 = v.x; lb1 = v.y;
+            v = v2_exp_clamped(ea0, sT); ta0 = v.x; if (ra & 1u) acc0[NA - 1] += v.y;
+            v = v2_exp_clamped(ea1, sT); ta1 = v.x; if (ra & 1u) acc1[NA - 1] += v.y;
+            v = v2_exp_clamped(eb0, sT); tb0 = v.x; if (rb & 1u) acc0[NA - 1] += v.y;
+            v = v2_exp_clamped(eb1, sT); tb1 = v.x; if (rb & 1u) acc1[NA - 1] += v.y;
         }
-        v2_tail<Q, Y>(da0, ca, la0, ta0, acc0, sT, k3ff);
-        v2_tail<Q, Y>(da1, ca, la1, ta1, acc1, sT, k3ff);
-        v2_tail<Q, Y>(db0, cb, lb0, tb0, acc0, sT, k3ff);
-        v2_tail<Q, Y>(db1, cb, lb1, tb1, acc1, sT, k3ff);
-        xa0 = xb0; xa1 = xb1; io_prev = iob;
+        v2_tail<Q>(da0, ca, ta0, acc0, sT, k3ff);
+        v2_tail<Q>(da1, ca, ta1, acc1, sT, k3ff);
+        v2_tail<Q>(db0, cb, tb0, acc0, sT, k3ff);
+        v2_tail<Q>(db1, cb, tb1, acc1, sT, k3ff);
     }
     if (m < m_hi) {                                              // odd tail: one record
         uint32_t r;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));
         const uint32_t io = r & 0xFC00u;
-        if (io != io_prev) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xa0), "=d"(xa1) : "r"(sXI_addr + io));
+        if (io != io_prev) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi0), "=d"(xi1) : "r"(sXI_addr + io));
         double xj0, xj1;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj0), "=d"(xj1) : "r"(sXJ_addr + (r >> 16)));
         double c[Q > 0 ? Q : 1];
 #pragma unroll
         for (int u = 0; u < Q; ++u) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
-        const double d0 = proj_diff<DIFF>(xa0, xj0, diff_type), d1 = proj_diff<DIFF>(xa1, xj1, diff_type);
-        double eta0 = fma(beta0[1], d0, beta0[0]), eta1 = fma(beta1[1], d1, beta1[0]);
+        const double d0 = proj_diff<DIFF>(xi0, xj0, diff_type), d1 = proj_diff<DIFF>(xi1, xj1, diff_type);
+        double e0 = fma(beta0[1], d0, beta0[0]), e1 = fma(beta1[1], d1, beta1[0]);
 #pragma unroll
-        for (int u = 0; u < Q; ++u) { eta0 = fma(beta0[2 + u], c[u], eta0); eta1 = fma(beta1[2 + u], c[u], eta1); }
-        const double2 a = v2_exp_clamped(eta0, sT), b = v2_exp_clamped(eta1, sT);
-        v2_tail<Q, Y>(d0, c, a.y, a.x, acc0, sT, k3ff);
-        v2_tail<Q, Y>(d1, c, b.y, b.x, acc1, sT, k3ff);
+        for (int u = 0; u < Q; ++u) { e0 = fma(beta0[2 + u], c[u], e0); e1 = fma(beta1[2 + u], c[u], e1); }
+        const double2 a = v2_exp_clamped(e0, sT), b = v2_exp_clamped(e1, sT);
+        if (r & 1u) { acc0[NA - 1] += a.y; acc1[NA - 1] += b.y; }
+        v2_tail<Q>(d0, c, a.x, acc0, sT, k3ff);
+        v2_tail<Q>(d1, c, b.x, acc1, sT, k3ff);
     }
 }
 
@@ -649,9 +642,9 @@ pass2_kernel(PassArgs P) {
 
     if (MODE == MODE_IRLS_FULL) {   // table image
         nb_tables2 *sT = (nb_tables2 *)(smem_raw + L::TAB);
-        const nb_tables *g = P.tables;
-        for (int e = tid; e < 64; e += V2_THREADS) { sT->exp_t[e] = g->exp_t[e]; sT->log_eln2_rot[(e + 63) & 63] = g->log_eln2[e]; }
-        for (int e = tid; e < 128; e += V2_THREADS) sT->log_rl[e] = make_double2(g->log_rc[e], g->log_lrc[e]);
+        const nb_tables256 *g = P.tables256;
+        for (int e = tid; e < 64; e += V2_THREADS) sT->log_eln2_rot[(e + 63) & 63] = g->log_eln2[e];
+        for (int e = tid; e < 256; e += V2_THREADS) { sT->exp_t[e] = g->exp_t[e]; sT->log_rl[e] = make_double2(g->log_rc[e], g->log_lrc[e]); }
     }
     const uint32_t sT_addr = sbase + L::TAB;
     const uint32_t sXI_addr = sbase + L::XI + (uint32_t)tl * 16u;
@@ -660,8 +653,8 @@ pass2_kernel(PassArgs P) {
     if (MODE == MODE_IRLS_FULL) {
 #pragma unroll
         for (int r = 0; r < K; ++r) {
-            beta0[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl] * c_k[11];        // units of ln2/64
-            beta1[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1] * c_k[11];
+            beta0[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl] * c_k[9];         // units of ln2/256
+            beta1[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1] * c_k[9];
         }
     }
     double acc0[NA], acc1[NA];
@@ -731,8 +724,7 @@ pass2_kernel(PassArgs P) {
             int ms = (int)(rmid - rc);                      // first miss record of this chunk
             ms = ms < 0 ? 0 : (ms > n ? n : ms);
             if constexpr (MODE == MODE_IRLS_FULL) {
-                v2_range<Q, DIFF, 0, NSL>(0, ms, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1);
-                v2_range<Q, DIFF, 1, NSL>(ms, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1);
+                v2_range<Q, DIFF, NSL>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1);
             } else if constexpr (MODE == MODE_LM) {
                 m2_range<MODE_LM, Q, DIFF, 0, NSL>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc0, acc1);
             } else {
@@ -828,6 +820,7 @@ struct SolveArgs {
     int nattr, nattr_pad;
     double *beta, *se;             // [KMAX][nattr_pad]
     double *dev_old;               // [nattr_pad]
+    double *hit_d, *miss_d;        // [nattr_pad] sum of the attribute diff over the hit / miss records (from pass 0)
     unsigned char *active;         // [nattr_pad]
     unsigned char *tile_active;    // [n attr tiles]
     int *iters; int *flags;        // [nattr_pad]
@@ -964,6 +957,8 @@ __global__ void irls_init_kernel(SolveArgs S) {
         for (int u = r; u < Q; ++u) { A[2 + r][2 + u] = A[2 + u][2 + r] = w0 * Scc[cc]; ++cc; }
     }
     S.dev_old[a] = M * (2.0 * 0.2876820724517809);         // sum of dev.resids at mustart: 2*log(4/3) each
+    S.hit_d[a] = 0.5 * (m[0] - m[2]);                       // S(d) = hits + misses, S(d*s) = misses - hits
+    S.miss_d[a] = 0.5 * (m[0] + m[2]);
     double x[K], dinv[K];
     bool al[K];
     chol_solve<K>(A, b, 1e-13, x, dinv, al);
@@ -998,9 +993,20 @@ __global__ void irls_step_kernel(SolveArgs S) {
     double A[K][K], b[K];                                   // X'WX and the score X'(y - mu)
     int n = 0;
     for (int r = 0; r < K; ++r) for (int c = r; c < K; ++c) { A[r][c] = A[c][r] = m[n]; ++n; }
-    for (int r = 0; r < K; ++r) b[r] = m[n + r];
-    // residual deviance: 2 * sum[ log(1 + t) - y * log(t) ]; the miss part is accumulated in units of ln2/64
-    const double dev = 2.0 * (m[NA - 2] - (0.6931471805599453 / 64.0) * m[NA - 1]);
+    // hit / miss moments of the features v = [1, d, c_1..c_q]: attribute-independent ones from the shared moments
+    // (M, S(s), ., S(c), S(c s), ...), the attribute diff from pass 0
+    const double Mtot = S.shared[0], Ss = S.shared[1];
+    const double *Sc = S.shared + 3, *Scs = S.shared + 3 + Q;
+    double hitv[K], missv[K];
+    hitv[0] = 0.5 * (Mtot - Ss); missv[0] = 0.5 * (Mtot + Ss);
+    hitv[1] = S.hit_d[a]; missv[1] = S.miss_d[a];
+    for (int r = 0; r < Q; ++r) { hitv[2 + r] = 0.5 * (Sc[r] - Scs[r]); missv[2 + r] = 0.5 * (Sc[r] + Scs[r]); }
+    // score X'(y - mu) = sum over all of (1 - mu) v  -  sum over hits of v
+    for (int r = 0; r < K; ++r) b[r] = m[n + r] - hitv[r];
+    // residual deviance = 2 * sum[ log(1 + t) - y * log(t) ], log t = eta = beta . v except for clamped records
+    double lin = 0.0;
+    for (int r = 0; r < K; ++r) lin += S.beta[(int64_t)r * S.nattr_pad + a] * missv[r];
+    const double dev = 2.0 * (m[NA - 2] - lin - m[NA - 1]);
     bool finish = false;
     int flags = 0;
     {
@@ -1057,12 +1063,28 @@ int dmalloc(T **p, size_t n) {
 }
 
 nb_tables *g_tables_dev[64] = {nullptr};
+nb_tables256 *g_tables256_dev[64] = {nullptr};
+
+int get_tables256(npdrb_ctx *ctx, const nb_tables256 **out) {
+    if (!g_tables256_dev[ctx->device & 63]) {
+        static const nb_tables256 host_tables = NB_TABLES256_STATIC_INIT;
+        nb_tables256 *d = nullptr;
+        cudaError_t e = (cudaMalloc)((void **)&d, sizeof(nb_tables256));       // lives as long as the process: not from the cache
+        if (e != cudaSuccess) { npdrb_set_error("cudaMalloc(tables256): %s", cudaGetErrorString(e)); return NPDRB_ENOMEM; }
+        NB_CUDA(cudaMemcpyAsync(d, &host_tables, sizeof(nb_tables256), cudaMemcpyHostToDevice, ctx->stream));
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+        g_tables256_dev[ctx->device & 63] = d;
+    }
+    *out = g_tables256_dev[ctx->device & 63];
+    return NPDRB_OK;
+}
 
 int get_tables(npdrb_ctx *ctx, const nb_tables **out) {
     if (!g_tables_dev[ctx->device & 63]) {
         static const nb_tables host_tables = NB_TABLES_STATIC_INIT;
         nb_tables *d = nullptr;
-        NB_CHECK(dmalloc(&d, 1));
+        cudaError_t e = (cudaMalloc)((void **)&d, sizeof(nb_tables));           // lives as long as the process: not from the cache
+        if (e != cudaSuccess) { npdrb_set_error("cudaMalloc(tables): %s", cudaGetErrorString(e)); return NPDRB_ENOMEM; }
         NB_CUDA(cudaMemcpyAsync(d, &host_tables, sizeof(nb_tables), cudaMemcpyHostToDevice, ctx->stream));
         NB_CUDA(cudaStreamSynchronize(ctx->stream));
         g_tables_dev[ctx->device & 63] = d;
@@ -1377,6 +1399,8 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     NB_CHECK(dmalloc(&d_part, (size_t)part_total));
     NB_CHECK(dmalloc(&d_stats, (size_t)nattr * 8));
     NB_CHECK(dmalloc(&d_beta, (size_t)KMAX * nattr_pad)); NB_CHECK(dmalloc(&d_se, (size_t)KMAX * nattr_pad));
+    double *d_hitd = nullptr, *d_missd = nullptr;
+    NB_CHECK(dmalloc(&d_hitd, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_missd, (size_t)nattr_pad));
     NB_CHECK(dmalloc(&d_devold, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_active, (size_t)nattr_pad));
     NB_CHECK(dmalloc(&d_tile_active, (size_t)n_at)); NB_CHECK(dmalloc(&d_iters, (size_t)nattr_pad));
     NB_CHECK(dmalloc(&d_flags, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_nactive, 1));
@@ -1386,11 +1410,14 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     NB_CUDA(cudaMemsetAsync(d_iters, 0, sizeof(int) * nattr_pad, ctx->stream));
 
     const nb_tables *d_tab = nullptr;
+    const nb_tables256 *d_tab256 = nullptr;
     NB_CHECK(get_tables(ctx, &d_tab));
+    NB_CHECK(get_tables256(ctx, &d_tab256));
 
     SolveArgs S;
     memset(&S, 0, sizeof(S));
     S.partials = d_part; S.nattr = (int)nattr; S.nattr_pad = (int)nattr_pad;
+    S.hit_d = d_hitd; S.miss_d = d_missd;
     S.beta = d_beta; S.se = d_se; S.dev_old = d_devold; S.active = d_active; S.tile_active = d_tile_active;
     S.iters = d_iters; S.flags = d_flags; S.stats = d_stats; S.n_active = d_nactive;
     double Mw = 0;
@@ -1412,7 +1439,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             P.rec = st.rec; P.yv = st.yv;
             for (int c = 0; c < NPDRB_MAX_COVARS; ++c) P.cd[c] = st.cd[c];
             P.tile_ptr = st.tile_ptr; P.tile_mid = st.tile_mid; P.tile_ib = st.tile_ib; P.tile_jb = st.tile_jb; P.chunk_tile = st.chunk_tile;
-            P.beta = d_beta; P.tile_active = tile_active; P.partials = pp; P.tables = d_tab; P.diff_type = diff_type;
+            P.beta = d_beta; P.tile_active = tile_active; P.partials = pp; P.tables = d_tab; P.tables256 = d_tab256; P.diff_type = diff_type;
             int rc;
             if (use_v2(q)) {
                 rc = mode == MODE_LM ? launch_pass2<MODE_LM>(ctx, q, P, (int)n_at, st.n_chunks)
@@ -1517,6 +1544,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     for (double v : pass_evals) s->evals_pass_full += v;
     for (cudaEvent_t e : pev) cudaEventDestroy(e);
     if (irls_passes) *irls_passes = passes;
+    cudaFree(d_hitd); cudaFree(d_missd);
     cudaFree(d_part); cudaFree(d_beta); cudaFree(d_se); cudaFree(d_devold); cudaFree(d_stats);
     cudaFree(d_active); cudaFree(d_tile_active); cudaFree(d_iters); cudaFree(d_flags); cudaFree(d_nactive);
     return NPDRB_OK;

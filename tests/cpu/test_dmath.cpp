@@ -4,6 +4,7 @@
 #include <random>
 #include "dmath.cuh"
 static const nb_tables T = NB_TABLES_STATIC_INIT;
+static const nb_tables256 T2 = NB_TABLES256_STATIC_INIT;
 int main() {
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(-30.0, 30.0);
@@ -42,5 +43,20 @@ int main() {
         if (ab / sc > fa_log) fa_log = ab / sc;
     }
     printf("fast: max_rel_exp=%.3e max_log_err(rel to max(1,log))=%.3e\n", fr_exp, fa_log);
-    return !(max_rel_exp < 4e-16 && max_abs_log < 8e-15 && max_rel_log < 1e-15 && fr_exp < 6e-14 && fa_log < 2e-15);
+    // 256-entry variants used by pass2_kernel<IRLS_FULL>
+    double g_exp = 0, g_log = 0;
+    for (int it = 0; it < 4000000; ++it) {
+        double eta = (it < 2000000) ? U(rng) : U(rng) / 30.0;
+        double t = nb_exp_fast256(eta * NB_256_OVER_LN2, T2.exp_t);
+        long double te = expl((long double)eta);
+        double rel = (double)fabsl(((long double)t - te) / te);
+        if (rel > g_exp) g_exp = rel;
+        double u = 1.0 + (double)te;
+        double ab = (double)fabsl((long double)nb_log_ge1_fast256(u, T2.log_rc, T2.log_lrc, T2.log_eln2) - logl((long double)u));
+        double sc = (double)logl((long double)u); if (sc < 1.0) sc = 1.0;
+        if (ab / sc > g_log) g_log = ab / sc;
+    }
+    printf("fast256: max_rel_exp=%.3e max_log_err(rel to max(1,log))=%.3e\n", g_exp, g_log);
+    return !(max_rel_exp < 4e-16 && max_abs_log < 8e-15 && max_rel_log < 1e-15 && fr_exp < 6e-14 && fa_log < 2e-15 &&
+             g_exp < 2e-13 && g_log < 8e-15);
 }

@@ -262,7 +262,9 @@ def test_mutual_pair_folding_is_exact(nb, reg):
     finally:
         del os.environ["NPDRB_NO_FOLD"]
     assert a["n_unique_pairs"] < a["n_pairs"]                      # there are mutual pairs to fold
-    _stats_close(a["stats"], b["stats"], 1e-11, "fold vs no fold")
+    # only the summation order differs; the IRLS fixed point is located to ~1e-15 absolute (the score sums M/2-sized
+    # terms to ~0), i.e. ~1e-11 relative for the smallest coefficients
+    _stats_close(a["stats"], b["stats"], 1e-9, "fold vs no fold")
 
 
 def test_diff_regression_and_unireg(nb, oracle):
