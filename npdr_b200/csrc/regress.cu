@@ -187,13 +187,18 @@ shared_moments_kernel(SharedArgs a) {
 }
 
 // ------------------------------------------------------------------ the pass kernel
-struct PassArgs {
-    const double *XT; int64_t ldt; int64_t N; int nattr; int nattr_pad;
+struct StreamArgs {                // one bucketed pair stream (see nb_stream)
     const uint32_t *rec; const double *yv; const double *cd[NPDRB_MAX_COVARS];
     const int64_t *tile_ptr; const int64_t *tile_mid; const int32_t *tile_ib; const int32_t *tile_jb; const int32_t *chunk_tile;
+    double *partials;              // [n_chunks][NACC][nattr_pad]
+};
+// Both weighted streams of a pass go into ONE launch (grid.y = chunks of stream 0 followed by chunks of stream 1), so the
+// pass pays one wave-quantisation tail instead of two.
+struct PassArgs {
+    const double *XT; int64_t ldt; int64_t N; int nattr; int nattr_pad;
+    StreamArgs st[2]; int n_chunks0;
     const double *beta;            // [KMAX][nattr_pad] current coefficients (IRLS_FULL)
     const unsigned char *tile_active;  // per attribute tile, or NULL
-    double *partials;              // [n_chunks][NACC][nattr_pad]
     const nb_tables *tables;       // device copy of the exp/log tables (v1 kernel)
     const nb_tables256 *tables256; // 256-entry tables (v2 kernel)
     int diff_type;
@@ -219,7 +224,10 @@ pass_kernel(PassArgs P) {
 
     const int tid = threadIdx.x;
     const int al = tid % TA, slice = tid / TA;
-    const int at = blockIdx.x, chunk = blockIdx.y;
+    const int at = blockIdx.x;
+    const int sidx = ((int)blockIdx.y >= P.n_chunks0) ? 1 : 0;
+    const int chunk = (int)blockIdx.y - (sidx ? P.n_chunks0 : 0);
+    const StreamArgs &A = P.st[sidx];
     if (P.tile_active && !P.tile_active[at]) return;
     const int64_t a0 = (int64_t)at * TA;
 
@@ -237,11 +245,11 @@ pass_kernel(PassArgs P) {
 #pragma unroll
     for (int n = 0; n < NA; ++n) acc[n] = 0.0;
 
-    const int t_begin = P.chunk_tile[chunk], t_end = P.chunk_tile[chunk + 1];
+    const int t_begin = A.chunk_tile[chunk], t_end = A.chunk_tile[chunk + 1];
     int cur_ib = -1;
     for (int t = t_begin; t < t_end; ++t) {
-        const int ib = P.tile_ib[t], jb = P.tile_jb[t];
-        const int64_t r0 = P.tile_ptr[t], r1 = P.tile_ptr[t + 1];
+        const int ib = A.tile_ib[t], jb = A.tile_jb[t];
+        const int64_t r0 = A.tile_ptr[t], r1 = A.tile_ptr[t + 1];
         __syncthreads();                                  // previous tile fully consumed
         // stage attribute tiles: 16-byte loads, rows are TA contiguous doubles of XT (zero padded)
         {
@@ -265,10 +273,10 @@ pass_kernel(PassArgs P) {
             const int n = (int)((r1 - rc < RCHUNK) ? (r1 - rc) : RCHUNK);
             if (rc != r0) __syncthreads();                // previous record chunk consumed
             for (int e = tid; e < n; e += RTHREADS) {
-                sREC[e] = P.rec[rc + e];
+                sREC[e] = A.rec[rc + e];
 #pragma unroll
-                for (int c = 0; c < Q; ++c) sCD[c * RCHUNK + e] = P.cd[c][rc + e];
-                if (MODE == MODE_LM) sCD[Q * RCHUNK + e] = P.yv[rc + e];
+                for (int c = 0; c < Q; ++c) sCD[c * RCHUNK + e] = A.cd[c][rc + e];
+                if (MODE == MODE_LM) sCD[Q * RCHUNK + e] = A.yv[rc + e];
             }
             __syncthreads();
 #pragma unroll 2
@@ -355,7 +363,7 @@ pass_kernel(PassArgs P) {
         double s = red[(0 * NA + n) * TA + a];
 #pragma unroll
         for (int sl = 1; sl < NSLICE; ++sl) s += red[(sl * NA + n) * TA + a];
-        P.partials[((int64_t)chunk * NA + n) * P.nattr_pad + a0 + a] = s;
+        A.partials[((int64_t)chunk * NA + n) * P.nattr_pad + a0 + a] = s;
     }
 }
 
@@ -409,7 +417,7 @@ __device__ __forceinline__ double v2_exp_fast(double sv, uint32_t sT) {         
     double tj;
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x7F8)));
     const double v = fma(tj, qq, tj);
-    return __hiloint2double(__double2hiint(v) + ((ki & 0xFFFFFF00) << 12), __double2loint(v));   // * 2^(ki >> 8)
+    return __hiloint2double(__double2hiint(v) + (ki & 0xFFFFFF00) * 4096, __double2loint(v));    // * 2^(ki >> 8): one LOP3 + one IMAD
 }
 // logit linkinv with R's clamps (stats family.c): eta < -30 -> DBL_EPSILON, eta > 30 -> 1/DBL_EPSILON.
 // -> (t, log t - eta): the second component is the deviance correction of a clamped record (0 otherwise)
@@ -636,7 +644,10 @@ pass2_kernel(PassArgs P) {
 
     const int tid = threadIdx.x;
     const int tl = tid % V2_TPS, slice = tid / V2_TPS;
-    const int at = blockIdx.x, chunk = blockIdx.y;
+    const int at = blockIdx.x;
+    const int sidx = ((int)blockIdx.y >= P.n_chunks0) ? 1 : 0;
+    const int chunk = (int)blockIdx.y - (sidx ? P.n_chunks0 : 0);
+    const StreamArgs &A = P.st[sidx];
     if (MODE == MODE_IRLS_FULL && P.tile_active && !P.tile_active[at]) return;
     const int64_t a0 = (int64_t)at * TA;
 
@@ -661,7 +672,7 @@ pass2_kernel(PassArgs P) {
 #pragma unroll
     for (int n = 0; n < NA; ++n) { acc0[n] = 0.0; acc1[n] = 0.0; }
 
-    const int t_begin = P.chunk_tile[chunk], t_end = P.chunk_tile[chunk + 1];
+    const int t_begin = A.chunk_tile[chunk], t_end = A.chunk_tile[chunk + 1];
 
     // async stage of a [64][128] double tile (rows are TA contiguous doubles of XT, zero padded)
     auto stage_tile = [&](uint32_t dst, int block) {
@@ -675,27 +686,27 @@ pass2_kernel(PassArgs P) {
     auto stage_records = [&](int buf, int64_t rc, int n) {
         const uint32_t rdst = sbase + L::REC + buf * L::REC_BYTES, cdst = sbase + L::CD + buf * L::CD_BYTES;
         for (int e = tid; e < n; e += V2_THREADS) {
-            cp_async4(rdst + 4u * e, P.rec + rc + e);
+            cp_async4(rdst + 4u * e, A.rec + rc + e);
 #pragma unroll
-            for (int c = 0; c < Q; ++c) cp_async8(cdst + 8u * (c * V2_RCHUNK + e), P.cd[c] + rc + e);
-            if (MODE == MODE_LM) cp_async8(cdst + 8u * (Q * V2_RCHUNK + e), P.yv + rc + e);
+            for (int c = 0; c < Q; ++c) cp_async8(cdst + 8u * (c * V2_RCHUNK + e), A.cd[c] + rc + e);
+            if (MODE == MODE_LM) cp_async8(cdst + 8u * (Q * V2_RCHUNK + e), A.yv + rc + e);
         }
     };
     auto first_chunk_len = [&](int t) -> int {
-        const int64_t len = P.tile_ptr[t + 1] - P.tile_ptr[t];
+        const int64_t len = A.tile_ptr[t + 1] - A.tile_ptr[t];
         return (int)(len < V2_RCHUNK ? len : V2_RCHUNK);
     };
 
     int cur_ib = -1;
     if (t_begin < t_end) {                                 // prologue: tile t_begin in flight
-        stage_tile(sbase + L::XJ, P.tile_jb[t_begin]);
-        stage_records(0, P.tile_ptr[t_begin], first_chunk_len(t_begin));
+        stage_tile(sbase + L::XJ, A.tile_jb[t_begin]);
+        stage_records(0, A.tile_ptr[t_begin], first_chunk_len(t_begin));
         cp_async_commit();
     }
     for (int t = t_begin; t < t_end; ++t) {
         const int buf = (t - t_begin) & 1;
-        const int ib = P.tile_ib[t];
-        const int64_t r0 = P.tile_ptr[t], r1 = P.tile_ptr[t + 1], rmid = P.tile_mid[t];
+        const int ib = A.tile_ib[t];
+        const int64_t r0 = A.tile_ptr[t], r1 = A.tile_ptr[t + 1], rmid = A.tile_mid[t];
         if (ib != cur_ib) {                                // new I block (once per row of tiles): nobody reads XI now? ->
             __syncthreads();                               // all threads are done with the previous tile's compute
             stage_tile(sbase + L::XI, ib);
@@ -705,8 +716,8 @@ pass2_kernel(PassArgs P) {
         cp_async_wait_all();
         __syncthreads();                                   // tile t staged; previous tile's buffers are free
         if (t + 1 < t_end) {                               // prefetch tile t+1 into the other buffers
-            stage_tile(sbase + L::XJ + (buf ^ 1) * (BJ * TA * 8), P.tile_jb[t + 1]);
-            stage_records(buf ^ 1, P.tile_ptr[t + 1], first_chunk_len(t + 1));
+            stage_tile(sbase + L::XJ + (buf ^ 1) * (BJ * TA * 8), A.tile_jb[t + 1]);
+            stage_records(buf ^ 1, A.tile_ptr[t + 1], first_chunk_len(t + 1));
             cp_async_commit();
         }
         const uint32_t sXJ_addr = sbase + L::XJ + buf * (BJ * TA * 8) + (uint32_t)tl * 16u;
@@ -751,7 +762,7 @@ pass2_kernel(PassArgs P) {
         double sacc = red[(0 * NA + n) * TA + a];
 #pragma unroll
         for (int sl = 1; sl < NSL; ++sl) sacc += red[(sl * NA + n) * TA + a];
-        P.partials[((int64_t)chunk * NA + n) * P.nattr_pad + a0 + a] = sacc;
+        A.partials[((int64_t)chunk * NA + n) * P.nattr_pad + a0 + a] = sacc;
     }
 }
 
@@ -1430,30 +1441,31 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     S.M = Mw;
 
     auto run_pass = [&](int mode, const unsigned char *tile_active) -> int {
+        PassArgs P;
+        memset(&P, 0, sizeof(P));
+        P.XT = s->dXT; P.ldt = s->ldt; P.N = N; P.nattr = (int)nattr; P.nattr_pad = (int)nattr_pad;
+        P.beta = d_beta; P.tile_active = tile_active; P.tables = d_tab; P.tables256 = d_tab256; P.diff_type = diff_type;
         double *pp = d_part;
+        int total_chunks = 0;
         for (int i = 0; i < s->n_streams; ++i) {
             const nb_stream &st = s->streams[i];
-            PassArgs P;
-            memset(&P, 0, sizeof(P));
-            P.XT = s->dXT; P.ldt = s->ldt; P.N = N; P.nattr = (int)nattr; P.nattr_pad = (int)nattr_pad;
-            P.rec = st.rec; P.yv = st.yv;
-            for (int c = 0; c < NPDRB_MAX_COVARS; ++c) P.cd[c] = st.cd[c];
-            P.tile_ptr = st.tile_ptr; P.tile_mid = st.tile_mid; P.tile_ib = st.tile_ib; P.tile_jb = st.tile_jb; P.chunk_tile = st.chunk_tile;
-            P.beta = d_beta; P.tile_active = tile_active; P.partials = pp; P.tables = d_tab; P.tables256 = d_tab256; P.diff_type = diff_type;
-            int rc;
-            if (use_v2(q)) {
-                rc = mode == MODE_LM ? launch_pass2<MODE_LM>(ctx, q, P, (int)n_at, st.n_chunks)
-                   : mode == MODE_SIGN ? launch_pass2<MODE_SIGN>(ctx, q, P, (int)n_at, st.n_chunks)
-                                       : launch_pass2<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, st.n_chunks);
-            } else {
-                rc = mode == MODE_LM ? launch_pass<MODE_LM>(ctx, q, P, (int)n_at, st.n_chunks)
-                   : mode == MODE_SIGN ? launch_pass<MODE_SIGN>(ctx, q, P, (int)n_at, st.n_chunks)
-                                       : launch_pass<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, st.n_chunks);
-            }
-            if (rc) return rc;
+            StreamArgs &A = P.st[i];
+            A.rec = st.rec; A.yv = st.yv;
+            for (int c = 0; c < NPDRB_MAX_COVARS; ++c) A.cd[c] = st.cd[c];
+            A.tile_ptr = st.tile_ptr; A.tile_mid = st.tile_mid; A.tile_ib = st.tile_ib; A.tile_jb = st.tile_jb;
+            A.chunk_tile = st.chunk_tile; A.partials = pp;
             pp += part_stride[i];
+            total_chunks += st.n_chunks;
         }
-        return NPDRB_OK;
+        P.n_chunks0 = s->streams[0].n_chunks;
+        if (use_v2(q)) {
+            return mode == MODE_LM ? launch_pass2<MODE_LM>(ctx, q, P, (int)n_at, total_chunks)
+                 : mode == MODE_SIGN ? launch_pass2<MODE_SIGN>(ctx, q, P, (int)n_at, total_chunks)
+                                     : launch_pass2<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, total_chunks);
+        }
+        return mode == MODE_LM ? launch_pass<MODE_LM>(ctx, q, P, (int)n_at, total_chunks)
+             : mode == MODE_SIGN ? launch_pass<MODE_SIGN>(ctx, q, P, (int)n_at, total_chunks)
+                                 : launch_pass<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, total_chunks);
     };
 
     int passes = 0;
