@@ -241,20 +241,41 @@ def main():
         eng.close()
         return stats, info, km, sm, passes
 
-    # host copies for the end-to-end arm (pinned)
-    hX = hy = hC = None
-    if not args.no_e2e:
+    # host copies for the end-to-end arm (pinned; rank 0 only -- the other ranks receive X over NVLink)
+    hX = hy = hC = hXt = None
+    e2e_dev = None
+    if not args.no_e2e and rank == 0:
         hXt = torch.empty((p, N), dtype=torch.float64, pin_memory=True)
         hXt.copy_(data["dX"][:, :N])
         hX = hXt.numpy().T                                       # (N, p) Fortran-ordered view of pinned memory
         hy = data["dy"].cpu().numpy()
         hC = np.asfortranarray(data["dC"].cpu().numpy().T) if q else None
+    if not args.no_e2e and world > 1:
+        e2e_dev = dict(dX=torch.zeros((p, data["ldx"]), dtype=torch.float64, device=device),
+                       dy=torch.zeros(N, dtype=torch.float64, device=device),
+                       dC=torch.zeros((q, N), dtype=torch.float64, device=device) if q else None)
+        hy_t = torch.from_numpy(hy).pin_memory() if rank == 0 else None
+        hC_t = torch.from_numpy(np.ascontiguousarray(hC.T)).pin_memory() if (rank == 0 and q) else None
 
     def one_step_e2e():
-        eng = GpuEngine(X=hX, y=hy, C=hC, device_index=local_rank)     # H2D upload inside
+        if world == 1:
+            eng = GpuEngine(X=hX, y=hy, C=hC, device_index=local_rank)   # host-buffer C ABI: H2D upload inside
+        else:
+            # rank 0 uploads the host buffers once and broadcasts them over NVLink (NCCL); every rank then shards
+            if rank == 0:
+                e2e_dev["dX"][:, :N].copy_(hXt, non_blocking=True)
+                e2e_dev["dy"].copy_(hy_t, non_blocking=True)
+                if q:
+                    e2e_dev["dC"].copy_(hC_t, non_blocking=True)
+            dist.broadcast(e2e_dev["dX"], 0)
+            dist.broadcast(e2e_dev["dy"], 0)
+            if q:
+                dist.broadcast(e2e_dev["dC"], 0)
+            eng = GpuEngine(device_index=local_rank, dX=e2e_dev["dX"], ldx=data["ldx"], dy=e2e_dev["dy"], dC=e2e_dev["dC"],
+                            N=N, p=p, q=q)
         stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, data["covar_diff_type"])
         eng.close()
-        return stats, info                                              # stats are host numpy: D2H done
+        return stats, info                                              # stats are host numpy on rank 0: D2H done
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -290,8 +311,9 @@ def main():
         ms_e, _, _ = timed(one_step_e2e, e_steps, 1)
         ms_e /= e_steps
         e2e = {"value": float(p) * M / (ms_e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e,
-               "h2d_bytes_per_step": int(world * (N * p * 8 + N * 8 + N * q * 8)), "d2h_bytes_per_step": int(p * 8 * 8),
-               "note": "host-buffer path: pinned X/y(/C) uploaded on every rank, statistics read back, every step"}
+               "h2d_bytes_per_step": int(N * p * 8 + N * 8 + N * q * 8), "d2h_bytes_per_step": int(p * 8 * 8),
+               "note": ("host-buffer C-ABI path: pinned X/y(/C) uploaded and statistics read back every step" if world == 1 else
+                        "rank 0 uploads pinned X/y(/C) and broadcasts over NVLink (NCCL) every step; statistics read back on rank 0")}
 
     if rank != 0:
         if world > 1:
