@@ -10,6 +10,7 @@
  *   npdrb_distances          <- npdrDistances       R/nearestNeighbors.R:63-101
  *   npdrb_nearest_neighbors  <- nearestNeighbors    R/nearestNeighbors.R:153-285 (+ get_Ri_nearest :622-634,
  *                                                    uniqueNeighbors :572-583, knnVec :603-607)
+ *   npdrb_nearest_neighbors_hitmiss <- nearestNeighborsSeparateHitMiss   R/nearestNeighbors.R:318-551
  *   npdrb_knn_surf           <- knnSURF             R/utils.R:12-18
  *   npdrb_regress            <- the regression loop + diffRegression   R/npdr.R:391-430, 18-71
  *   npdrb_npdr               <- npdr() between argument parsing and order()/p.adjust()
@@ -92,7 +93,8 @@ typedef struct {
     int32_t neighbor_sampling_unique;              /* neighbor.sampling == "unique", R/npdr.R:271-277 */
     int32_t fast_euclidean;                        /* 1: allow FMA contraction in the euclidean sum (<=1e-12 rel) */
     int32_t return_pairs;                          /* 1: also return the (Ri, NN) list */
-    int32_t reserved[8];
+    int32_t separate_hitmiss_nbds;                 /* separate.hitmiss.nbds, R/npdr.R:160,215-251 (binomial outcome = class labels) */
+    int32_t reserved[7];
 } npdrb_opts;
 
 typedef struct {
@@ -146,6 +148,13 @@ int npdrb_nearest_neighbors(npdrb_ctx *ctx, const double *X, int64_t N, int64_t 
                             int32_t nbd_metric, const double *sd_vec, double sd_frac, int64_t k,
                             int32_t unique_sampling, int32_t **Ri, int32_t **NN, int64_t *M,
                             int64_t *n_unique, int64_t *n_empty, double *radius_out);
+/* nearestNeighborsSeparateHitMiss: hit and miss neighbourhoods formed separately (class-conditional radii for
+ * surf/multisurf, class-conditional k for relieff), listed hits first.  pheno: N class labels (two classes).
+ * r_hit_out / r_miss_out (length N) may be NULL. */
+int npdrb_nearest_neighbors_hitmiss(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *pheno,
+                                    int32_t nbd_method, int32_t nbd_metric, double sd_frac, int64_t k,
+                                    int32_t unique_sampling, int32_t **Ri, int32_t **NN, int64_t *M, int64_t *n_unique,
+                                    double *r_hit_out, double *r_miss_out);
 /* regression loop over all p attributes for a given pair list.
  * y: length N outcome (lm: numeric; binomial: class labels, any two distinct doubles); pheno diff is formed
  * here as in R/npdr.R:299-308.  C: N x q covariates or NULL.  stats_out: p x 8 row-major. */
@@ -176,6 +185,11 @@ int npdrb_session_set_sd_vec(npdrb_session *s, const double *sd_vec_host);   /* 
 /* neighbour lists for the owned rows; *M_local = number of pairs found */
 int npdrb_session_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local,
                             int64_t *n_empty_local);
+/* separate hit/miss neighbourhoods for the owned rows, class labels = the session's outcome vector
+ * (multisurf and relieff shard by rows; surf needs the whole matrix on one device) */
+int npdrb_session_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local,
+                                    int64_t *n_empty_local);
+int npdrb_session_copy_radius2(npdrb_session *s, double *radius_host);      /* owned rows: miss radius */
 /* SURF needs one global mean/sd (R/nearestNeighbors.R:234-241).  Partial moments of the owned rows:
  * out4[0] = sum of all owned entries, out4[1] = sum over the owned part of the strict upper triangle,
  * out4[2] = its count, out4[3] = sum over that part of (d - centre)^2.  Multi-rank hosts call it with

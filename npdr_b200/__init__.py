@@ -5,8 +5,8 @@ over the C ABI of libnpdr_b200.so.  No CPU fallback: compute calls raise if the 
 or an sm_100 device is missing.
 """
 from ._lib import NpdrB200Error, Context, Session, context  # noqa: F401
-from .api import (npdr, npdrDiff, npdrDistances, nearestNeighbors, uniqueNeighbors, knnVec, knnSURF,  # noqa: F401
-                  diffRegression, uniReg)
+from .api import (npdr, npdrDiff, npdrDistances, nearestNeighbors, nearestNeighborsSeparateHitMiss,  # noqa: F401
+                  uniqueNeighbors, knnVec, knnSURF, diffRegression, uniReg)
 from . import rstats  # noqa: F401
 
 __version__ = "0.1.0"

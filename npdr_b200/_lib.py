@@ -33,7 +33,7 @@ class Opts(C.Structure):
                 ("nbd_metric", C.c_int32), ("knn", C.c_int64), ("msurf_sd_frac", C.c_double),
                 ("n_covars", C.c_int32), ("covar_diff_type", C.c_int32 * MAX_COVARS),
                 ("neighbor_sampling_unique", C.c_int32), ("fast_euclidean", C.c_int32),
-                ("return_pairs", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("return_pairs", C.c_int32), ("separate_hitmiss_nbds", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class Result(C.Structure):
@@ -71,6 +71,8 @@ SIGNATURES = {
     "npdrb_nearest_neighbors": (C.c_int, [_vp, _dp, _i64, _i64, _i32, _i32, _dp, C.c_double, _i64, _i32,
                                           C.POINTER(_ip), C.POINTER(_ip), C.POINTER(_i64), C.POINTER(_i64),
                                           C.POINTER(_i64), _dp]),
+    "npdrb_nearest_neighbors_hitmiss": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _i32, _i32, C.c_double, _i64, _i32,
+                                                  C.POINTER(_ip), C.POINTER(_ip), C.POINTER(_i64), C.POINTER(_i64), _dp, _dp]),
     "npdrb_regress": (C.c_int, [_vp, _dp, _i64, _i64, _ip, _ip, _i64, _dp, _dp, _i32, _ip, _i32, _i32, _dp]),
     "npdrb_npdr": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, C.POINTER(Opts), C.POINTER(Result)]),
     "npdrb_unireg": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, _i32, _i32, _dp]),
@@ -82,6 +84,8 @@ SIGNATURES = {
     "npdrb_session_set_device_distances": (C.c_int, [_vp, _vp, _i64, _i64, _i64]),
     "npdrb_session_set_sd_vec": (C.c_int, [_vp, _dp]),
     "npdrb_session_neighbors": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "npdrb_session_neighbors_hitmiss": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "npdrb_session_copy_radius2": (C.c_int, [_vp, _dp]),
     "npdrb_session_surf_partial": (C.c_int, [_vp, C.c_double, _dp]),
     "npdrb_session_set_surf_radius": (C.c_int, [_vp, C.c_double]),
     "npdrb_session_local_pairs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
@@ -248,6 +252,16 @@ class Session:
         M, ne = _i64(), _i64()
         check(load().npdrb_session_neighbors(self.handle, NBD[method], float(sd_frac), int(k), C.byref(M), C.byref(ne)))
         return M.value, ne.value
+
+    def neighbors_hitmiss(self, method="relieff", sd_frac=0.5, k=0):
+        M, ne = _i64(), _i64()
+        check(load().npdrb_session_neighbors_hitmiss(self.handle, NBD[method], float(sd_frac), int(k), C.byref(M), C.byref(ne)))
+        return M.value, ne.value
+
+    def copy_radius2(self):
+        out = np.empty(self.nrows)
+        check(load().npdrb_session_copy_radius2(self.handle, dptr(out)))
+        return out
 
     def surf_partial(self, centre=0.0):
         out = np.zeros(4)

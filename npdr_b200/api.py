@@ -8,6 +8,7 @@ the p-value / ordering / p.adjust residue in `rstats` (it stays in R in the R de
   npdrDiff           R/nearestNeighbors.R:15-40
   npdrDistances      R/nearestNeighbors.R:63-101
   nearestNeighbors   R/nearestNeighbors.R:153-285
+  nearestNeighborsSeparateHitMiss   R/nearestNeighbors.R:318-551
   uniqueNeighbors    R/nearestNeighbors.R:572-583
   knnVec             R/nearestNeighbors.R:603-607
   knnSURF            R/utils.R:12-18
@@ -158,6 +159,42 @@ def nearestNeighbors(attr_mat, nbd_method="multisurf", nbd_metric="manhattan", s
     else:  # pragma: no cover
         out = np.column_stack([ri, nn])
     return (out, info) if return_info else out
+
+
+def nearestNeighborsSeparateHitMiss(attr_mat, pheno_vec, nbd_method="relieff", nbd_metric="manhattan", sd_frac=0.5, k=0,
+                                    neighbor_sampling="none", att_to_remove=(), fast_dist=False, dopar_nn=False, device=0,
+                                    return_info=False):
+    """Hit and miss neighbourhoods formed separately, hits listed first (R/nearestNeighbors.R:318-551).
+    pheno_vec: two-class labels (the reference coerces them with as.numeric(as.character()))."""
+    if nbd_method not in NBD:
+        raise ValueError(f"unknown nbd.method {nbd_method!r}")
+    if nbd_metric not in METRIC:
+        raise ValueError(f"unknown nbd.metric {nbd_metric!r}")
+    if att_to_remove is not None and len(att_to_remove):
+        if pd is not None and isinstance(attr_mat, pd.DataFrame):
+            try:
+                attr_mat = attr_mat.drop(columns=list(att_to_remove))
+            except KeyError:
+                pass
+        else:
+            Xa = np.asarray(attr_mat)
+            attr_mat = Xa[:, [c for c in range(Xa.shape[1]) if c not in set(att_to_remove)]]
+    X, _ = _as_matrix(attr_mat)
+    y = _code_outcome(pheno_vec, "binomial")
+    if np.unique(y).size != 2:
+        raise ValueError("nearestNeighborsSeparateHitMiss needs a two-class outcome")
+    N, p = X.shape
+    Ri = C.POINTER(C.c_int32)(); NN = C.POINTER(C.c_int32)()
+    M = C.c_int64(); nu = C.c_int64()
+    rh = np.full(N, np.nan); rm = np.full(N, np.nan)
+    check(_lib.load().npdrb_nearest_neighbors_hitmiss(context(device).handle, dptr(X), N, p, dptr(f64(y)), NBD[nbd_method],
+                                                      METRIC[nbd_metric], float(sd_frac), int(k), int(neighbor_sampling == "unique"),
+                                                      C.byref(Ri), C.byref(NN), C.byref(M), C.byref(nu), dptr(rh), dptr(rm)))
+    ri = _lib.take_int_array(Ri, M.value); nn = _lib.take_int_array(NN, M.value)
+    out = pd.DataFrame({"Ri_idx": ri, "NN_idx": nn}) if pd is not None else np.column_stack([ri, nn])
+    if return_info:
+        return out, {"n_unique": nu.value, "radius_hit": rh, "radius_miss": rm}
+    return out
 
 
 def _pairs_arrays(neighbor_pairs):
@@ -318,8 +355,9 @@ def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-a
         raise NotImplementedError("use.glmnet=TRUE (npdrNET, R/npdr.R:513-632) is outside the accelerated path")
     if attr_diff_type == "correlation-data":
         raise NotImplementedError("attr.diff.type='correlation-data' (R/npdr.R:176-205) is outside the accelerated path")
-    if separate_hitmiss_nbds:
-        raise NotImplementedError("separate.hitmiss.nbds=TRUE (nearestNeighborsSeparateHitMiss) is a 'next' row (DESIGN.md)")
+    if separate_hitmiss_nbds and (nbd_metric == "precomputed" or (rm_attr_from_dist is not None and len(rm_attr_from_dist))):
+        raise NotImplementedError("separate.hitmiss.nbds with precomputed distances / rm.attr.from.dist: use "
+                                  "nearestNeighborsSeparateHitMiss() and the two-step path")
     if regression_type not in REG:
         raise ValueError(f"unknown regression.type {regression_type!r}")
     if attr_diff_type not in DIFF or attr_diff_type == "raw":
@@ -354,6 +392,7 @@ def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-a
             o.covar_diff_type[i] = DIFF[t]
         o.neighbor_sampling_unique = int(neighbor_sampling == "unique")
         o.return_pairs = int(bool(return_info))
+        o.separate_hitmiss_nbds = int(bool(separate_hitmiss_nbds))
         res = _lib.Result()
         check(L.npdrb_npdr(ctx.handle, dptr(X), N, p, dptr(f64(y)), dptr(Cm), C.byref(o), C.byref(res)))
         stats = np.ctypeslib.as_array(res.stats, shape=(p, STATS_PER_ATTR)).copy()

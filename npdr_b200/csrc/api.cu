@@ -277,7 +277,7 @@ void npdrb_session_destroy(npdrb_session *s) {
     if (s->own_y) cudaFree(s->dy);
     if (s->own_C) cudaFree(s->dC);
     if (s->own_D) cudaFree(s->dD);
-    cudaFree(s->d_sd_vec); cudaFree(s->d_radius);
+    cudaFree(s->d_sd_vec); cudaFree(s->d_radius); cudaFree(s->d_radius2);
     cudaFree(s->dRiL); cudaFree(s->dNNL); cudaFree(s->d_rowptr);
     if (s->own_pairs) { cudaFree(s->dRi); cudaFree(s->dNN); }
     cudaFree(s->dXT);
@@ -357,6 +357,20 @@ int npdrb_session_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac
                             int64_t *n_empty_local) {
     NB_CUDA(cudaSetDevice(s->ctx->device));
     return nb_neighbors(s, nbd_method, sd_frac, k, M_local, n_empty_local);
+}
+
+int npdrb_session_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local,
+                                    int64_t *n_empty_local) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_neighbors_hitmiss(s, nbd_method, sd_frac, k, M_local, n_empty_local);
+}
+
+int npdrb_session_copy_radius2(npdrb_session *s, double *radius_host) {
+    if (!s->d_radius2) { npdrb_set_error("copy_radius2: no hit/miss radii"); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    NB_CUDA(cudaMemcpyAsync(radius_host, s->d_radius2, sizeof(double) * (size_t)s->nrows, cudaMemcpyDeviceToHost, s->ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return NPDRB_OK;
 }
 
 int npdrb_session_set_surf_radius(npdrb_session *s, double radius) {
@@ -505,7 +519,7 @@ static int pairs_to_host(npdrb_session *s, int32_t **Ri, int32_t **NN) {
 // distances (or adoption of a precomputed matrix) + neighbours on one device; leaves the list imported in s
 static int neighbors_stage(npdrb_session *s, const double *X_or_D_host, int32_t nbd_method, int32_t nbd_metric,
                            const double *sd_vec, double sd_frac, int64_t k, int32_t fast_euclidean,
-                           int64_t *M, int64_t *n_empty) {
+                           int64_t *M, int64_t *n_empty, int32_t hitmiss = 0) {
     npdrb_ctx *ctx = s->ctx;
     const int64_t N = s->N;
     if (nbd_metric == NPDRB_METRIC_PRECOMPUTED) {
@@ -523,7 +537,8 @@ static int neighbors_stage(npdrb_session *s, const double *X_or_D_host, int32_t 
         NB_CHECK(nb_distances(s, nbd_metric, fast_euclidean, 0, N));
     }
     NB_CHECK(npdrb_session_set_sd_vec(s, sd_vec));
-    NB_CHECK(nb_neighbors(s, nbd_method, sd_frac, k, M, n_empty));
+    if (hitmiss) NB_CHECK(nb_neighbors_hitmiss(s, nbd_method, sd_frac, k, M, n_empty));
+    else NB_CHECK(nb_neighbors(s, nbd_method, sd_frac, k, M, n_empty));
     NB_CHECK(npdrb_session_import_pairs(s, s->dRiL, s->dNNL, s->M_local));
     return NPDRB_OK;
 }
@@ -542,6 +557,27 @@ int npdrb_nearest_neighbors(npdrb_ctx *ctx, const double *X, int64_t N, int64_t 
     if (!rc) rc = nb_unique_pairs(s, unique_sampling, &nu);
     if (!rc) rc = pairs_to_host(s, Ri, NN);
     if (!rc) { *M = s->M; if (n_unique) *n_unique = nu; if (n_empty) *n_empty = ne; }
+    npdrb_session_destroy(s);
+    return rc;
+}
+
+int npdrb_nearest_neighbors_hitmiss(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *pheno,
+                                    int32_t nbd_method, int32_t nbd_metric, double sd_frac, int64_t k,
+                                    int32_t unique_sampling, int32_t **Ri, int32_t **NN, int64_t *M, int64_t *n_unique,
+                                    double *r_hit_out, double *r_miss_out) {
+    if (!ctx) { npdrb_set_error("npdrb_nearest_neighbors_hitmiss: null context (no device)"); return NPDRB_ENODEVICE; }
+    if (!pheno) { npdrb_set_error("npdrb_nearest_neighbors_hitmiss: class labels missing"); return NPDRB_EINVAL; }
+    npdrb_session *s = nullptr;
+    const bool pre = nbd_metric == NPDRB_METRIC_PRECOMPUTED;
+    NB_CHECK(npdrb_session_create(ctx, N, pre ? N : p, 0, &s));
+    int rc = npdrb_session_upload(s, pre ? nullptr : X, pheno, nullptr);
+    int64_t Ml = 0, ne = 0, nu = 0;
+    if (!rc) rc = neighbors_stage(s, X, nbd_method, nbd_metric, nullptr, sd_frac, k, 0, &Ml, &ne, 1);
+    if (!rc && r_hit_out && nbd_method != NPDRB_NBD_RELIEFF) rc = npdrb_session_copy_radius(s, r_hit_out);
+    if (!rc && r_miss_out && nbd_method != NPDRB_NBD_RELIEFF) rc = npdrb_session_copy_radius2(s, r_miss_out);
+    if (!rc) rc = nb_unique_pairs(s, unique_sampling, &nu);
+    if (!rc) rc = pairs_to_host(s, Ri, NN);
+    if (!rc) { *M = s->M; if (n_unique) *n_unique = nu; }
     npdrb_session_destroy(s);
     return rc;
 }
@@ -580,7 +616,8 @@ int npdrb_npdr(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const doub
     int64_t M = 0, ne = 0, nu = 0;
     int64_t k = o->knn;
     if (o->nbd_method == NPDRB_NBD_RELIEFF && k <= 0) k = npdrb_knn_surf(N, o->msurf_sd_frac);
-    if (!rc) rc = neighbors_stage(s, nullptr, o->nbd_method, o->nbd_metric, nullptr, o->msurf_sd_frac, k, o->fast_euclidean, &M, &ne);
+    if (!rc) rc = neighbors_stage(s, nullptr, o->nbd_method, o->nbd_metric, nullptr, o->msurf_sd_frac, k, o->fast_euclidean, &M, &ne,
+                                  o->separate_hitmiss_nbds);
     if (!rc) rc = nb_unique_pairs(s, o->neighbor_sampling_unique, &nu);
     if (!rc && s->M <= 0) { npdrb_set_error("npdr: no neighbour pairs found"); rc = NPDRB_EDATA; }
     int32_t passes = 0;

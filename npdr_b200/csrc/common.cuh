@@ -87,6 +87,7 @@ struct npdrb_session {
     double *dD = nullptr; int64_t ldd = 0; int64_t row0 = 0, nrows = 0; bool own_D = false;
     double *d_sd_vec = nullptr;                                          // optional user sd.vec (length N)
     double *d_radius = nullptr;                                          // owned rows
+    double *d_radius2 = nullptr;                                         // owned rows: miss radius (separate hit/miss neighbourhoods)
     bool have_surf_radius = false; double surf_radius = 0.0;
     // local neighbour segment
     int32_t *dRiL = nullptr, *dNNL = nullptr; int64_t M_local = 0; int64_t n_empty_local = 0;
@@ -110,6 +111,7 @@ struct npdrb_session {
 // stage implementations (one .cu each)
 int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
 int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local, int64_t *n_empty);
+int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local, int64_t *n_empty);
 int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_unique);
 int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t regression_type, int32_t attr_diff_type,
                const int32_t *covar_diff_type, double *stats_out_host, int32_t *irls_passes);

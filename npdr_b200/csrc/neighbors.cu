@@ -373,6 +373,253 @@ compact_pairs_kernel(const int32_t *__restrict__ Ri, const int32_t *__restrict__
     }
 }
 
+// ================================================================ separate hit / miss neighbourhoods
+// nearestNeighborsSeparateHitMiss (R/nearestNeighbors.R:318-551).  Same distance block; per owned instance the hits
+// (same class, not self) and the misses (other class) get their own radius / their own k, and are listed hits first.
+
+// multisurf radii (:483-500): radius = mean(d[subset]) - sd.frac * sd(d[subset]), base-R mean() and sd() both start from
+// the same long-double two-pass mean; xf80 reproduces them bit for bit.  One lane per owned row, 32x32 transposed tiles.
+__global__ void __launch_bounds__(128)
+radius_hitmiss_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t row0, int64_t nrows,
+                      const double *__restrict__ y, double sd_frac, double *__restrict__ r_hit, double *__restrict__ r_miss) {
+    __shared__ double tile[4][32][33];
+    __shared__ double ycol[4][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t rbase = ((int64_t)blockIdx.x * 4 + w) * 32;
+    if (rbase >= nrows) return;
+    const int64_t r = rbase + lane, g = row0 + r;
+    const bool valid = r < nrows;
+    const double yg = valid ? y[g] : 0.0;
+    xf80 T[2] = {xf_zero(), xf_zero()}, XM[2] = {xf_zero(), xf_zero()}, SS[2] = {xf_zero(), xf_zero()};
+    int64_t cnt[2] = {0, 0};
+    for (int pass = 0; pass < 3; ++pass) {
+        xf80 acc[2] = {xf_zero(), xf_zero()};
+        int64_t c2[2] = {0, 0};
+        for (int64_t c0 = 0; c0 < N; c0 += 32) {
+            for (int rr = 0; rr < 32; ++rr) {
+                int64_t row = rbase + rr, col = c0 + lane;
+                tile[w][rr][lane] = (row < nrows && col < N) ? D[row * ldd + col] : 0.0;
+            }
+            ycol[w][lane] = (c0 + lane < N) ? y[c0 + lane] : 0.0;
+            __syncwarp();
+            if (valid) {
+                const int lim = (int)((N - c0 < 32) ? (N - c0) : 32);
+                for (int cc = 0; cc < lim; ++cc) {
+                    const int64_t j = c0 + cc;
+                    const bool same = (ycol[w][cc] == yg);
+                    if (same && j == g) continue;
+                    const int k = same ? 0 : 1;
+                    xf80 x = xf_from_double(tile[w][lane][cc]);
+                    if (pass == 0) { acc[k] = xf_add(acc[k], x); c2[k]++; }
+                    else if (pass == 1) acc[k] = xf_add(acc[k], xf_sub(x, T[k]));
+                    else { xf80 d = xf_sub(x, XM[k]); acc[k] = xf_add(acc[k], xf_mul(d, d)); }
+                }
+            }
+            __syncwarp();
+        }
+        for (int k = 0; k < 2; ++k) {
+            if (pass == 0) { cnt[k] = c2[k]; T[k] = cnt[k] > 0 ? xf_div(acc[k], xf_from_int(cnt[k])) : xf_zero(); }
+            else if (pass == 1) { if (cnt[k] > 0) T[k] = xf_add(T[k], xf_div(acc[k], xf_from_int(cnt[k]))); XM[k] = xf_from_double(xf_to_double(T[k])); }
+            else SS[k] = acc[k];
+        }
+    }
+    if (!valid) return;
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+    double out[2];
+    for (int k = 0; k < 2; ++k) {
+        if (cnt[k] < 2) { out[k] = nanv; continue; }                        // sd() of < 2 values is NA in R
+        const double mean = xf_to_double(XM[k]);
+        const double sdv = sqrt(xf_to_double(xf_div(SS[k], xf_from_int(cnt[k] - 1))));
+        out[k] = __dsub_rn(mean, __dmul_rn(sd_frac, sdv));
+    }
+    r_hit[r] = out[0];
+    r_miss[r] = out[1];
+}
+
+// surf radii (:456-481), exact for N <= 1024: one thread replays mean()/sd() of the concatenated hit and miss vectors
+__global__ void surf_hitmiss_serial_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, const double *__restrict__ y,
+                                           double sd_frac, double *__restrict__ out2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int k = 0; k < 2; ++k) {
+        xf80 s = xf_zero(); int64_t c = 0;
+        for (int64_t i = 0; i < N; ++i) for (int64_t j = 0; j < N; ++j) {
+            const bool same = y[j] == y[i];
+            if (k == 0 ? (same && j != i) : !same) { s = xf_add(s, xf_from_double(D[i * ldd + j])); c++; }
+        }
+        xf80 t = xf_div(s, xf_from_int(c));
+        s = xf_zero();
+        for (int64_t i = 0; i < N; ++i) for (int64_t j = 0; j < N; ++j) {
+            const bool same = y[j] == y[i];
+            if (k == 0 ? (same && j != i) : !same) s = xf_add(s, xf_sub(xf_from_double(D[i * ldd + j]), t));
+        }
+        t = xf_add(t, xf_div(s, xf_from_int(c)));
+        const double mean = xf_to_double(t);
+        const xf80 xm = xf_from_double(mean);
+        s = xf_zero();
+        for (int64_t i = 0; i < N; ++i) for (int64_t j = 0; j < N; ++j) {
+            const bool same = y[j] == y[i];
+            if (k == 0 ? (same && j != i) : !same) { xf80 d = xf_sub(xf_from_double(D[i * ldd + j]), xm); s = xf_add(s, xf_mul(d, d)); }
+        }
+        const double var = xf_to_double(xf_div(s, xf_from_int(c - 1)));
+        out2[k] = __dsub_rn(mean, __dmul_rn(sd_frac, sqrt(var)));
+    }
+}
+// large N: per-row moments in double (<= few ulp from the sequential chain); out: nrows x 6 =
+// sum_hit, cnt_hit, ss_hit(centre_hit), sum_miss, cnt_miss, ss_miss(centre_miss)
+__global__ void surf_hitmiss_moments_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t row0, int64_t nrows,
+                                            const double *__restrict__ y, double ch, double cm, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nrows) return;
+    const int64_t g = row0 + r;
+    const double yg = y[g];
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t j = lane; j < N; j += 32) {
+        const double d = D[r * ldd + j];
+        const bool same = y[j] == yg;
+        if (same && j == g) continue;
+        if (same) { v[0] += d; v[1] += 1.0; v[2] += (d - ch) * (d - ch); }
+        else { v[3] += d; v[4] += 1.0; v[5] += (d - cm) * (d - cm); }
+    }
+    for (int k = 0; k < 6; ++k) for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) for (int k = 0; k < 6; ++k) out[r * 6 + k] = v[k];
+}
+
+// threshold selection (:529-533): hits = same class & d < r_hit & d > 0, then misses = other class & d < r_miss
+__global__ void count_hitmiss_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t row0, int64_t nrows,
+                                     const double *__restrict__ y, const double *__restrict__ r_hit, const double *__restrict__ r_miss,
+                                     int scalar, int64_t *__restrict__ counts, int32_t *__restrict__ n_hits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nrows) return;
+    const double rh = scalar ? r_hit[0] : r_hit[r], rm = scalar ? r_miss[0] : r_miss[r], yg = y[row0 + r];
+    const double *row = D + r * ldd;
+    int ch = 0, cm = 0;
+    for (int64_t j = lane; j < N; j += 32) {
+        const double v = row[j];
+        const bool same = y[j] == yg;
+        ch += (same && v < rh && v > 0.0) ? 1 : 0;
+        cm += (!same && v < rm) ? 1 : 0;
+    }
+    for (int o = 16; o; o >>= 1) { ch += __shfl_xor_sync(0xffffffffu, ch, o); cm += __shfl_xor_sync(0xffffffffu, cm, o); }
+    if (lane == 0) { counts[r] = ch + cm; n_hits[r] = ch; }
+}
+__global__ void write_hitmiss_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t row0, int64_t nrows,
+                                     const double *__restrict__ y, const double *__restrict__ r_hit, const double *__restrict__ r_miss,
+                                     int scalar, const int64_t *__restrict__ ptr, const int32_t *__restrict__ n_hits,
+                                     int32_t *__restrict__ Ri, int32_t *__restrict__ NN) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nrows) return;
+    const double rh = scalar ? r_hit[0] : r_hit[r], rm = scalar ? r_miss[0] : r_miss[r], yg = y[row0 + r];
+    const double *row = D + r * ldd;
+    int64_t oh = ptr[r], om = ptr[r] + n_hits[r];
+    const int32_t ri = (int32_t)(row0 + r + 1);
+    for (int64_t j0 = 0; j0 < N; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const double v = (j < N) ? row[j] : 0.0;
+        const bool same = (j < N) && (y[j] == yg);
+        const bool sh = (j < N) && same && v < rh && v > 0.0;
+        const bool sm = (j < N) && !same && v < rm;
+        const unsigned mh = __ballot_sync(0xffffffffu, sh), mm = __ballot_sync(0xffffffffu, sm);
+        const unsigned lt = (1u << lane) - 1u;
+        if (sh) { int64_t pos = oh + __popc(mh & lt); Ri[pos] = ri; NN[pos] = (int32_t)(j + 1); }
+        if (sm) { int64_t pos = om + __popc(mm & lt); Ri[pos] = ri; NN[pos] = (int32_t)(j + 1); }
+        oh += __popc(mh); om += __popc(mm);
+    }
+}
+
+// relieff (:385-427): order(d[Ri, ]) restricted to the hits / to the misses; neighbours = hits[2:(k.hits+1)], misses[1:k.miss].
+// One CTA per owned row.  For each class subset: 8-pass radix select of the rank-n key, gather everything below the cut,
+// then as many cut-valued entries as still needed in ascending index order (order() breaks ties by index), bitonic sort
+// by (key, index), write.  n <= RH_CAP entries per subset.
+constexpr int RH_CAP = 8192;
+__device__ void hm_select_sorted(const double *__restrict__ row, const double *__restrict__ y, double yg, bool want_same,
+                                 int64_t N, int n_want, uint64_t *skeys, int32_t *sidx, unsigned *hist, int *n_out) {
+    __shared__ uint64_t prefix_s, mask_s;
+    __shared__ int64_t rank_s;
+    __shared__ int fill_s, need_s, wsum[8];
+    if (threadIdx.x == 0) { prefix_s = 0; mask_s = 0; rank_s = n_want; fill_s = 0; }
+    __syncthreads();
+    if (n_want <= 0) { if (threadIdx.x == 0) *n_out = 0; __syncthreads(); return; }
+    for (int pass = 7; pass >= 0; --pass) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint64_t prefix = prefix_s, mask = mask_s;
+        const int shift = pass * 8;
+        for (int64_t j = threadIdx.x; j < N; j += 256) {
+            if ((y[j] == yg) != want_same) continue;
+            uint64_t key = dkey(row[j]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int64_t rank = rank_s, cum = 0;
+            int b = 0;
+            for (; b < 256; ++b) { if (cum + hist[b] >= rank) break; cum += hist[b]; }
+            rank_s = rank - cum;
+            prefix_s = prefix | ((uint64_t)b << shift);
+            mask_s = mask | (0xFFull << shift);
+        }
+        __syncthreads();
+    }
+    const uint64_t cut = prefix_s;
+    for (int64_t j = threadIdx.x; j < N; j += 256) {               // strictly below the cut: all of them (< n_want)
+        if ((y[j] == yg) != want_same) continue;
+        uint64_t key = dkey(row[j]);
+        if (key < cut) { int pos = atomicAdd(&fill_s, 1); skeys[pos] = key; sidx[pos] = (int32_t)(j + 1); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) need_s = n_want - fill_s;
+    __syncthreads();
+    // cut-valued entries in ascending index order until n_want is reached (ordered block compaction)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t base = 0; base < N && need_s > 0; base += 256) {
+        const int64_t j = base + threadIdx.x;
+        const bool f = (j < N) && ((y[j] == yg) == want_same) && (dkey(row[j]) == cut);
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[w] = __popc(m);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int i = 0; i < 8; ++i) { if (i < w) off += wsum[i]; tot += wsum[i]; }
+        const int pos = off + __popc(m & ((1u << lane) - 1u));
+        const int need = need_s, fill = fill_s;
+        if (f && pos < need) { skeys[fill + pos] = cut; sidx[fill + pos] = (int32_t)(j + 1); }
+        __syncthreads();
+        if (threadIdx.x == 0) { const int take = tot < need ? tot : need; fill_s = fill + take; need_s = need - take; }
+        __syncthreads();
+    }
+    const int n = fill_s;
+    bitonic_sort(skeys, sidx, n);
+    if (threadIdx.x == 0) *n_out = n;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+relieff_hitmiss_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t row0, int64_t nrows,
+                       const double *__restrict__ y, double y_first, int kh_first, int km_first, int kh_other, int km_other,
+                       const int64_t *__restrict__ ptr, int32_t *__restrict__ Ri, int32_t *__restrict__ NN) {
+    extern __shared__ unsigned char sm_raw[];
+    uint64_t *skeys = (uint64_t *)sm_raw;
+    int32_t *sidx = (int32_t *)(skeys + RH_CAP);
+    __shared__ unsigned hist[256];
+    __shared__ int n_sel;
+    const int64_t r = blockIdx.x;
+    const double *row = D + r * ldd;
+    const double yg = y[row0 + r];
+    const int kh = (yg == y_first) ? kh_first : kh_other, km = (yg == y_first) ? km_first : km_other;
+    int64_t off = ptr[r];
+    const int32_t ri = (int32_t)(row0 + r + 1);
+    hm_select_sorted(row, y, yg, true, N, kh + 1, skeys, sidx, hist, &n_sel);       // hits incl. the first of the order (self)
+    int n = n_sel;
+    for (int t = threadIdx.x + 1; t < n; t += 256) { Ri[off + t - 1] = ri; NN[off + t - 1] = sidx[t]; }   // hits[2:(k.hits+1)]
+    off += (n > 0 ? n - 1 : 0);
+    __syncthreads();
+    hm_select_sorted(row, y, yg, false, N, km, skeys, sidx, hist, &n_sel);          // misses[1:k.miss]
+    n = n_sel;
+    for (int t = threadIdx.x; t < n; t += 256) { Ri[off + t] = ri; NN[off + t] = sidx[t]; }
+}
+
 __global__ void diff_vectors_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t n, int type,
                                     double norm_fac, double *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -525,6 +772,146 @@ int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k
         }
     }
     cudaFree(d_counts); cudaFree(d_nempty);
+    s->M_local = tot[0];
+    s->n_empty_local = tot[1];
+    if (M_local) *M_local = tot[0];
+    if (n_empty) *n_empty = tot[1];
+    NB_CUDA(cudaEventRecord(s->ev[1], ctx->stream));
+    NB_CUDA(cudaEventSynchronize(s->ev[1]));
+    float ms = 0;
+    NB_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+    s->ms_neighbors = ms;
+    return NPDRB_OK;
+}
+
+// nearestNeighborsSeparateHitMiss on the owned rows (uses the session's outcome vector as class labels)
+int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local, int64_t *n_empty) {
+    npdrb_ctx *ctx = s->ctx;
+    (void)k;                                                     // the reference uses k only through sd.frac (:385-393)
+    if (!s->dD) { npdrb_set_error("neighbors_hitmiss: compute or set distances first"); return NPDRB_EINVAL; }
+    if (!s->dy) { npdrb_set_error("neighbors_hitmiss: the outcome (class labels) is not set"); return NPDRB_EINVAL; }
+    if (nbd_method < 0 || nbd_method > NPDRB_NBD_RELIEFF) { npdrb_set_error("neighbors_hitmiss: bad nbd_method"); return NPDRB_EINVAL; }
+    const int64_t N = s->N, nrows = s->nrows;
+    if (N < 4) { npdrb_set_error("neighbors_hitmiss: need at least 4 instances"); return NPDRB_EINVAL; }
+    NB_CUDA(cudaEventRecord(s->ev[0], ctx->stream));
+    // class sizes (two classes; the reference's table(pheno.vec))
+    std::vector<double> hy((size_t)N);
+    NB_CUDA(cudaMemcpyAsync(hy.data(), s->dy, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double y_first = hy[0];
+    int64_t n_first = 0;
+    for (int64_t i = 0; i < N; ++i) n_first += (hy[(size_t)i] == y_first) ? 1 : 0;
+    const int64_t n_other = N - n_first;
+    if (n_first == 0 || n_other == 0) { npdrb_set_error("neighbors_hitmiss: the outcome has a single class"); return NPDRB_EDATA; }
+
+    if (s->dRiL) { cudaFree(s->dRiL); s->dRiL = nullptr; }
+    if (s->dNNL) { cudaFree(s->dNNL); s->dNNL = nullptr; }
+    if (!s->d_radius) NB_CUDA(cudaMalloc(&s->d_radius, sizeof(double) * (size_t)N));
+    if (!s->d_radius2) NB_CUDA(cudaMalloc(&s->d_radius2, sizeof(double) * (size_t)N));
+    if (!s->d_rowptr) NB_CUDA(cudaMalloc(&s->d_rowptr, sizeof(int64_t) * (size_t)(N + 2)));
+    int64_t tot[2] = {0, 0};
+    if (nbd_method == NPDRB_NBD_RELIEFF) {
+        int64_t kh[2], km[2];                                    // [class of y_first, other class]
+        if (n_first == n_other) {
+            kh[0] = kh[1] = km[0] = km[1] = (int64_t)floor(0.5 * (double)npdrb_knn_surf(N - 1, sd_frac));
+        } else {
+            kh[0] = npdrb_knn_surf(n_first - 1, sd_frac); km[0] = npdrb_knn_surf(n_other, sd_frac);
+            kh[1] = npdrb_knn_surf(n_other - 1, sd_frac); km[1] = npdrb_knn_surf(n_first, sd_frac);
+        }
+        for (int c = 0; c < 2; ++c) {
+            const int64_t nh = c == 0 ? n_first : n_other, nm = N - nh;
+            if (kh[c] + 1 > nh) kh[c] = nh - 1;                  // positions past the end of the list are dropped (R: NA)
+            if (km[c] > nm) km[c] = nm;
+            if (kh[c] < 0) kh[c] = 0;
+            if (kh[c] + 1 > RH_CAP || km[c] > RH_CAP) { npdrb_set_error("neighbors_hitmiss: k.hits/k.miss above %d not supported", RH_CAP - 1); return NPDRB_EINVAL; }
+        }
+        std::vector<int64_t> hptr((size_t)nrows + 1);
+        int64_t run = 0, empty = 0;
+        for (int64_t r = 0; r < nrows; ++r) {
+            const int c = (hy[(size_t)(s->row0 + r)] == y_first) ? 0 : 1;
+            hptr[(size_t)r] = run;
+            const int64_t cnt = kh[c] + km[c];
+            if (cnt == 0) empty++;
+            run += cnt;
+        }
+        hptr[(size_t)nrows] = run;
+        tot[0] = run; tot[1] = empty;
+        NB_CUDA(cudaMemcpyAsync(s->d_rowptr, hptr.data(), sizeof(int64_t) * hptr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        NB_CUDA(cudaMalloc(&s->dRiL, sizeof(int32_t) * (size_t)(run > 0 ? run : 1)));
+        NB_CUDA(cudaMalloc(&s->dNNL, sizeof(int32_t) * (size_t)(run > 0 ? run : 1)));
+        const size_t smem = (size_t)RH_CAP * (sizeof(uint64_t) + sizeof(int32_t));
+        NB_CUDA(cudaFuncSetAttribute(relieff_hitmiss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        relieff_hitmiss_kernel<<<(unsigned)nrows, 256, smem, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows, s->dy, y_first,
+                                                                            (int)kh[0], (int)km[0], (int)kh[1], (int)km[1],
+                                                                            s->d_rowptr, s->dRiL, s->dNNL);
+        NB_LAUNCH_CHECK(ctx);
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+        int scalar = 0;
+        if (nbd_method == NPDRB_NBD_MULTISURF) {
+            radius_hitmiss_kernel<<<(unsigned)nb_cdiv(nrows, 128), 128, 0, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows, s->dy,
+                                                                                        sd_frac, s->d_radius, s->d_radius2);
+            NB_LAUNCH_CHECK(ctx);
+        } else {
+            scalar = 1;
+            if (nrows != N) { npdrb_set_error("surf hit/miss radii on a row block are not supported"); return NPDRB_EINVAL; }
+            double *d_two = nullptr;
+            NB_CUDA(cudaMalloc(&d_two, sizeof(double) * 2));
+            double two[2];
+            if (N <= 1024) {
+                surf_hitmiss_serial_kernel<<<1, 32, 0, ctx->stream>>>(s->dD, s->ldd, N, s->dy, sd_frac, d_two);
+                NB_LAUNCH_CHECK(ctx);
+                NB_CUDA(cudaMemcpyAsync(two, d_two, sizeof(two), cudaMemcpyDeviceToHost, ctx->stream));
+                NB_CUDA(cudaStreamSynchronize(ctx->stream));
+            } else {                                             // parallel moments (documented deviation, <= few ulp)
+                double *d_m = nullptr;
+                NB_CUDA(cudaMalloc(&d_m, sizeof(double) * 6 * (size_t)nrows));
+                std::vector<double> hm(6 * (size_t)nrows);
+                double centre[2] = {0.0, 0.0};
+                long double acc[6];
+                for (int round = 0; round < 2; ++round) {
+                    surf_hitmiss_moments_kernel<<<(unsigned)nb_cdiv(nrows, 8), 256, 0, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows,
+                                                                                                    s->dy, centre[0], centre[1], d_m);
+                    NB_LAUNCH_CHECK(ctx);
+                    NB_CUDA(cudaMemcpyAsync(hm.data(), d_m, sizeof(double) * hm.size(), cudaMemcpyDeviceToHost, ctx->stream));
+                    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+                    for (int q6 = 0; q6 < 6; ++q6) acc[q6] = 0;
+                    for (int64_t r = 0; r < nrows; ++r) for (int q6 = 0; q6 < 6; ++q6) acc[q6] += hm[(size_t)r * 6 + q6];
+                    centre[0] = (double)(acc[0] / acc[1]); centre[1] = (double)(acc[3] / acc[4]);
+                }
+                two[0] = centre[0] - sd_frac * sqrt((double)(acc[2] / (acc[1] - 1)));
+                two[1] = centre[1] - sd_frac * sqrt((double)(acc[5] / (acc[4] - 1)));
+                cudaFree(d_m);
+            }
+            cudaFree(d_two);
+            std::vector<double> rep((size_t)nrows, two[0]), rep2((size_t)nrows, two[1]);
+            NB_CUDA(cudaMemcpyAsync(s->d_radius, rep.data(), sizeof(double) * rep.size(), cudaMemcpyHostToDevice, ctx->stream));
+            NB_CUDA(cudaMemcpyAsync(s->d_radius2, rep2.data(), sizeof(double) * rep2.size(), cudaMemcpyHostToDevice, ctx->stream));
+            NB_CUDA(cudaStreamSynchronize(ctx->stream));
+            scalar = 0;                                          // radii are replicated per row
+        }
+        int64_t *d_counts = nullptr, *d_nempty = nullptr; int32_t *d_nh = nullptr;
+        NB_CUDA(cudaMalloc(&d_counts, sizeof(int64_t) * (size_t)nrows));
+        NB_CUDA(cudaMalloc(&d_nempty, sizeof(int64_t)));
+        NB_CUDA(cudaMalloc(&d_nh, sizeof(int32_t) * (size_t)nrows));
+        const unsigned wgrid = (unsigned)nb_cdiv(nrows, 8);
+        count_hitmiss_kernel<<<wgrid, 256, 0, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows, s->dy, s->d_radius, s->d_radius2, scalar,
+                                                             d_counts, d_nh);
+        NB_LAUNCH_CHECK(ctx);
+        scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, nrows, s->d_rowptr, d_nempty);
+        NB_LAUNCH_CHECK(ctx);
+        NB_CUDA(cudaMemcpyAsync(&tot[0], s->d_rowptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NB_CUDA(cudaMemcpyAsync(&tot[1], d_nempty, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int64_t M = tot[0];
+        NB_CUDA(cudaMalloc(&s->dRiL, sizeof(int32_t) * (size_t)(M > 0 ? M : 1)));
+        NB_CUDA(cudaMalloc(&s->dNNL, sizeof(int32_t) * (size_t)(M > 0 ? M : 1)));
+        write_hitmiss_kernel<<<wgrid, 256, 0, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows, s->dy, s->d_radius, s->d_radius2, scalar,
+                                                             s->d_rowptr, d_nh, s->dRiL, s->dNNL);
+        NB_LAUNCH_CHECK(ctx);
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_counts); cudaFree(d_nempty); cudaFree(d_nh);
+    }
     s->M_local = tot[0];
     s->n_empty_local = tot[1];
     if (M_local) *M_local = tot[0];

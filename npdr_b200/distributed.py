@@ -47,8 +47,9 @@ class Engine:
     """Per-rank compute interface used by npdr_sharded()."""
     device = torch.device("cpu")
 
-    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k):
-        """-> (Ri, NN) int32 tensors on self.device for the owned rows (1-based, reference order)."""
+    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k, hitmiss=False):
+        """-> (Ri, NN) int32 tensors on self.device for the owned rows (1-based, reference order).
+        hitmiss: separate hit/miss neighbourhoods (nearestNeighborsSeparateHitMiss)."""
         raise NotImplementedError
 
     def surf_partial(self, row0, nrows, nbd_metric, centre):
@@ -80,7 +81,7 @@ def all_gather_varlen(t, group=None):
 
 def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numeric-abs", nbd_method="multisurf",
                  nbd_metric="manhattan", knn=0, msurf_sd_frac=0.5, covar_diff_type=(), neighbor_sampling="none",
-                 group=None):
+                 group=None, separate_hitmiss_nbds=False):
     """Run the path sharded over the default process group.  Every rank returns
     (stats [p, 8] on rank 0 else None, info dict)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -88,6 +89,8 @@ def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numer
     row0, nrows = partition_rows(N, world)[rank]
     dev = engine.device
 
+    if nbd_method == "surf" and separate_hitmiss_nbds and world > 1:
+        raise NotImplementedError("surf hit/miss radii need the whole distance matrix on one device")
     if nbd_method == "surf" and world > 1:
         # one global mean / sd: two scalar all-reduces (R/nearestNeighbors.R:234-241)
         m0 = torch.tensor(engine.surf_partial(row0, nrows, nbd_metric, 0.0) if nrows else [0.0] * 4, dtype=torch.float64, device=dev)
@@ -100,7 +103,7 @@ def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numer
         engine.set_surf_radius(radius)
 
     if nrows > 0:
-        ri, nn = engine.neighbors_block(row0, nrows, nbd_method, nbd_metric, msurf_sd_frac, knn)
+        ri, nn = engine.neighbors_block(row0, nrows, nbd_method, nbd_metric, msurf_sd_frac, knn, separate_hitmiss_nbds)
     else:
         ri = torch.zeros(0, dtype=torch.int32, device=dev); nn = torch.zeros(0, dtype=torch.int32, device=dev)
     if world > 1:
@@ -154,9 +157,9 @@ class GpuEngine(Engine):
             self.session.distances(nbd_metric, False, row0, nrows)
             self._metric_done = key
 
-    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k):
+    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k, hitmiss=False):
         self._ensure_distances(row0, nrows, nbd_metric)
-        M, _ = self.session.neighbors(nbd_method, sd_frac, k)
+        M, _ = (self.session.neighbors_hitmiss if hitmiss else self.session.neighbors)(nbd_method, sd_frac, k)
         ri = torch.empty(max(M, 1), dtype=torch.int32, device=self.device)[:M]
         nn = torch.empty(max(M, 1), dtype=torch.int32, device=self.device)[:M]
         if M:

@@ -278,6 +278,112 @@ int orc_neighbors(const double *D, int64_t N, int method, int64_t k, const doubl
     return ORC_OK;
 }
 
+/* nearestNeighborsSeparateHitMiss, R/nearestNeighbors.R:318-551 (npdr(separate.hitmiss.nbds = TRUE), R/npdr.R:215-251).
+ * Same distance matrix; hit and miss neighbourhoods are formed separately and listed hits first, then misses.
+ *  multisurf (:483-500): per Ri, radius_hit = mean(d[hits, not self]) - sd.frac*sd(same), radius_miss likewise over misses
+ *                        (base-R mean(): long double two-pass; sd(): cov.c as in r_var);
+ *  surf (:456-481):      one hit radius from the concatenation over i of d[i, hits(i) without self], one miss radius;
+ *  selection (:529-533): hits = same class & d < r_hit & d > 0; misses = other class & d < r_miss (no d > 0 test), each ascending j;
+ *  relieff (:385-427):   order(d[Ri, ]) (stable), hits = that order restricted to the class of Ri, misses = the rest;
+ *                        balanced classes: k.hits = k.miss = floor(0.5*knnSURF(N-1, sd.frac)); else knnSURF(m.hits), knnSURF(m.miss)
+ *                        with m.hits = #hits incl. self - 1; neighbours = hits[2:(k.hits+1)] then misses[1:k.miss].
+ *                        (k is only used through sd.frac; positions past the end of a list are dropped here, R would yield NA.)
+ * pheno: class labels as doubles (as.numeric(as.character(pheno.vec)) in the reference). */
+static double r_mean_skip(const double *x, const uint8_t *use, int64_t n, int64_t *cnt_out) {
+    long double s = 0.0L; int64_t c = 0;
+    for (int64_t i = 0; i < n; ++i) if (use[i]) { s += x[i]; c++; }
+    s /= c;
+    long double t = 0.0L;
+    for (int64_t i = 0; i < n; ++i) if (use[i]) t += (x[i] - s);
+    s += t / c;
+    if (cnt_out) *cnt_out = c;
+    return (double)s;
+}
+static double r_var_mask(const double *x, const uint8_t *use, int64_t n) {
+    int64_t c = 0;
+    long double xm = r_mean_skip(x, use, n, &c);           /* identical recipe to cov.c MEAN_ */
+    long double sum = 0.0L;
+    for (int64_t k = 0; k < n; ++k) if (use[k]) sum += (x[k] - xm) * (x[k] - xm);
+    return (double)(sum / (c - 1));
+}
+
+int orc_radius_hitmiss_multisurf(const double *D, int64_t N, const double *pheno, double sd_frac,
+                                 double *r_hit, double *r_miss) {
+#pragma omp parallel
+    {
+        uint8_t *use = (uint8_t *)malloc((size_t)N);
+#pragma omp for schedule(static)
+        for (int64_t c = 0; c < N; ++c) {
+            const double *col = D + c * N;                 /* dist.mat[i, ] == column i (symmetric) */
+            for (int64_t j = 0; j < N; ++j) use[j] = (uint8_t)(j != c && pheno[j] == pheno[c]);
+            r_hit[c] = r_mean_skip(col, use, N, NULL) - sd_frac * sqrt(r_var_mask(col, use, N));
+            for (int64_t j = 0; j < N; ++j) use[j] = (uint8_t)(pheno[j] != pheno[c]);
+            r_miss[c] = r_mean_skip(col, use, N, NULL) - sd_frac * sqrt(r_var_mask(col, use, N));
+        }
+        free(use);
+    }
+    return ORC_OK;
+}
+
+int orc_radius_hitmiss_surf(const double *D, int64_t N, const double *pheno, double sd_frac, double *r_hit, double *r_miss) {
+    double *h = (double *)malloc(sizeof(double) * (size_t)N * (size_t)N), *m = (double *)malloc(sizeof(double) * (size_t)N * (size_t)N);
+    uint8_t *use = (uint8_t *)malloc((size_t)N * (size_t)N);
+    if (!h || !m || !use) return ORC_ENOMEM;
+    int64_t nh = 0, nm = 0;
+    for (int64_t i = 0; i < N; ++i)                         /* unlist(list of rows): row i, ascending j */
+        for (int64_t j = 0; j < N; ++j) {
+            if (j != i && pheno[j] == pheno[i]) h[nh++] = D[i * N + j];
+            if (pheno[j] != pheno[i]) m[nm++] = D[i * N + j];
+        }
+    memset(use, 1, (size_t)N * (size_t)N);
+    *r_hit = r_mean_skip(h, use, nh, NULL) - sd_frac * sqrt(r_var_mask(h, use, nh));
+    *r_miss = r_mean_skip(m, use, nm, NULL) - sd_frac * sqrt(r_var_mask(m, use, nm));
+    free(h); free(m); free(use);
+    return ORC_OK;
+}
+
+int orc_neighbors_hitmiss(const double *D, int64_t N, const double *pheno, int method, double sd_frac,
+                          const double *r_hit, const double *r_miss,
+                          int32_t **Ri_out, int32_t **NN_out, int64_t *M_out) {
+    int64_t cap = 1024, M = 0;
+    int32_t *Ri = (int32_t *)malloc(sizeof(int32_t) * cap), *NN = (int32_t *)malloc(sizeof(int32_t) * cap);
+    dj_t *buf = (dj_t *)malloc(sizeof(dj_t) * (size_t)(N > 0 ? N : 1));
+    if (!Ri || !NN || !buf) return ORC_ENOMEM;
+#define ORC_PUSH(c_, j_) do { if (M == cap) { cap *= 2; Ri = realloc(Ri, sizeof(int32_t) * cap); NN = realloc(NN, sizeof(int32_t) * cap); \
+        if (!Ri || !NN) return ORC_ENOMEM; } Ri[M] = (int32_t)((c_) + 1); NN[M] = (int32_t)((j_) + 1); ++M; } while (0)
+    /* class balance: table(as.character(pheno.vec)) with two classes */
+    int64_t n_first = 0;
+    for (int64_t i = 0; i < N; ++i) if (pheno[i] == pheno[0]) n_first++;
+    const int balanced = (2 * n_first == N);
+    for (int64_t c = 0; c < N; ++c) {
+        const double *col = D + c * N;
+        if (method == ORC_NBD_RELIEFF) {
+            for (int64_t j = 0; j < N; ++j) { buf[j].d = col[j]; buf[j].j = (int32_t)j; }
+            qsort(buf, (size_t)N, sizeof(dj_t), cmp_dj);            /* order(): ascending, ties by index */
+            int64_t n_hits = 0, n_miss = 0;
+            for (int64_t j = 0; j < N; ++j) { if (pheno[j] == pheno[c]) n_hits++; else n_miss++; }
+            int64_t k_hits, k_miss;
+            if (balanced) { k_hits = (int64_t)floor(0.5 * (double)orc_knn_surf(N - 1, sd_frac)); k_miss = k_hits; }
+            else { k_hits = orc_knn_surf(n_hits - 1, sd_frac); k_miss = orc_knn_surf(n_miss, sd_frac); }
+            int64_t seen = 0;
+            for (int64_t t = 0; t < N && seen < k_hits + 1; ++t)
+                if (pheno[buf[t].j] == pheno[c]) { seen++; if (seen >= 2) ORC_PUSH(c, buf[t].j); }     /* hits[2:(k.hits+1)] */
+            seen = 0;
+            for (int64_t t = 0; t < N && seen < k_miss; ++t)
+                if (pheno[buf[t].j] != pheno[c]) { seen++; ORC_PUSH(c, buf[t].j); }
+        } else {
+            const double rh = (method == ORC_NBD_SURF) ? r_hit[0] : r_hit[c];
+            const double rm = (method == ORC_NBD_SURF) ? r_miss[0] : r_miss[c];
+            for (int64_t j = 0; j < N; ++j) if (pheno[j] == pheno[c] && col[j] < rh && col[j] > 0) ORC_PUSH(c, j);
+            for (int64_t j = 0; j < N; ++j) if (pheno[j] != pheno[c] && col[j] < rm) ORC_PUSH(c, j);
+        }
+    }
+#undef ORC_PUSH
+    free(buf);
+    *Ri_out = Ri; *NN_out = NN; *M_out = M;
+    return ORC_OK;
+}
+
 void orc_free(void *p) { free(p); }
 
 /* uniqueNeighbors, R/nearestNeighbors.R:572-583: key = "min,max"; keep rows that are

@@ -136,6 +136,31 @@ def nearest_neighbors(X, nbd_method="multisurf", nbd_metric="manhattan", sd_frac
     return ri, nn, D, r
 
 
+def nearest_neighbors_hitmiss(X, pheno, nbd_method="relieff", nbd_metric="manhattan", sd_frac=0.5, k=0):
+    """nearestNeighborsSeparateHitMiss(), R/nearestNeighbors.R:318-551 -> (Ri, NN, D, r_hit, r_miss)."""
+    D = _f64(X) if nbd_metric == "precomputed" else distances(X, nbd_metric)
+    N = D.shape[0]
+    ph = _f64(np.asarray(pheno, dtype=np.float64))
+    rh = np.zeros(N); rm = np.zeros(N)
+    if nbd_method == "multisurf":
+        rc = lib().orc_radius_hitmiss_multisurf(_d(D), C.c_int64(N), _d(ph), C.c_double(sd_frac), _d(rh), _d(rm))
+        assert rc == 0
+    elif nbd_method == "surf":
+        a = C.c_double(); b = C.c_double()
+        rc = lib().orc_radius_hitmiss_surf(_d(D), C.c_int64(N), _d(ph), C.c_double(sd_frac), C.byref(a), C.byref(b))
+        assert rc == 0
+        rh[:] = a.value; rm[:] = b.value
+    Ri = _ip(); NN = _ip(); M = C.c_int64()
+    rc = lib().orc_neighbors_hitmiss(_d(D), C.c_int64(N), _d(ph), C.c_int(NBD[nbd_method]), C.c_double(sd_frac), _d(rh), _d(rm),
+                                     C.byref(Ri), C.byref(NN), C.byref(M))
+    assert rc == 0
+    m = M.value
+    ri = np.ctypeslib.as_array(Ri, shape=(max(m, 1),))[:m].copy()
+    nn = np.ctypeslib.as_array(NN, shape=(max(m, 1),))[:m].copy()
+    lib().orc_free(Ri); lib().orc_free(NN)
+    return ri, nn, D, rh, rm
+
+
 def unique_neighbors(Ri, NN, N):
     Ri = np.ascontiguousarray(Ri, dtype=np.int32); NN = np.ascontiguousarray(NN, dtype=np.int32)
     keep = np.zeros(Ri.size, dtype=np.uint8)

@@ -32,7 +32,6 @@ npdr <- function(outcome, dataset, regression.type = "binomial", attr.diff.type 
                  unique.dof = FALSE, external.dist = NULL) {
   if (use.glmnet) stop("npdr_b200: use.glmnet = TRUE is not accelerated; call the reference npdr()")
   if (attr.diff.type == "correlation-data") stop("npdr_b200: correlation-data is not accelerated")
-  if (separate.hitmiss.nbds) stop("npdr_b200: separate.hitmiss.nbds is not accelerated yet")
   if (length(outcome) == 1) {                                   # R/npdr.R:166-173
     pheno.vec <- dataset[, outcome]
     attr.mat <- dataset[, setdiff(if (is.character(outcome)) colnames(dataset) else seq_len(ncol(dataset)), outcome), drop = FALSE]
@@ -47,7 +46,8 @@ npdr <- function(outcome, dataset, regression.type = "binomial", attr.diff.type 
     C <- as.matrix(covars); ncov <- length(covar.diff.type); C <- C[, seq_len(ncov), drop = FALSE] + 0
   }
   io <- c(.reg_code[[regression.type]], .diff_code[[attr.diff.type]], .nbd_code[[nbd.method]], .metric_code[[nbd.metric]],
-          as.integer(knn), ncov, as.integer(neighbor.sampling == "unique"), .diff_code[covar.diff.type])
+          as.integer(knn), ncov, as.integer(neighbor.sampling == "unique"), as.integer(separate.hitmiss.nbds),
+          .diff_code[covar.diff.type])
   r <- .Call("C_npdrb_npdr", unname(X) + 0, y, C, as.integer(io), msurf.sd.frac, PACKAGE = "npdrb200")
   s <- t(r$stats)                                               # p x 8: beta_a, stat_a, beta_0, stat_0, df, r2|dev, iters, flags
   res.df <- if (unique.dof) r$n_unique_pairs - 2 else s[, 5]    # R/npdr.R:419-423

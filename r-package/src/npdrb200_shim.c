@@ -61,10 +61,10 @@ SEXP C_npdrb_npdr(SEXP X, SEXP y, SEXP C, SEXP iopts, SEXP sd_frac) {
     const R_xlen_t N = INTEGER(dim)[0], p = INTEGER(dim)[1];
     npdrb_opts o;
     npdrb_opts_default(&o);
-    const int *io = INTEGER(iopts);     /* regression, attr diff, nbd method, nbd metric, knn, n_covars, unique, covar types... */
+    const int *io = INTEGER(iopts);     /* regression, attr diff, nbd method, nbd metric, knn, n_covars, unique, hit/miss, covar types... */
     o.regression_type = io[0]; o.attr_diff_type = io[1]; o.nbd_method = io[2]; o.nbd_metric = io[3];
-    o.knn = io[4]; o.n_covars = io[5]; o.neighbor_sampling_unique = io[6];
-    for (int c = 0; c < o.n_covars && c < NPDRB_MAX_COVARS; ++c) o.covar_diff_type[c] = io[7 + c];
+    o.knn = io[4]; o.n_covars = io[5]; o.neighbor_sampling_unique = io[6]; o.separate_hitmiss_nbds = io[7];
+    for (int c = 0; c < o.n_covars && c < NPDRB_MAX_COVARS; ++c) o.covar_diff_type[c] = io[8 + c];
     o.msurf_sd_frac = Rf_asReal(sd_frac);
     npdrb_result res;
     int rc = npdrb_npdr(ctx_get(), REAL(X), N, p, REAL(y), Rf_isNull(C) ? NULL : REAL(C), &o, &res);

@@ -28,10 +28,12 @@ class OracleEngine:
             self.D = self.O.distances(self.X, metric)
         return self.D
 
-    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k):
+    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k, hitmiss=False):
         D = self._dist(nbd_metric)
         N = D.shape[0]
-        if nbd_method == "relieff":
+        if hitmiss:
+            ri, nn, _, _, _ = self.O.nearest_neighbors_hitmiss(D, self.y, nbd_method, "precomputed", sd_frac, k)
+        elif nbd_method == "relieff":
             kk = k if k else self.O.knn_surf(N, sd_frac)
             ri, nn, _ = self.O.neighbors(D, "relieff", k=kk)
         elif nbd_method == "surf":
@@ -75,7 +77,7 @@ def _case(seed=0):
     return X, y, C
 
 
-def _worker(rank, world, port, method, q):
+def _worker(rank, world, port, method, q, hitmiss=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import sys
     sys.path.insert(0, ROOT)
@@ -84,7 +86,7 @@ def _worker(rank, world, port, method, q):
     X, y, C = _case()
     eng = OracleEngine(X, y, C)
     stats, info = npdr_sharded(eng, X.shape[0], X.shape[1], "binomial", "numeric-abs", method, "manhattan", 0, 0.5,
-                               ("match-mismatch", "numeric-abs"))
+                               ("match-mismatch", "numeric-abs"), separate_hitmiss_nbds=hitmiss)
     if rank == 0:
         q.put((stats, info))
     dist.barrier()
@@ -96,13 +98,14 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("world,method", [(2, "multisurf"), (3, "multisurf"), (2, "surf"), (2, "relieff")])
-def test_sharded_equals_unsharded(world, method):
+@pytest.mark.parametrize("world,method,hitmiss", [(2, "multisurf", False), (3, "multisurf", False), (2, "surf", False),
+                                                  (2, "relieff", False), (2, "multisurf", True)])
+def test_sharded_equals_unsharded(world, method, hitmiss):
     from oracle import oracle as O
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, method, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, method, q, hitmiss)) for r in range(world)]
     for p_ in procs:
         p_.start()
     stats, info = q.get(timeout=240)
@@ -110,7 +113,10 @@ def test_sharded_equals_unsharded(world, method):
         p_.join(timeout=60)
         assert p_.exitcode == 0
     X, y, C = _case()
-    ri, nn, D, r = O.nearest_neighbors(X, method)
+    if hitmiss:
+        ri, nn, D, _, _ = O.nearest_neighbors_hitmiss(X, y, method)
+    else:
+        ri, nn, D, r = O.nearest_neighbors(X, method)
     assert info["n_pairs"] == ri.size and sum(info["pair_counts"]) == ri.size
     cd = np.column_stack([O.pair_diffs(C[:, 0], ri, nn, "match-mismatch"), O.pair_diffs(C[:, 1], ri, nn, "numeric-abs")])
     exp = O.regress_attrs(X, ri, nn, O.pair_diffs(y, ri, nn, "match-mismatch"), cd)

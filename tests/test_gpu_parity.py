@@ -166,6 +166,39 @@ def test_neighbors_options(nb, oracle):
     assert np.array_equal(out["Ri_idx"], ri) and info["n_empty"] == 120 - np.unique(ri).size
 
 
+@pytest.mark.parametrize("method", ["multisurf", "surf", "relieff"])
+@pytest.mark.parametrize("kind", ["balanced", "imbalanced", "snp"])
+def test_separate_hitmiss_neighbors_bit_exact(nb, oracle, method, kind):
+    """nearestNeighborsSeparateHitMiss: pair list (hits first, then misses) and class-conditional radii vs the oracle."""
+    rng = np.random.default_rng(abs(hash((method, kind))) % 2**32)
+    N, p = 190, 35
+    X = rng.integers(0, 3, size=(N, p)).astype(float) if kind == "snp" else rng.normal(size=(N, p))
+    y = np.zeros(N); y[rng.permutation(N)[: (N // 2 if kind != "imbalanced" else N // 3)]] = 1.0
+    X[y == 1, :3] += 0.8
+    X = np.asfortranarray(X)
+    ri, nn, D, rh, rm = oracle.nearest_neighbors_hitmiss(X, y, method, "manhattan", 0.5)
+    out, info = nb.nearestNeighborsSeparateHitMiss(X, y, method, "manhattan", sd_frac=0.5, return_info=True)
+    assert np.array_equal(out["Ri_idx"].to_numpy(), ri), (method, kind)
+    assert np.array_equal(out["NN_idx"].to_numpy(), nn), (method, kind)
+    if method != "relieff":
+        assert np.array_equal(info["radius_hit"], rh) and np.array_equal(info["radius_miss"], rm)
+    # hits precede misses inside every Ri group
+    hit = (y[ri - 1] == y[nn - 1]).astype(int)
+    for g in np.unique(ri)[:20]:
+        h = hit[ri == g]
+        assert np.all(np.diff(h) <= 0)
+
+
+def test_npdr_separate_hitmiss(nb, oracle):
+    c = load_case("cfg1")
+    for method in ("multisurf", "relieff"):
+        out, info = nb.npdr(c["y"], c["X"], "binomial", nbd_method=method, separate_hitmiss_nbds=True, return_info=True)
+        ri, nn, _, _, _ = oracle.nearest_neighbors_hitmiss(c["X"], c["y"], method)
+        assert np.array_equal(info["Ri"], ri) and np.array_equal(info["NN"], nn)
+        exp = oracle.regress_attrs(c["X"], ri, nn, oracle.pair_diffs(c["y"], ri, nn, "match-mismatch"))
+        _stats_close(info["stats"], exp, RTOL_IRLS, f"hitmiss {method}")
+
+
 def test_surf_large_n_close(nb, oracle):
     """N > 1024: the SURF radius comes from parallel moments (<= 1 ulp-level deviation)."""
     rng = np.random.default_rng(12)

@@ -85,7 +85,7 @@ def test_unsupported_branches_raise():
     with pytest.raises(NotImplementedError):
         nb.npdr(y, X, attr_diff_type="correlation-data")
     with pytest.raises(NotImplementedError):
-        nb.npdr(y, X, separate_hitmiss_nbds=True)
+        nb.npdr(y, X, separate_hitmiss_nbds=True, rm_attr_from_dist=["1"])
     with pytest.raises(ValueError):
         nb.npdr(y, X, regression_type="poisson")
     with pytest.raises(ValueError):

@@ -94,6 +94,32 @@ def test_neighbors_semantics(oracle):
     assert 8 not in nn[ri == 4] and 4 not in nn[ri == 8]                         # duplicates dropped by filter(> 0)
 
 
+def test_hitmiss_neighbors_semantics(oracle):
+    """nearestNeighborsSeparateHitMiss restated independently in numpy (R/nearestNeighbors.R:318-551)."""
+    rng = np.random.default_rng(8)
+    N = 60
+    X = np.asfortranarray(rng.normal(size=(N, 15)))
+    y = (np.arange(N) % 3 == 0).astype(float)                                    # imbalanced 20 / 40
+    D = oracle.distances(X)
+    ri, nn, _, rh, rm = oracle.nearest_neighbors_hitmiss(X, y, "multisurf")
+    for c in (0, 1, 7, 59):
+        hits = [j for j in range(N) if j != c and y[j] == y[c]]; miss = [j for j in range(N) if y[j] != y[c]]
+        eh = np.mean(D[hits, c]) - 0.5 * np.std(D[hits, c], ddof=1); em = np.mean(D[miss, c]) - 0.5 * np.std(D[miss, c], ddof=1)
+        assert abs(rh[c] - eh) < 1e-12 * eh and abs(rm[c] - em) < 1e-12 * em
+        want = [j + 1 for j in hits if 0 < D[j, c] < rh[c]] + [j + 1 for j in miss if D[j, c] < rm[c]]
+        assert list(nn[ri == c + 1]) == want
+    ri, nn, _, _, _ = oracle.nearest_neighbors_hitmiss(X, y, "relieff")
+    for c in (0, 1, 59):
+        order = sorted(range(N), key=lambda j: (D[j, c], j))
+        hits = [j for j in order if y[j] == y[c]]; miss = [j for j in order if y[j] != y[c]]
+        kh = oracle.knn_surf(len(hits) - 1, 0.5); km = oracle.knn_surf(len(miss), 0.5)
+        assert list(nn[ri == c + 1]) == [j + 1 for j in hits[1:kh + 1]] + [j + 1 for j in miss[:km]]
+    yb = (np.arange(N) % 2).astype(float)                                        # balanced: k = floor(knnSURF(N-1)/2) each
+    ri, nn, _, _, _ = oracle.nearest_neighbors_hitmiss(X, yb, "relieff")
+    k = int(np.floor(0.5 * oracle.knn_surf(N - 1, 0.5)))
+    assert np.all(np.bincount(ri)[1:] == 2 * k)
+
+
 def test_unique_neighbors_and_knnvec(oracle):
     ri = np.array([1, 1, 2, 2, 3, 3], dtype=np.int32); nn = np.array([2, 3, 1, 3, 1, 2], dtype=np.int32)
     n, keep = oracle.unique_neighbors(ri, nn, 3)
