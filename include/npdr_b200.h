@@ -56,7 +56,7 @@ enum { NPDRB_DIFF_NUMERIC_ABS = 0, NPDRB_DIFF_NUMERIC_SQR = 1, NPDRB_DIFF_ALLELE
 /* npdrDistances metric, R/nearestNeighbors.R:63-101; PRECOMPUTED: R/nearestNeighbors.R:171-176 */
 enum { NPDRB_METRIC_MANHATTAN = 0, NPDRB_METRIC_EUCLIDEAN = 1, NPDRB_METRIC_ALLELE_SHARING_MANHATTAN = 2,
        NPDRB_METRIC_RELIEF_SCALED_MANHATTAN = 3, NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN = 4,
-       NPDRB_METRIC_PRECOMPUTED = 5 };
+       NPDRB_METRIC_PRECOMPUTED = 5, NPDRB_METRIC_HAMMING = 6 /* hamming.binary, R/utils.R:185-188 */ };
 /* nbd.method, R/nearestNeighbors.R:153-154 */
 enum { NPDRB_NBD_MULTISURF = 0, NPDRB_NBD_SURF = 1, NPDRB_NBD_RELIEFF = 2 };
 /* regression.type, R/npdr.R:152 */

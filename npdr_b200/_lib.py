@@ -16,7 +16,7 @@ STATS_PER_ATTR = 8
 MAX_COVARS = 4
 DIFF = {"numeric-abs": 0, "manhattan": 0, "numeric-sqr": 1, "allele-sharing": 2, "match-mismatch": 3, "raw": 4}
 METRIC = {"manhattan": 0, "euclidean": 1, "allele-sharing-manhattan": 2, "relief-scaled-manhattan": 3,
-          "relief-scaled-euclidean": 4, "precomputed": 5}
+          "relief-scaled-euclidean": 4, "precomputed": 5, "hamming": 6}
 NBD = {"multisurf": 0, "surf": 1, "relieff": 2}
 REG = {"lm": 0, "binomial": 1}
 ENODEVICE = 2

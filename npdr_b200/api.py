@@ -107,8 +107,6 @@ def npdrDistances(attr_mat, metric="manhattan", fast_dist=False, device=0, fast_
     """m x m distance matrix (R/nearestNeighbors.R:63-101).  fast_dist is accepted for signature
     compatibility (it selects wordspace::dist.matrix in the reference)."""
     X, _ = _as_matrix(attr_mat)
-    if metric == "hamming":
-        raise NotImplementedError("metric='hamming' is outside the accelerated path this round (DESIGN.md)")
     if metric not in METRIC or metric == "precomputed":
         return None        # the reference falls through and returns NULL for unknown metrics (:97-100)
     N, p = X.shape

@@ -27,7 +27,7 @@ constexpr int DTHREADS = 256;
 constexpr int STAGE_DOUBLES = BK * TM;                 // one operand, one stage
 constexpr size_t DIST_SMEM = (size_t)STAGES * 2 * STAGE_DOUBLES * sizeof(double) + 128 /*barriers*/ + 128 /*align*/;
 
-enum { MODE_MANHATTAN = 0, MODE_EUCLID_EXACT = 1, MODE_EUCLID_FMA = 2 };
+enum { MODE_MANHATTAN = 0, MODE_EUCLID_EXACT = 1, MODE_EUCLID_FMA = 2, MODE_HAMMING = 3 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -70,6 +70,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 
 template <int MODE>
 __device__ __forceinline__ void accumulate(double &acc, double a, double b) {
+    if (MODE == MODE_HAMMING) {
+        // hamming.binary (R/utils.R:185-188): t(1 - X) %*% X + its transpose = sum (1-a) b + (1-b) a
+        // (= the number of differing attributes for 0/1 data; every partial sum is then an exact integer)
+        acc = __dadd_rn(acc, __dadd_rn(__dmul_rn(__dsub_rn(1.0, a), b), __dmul_rn(__dsub_rn(1.0, b), a)));
+        return;
+    }
     double d = __dsub_rn(a, b);
     if (MODE == MODE_MANHATTAN) acc = __dadd_rn(acc, fabs(d));
     else if (MODE == MODE_EUCLID_EXACT) acc = __dadd_rn(acc, __dmul_rn(d, d));
@@ -180,7 +186,7 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t p, 
             for (int cc = 0; cc < 8; ++cc) {
                 const int64_t j = (int64_t)j0 + (cc >> 1) * 32 + tx * 2 + (cc & 1);
                 double v = acc[r][cc];
-                if (MODE != MODE_MANHATTAN) v = sqrt(v);
+                if (MODE == MODE_EUCLID_EXACT || MODE == MODE_EUCLID_FMA) v = sqrt(v);
                 if (i < row0 + nrows && i < N && j < N) {
                     Dout[(i - row0) * ldd + j] = v;
                     if (symmetric && !diag) Dout[j * ldd + i] = v;      // row0 == 0 in symmetric mode
@@ -221,7 +227,7 @@ dist_simple_kernel(const double *__restrict__ X, int64_t ldx, int64_t N, int64_t
         for (int c = 0; c < 4; ++c) {
             int64_t i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
             double v = acc[r][c];
-            if (MODE != MODE_MANHATTAN) v = sqrt(v);
+            if (MODE == MODE_EUCLID_EXACT || MODE == MODE_EUCLID_FMA) v = sqrt(v);
             if (i < row0 + nrows && i < N && j < N) Dout[(i - row0) * ldd + j] = v;
         }
 }
@@ -313,7 +319,7 @@ int launch_simple(npdrb_session *s, const double *X, int64_t row0, int64_t nrows
 int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows) {
     npdrb_ctx *ctx = s->ctx;
     if (!s->dX) { npdrb_set_error("distances: no attribute matrix in the session"); return NPDRB_EINVAL; }
-    if (metric < 0 || metric > NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN) {
+    if ((metric < 0 || metric > NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN) && metric != NPDRB_METRIC_HAMMING) {
         npdrb_set_error("distances: unsupported metric %d", metric);
         return NPDRB_EINVAL;
     }
@@ -331,23 +337,26 @@ int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64
 
     NB_CUDA(cudaEventRecord(s->ev[0], ctx->stream));
     const double *X = s->dX;
-    if (metric >= NPDRB_METRIC_ALLELE_SHARING_MANHATTAN) {
+    if (metric >= NPDRB_METRIC_ALLELE_SHARING_MANHATTAN && metric <= NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN) {
         if (!s->dXs) NB_CUDA(cudaMalloc(&s->dXs, sizeof(double) * (size_t)s->ldx * (size_t)s->p));
         prescale_kernel<<<(unsigned)s->p, 256, 0, ctx->stream>>>(s->dX, s->ldx, s->N, metric, s->dXs);
         NB_LAUNCH_CHECK(ctx);
         X = s->dXs;
     }
     const bool euclid = (metric == NPDRB_METRIC_EUCLIDEAN || metric == NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN);
-    const int mode = !euclid ? MODE_MANHATTAN : (fast_euclidean ? MODE_EUCLID_FMA : MODE_EUCLID_EXACT);
+    const int mode = metric == NPDRB_METRIC_HAMMING ? MODE_HAMMING
+                   : !euclid ? MODE_MANHATTAN : (fast_euclidean ? MODE_EUCLID_FMA : MODE_EUCLID_EXACT);
     const char *kenv = getenv("NPDRB_DIST_KERNEL");
     const bool simple = kenv && strcmp(kenv, "simple") == 0;
     int rc;
     if (simple) {
         rc = mode == MODE_MANHATTAN ? launch_simple<MODE_MANHATTAN>(s, X, row0, nrows)
+           : mode == MODE_HAMMING ? launch_simple<MODE_HAMMING>(s, X, row0, nrows)
            : mode == MODE_EUCLID_EXACT ? launch_simple<MODE_EUCLID_EXACT>(s, X, row0, nrows)
                                        : launch_simple<MODE_EUCLID_FMA>(s, X, row0, nrows);
     } else {
         rc = mode == MODE_MANHATTAN ? launch_tma<MODE_MANHATTAN>(s, X, row0, nrows, symmetric)
+           : mode == MODE_HAMMING ? launch_tma<MODE_HAMMING>(s, X, row0, nrows, symmetric)
            : mode == MODE_EUCLID_EXACT ? launch_tma<MODE_EUCLID_EXACT>(s, X, row0, nrows, symmetric)
                                        : launch_tma<MODE_EUCLID_FMA>(s, X, row0, nrows, symmetric);
     }

@@ -144,9 +144,10 @@ int orc_distances(const double *X, int64_t N, int64_t p, int metric, double *D) 
  * input (X there is attributes x instances).  Restated directly: number of attributes
  * on which two 0/1 instances differ. */
 int orc_hamming(const double *X, int64_t N, int64_t p, double *D) {
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < N; ++i)
         for (int64_t j = 0; j < N; ++j) {
-            double s = 0.0;
+            double s = 0.0;                                   /* diagonal = 2 sum x(1-x): 0 for 0/1 data, as in R */
             for (int64_t k = 0; k < p; ++k)
                 s += (1.0 - X[k * N + i]) * X[k * N + j] + (1.0 - X[k * N + j]) * X[k * N + i];
             D[j * N + i] = s;

@@ -79,6 +79,12 @@ def test_distances_fixtures_and_scaled_metrics(nb, oracle):
         assert np.array_equal(nb.npdrDistances(X, m), oracle.distances(X, m)), m
     G = np.asfortranarray(rng.integers(0, 3, size=(70, 200)).astype(float))
     assert np.array_equal(nb.npdrDistances(G, "allele-sharing-manhattan"), oracle.distances(G, "allele-sharing-manhattan"))
+    B = np.asfortranarray(rng.integers(0, 2, size=(133, 257)).astype(float))
+    H = nb.npdrDistances(B, "hamming")
+    assert np.array_equal(H, oracle.distances(B, "hamming")) and np.array_equal(H, (B[:, None, :] != B[None, :, :]).sum(-1))
+    out = nb.nearestNeighbors(B, "multisurf", "hamming")
+    ri, nn, _, _ = oracle.nearest_neighbors(B, "multisurf", "hamming")
+    assert np.array_equal(out["Ri_idx"], ri) and np.array_equal(out["NN_idx"], nn)
     assert nb.npdrDistances(X, "no-such-metric") is None          # the reference returns NULL
 
 
