@@ -14,6 +14,7 @@ the p-value / ordering / p.adjust residue in `rstats` (it stays in R in the R de
   knnSURF            R/utils.R:12-18
   diffRegression     R/npdr.R:18-71
   uniReg             R/utils.R:66-157
+  vwok               R/adaptive.R:39-234 (batched-k caller: one distance matrix for the whole k grid)
 """
 import ctypes as C
 import sys
@@ -455,3 +456,62 @@ def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-a
         info["order"] = o
         return out, info
     return out
+
+
+def npdr_k_grid(outcome, dataset, k_grid=None, regression_type="binomial", attr_diff_type="numeric-abs",
+                nbd_metric="manhattan", msurf_sd_frac=0.5, separate_hitmiss_nbds=False, padj_method="bonferroni", device=0):
+    """npdr(nbd.method = "relieff", knn = k) for every k of a grid on ONE resident problem: the attribute matrix is
+    uploaded once, the distance matrix and the instance-major attribute copy are computed once and reused for all k
+    (what vwok's foreach loop recomputes per k, R/adaptive.R:85-111).
+    -> dict(att, k_grid, beta_Z [p, len(k_grid)], pval_adj [p, len(k_grid)], beta_raw, pval_att), attributes in input order."""
+    X, att_names, pheno = _split_outcome(outcome, dataset)
+    y = _code_outcome(pheno, regression_type)
+    N, p = X.shape
+    ks = list(range(1, N)) if k_grid is None else [int(k) for k in k_grid]       # seq.int(m - 1), R/adaptive.R:73
+    ctx = context(device)
+    s = _lib.Session(ctx, N, p, 0)
+    try:
+        s.upload(X, y)
+        s.distances(nbd_metric, False, 0, N)
+        bz = np.empty((p, len(ks))); br = np.empty((p, len(ks))); pa = np.empty((p, len(ks))); padj = np.empty((p, len(ks)))
+        for c, k in enumerate(ks):
+            if separate_hitmiss_nbds:
+                s.neighbors_hitmiss("relieff", msurf_sd_frac, k)
+            else:
+                s.neighbors("relieff", msurf_sd_frac, k)
+            a, b, m = s.local_pairs()
+            s.import_pairs(a, b, m)
+            st = s.regress(0, p, regression_type, attr_diff_type, ())
+            pv, _ = _pvalues(st, regression_type)
+            bz[:, c] = st[:, 1]; br[:, c] = st[:, 0]; pa[:, c] = pv
+            padj[:, c] = rstats.p_adjust(pv, padj_method)
+    finally:
+        s.close()
+    return {"att": att_names, "k_grid": ks, "beta_Z": bz, "beta_raw": br, "pval_att": pa, "pval_adj": padj}
+
+
+def vwok(dats, k_grid=None, verbose=False, attr_diff_type="numeric-abs", corr_attr_names=None, signal_names=None,
+         separate_hitmiss_nbds=False, label="class", device=0):
+    """Variable-Wise Optimized k (R/adaptive.R:39-234): NPDR for every k of the grid, then per attribute the k with the
+    largest standardized beta.  Returns {"vwok.out": DataFrame(att, best.ks, betas, pval.att) sorted by decreasing beta,
+    "betas": p x |k| frame, "pvals": p x |k| frame}; rows of the per-k matrices are ordered by attribute name as the
+    reference's arrange(att) does.  The auPRC part (PRROC, signal.names) and correlation-data are not accelerated."""
+    if attr_diff_type == "correlation-data":
+        raise NotImplementedError("vwok(attr.diff.type='correlation-data') is outside the accelerated path")
+    if signal_names is not None:
+        raise NotImplementedError("vwok(signal.names=...): the PRROC auPRC scoring is outside the accelerated path")
+    if pd is None or not isinstance(dats, pd.DataFrame):
+        raise TypeError("dats must be a pandas DataFrame that contains the outcome column `label`")
+    g = npdr_k_grid(label, dats, k_grid, "binomial", "numeric-abs", "manhattan", 0.5, separate_hitmiss_nbds, "bonferroni", device)
+    order = sorted(range(len(g["att"])), key=lambda i: g["att"][i])              # arrange(att)
+    atts = [g["att"][i] for i in order]
+    cols = [f"k.{k}" for k in g["k_grid"]]
+    betas = pd.DataFrame(g["beta_Z"][order], index=atts, columns=cols)
+    pvals = pd.DataFrame(g["pval_adj"][order], index=atts, columns=cols)
+    best = np.nanargmax(betas.to_numpy(), axis=1)                                # which.max: first maximum
+    out = pd.DataFrame({"att": atts, "best.ks": best + 1,
+                        "betas": betas.to_numpy()[np.arange(len(atts)), best],
+                        "pval.att": pvals.to_numpy()[np.arange(len(atts)), best]})
+    out = out.sort_values("betas", ascending=False, kind="stable").reset_index(drop=True)
+    return {"vwok.out": out, "betas": betas, "pvals": pvals}
+

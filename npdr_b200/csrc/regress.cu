@@ -80,6 +80,37 @@ __global__ void tile_keys_kernel(const int32_t *__restrict__ Ri, const int32_t *
     idx[m] = (uint32_t)m;
 }
 
+// per attribute: an upper bound of the projected diff over any pair (max - min of the column, mapped through the diff type);
+// used by the IRLS step kernel to bound |x'delta| and |eta| (see irls_step_kernel)
+__global__ void __launch_bounds__(256)
+column_dmax_kernel(const double *__restrict__ X, int64_t ldx, int64_t N, int64_t attr0, int64_t nattr, int diff_type,
+                   double *__restrict__ dmax) {
+    __shared__ double smin[256], smax[256];
+    const int64_t a = blockIdx.x;
+    if (a >= nattr) return;
+    const double *c = X + (attr0 + a) * ldx;
+    double mn = c[0], mx = c[0];
+    for (int64_t i = threadIdx.x; i < N; i += 256) { mn = fmin(mn, c[i]); mx = fmax(mx, c[i]); }
+    smin[threadIdx.x] = mn; smax[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + o]); smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + o]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double range = smax[0] - smin[0];
+        double v;
+        switch (diff_type) {
+        case NPDRB_DIFF_NUMERIC_SQR: v = range * range; break;
+        case NPDRB_DIFF_ALLELE_SHARING: v = 0.5 * range; break;
+        case NPDRB_DIFF_MATCH_MISMATCH: v = 1.0; break;
+        case NPDRB_DIFF_RAW: v = fmax(fabs(smax[0]), fabs(smin[0])); break;
+        default: v = range;
+        }
+        dmax[a] = v;
+    }
+}
+
 __global__ void tile_hist_kernel(const uint32_t *__restrict__ keys, int64_t M, unsigned *__restrict__ hist) {
     int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m < M) atomicAdd(&hist[keys[m]], 1u);
@@ -832,6 +863,9 @@ struct SolveArgs {
     double *beta, *se;             // [KMAX][nattr_pad]
     double *dev_old;               // [nattr_pad]
     double *hit_d, *miss_d;        // [nattr_pad] sum of the attribute diff over the hit / miss records (from pass 0)
+    const double *dmax;            // [nattr] upper bound of the attribute diff over any pair
+    double cmax[NPDRB_MAX_COVARS]; // upper bounds of the covariate diffs
+    int speculate;                 // 1: finish without the confirming pass when the predicted deviance change is far below epsilon
     unsigned char *active;         // [nattr_pad]
     unsigned char *tile_active;    // [n attr tiles]
     int *iters; int *flags;        // [nattr_pad]
@@ -1055,10 +1089,44 @@ __global__ void irls_step_kernel(SolveArgs S) {
         S.active[a] = 0;
         return;
     }
+    double bnew[K], senew[K];
     for (int r = 0; r < K; ++r) {                           // Newton / IRLS update: beta + (X'WX)^-1 X'(y - mu)
         const double old = S.beta[(int64_t)r * S.nattr_pad + a];
-        S.beta[(int64_t)r * S.nattr_pad + a] = al[r] ? 0.0 : old + x[r];
-        S.se[(int64_t)r * S.nattr_pad + a] = al[r] ? nanv : sqrt(dinv[r]);
+        bnew[r] = al[r] ? 0.0 : old + x[r];
+        senew[r] = al[r] ? nanv : sqrt(dinv[r]);
+    }
+    if (S.speculate && S.pass < 25) {
+        // glm.fit would now run iteration pass+1: weights at the CURRENT beta (the system just solved), new coefficients
+        // bnew, then test |dev_new - dev| / (|dev_new| + 0.1) < 1e-8.  With A delta = s the deviance along the step is
+        //   dev_new - dev = -delta.s + R3,   |R3| <= (max|g3|/3) * sum |x.delta|^3 <= 0.0321 * M * B^3,
+        // g = log(1 + e^eta), g3 its third derivative (max 1/(6 sqrt 3)), B >= max |x.delta| from the per-attribute range
+        // bounds.  If even the bound is 10x below epsilon (and no eta can reach the +-30 clamps), iteration pass+1 is known
+        // to converge: its coefficients are bnew and its QR (standard errors) is the system just solved, so the confirming
+        // pass over the pairs is skipped.  Same beta, se and iteration count as running it; the reported deviance is
+        // dev - delta.s (error <= R3).
+        double vmax[K];
+        vmax[0] = 1.0; vmax[1] = S.dmax[a];
+        for (int r = 0; r < Q; ++r) vmax[2 + r] = S.cmax[r];
+        double pred = 0.0, B = 0.0, E = 0.0;
+        for (int r = 0; r < K; ++r) {
+            if (al[r]) continue;
+            pred += x[r] * b[r];
+            B += fabs(x[r]) * vmax[r];
+            E += fmax(fabs(bnew[r]), fabs(bnew[r] - x[r])) * vmax[r];
+        }
+        const double r3 = 0.0321 * S.M * B * B * B;
+        const double dev_new_lo = dev - fabs(pred) - r3;
+        if (E < 30.0 && pred >= 0.0 && isfinite(pred) && (fabs(pred) + r3) < 1e-9 * (fabs(dev_new_lo) + 0.1)) {
+            int rank = 0;
+            for (int r = 0; r < K; ++r) rank += al[r] ? 0 : 1;
+            write_stats(S.stats + (int64_t)a * 8, bnew, senew, al, K, S.M - (double)rank, dev - pred, S.pass + 1, 0);
+            S.active[a] = 0;
+            return;
+        }
+    }
+    for (int r = 0; r < K; ++r) {
+        S.beta[(int64_t)r * S.nattr_pad + a] = bnew[r];
+        S.se[(int64_t)r * S.nattr_pad + a] = senew[r];
     }
     S.iters[a] = S.pass + 1;
     S.tile_active[a / TA] = 1;
@@ -1412,6 +1480,12 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     NB_CHECK(dmalloc(&d_beta, (size_t)KMAX * nattr_pad)); NB_CHECK(dmalloc(&d_se, (size_t)KMAX * nattr_pad));
     double *d_hitd = nullptr, *d_missd = nullptr;
     NB_CHECK(dmalloc(&d_hitd, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_missd, (size_t)nattr_pad));
+    double *d_dmax = nullptr;
+    NB_CHECK(dmalloc(&d_dmax, (size_t)nattr_pad));
+    if (!lm) {
+        column_dmax_kernel<<<(unsigned)nattr, 256, 0, ctx->stream>>>(s->dX, s->ldx, N, attr0, nattr, diff_type, d_dmax);
+        NB_LAUNCH_CHECK(ctx);
+    }
     NB_CHECK(dmalloc(&d_devold, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_active, (size_t)nattr_pad));
     NB_CHECK(dmalloc(&d_tile_active, (size_t)n_at)); NB_CHECK(dmalloc(&d_iters, (size_t)nattr_pad));
     NB_CHECK(dmalloc(&d_flags, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_nactive, 1));
@@ -1428,7 +1502,26 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     SolveArgs S;
     memset(&S, 0, sizeof(S));
     S.partials = d_part; S.nattr = (int)nattr; S.nattr_pad = (int)nattr_pad;
-    S.hit_d = d_hitd; S.miss_d = d_missd;
+    S.hit_d = d_hitd; S.miss_d = d_missd; S.dmax = d_dmax;
+    {
+        const char *ns = getenv("NPDRB_NO_SPECULATE");
+        S.speculate = (ns && ns[0] == '1') ? 0 : 1;
+        if (!lm && q > 0) {                                  // covariate diff bounds from the column ranges (N x q is tiny)
+            std::vector<double> hc((size_t)N * q);
+            NB_CUDA(cudaMemcpyAsync(hc.data(), s->dC, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            NB_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int c = 0; c < q; ++c) {
+                double mn = hc[(size_t)c * N], mx = mn;
+                for (int64_t i = 1; i < N; ++i) { const double v = hc[(size_t)c * N + i]; if (v < mn) mn = v; if (v > mx) mx = v; }
+                const int ct = cov_type ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH;
+                const double range = mx - mn;
+                S.cmax[c] = y_raw ? fmax(fabs(mx), fabs(mn))
+                          : ct == NPDRB_DIFF_NUMERIC_SQR ? range * range
+                          : ct == NPDRB_DIFF_ALLELE_SHARING ? 0.5 * range
+                          : ct == NPDRB_DIFF_MATCH_MISMATCH ? 1.0 : range;
+            }
+        }
+    }
     S.beta = d_beta; S.se = d_se; S.dev_old = d_devold; S.active = d_active; S.tile_active = d_tile_active;
     S.iters = d_iters; S.flags = d_flags; S.stats = d_stats; S.n_active = d_nactive;
     double Mw = 0;
@@ -1556,7 +1649,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     for (double v : pass_evals) s->evals_pass_full += v;
     for (cudaEvent_t e : pev) cudaEventDestroy(e);
     if (irls_passes) *irls_passes = passes;
-    cudaFree(d_hitd); cudaFree(d_missd);
+    cudaFree(d_hitd); cudaFree(d_missd); cudaFree(d_dmax);
     cudaFree(d_part); cudaFree(d_beta); cudaFree(d_se); cudaFree(d_devold); cudaFree(d_stats);
     cudaFree(d_active); cudaFree(d_tile_active); cudaFree(d_iters); cudaFree(d_flags); cudaFree(d_nactive);
     return NPDRB_OK;

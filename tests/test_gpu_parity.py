@@ -306,6 +306,27 @@ def test_mutual_pair_folding_is_exact(nb, reg):
     _stats_close(a["stats"], b["stats"], 1e-9, "fold vs no fold")
 
 
+def test_speculative_convergence_is_faithful(nb):
+    """The IRLS step skips the confirming pass when the quadratic model + remainder bound puts the next deviance change
+    >= 10x below epsilon: coefficients, standard errors and iteration counts must equal the fully confirmed run."""
+    rng = np.random.default_rng(41)
+    N, p = 260, 200
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    y = (rng.random(N) < 0.5).astype(float)
+    X[:, :6] += 1.2 * y[:, None]                                    # strong effects: more IRLS iterations
+    C = np.asfortranarray(np.column_stack([rng.integers(0, 2, N).astype(float), rng.normal(40, 12, N).round()]))
+    for kw in (dict(), dict(covars=C, covar_diff_type=["match-mismatch", "numeric-abs"])):
+        _, a = nb.npdr(y, X, "binomial", return_info=True, **kw)
+        os.environ["NPDRB_NO_SPECULATE"] = "1"
+        try:
+            _, b = nb.npdr(y, X, "binomial", return_info=True, **kw)
+        finally:
+            del os.environ["NPDRB_NO_SPECULATE"]
+        assert b["irls_passes"] >= a["irls_passes"] + 1             # at least the confirming pass was saved
+        assert np.array_equal(a["stats"][:, 6], b["stats"][:, 6])   # identical iteration counts
+        _stats_close(a["stats"], b["stats"], 1e-10, "speculative vs confirmed")
+
+
 def test_diff_regression_and_unireg(nb, oracle):
     import pandas as pd
     rng = np.random.default_rng(22)
@@ -329,6 +350,26 @@ def test_diff_regression_and_unireg(nb, oracle):
     coef, se, _ = oracle.glm_binomial(np.asfortranarray(np.column_stack([np.ones(100), c["X"][:, j]])), c["y"])
     assert abs(tab.iloc[0, 0] - coef[1]) <= 1e-4 * abs(coef[1]) and abs(tab.iloc[0, 1] - coef[1] / se[1]) <= 1e-4 * abs(coef[1] / se[1])
     assert np.all(np.diff(tab["pval"].to_numpy()) >= 0)
+
+
+def test_vwok_batched_k(nb, oracle):
+    """Batched-k caller: one distance matrix for the whole k grid == independent npdr(relieff, knn = k) calls."""
+    import pandas as pd
+    c = load_case("cfg1")
+    df = pd.DataFrame(c["X"][:, :30], columns=c["names"][:30]); df["class"] = c["y"]
+    grid = [3, 10, 30, 48]
+    out = nb.vwok(df, k_grid=grid)
+    assert list(out["vwok.out"].columns) == ["att", "best.ks", "betas", "pval.att"] and out["betas"].shape == (30, 4)
+    assert np.all(np.diff(out["vwok.out"]["betas"].to_numpy()) <= 0)
+    for ci, k in enumerate(grid):
+        single, info = nb.npdr("class", df, "binomial", nbd_method="relieff", knn=k, return_info=True)
+        z = dict(zip(single["att"], single["beta.Z.att"])); pa = dict(zip(single["att"], single["pval.adj"]))
+        for a in out["betas"].index:
+            assert out["betas"].loc[a, f"k.{k}"] == z[a] and out["pvals"].loc[a, f"k.{k}"] == pa[a]
+    ri, nn, _, _ = oracle.nearest_neighbors(np.asfortranarray(c["X"][:, :30]), "relieff", "manhattan", 0.5, 10)
+    exp = oracle.regress_attrs(np.asfortranarray(c["X"][:, :30]), ri, nn, oracle.pair_diffs(c["y"], ri, nn, "match-mismatch"))
+    got = out["betas"]["k.10"].reindex(c["names"][:30]).to_numpy()
+    assert np.max(np.abs(got - exp[:, 1]) / np.abs(exp[:, 1])) < RTOL_IRLS
 
 
 def test_error_behaviour(nb):
