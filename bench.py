@@ -348,15 +348,27 @@ def main():
         pass
     p_local = info["attrs"][1]
     alg_bytes = n_full * (N * p_local * 8 + km["records"] * (4 + 8 * q) + p_local * 8 * 16)   # per pass: X slab once, record stream once, partials
+    traffic = traffic_src = None                  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if tj["workload"] == wl_name and tj["n_gpus"] == world:
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+            traffic_src = tj["source"]
+    except Exception:
+        pass
     roofline = {"kernel": "pass2_kernel<IRLS_FULL, q, diff> (binomial IRLS pass, npdr_b200/csrc/regress.cu)", "bound": "fp64",
                 "achieved": achieved, "peak": peak["dfma_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peak["dfma_tflops"] if peak["dfma_tflops"] else None, "traffic": None,
+                "frac": achieved / peak["dfma_tflops"] if peak["dfma_tflops"] else None, "traffic": traffic,
+                "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes / n_full,
                 "peak_source": "measured live by npdrb_measure_fp64_peak (DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
                 "launches": n_full, "avg_launch_ms": km["pass_full_ms"] / n_full,
                 "flops_per_eval_iteration": f_bin(q), "evals_per_launch_avg": km["evals_pass_full"] / n_full,
                 "note": "achieved = executed attribute x record evaluations x F_bin(q) (SURVEY 8d canonical count) / CUDA-event "
                         "launch time; records = pairs after folding mutual (i,j)/(j,i) pairs into one weight-2 record; the "
-                        "kernel issues ~27 FP64 + ~23 other instructions per evaluation at q = 0 (DESIGN.md 4)",
+                        "kernel issues 24 FP64 + 17 other instructions per evaluation at q = 0 (37 + 18.5 at q = 2; SASS count, DESIGN.md 4); "
+                        "an FP64 warp instruction holds the dispatch port for 2 cycles, so the issue-limited ceiling of this mix "
+                        "is 48/65 = 74 % FP64-pipe activity (ncu: 68.6 %)",
                 "records_per_pair": km["records"] / max(info["n_pairs_used"], 1),
                 "share_of_step": km["pass_full_ms"] / ms_step,
                 "hbm": {"achieved": alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9 if km["pass_full_ms"] > 0 else 0.0,

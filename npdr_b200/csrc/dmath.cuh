@@ -163,3 +163,46 @@ NB_HD double nb_log_ge1_fast256(double u, const double* __restrict__ log_rc, con
     return (log_eln2[e & 63] + log_lrc[i]) + p;
 }
 
+
+// ---- v3 variants (what pass2_kernel<IRLS_FULL> evaluates now) ---------------------------------
+// One FP64 instruction less on each side of the reciprocal:
+//  * u = 1 + exp(eta) directly: the polynomial returns exp(frac*ln2/256) (not exp - 1), the 2^(k>>8) scale is applied to
+//    the table value (integer add on its high word) and one FMA forms 1 + T_j * poly.  Relative error of the exp part:
+//    dropped term (ln2/512)^4/24 = 1.4e-13 plus one extra rounding (1.1e-16).
+//  * log(u), u >= 1: 512 mantissa bins (|f| <= 2^-10 + 2^-24), degree-3 log1p (dropped term <= f^4/4 = 2.3e-13
+//    absolute, mean 4.6e-14), the table term is folded into the final FMA and the exponent e is returned as an integer:
+//    the kernel sums e in an integer register and multiplies by ln2 once per work item (no e*ln2 table, no FP64 add).
+struct nb_tables512 {
+    double exp_t[256];     // 2^(j/256)
+    double log_rc[512];    // ~1/centre of mantissa bin i of width 1/512 (24 significant bits)
+    double log_lrc[512];   // -log(log_rc[i])
+};
+#define NB_TABLES512_STATIC_INIT { NB_EXP256_TABLE_INIT, NB_LOG512_RC_TABLE_INIT, NB_LOG512_LRC_TABLE_INIT }
+
+NB_HD double nb_one_plus_exp256(double sv, const double* __restrict__ exp_t) {      // sv = eta * 256/ln2, |eta| < 30
+    const double magic = 6755399441055744.0;
+    const double c = NB_LN2_256;
+    double tt = sv + magic;
+    int32_t ki = (int32_t)(uint32_t)nb_d2u(tt);
+    double kf = tt - magic;
+    double fr = sv - kf;
+    double qq = nb_fma(fr, c * c * c / 6.0, c * c / 2.0);
+    qq = nb_fma(qq, fr, c);
+    qq = nb_fma(qq, fr, 1.0);
+    uint32_t j = (uint32_t)ki & 255u;
+    uint64_t b = nb_d2u(exp_t[j]);
+    uint32_t hi = ((uint32_t)(b >> 32) - j * 4096u) + (uint32_t)ki * 4096u;      // the kernel's table image holds the first term
+    double tjs = nb_u2d(((uint64_t)hi << 32) | (b & 0xFFFFFFFFull));
+    return nb_fma(tjs, qq, 1.0);
+}
+
+NB_HD double nb_log_mant512(double u, const double* __restrict__ log_rc, const double* __restrict__ log_lrc, int32_t* e) {
+    uint64_t b = nb_d2u(u);
+    *e = (int32_t)(b >> 52) - 1023;
+    int32_t i = (int32_t)((b >> 43) & 511);
+    double m = nb_u2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    double f = nb_fma(m, log_rc[i], -1.0);
+    double s = f + log_lrc[i];
+    double p = nb_fma(f, 1.0 / 3.0, -0.5);
+    return nb_fma(p, f * f, s);                               // log(u) = e*ln2 + this
+}

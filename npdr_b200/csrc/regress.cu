@@ -231,7 +231,9 @@ struct PassArgs {
     const double *beta;            // [KMAX][nattr_pad] current coefficients (IRLS_FULL)
     const unsigned char *tile_active;  // per attribute tile, or NULL
     const nb_tables *tables;       // device copy of the exp/log tables (v1 kernel)
-    const nb_tables256 *tables256; // 256-entry tables (v2 kernel)
+    const nb_tables512 *tables512; // exp 256 / log 512 tables (v2 kernel)
+    const double *dmax;            // [nattr_pad] bound on the attribute diff (v2 IRLS pass: clamp pre-check)
+    double cmax[NPDRB_MAX_COVARS]; // bounds on the covariate diffs
     int diff_type;
 };
 
@@ -255,9 +257,11 @@ pass_kernel(PassArgs P) {
 
     const int tid = threadIdx.x;
     const int al = tid % TA, slice = tid / TA;
-    const int at = blockIdx.x;
-    const int sidx = ((int)blockIdx.y >= P.n_chunks0) ? 1 : 0;
-    const int chunk = (int)blockIdx.y - (sidx ? P.n_chunks0 : 0);
+    // chunk index is the fast grid dimension: the CTAs resident at any moment share a few attribute tiles, whose XT slabs
+    // (N x 128 doubles each) then stay in L2 while every chunk of the pair stream sweeps over them
+    const int at = blockIdx.y;
+    const int sidx = ((int)blockIdx.x >= P.n_chunks0) ? 1 : 0;
+    const int chunk = (int)blockIdx.x - (sidx ? P.n_chunks0 : 0);
     const StreamArgs &A = P.st[sidx];
     if (P.tile_active && !P.tile_active[at]) return;
     const int64_t a0 = (int64_t)at * TA;
@@ -413,13 +417,15 @@ pass_kernel(PassArgs P) {
 //     nb_exp_fast / nb_log_ge1_fast recurrences (dmath.cuh carries the error budget and the host test).
 // The v2 kernel carries the linear predictor in units of ln2/256: s = eta * 256/ln2 (the coefficients are pre-scaled
 // when they are loaded), so k = rint(s) and the reduced argument frac = s - k (exact) need no multiplication, and
-// exp(eta) = 2^(k/256) * exp(frac * ln2/256) with the ln2/256 powers folded into the polynomial coefficients
-// (nb_exp_fast256 / nb_log_ge1_fast256 in dmath.cuh are the host-tested statements of the same recurrences).
+// exp(eta) = 2^(k/256) * exp(frac * ln2/256) with the ln2/256 powers folded into the polynomial coefficients.  The
+// shared table image stores 2^(j/256) with j * 4096 pre-subtracted from its high word, so one IMAD (k * 4096 + high
+// word) applies the 2^(k >> 8) scale without masking k
+// (nb_one_plus_exp256 / nb_log_mant512 in dmath.cuh are the host-tested statements of the same recurrences).
 #define NB_C NB_LN2_256
 __constant__ double c_k[10] = {
     6755399441055744.0,                                                  // 0     1.5 * 2^52 (round-to-integer magic)
     NB_C * NB_C * NB_C / 6.0, NB_C * NB_C / 2.0, NB_C,                   // 1..3  exp polynomial in frac
-    -0.25, 1.0 / 3.0, -0.5,                                              // 4..6  log polynomial
+    NB_LN2, 1.0 / 3.0, -0.5,                                             // 4..6  ln2; log1p polynomial
     NB_LOG_INV_EPS * NB_256_OVER_LN2,                                    // 7     log(1/DBL_EPSILON) in units of ln2/256
     30.0 * NB_256_OVER_LN2,                                              // 8     clamp threshold in the same units
     NB_256_OVER_LN2                                                      // 9
@@ -427,8 +433,7 @@ __constant__ double c_k[10] = {
 
 struct nb_tables2 {                 // shared-memory image used by v2
     double exp_t[256];              // 2^(j/256)
-    double2 log_rl[256];            // (rc_i, -log rc_i)
-    double log_eln2_rot[64];        // entry (e - 1) & 63 holds e * ln2
+    double2 log_rl[512];            // (rc_i, -log rc_i), 512 mantissa bins
 };
 
 constexpr int V2_TPS = TA / 2;      // threads per slice (64)
@@ -437,50 +442,52 @@ constexpr int V2_TPS = TA / 2;      // threads per slice (64)
 __host__ __device__ constexpr int v2_nslice(int mode, int q) { return (mode == MODE_IRLS_FULL && q >= 2) ? 6 : 8; }
 constexpr int V2_RCHUNK = 512;      // records per staged chunk (two buffers)
 
-__device__ __forceinline__ double v2_exp_fast(double sv, uint32_t sT) {            // sv = eta * 256/ln2, |eta| < 30
+// u = 1 + exp(eta) (dmath.cuh: nb_one_plus_exp256 is the host-tested statement of the same recurrence)
+__device__ __forceinline__ double v2_u1_fast(double sv, uint32_t sT) {             // sv = eta * 256/ln2, |eta| < 30
     const double tt = sv + c_k[0];
-    const int ki = __double2loint(tt);
+    const int ki = __double2loint(tt);                           // rint(eta * 256/ln2)
     const double kf = tt - c_k[0];
     const double fr = sv - kf;                                   // exact, |fr| <= 1/2
     double qq = fma(fr, c_k[1], c_k[2]);
     qq = fma(qq, fr, c_k[3]);
-    qq = qq * fr;                                                // exp(fr * ln2/256) - 1
+    qq = fma(qq, fr, 1.0);                                       // exp(fr * ln2/256)
     double tj;
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x7F8)));
-    const double v = fma(tj, qq, tj);
-    return __hiloint2double(__double2hiint(v) + (ki & 0xFFFFFF00) * 4096, __double2loint(v));    // * 2^(ki >> 8): one LOP3 + one IMAD
+    int thi;
+    asm("mad.lo.s32 %0, %1, 4096, %2;" : "=r"(thi) : "r"(ki), "r"(__double2hiint(tj)));    // * 2^(k >> 8) (entry is pre-biased by -j * 4096)
+    return fma(__hiloint2double(thi, __double2loint(tj)), qq, 1.0);
 }
 // logit linkinv with R's clamps (stats family.c): eta < -30 -> DBL_EPSILON, eta > 30 -> 1/DBL_EPSILON.
-// -> (t, log t - eta): the second component is the deviance correction of a clamped record (0 otherwise)
+// -> (1 + t, log t - eta): the second component is the deviance correction of a clamped record (0 otherwise)
 __device__ __noinline__ double2 v2_exp_clamped(double sv, uint32_t sT) {
-    if (sv > c_k[8]) return make_double2(4503599627370496.0, (c_k[7] - sv) * NB_C);
-    if (sv < -c_k[8]) return make_double2(2.220446049250313e-16, (-c_k[7] - sv) * NB_C);
-    return make_double2(v2_exp_fast(sv, sT), 0.0);
+    if (sv > c_k[8]) return make_double2(1.0 + 4503599627370496.0, (c_k[7] - sv) * NB_C);
+    if (sv < -c_k[8]) return make_double2(1.0 + 2.220446049250313e-16, (-c_k[7] - sv) * NB_C);
+    return make_double2(v2_u1_fast(sv, sT), 0.0);
 }
 
-// everything after t = exp(eta): weight, log(1 + t), accumulation -- independent of the outcome
+// everything after u1 = 1 + exp(eta): weight, log(u1), accumulation -- independent of the outcome.  The binary
+// exponent of u1 is summed in the integer register esum (x ln2 once per work item); acc[NA - 2] takes the mantissa part.
 template <int Q>
-__device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 ? Q : 1], const double t,
-                                        double (&acc)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], const uint32_t sT, const int k3ff) {
+__device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 ? Q : 1], const double u1,
+                                        double (&acc)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], unsigned &esum, const uint32_t sT, const int k3ff) {
     constexpr int K = 2 + Q;
     constexpr int NA = K * (K + 1) / 2 + K + 2;
-    const double u1 = 1.0 + t;
     double inv;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(u1));
     inv = fma(inv, fma(-u1, inv, 1.0), inv);                    // 1/(1+t) = 1 - mu
     const double w = fma(-inv, inv, inv);                       // mu(1-mu) = (1-mu) - (1-mu)^2 = mu.eta for the logit link
     const int hi = __double2hiint(u1);
-    double rc, lrc, el;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lrc) : "r"(sT + 2048u + (uint32_t)((hi >> 8) & 0xFF0)));
-    asm("ld.shared.f64 %0, [%1];" : "=d"(el) : "r"(sT + 2048u + 4096u + (uint32_t)((hi >> 17) & 0x1F8)));
+    double rc, lrc;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lrc) : "r"(sT + 2048u + (uint32_t)((hi >> 7) & 0x1FF0)));
+    esum += (unsigned)(hi >> 20);                                           // biased exponent; 1023 x (records) comes off at the end
     int mhi;
     asm("lop3.b32 %0, %1, 0x000FFFFF, %2, 0xEA;" : "=r"(mhi) : "r"(hi), "r"(k3ff));     // (hi & 0xFFFFF) | 0x3FF00000
     const double m = __hiloint2double(mhi, __double2loint(u1));
     const double f = fma(m, rc, -1.0);
-    double pp = fma(f, c_k[4], c_k[5]);
-    pp = fma(pp, f, c_k[6]);
-    pp = fma(pp, f * f, f);
-    acc[NA - 2] += (el + lrc) + pp;                             // log(1 + t) = -log(1 - mu)
+    const double sl = f + lrc;
+    double pp = fma(f, c_k[5], c_k[6]);
+    pp = fma(pp, f * f, sl);
+    acc[NA - 2] += pp;                                          // log(u1) - e*ln2;  log(1 + t) = -log(1 - mu)
     double wv[K];
     wv[0] = w;
     wv[1] = w * d;
@@ -504,25 +511,26 @@ __device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 
 
 // records [m_begin, m_end) of the staged chunk, this thread's slice.  Two records x two attributes are in flight per
 // thread: four independent exp -> reciprocal -> log chains.
-template <int Q, int DIFF, int NSL>
+template <int Q, int DIFF, int NSL, bool CHECK>
 __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint32_t sREC_addr, uint32_t sCD_addr,
                                          uint32_t sXI_addr, uint32_t sXJ_addr, uint32_t sT, int diff_type,
                                          const double (&beta0)[2 + Q], const double (&beta1)[2 + Q],
                                          double (&acc0)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2],
-                                         double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2]) {
+                                         double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], unsigned &esum0, unsigned &esum1, int &nrec) {
     constexpr int NA = (2 + Q) * (3 + Q) / 2 + (2 + Q) + 2;
     const int k3ff = 0x3FF00000;
     // each slice walks a CONTIGUOUS part of the range: records are in list order (grouped by Ri), so the I row
-    // repeats for several records in a row and stays in registers (halves the shared-memory tile traffic)
-    const int len = m_end - m_begin, per = (len + NSL - 1) / NSL;
+    // repeats for several records in a row and stays in registers (halves the shared-memory tile traffic).
+    // m_begin is even and slices are an even number of records long: record pairs are fetched with one 8-byte load.
+    const int len = m_end - m_begin, per = (((len + NSL - 1) / NSL) + 1) & ~1;
     const int m_lo = m_begin + slice * per, m_hi = (m_lo + per < m_end) ? (m_lo + per) : m_end;
+    if (m_hi > m_lo) nrec += m_hi - m_lo;
     uint32_t io_prev = 0xFFFFFFFFu;
     double xi0 = 0.0, xi1 = 0.0;                                 // cached I row (two attributes)
     int m = m_lo;
     for (; m + 1 < m_hi; m += 2) {
         uint32_t ra, rb;                                         // (il << 10) | (jl << 26) | y: byte offsets of the two rows
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ra) : "r"(sREC_addr + 4u * m));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rb) : "r"(sREC_addr + 4u * m + 4u));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ra), "=r"(rb) : "r"(sREC_addr + 4u * m));
         const uint32_t ioa = ra & 0xFC00u, iob = rb & 0xFC00u;
         double ja0, ja1, jb0, jb1;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ja0), "=d"(ja1) : "r"(sXJ_addr + (ra >> 16)));
@@ -545,12 +553,16 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
             ea0 = fma(beta0[2 + u], ca[u], ea0); ea1 = fma(beta1[2 + u], ca[u], ea1);
             eb0 = fma(beta0[2 + u], cb[u], eb0); eb1 = fma(beta1[2 + u], cb[u], eb1);
         }
-        const int hmax = max(max(__double2hiint(ea0) & 0x7fffffff, __double2hiint(ea1) & 0x7fffffff),
-                             max(__double2hiint(eb0) & 0x7fffffff, __double2hiint(eb1) & 0x7fffffff));
         double ta0, ta1, tb0, tb1;
-        if (hmax < 0x40C5A380) {                                 // |s| < 11079 < 30 * 256/ln2 (= 11079.9) for all four
-            ta0 = v2_exp_fast(ea0, sT); ta1 = v2_exp_fast(ea1, sT);
-            tb0 = v2_exp_fast(eb0, sT); tb1 = v2_exp_fast(eb1, sT);
+        bool fast = true;
+        if (CHECK) {                                             // !CHECK: the CTA proved |eta| < 30 for all its records up front
+            const int hmax = max(max(__double2hiint(ea0) & 0x7fffffff, __double2hiint(ea1) & 0x7fffffff),
+                                 max(__double2hiint(eb0) & 0x7fffffff, __double2hiint(eb1) & 0x7fffffff));
+            fast = hmax < 0x40C5A380;                            // |s| < 11079 < 30 * 256/ln2 (= 11079.9) for all four
+        }
+        if (fast) {
+            ta0 = v2_u1_fast(ea0, sT); ta1 = v2_u1_fast(ea1, sT);
+            tb0 = v2_u1_fast(eb0, sT); tb1 = v2_u1_fast(eb1, sT);
         } else {                                                 // rare: R's eta clamps; misses carry a deviance correction
             double2 v;
             v = v2_exp_clamped(ea0, sT); ta0 = v.x; if (ra & 1u) acc0[NA - 1] += v.y;
@@ -558,10 +570,10 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
             v = v2_exp_clamped(eb0, sT); tb0 = v.x; if (rb & 1u) acc0[NA - 1] += v.y;
             v = v2_exp_clamped(eb1, sT); tb1 = v.x; if (rb & 1u) acc1[NA - 1] += v.y;
         }
-        v2_tail<Q>(da0, ca, ta0, acc0, sT, k3ff);
-        v2_tail<Q>(da1, ca, ta1, acc1, sT, k3ff);
-        v2_tail<Q>(db0, cb, tb0, acc0, sT, k3ff);
-        v2_tail<Q>(db1, cb, tb1, acc1, sT, k3ff);
+        v2_tail<Q>(da0, ca, ta0, acc0, esum0, sT, k3ff);
+        v2_tail<Q>(da1, ca, ta1, acc1, esum1, sT, k3ff);
+        v2_tail<Q>(db0, cb, tb0, acc0, esum0, sT, k3ff);
+        v2_tail<Q>(db1, cb, tb1, acc1, esum1, sT, k3ff);
     }
     if (m < m_hi) {                                              // odd tail: one record
         uint32_t r;
@@ -577,16 +589,49 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         double e0 = fma(beta0[1], d0, beta0[0]), e1 = fma(beta1[1], d1, beta1[0]);
 #pragma unroll
         for (int u = 0; u < Q; ++u) { e0 = fma(beta0[2 + u], c[u], e0); e1 = fma(beta1[2 + u], c[u], e1); }
-        const double2 a = v2_exp_clamped(e0, sT), b = v2_exp_clamped(e1, sT);
-        if (r & 1u) { acc0[NA - 1] += a.y; acc1[NA - 1] += b.y; }
-        v2_tail<Q>(d0, c, a.x, acc0, sT, k3ff);
-        v2_tail<Q>(d1, c, b.x, acc1, sT, k3ff);
+        double2 a, b;
+        if (CHECK) { a = v2_exp_clamped(e0, sT); b = v2_exp_clamped(e1, sT); }
+        else { a = make_double2(v2_u1_fast(e0, sT), 0.0); b = make_double2(v2_u1_fast(e1, sT), 0.0); }
+        if (CHECK && (r & 1u)) { acc0[NA - 1] += a.y; acc1[NA - 1] += b.y; }
+        v2_tail<Q>(d0, c, a.x, acc0, esum0, sT, k3ff);
+        v2_tail<Q>(d1, c, b.x, acc1, esum1, sT, k3ff);
     }
 }
 
 // Moment passes (lm pass / closed-form first IRLS pass).  MODE_LM: S(d), S(d^2), S(d*y), S(d*c_r) with y from the yv
 // stream.  MODE_SIGN: the outcome is s = -1 (hit) / +1 (miss); with hits-then-misses ordering it is enough to keep S(d)
 // of the hits and of the misses apart: S(d) = hits + misses, S(d*s) = misses - hits (one add + one FMA per evaluation).
+template <int MODE, int Q, int DIFF, int Y>
+__device__ __forceinline__ void m2_one(uint32_t r, int m, double xj0, double xj1, uint32_t &io_prev, double &xi0, double &xi1,
+                                       uint32_t sCD_addr, uint32_t sXI_addr, int diff_type, double (&acc0)[3 + Q], double (&acc1)[3 + Q]) {
+    const uint32_t io = r & 0xFC00u;
+    if (io != io_prev) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi0), "=d"(xi1) : "r"(sXI_addr + io));
+        io_prev = io;
+    }
+    const double d0 = proj_diff<DIFF>(xi0, xj0, diff_type);
+    const double d1 = proj_diff<DIFF>(xi1, xj1, diff_type);
+    if (MODE == MODE_LM) {
+        double yv;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(yv) : "r"(sCD_addr + 8u * (Q * V2_RCHUNK + m)));
+        acc0[0] += d0; acc1[0] += d1;
+        acc0[2] = fma(d0, yv, acc0[2]); acc1[2] = fma(d1, yv, acc1[2]);
+    } else if (Y == 0) {
+        acc0[0] += d0; acc1[0] += d1;
+    } else {
+        acc0[2] += d0; acc1[2] += d1;
+    }
+    acc0[1] = fma(d0, d0, acc0[1]); acc1[1] = fma(d1, d1, acc1[1]);
+#pragma unroll
+    for (int u = 0; u < Q; ++u) {
+        double cu;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cu) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
+        acc0[3 + u] = fma(d0, cu, acc0[3 + u]); acc1[3 + u] = fma(d1, cu, acc1[3 + u]);
+    }
+}
+
+// The loop is latency bound (record -> row address -> row -> 3 FP64 ops), so four records are fetched with one 16-byte
+// load and their J rows are requested together before any of them is consumed.
 template <int MODE, int Q, int DIFF, int Y, int NSL>
 __device__ __forceinline__ void m2_range(int m_begin, int m_end, int slice, uint32_t sREC_addr, uint32_t sCD_addr,
                                          uint32_t sXI_addr, uint32_t sXJ_addr, int diff_type,
@@ -595,36 +640,31 @@ __device__ __forceinline__ void m2_range(int m_begin, int m_end, int slice, uint
     const int m_lo = m_begin + slice * per, m_hi = (m_lo + per < m_end) ? (m_lo + per) : m_end;
     uint32_t io_prev = 0xFFFFFFFFu;
     double xi0 = 0.0, xi1 = 0.0;
-#pragma unroll 2
-    for (int m = m_lo; m < m_hi; ++m) {
+    int m = m_lo;
+    for (; m < m_hi && (m & 3); ++m) {                           // peel to a 16-byte boundary of the record buffer
         uint32_t r;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));
         double xj0, xj1;
-        const uint32_t io = r & 0xFC00u;
-        if (io != io_prev) {
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi0), "=d"(xi1) : "r"(sXI_addr + io));
-            io_prev = io;
-        }
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj0), "=d"(xj1) : "r"(sXJ_addr + (r >> 16)));
-        const double d0 = proj_diff<DIFF>(xi0, xj0, diff_type);
-        const double d1 = proj_diff<DIFF>(xi1, xj1, diff_type);
-        if (MODE == MODE_LM) {
-            double yv;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(yv) : "r"(sCD_addr + 8u * (Q * V2_RCHUNK + m)));
-            acc0[0] += d0; acc1[0] += d1;
-            acc0[2] = fma(d0, yv, acc0[2]); acc1[2] = fma(d1, yv, acc1[2]);
-        } else if (Y == 0) {
-            acc0[0] += d0; acc1[0] += d1;
-        } else {
-            acc0[2] += d0; acc1[2] += d1;
-        }
-        acc0[1] = fma(d0, d0, acc0[1]); acc1[1] = fma(d1, d1, acc1[1]);
+        m2_one<MODE, Q, DIFF, Y>(r, m, xj0, xj1, io_prev, xi0, xi1, sCD_addr, sXI_addr, diff_type, acc0, acc1);
+    }
+    for (; m + 3 < m_hi; m += 4) {
+        uint32_t r[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sREC_addr + 4u * m));
+        double xj[4][2];
 #pragma unroll
-        for (int u = 0; u < Q; ++u) {
-            double cu;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cu) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
-            acc0[3 + u] = fma(d0, cu, acc0[3 + u]); acc1[3 + u] = fma(d1, cu, acc1[3 + u]);
-        }
+        for (int k = 0; k < 4; ++k)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj[k][0]), "=d"(xj[k][1]) : "r"(sXJ_addr + (r[k] >> 16)));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            m2_one<MODE, Q, DIFF, Y>(r[k], m + k, xj[k][0], xj[k][1], io_prev, xi0, xi1, sCD_addr, sXI_addr, diff_type, acc0, acc1);
+    }
+    for (; m < m_hi; ++m) {
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));
+        double xj0, xj1;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj0), "=d"(xj1) : "r"(sXJ_addr + (r >> 16)));
+        m2_one<MODE, Q, DIFF, Y>(r, m, xj0, xj1, io_prev, xi0, xi1, sCD_addr, sXI_addr, diff_type, acc0, acc1);
     }
 }
 
@@ -654,7 +694,7 @@ struct V2Layout {
     static constexpr uint32_t CD = REC + 2 * REC_BYTES;                              // two buffers
     static constexpr uint32_t CD_BYTES = (NCD > 0 ? NCD : 1) * V2_RCHUNK * 8;
     static constexpr uint32_t TAB = CD + 2 * CD_BYTES;
-    static constexpr uint32_t TOTAL = TAB + sizeof(nb_tables2);
+    static constexpr uint32_t TOTAL = TAB + (MODE == MODE_IRLS_FULL ? sizeof(nb_tables2) : 0);
     static constexpr int NSL = v2_nslice(MODE, Q);
     static constexpr int THREADS = V2_TPS * NSL;
     static constexpr uint32_t RED = NSL * NA * TA * 8;
@@ -675,18 +715,23 @@ pass2_kernel(PassArgs P) {
 
     const int tid = threadIdx.x;
     const int tl = tid % V2_TPS, slice = tid / V2_TPS;
-    const int at = blockIdx.x;
-    const int sidx = ((int)blockIdx.y >= P.n_chunks0) ? 1 : 0;
-    const int chunk = (int)blockIdx.y - (sidx ? P.n_chunks0 : 0);
+    // chunk index is the fast grid dimension: the CTAs resident at any moment share a few attribute tiles, whose XT slabs
+    // (N x 128 doubles each) then stay in L2 while every chunk of the pair stream sweeps over them
+    const int at = blockIdx.y;
+    const int sidx = ((int)blockIdx.x >= P.n_chunks0) ? 1 : 0;
+    const int chunk = (int)blockIdx.x - (sidx ? P.n_chunks0 : 0);
     const StreamArgs &A = P.st[sidx];
     if (MODE == MODE_IRLS_FULL && P.tile_active && !P.tile_active[at]) return;
     const int64_t a0 = (int64_t)at * TA;
 
     if (MODE == MODE_IRLS_FULL) {   // table image
         nb_tables2 *sT = (nb_tables2 *)(smem_raw + L::TAB);
-        const nb_tables256 *g = P.tables256;
-        for (int e = tid; e < 64; e += V2_THREADS) sT->log_eln2_rot[(e + 63) & 63] = g->log_eln2[e];
-        for (int e = tid; e < 256; e += V2_THREADS) { sT->exp_t[e] = g->exp_t[e]; sT->log_rl[e] = make_double2(g->log_rc[e], g->log_lrc[e]); }
+        const nb_tables512 *g = P.tables512;
+        for (int e = tid; e < 256; e += V2_THREADS) {          // high word pre-biased by -j * 4096 (see v2_u1_fast)
+            const double tj = g->exp_t[e];
+            sT->exp_t[e] = __hiloint2double(__double2hiint(tj) - e * 4096, __double2loint(tj));
+        }
+        for (int e = tid; e < 512; e += V2_THREADS) sT->log_rl[e] = make_double2(g->log_rc[e], g->log_lrc[e]);
     }
     const uint32_t sT_addr = sbase + L::TAB;
     const uint32_t sXI_addr = sbase + L::XI + (uint32_t)tl * 16u;
@@ -702,6 +747,17 @@ pass2_kernel(PassArgs P) {
     double acc0[NA], acc1[NA];
 #pragma unroll
     for (int n = 0; n < NA; ++n) { acc0[n] = 0.0; acc1[n] = 0.0; }
+    unsigned esum0 = 0, esum1 = 0; int nrec = 0;   // wrapping sums of the biased exponents of u1 = 1 + exp(eta); the true sum
+                                          // (<= 52 per record, < 2^25 records per thread) fits and survives the wrap
+    bool may_clamp = false;
+    if (MODE == MODE_IRLS_FULL) {         // can any record of this attribute tile reach R's |eta| > 30 clamps?
+        double b0 = fabs(beta0[0]) + fabs(beta0[1]) * P.dmax[a0 + 2 * tl];
+        double b1 = fabs(beta1[0]) + fabs(beta1[1]) * P.dmax[a0 + 2 * tl + 1];
+#pragma unroll
+        for (int u = 0; u < Q; ++u) { b0 += fabs(beta0[2 + u]) * P.cmax[u]; b1 += fabs(beta1[2 + u]) * P.cmax[u]; }
+        const double lim = c_k[8] * 0.999;
+        may_clamp = __syncthreads_or(!(b0 < lim) || !(b1 < lim)) != 0;    // NaN coefficients take the checked path
+    }
 
     const int t_begin = A.chunk_tile[chunk], t_end = A.chunk_tile[chunk + 1];
 
@@ -766,7 +822,8 @@ pass2_kernel(PassArgs P) {
             int ms = (int)(rmid - rc);                      // first miss record of this chunk
             ms = ms < 0 ? 0 : (ms > n ? n : ms);
             if constexpr (MODE == MODE_IRLS_FULL) {
-                v2_range<Q, DIFF, NSL>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1);
+                if (may_clamp) v2_range<Q, DIFF, NSL, true>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1, esum0, esum1, nrec);
+                else v2_range<Q, DIFF, NSL, false>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1, esum0, esum1, nrec);
             } else if constexpr (MODE == MODE_LM) {
                 m2_range<MODE_LM, Q, DIFF, 0, NSL>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc0, acc1);
             } else {
@@ -774,6 +831,10 @@ pass2_kernel(PassArgs P) {
                 m2_range<MODE_SIGN, Q, DIFF, 1, NSL>(ms, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc0, acc1);
             }
         }
+    }
+    if (MODE == MODE_IRLS_FULL) {                          // integer exponent sums -> log(u1) total
+        acc0[NA - 2] = fma((double)(int)(esum0 - 1023u * (unsigned)nrec), c_k[4], acc0[NA - 2]);
+        acc1[NA - 2] = fma((double)(int)(esum1 - 1023u * (unsigned)nrec), c_k[4], acc1[NA - 2]);
     }
     if (MODE == MODE_SIGN) {                               // (hits, misses) -> (S d, S d*s)
         const double h0 = acc0[0], m0 = acc0[2], h1 = acc1[0], m1 = acc1[2];
@@ -1142,19 +1203,19 @@ int dmalloc(T **p, size_t n) {
 }
 
 nb_tables *g_tables_dev[64] = {nullptr};
-nb_tables256 *g_tables256_dev[64] = {nullptr};
+nb_tables512 *g_tables512_dev[64] = {nullptr};
 
-int get_tables256(npdrb_ctx *ctx, const nb_tables256 **out) {
-    if (!g_tables256_dev[ctx->device & 63]) {
-        static const nb_tables256 host_tables = NB_TABLES256_STATIC_INIT;
-        nb_tables256 *d = nullptr;
-        cudaError_t e = (cudaMalloc)((void **)&d, sizeof(nb_tables256));       // lives as long as the process: not from the cache
-        if (e != cudaSuccess) { npdrb_set_error("cudaMalloc(tables256): %s", cudaGetErrorString(e)); return NPDRB_ENOMEM; }
-        NB_CUDA(cudaMemcpyAsync(d, &host_tables, sizeof(nb_tables256), cudaMemcpyHostToDevice, ctx->stream));
+int get_tables512(npdrb_ctx *ctx, const nb_tables512 **out) {
+    if (!g_tables512_dev[ctx->device & 63]) {
+        static const nb_tables512 host_tables = NB_TABLES512_STATIC_INIT;
+        nb_tables512 *d = nullptr;
+        cudaError_t e = (cudaMalloc)((void **)&d, sizeof(nb_tables512));       // lives as long as the process: not from the cache
+        if (e != cudaSuccess) { npdrb_set_error("cudaMalloc(tables512): %s", cudaGetErrorString(e)); return NPDRB_ENOMEM; }
+        NB_CUDA(cudaMemcpyAsync(d, &host_tables, sizeof(nb_tables512), cudaMemcpyHostToDevice, ctx->stream));
         NB_CUDA(cudaStreamSynchronize(ctx->stream));
-        g_tables256_dev[ctx->device & 63] = d;
+        g_tables512_dev[ctx->device & 63] = d;
     }
-    *out = g_tables256_dev[ctx->device & 63];
+    *out = g_tables512_dev[ctx->device & 63];
     return NPDRB_OK;
 }
 
@@ -1244,6 +1305,11 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     const int64_t n_at = nb_cdiv(s->xt_nattr > 0 ? s->xt_nattr : s->p, TA);
     int64_t target = (int64_t)(16.0 * ctx->sm_count * work_share);
     int64_t C = nb_cdiv(target > 1 ? target : 1, n_at);
+    {   // L2 residency: sm_count / (total chunks) attribute-tile slabs are live at once; keep them within ~48 MB
+        const double slab = (double)nb_round_up(N, BI > BJ ? BI : BJ) * TA * sizeof(double);
+        const int64_t c_l2 = (int64_t)ceil(ctx->sm_count * slab / (48.0 * 1024 * 1024) * work_share);
+        if (C < c_l2) C = c_l2;
+    }
     if (C < 1) C = 1;
     if (C > st.n_tiles) C = st.n_tiles;
     if (C < 1) C = 1;
@@ -1285,7 +1351,8 @@ template <int MODE, int Q, int DIFF>
 int launch_pass_t(npdrb_ctx *ctx, const PassArgs &P, int n_at, int n_chunks) {
     const size_t smem = pass_smem(MODE, Q);
     NB_CUDA(cudaFuncSetAttribute(pass_kernel<MODE, Q, DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)n_at, (unsigned)n_chunks);
+    if (n_at > 65535) { npdrb_set_error("regress: more than 65535 attribute tiles in one call; split the attribute range"); return NPDRB_EINVAL; }
+    dim3 grid((unsigned)n_chunks, (unsigned)n_at);
     pass_kernel<MODE, Q, DIFF><<<grid, RTHREADS, smem, ctx->stream>>>(P);
     NB_LAUNCH_CHECK(ctx);
     return NPDRB_OK;
@@ -1299,7 +1366,8 @@ template <int MODE, int Q, int DIFF>
 int launch_pass2_t(npdrb_ctx *ctx, const PassArgs &P, int n_at, int n_chunks) {
     const size_t smem = V2Layout<MODE, Q>::SMEM;
     NB_CUDA(cudaFuncSetAttribute(pass2_kernel<MODE, Q, DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)n_at, (unsigned)n_chunks);
+    if (n_at > 65535) { npdrb_set_error("regress: more than 65535 attribute tiles in one call; split the attribute range"); return NPDRB_EINVAL; }
+    dim3 grid((unsigned)n_chunks, (unsigned)n_at);
     pass2_kernel<MODE, Q, DIFF><<<grid, V2Layout<MODE, Q>::THREADS, smem, ctx->stream>>>(P);
     NB_LAUNCH_CHECK(ctx);
     return NPDRB_OK;
@@ -1482,6 +1550,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     NB_CHECK(dmalloc(&d_hitd, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_missd, (size_t)nattr_pad));
     double *d_dmax = nullptr;
     NB_CHECK(dmalloc(&d_dmax, (size_t)nattr_pad));
+    NB_CUDA(cudaMemsetAsync(d_dmax, 0, sizeof(double) * nattr_pad, ctx->stream));
     if (!lm) {
         column_dmax_kernel<<<(unsigned)nattr, 256, 0, ctx->stream>>>(s->dX, s->ldx, N, attr0, nattr, diff_type, d_dmax);
         NB_LAUNCH_CHECK(ctx);
@@ -1495,9 +1564,9 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     NB_CUDA(cudaMemsetAsync(d_iters, 0, sizeof(int) * nattr_pad, ctx->stream));
 
     const nb_tables *d_tab = nullptr;
-    const nb_tables256 *d_tab256 = nullptr;
+    const nb_tables512 *d_tab512 = nullptr;
     NB_CHECK(get_tables(ctx, &d_tab));
-    NB_CHECK(get_tables256(ctx, &d_tab256));
+    NB_CHECK(get_tables512(ctx, &d_tab512));
 
     SolveArgs S;
     memset(&S, 0, sizeof(S));
@@ -1537,7 +1606,9 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         PassArgs P;
         memset(&P, 0, sizeof(P));
         P.XT = s->dXT; P.ldt = s->ldt; P.N = N; P.nattr = (int)nattr; P.nattr_pad = (int)nattr_pad;
-        P.beta = d_beta; P.tile_active = tile_active; P.tables = d_tab; P.tables256 = d_tab256; P.diff_type = diff_type;
+        P.beta = d_beta; P.tile_active = tile_active; P.tables = d_tab; P.tables512 = d_tab512; P.diff_type = diff_type;
+        P.dmax = d_dmax;
+        for (int c = 0; c < NPDRB_MAX_COVARS; ++c) P.cmax[c] = S.cmax[c];
         double *pp = d_part;
         int total_chunks = 0;
         for (int i = 0; i < s->n_streams; ++i) {
