@@ -47,6 +47,14 @@ def f_bin(q):
     return 2 * ((k - 1) + k * (k + 1) // 2 + k) + (k - 1) + 7 + 48
 
 
+def fp64_instr(q):
+    """FP64 instructions the v2 IRLS pass kernel EXECUTES per attribute x record evaluation (SASS count):
+    12 (diff, range reduction, exp polynomial, 1+t, reciprocal, weight, deviance product) + 2(k-1) (eta, w*x) +
+    k(k+1)/2 (X'WX) + k (score), k = 2 + q: 19 at q = 0, 32 at q = 2."""
+    k = 2 + q
+    return 12 + 2 * (k - 1) + k * (k + 1) // 2 + k
+
+
 def gen_columns(gen, N, ncols, col0, p_total, n_func, f, g, sgn, device, dtype):
     """Columns [col0, col0+ncols) of the stand-in data: x = sqrt(.8 - l^2) z + sqrt(.2) f + l * s * g  (l = 0 for
     background attributes; for the n_func functional attributes the sign s flips between cases and controls on
@@ -339,8 +347,11 @@ def main():
     # roofline of the dominant kernel (IRLS pass kernel), rank 0's launches of the last step
     peak = ctx.fp64_peak()
     n_full = max(int(km["n_pass_full"]), 1)
-    flops = km["evals_pass_full"] * f_bin(q)
+    # issue-slot roofline: every FP64 instruction (DADD, DMUL or DFMA) takes one slot of the pipe whose peak the DFMA
+    # micro-benchmark measures as 2 flops per slot, so achieved = evaluations x executed FP64 instructions x 2 / time
+    flops = km["evals_pass_full"] * fp64_instr(q) * 2.0
     achieved = flops / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
+    canon = km["evals_pass_full"] * f_bin(q) / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
     hbm_peak = 6553.6
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -363,12 +374,18 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes / n_full,
                 "peak_source": "measured live by npdrb_measure_fp64_peak (DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
                 "launches": n_full, "avg_launch_ms": km["pass_full_ms"] / n_full,
-                "flops_per_eval_iteration": f_bin(q), "evals_per_launch_avg": km["evals_pass_full"] / n_full,
-                "note": "achieved = executed attribute x record evaluations x F_bin(q) (SURVEY 8d canonical count) / CUDA-event "
-                        "launch time; records = pairs after folding mutual (i,j)/(j,i) pairs into one weight-2 record; the "
-                        "kernel issues 24 FP64 + 17 other instructions per evaluation at q = 0 (37 + 18.5 at q = 2; SASS count, DESIGN.md 4); "
-                        "an FP64 warp instruction holds the dispatch port for 2 cycles, so the issue-limited ceiling of this mix "
-                        "is 48/65 = 74 % FP64-pipe activity (ncu: 68.6 %)",
+                "fp64_instr_per_eval": fp64_instr(q), "evals_per_launch_avg": km["evals_pass_full"] / n_full,
+                "note": "achieved = attribute x record evaluations per launch x FP64 instructions the kernel executes per evaluation "
+                        "(19 at q = 0, 32 at q = 2; SASS count, DESIGN.md 4) x 2 flops per issue slot / CUDA-event launch time, against "
+                        "the measured DFMA peak: frac is the FP64 pipe's issue-slot utilisation (ncu sm__pipe_fp64_cycles_active agrees). "
+                        "records = pairs after folding mutual (i,j)/(j,i) pairs into one weight-2 record.  The kernel also issues 12.5 "
+                        "(q = 0) / 13.5 (q = 2) non-FP64 instructions per evaluation; an FP64 warp instruction holds the dispatch "
+                        "port for 2 cycles, so the issue-limited ceiling of this mix is 38/50.5 = 75 % (q = 0), 64/77.5 = 83 % (q = 2)",
+                "canonical": {"flops_per_eval_iteration": f_bin(q), "achieved": canon,
+                              "frac": canon / peak["dfma_tflops"] if peak["dfma_tflops"] else None,
+                              "note": "SURVEY 8d's canonical count (exp = log = 20, reciprocal = 8 flops): exceeds 1 because the kernel "
+                                      "spends 7 FP64 instructions on exp, 2 on the reciprocal and replaces the per-record log by a running "
+                                      "product (one multiply per record, one log per thread)"},
                 "records_per_pair": km["records"] / max(info["n_pairs_used"], 1),
                 "share_of_step": km["pass_full_ms"] / ms_step,
                 "hbm": {"achieved": alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9 if km["pass_full_ms"] > 0 else 0.0,

@@ -433,7 +433,6 @@ __constant__ double c_k[10] = {
 
 struct nb_tables2 {                 // shared-memory image used by v2
     double exp_t[256];              // 2^(j/256)
-    double2 log_rl[512];            // (rc_i, -log rc_i), 512 mantissa bins
 };
 
 constexpr int V2_TPS = TA / 2;      // threads per slice (64)
@@ -465,29 +464,21 @@ __device__ __noinline__ double2 v2_exp_clamped(double sv, uint32_t sT) {
     return make_double2(v2_u1_fast(sv, sT), 0.0);
 }
 
-// everything after u1 = 1 + exp(eta): weight, log(u1), accumulation -- independent of the outcome.  The binary
-// exponent of u1 is summed in the integer register esum (x ln2 once per work item); acc[NA - 2] takes the mantissa part.
+// everything after u1 = 1 + exp(eta): weight, deviance, accumulation -- independent of the outcome.
+// Deviance: sum log(u1) = log(prod u1).  acc[NA - 2] is a running PRODUCT of the u1 (one DMUL per evaluation instead of
+// a table-driven log: 6 FP64 + 3 other instructions); v2_renorm moves its binary exponent into an integer register
+// every other record and the kernel takes one log() per thread at the end.  Error: one rounding (2^-53 relative) per
+// factor, i.e. <= n * 1.1e-16 ABSOLUTE on a sum of order 0.7 n -- tighter than any summed log.
 template <int Q>
 __device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 ? Q : 1], const double u1,
-                                        double (&acc)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], unsigned &esum, const uint32_t sT, const int k3ff) {
+                                        double (&acc)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2]) {
     constexpr int K = 2 + Q;
     constexpr int NA = K * (K + 1) / 2 + K + 2;
     double inv;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(u1));
     inv = fma(inv, fma(-u1, inv, 1.0), inv);                    // 1/(1+t) = 1 - mu
     const double w = fma(-inv, inv, inv);                       // mu(1-mu) = (1-mu) - (1-mu)^2 = mu.eta for the logit link
-    const int hi = __double2hiint(u1);
-    double rc, lrc;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lrc) : "r"(sT + 2048u + (uint32_t)((hi >> 7) & 0x1FF0)));
-    esum += (unsigned)(hi >> 20);                                           // biased exponent; 1023 x (records) comes off at the end
-    int mhi;
-    asm("lop3.b32 %0, %1, 0x000FFFFF, %2, 0xEA;" : "=r"(mhi) : "r"(hi), "r"(k3ff));     // (hi & 0xFFFFF) | 0x3FF00000
-    const double m = __hiloint2double(mhi, __double2loint(u1));
-    const double f = fma(m, rc, -1.0);
-    const double sl = f + lrc;
-    double pp = fma(f, c_k[5], c_k[6]);
-    pp = fma(pp, f * f, sl);
-    acc[NA - 2] += pp;                                          // log(u1) - e*ln2;  log(1 + t) = -log(1 - mu)
+    acc[NA - 2] *= u1;                                          // prod (1 + t);  log(1 + t) = -log(1 - mu)
     double wv[K];
     wv[0] = w;
     wv[1] = w * d;
@@ -509,6 +500,15 @@ __device__ __forceinline__ void v2_tail(const double d, const double (&c)[Q > 0 
     for (int u = 0; u < Q; ++u) acc[n_ + 2 + u] = fma(inv, c[u], acc[n_ + 2 + u]);
 }
 
+// running product in [1, 2^107) -> [1, 2): the biased exponent goes to esum (wrapping; 1023 x (calls) comes off at the end)
+__device__ __forceinline__ void v2_renorm(double &prod, unsigned &esum) {
+    const int hi = __double2hiint(prod);
+    esum += (unsigned)(hi >> 20);
+    int mhi;
+    asm("lop3.b32 %0, %1, 0x000FFFFF, 0x3FF00000, 0xEA;" : "=r"(mhi) : "r"(hi));         // (hi & 0xFFFFF) | 0x3FF00000
+    prod = __hiloint2double(mhi, __double2loint(prod));
+}
+
 // records [m_begin, m_end) of the staged chunk, this thread's slice.  Two records x two attributes are in flight per
 // thread: four independent exp -> reciprocal -> log chains.
 template <int Q, int DIFF, int NSL, bool CHECK>
@@ -516,15 +516,14 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
                                          uint32_t sXI_addr, uint32_t sXJ_addr, uint32_t sT, int diff_type,
                                          const double (&beta0)[2 + Q], const double (&beta1)[2 + Q],
                                          double (&acc0)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2],
-                                         double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], unsigned &esum0, unsigned &esum1, int &nrec) {
+                                         double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], unsigned &esum0, unsigned &esum1, int &nren) {
     constexpr int NA = (2 + Q) * (3 + Q) / 2 + (2 + Q) + 2;
-    const int k3ff = 0x3FF00000;
     // each slice walks a CONTIGUOUS part of the range: records are in list order (grouped by Ri), so the I row
     // repeats for several records in a row and stays in registers (halves the shared-memory tile traffic).
     // m_begin is even and slices are an even number of records long: record pairs are fetched with one 8-byte load.
     const int len = m_end - m_begin, per = (((len + NSL - 1) / NSL) + 1) & ~1;
     const int m_lo = m_begin + slice * per, m_hi = (m_lo + per < m_end) ? (m_lo + per) : m_end;
-    if (m_hi > m_lo) nrec += m_hi - m_lo;
+    if (m_hi > m_lo) nren += (m_hi - m_lo + 1) >> 1;             // one renormalisation per loop trip (+ one for an odd tail)
     uint32_t io_prev = 0xFFFFFFFFu;
     double xi0 = 0.0, xi1 = 0.0;                                 // cached I row (two attributes)
     int m = m_lo;
@@ -570,10 +569,12 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
             v = v2_exp_clamped(eb0, sT); tb0 = v.x; if (rb & 1u) acc0[NA - 1] += v.y;
             v = v2_exp_clamped(eb1, sT); tb1 = v.x; if (rb & 1u) acc1[NA - 1] += v.y;
         }
-        v2_tail<Q>(da0, ca, ta0, acc0, esum0, sT, k3ff);
-        v2_tail<Q>(da1, ca, ta1, acc1, esum1, sT, k3ff);
-        v2_tail<Q>(db0, cb, tb0, acc0, esum0, sT, k3ff);
-        v2_tail<Q>(db1, cb, tb1, acc1, esum1, sT, k3ff);
+        v2_tail<Q>(da0, ca, ta0, acc0);
+        v2_tail<Q>(da1, ca, ta1, acc1);
+        v2_tail<Q>(db0, cb, tb0, acc0);
+        v2_tail<Q>(db1, cb, tb1, acc1);
+        v2_renorm(acc0[NA - 2], esum0);
+        v2_renorm(acc1[NA - 2], esum1);
     }
     if (m < m_hi) {                                              // odd tail: one record
         uint32_t r;
@@ -593,8 +594,10 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         if (CHECK) { a = v2_exp_clamped(e0, sT); b = v2_exp_clamped(e1, sT); }
         else { a = make_double2(v2_u1_fast(e0, sT), 0.0); b = make_double2(v2_u1_fast(e1, sT), 0.0); }
         if (CHECK && (r & 1u)) { acc0[NA - 1] += a.y; acc1[NA - 1] += b.y; }
-        v2_tail<Q>(d0, c, a.x, acc0, esum0, sT, k3ff);
-        v2_tail<Q>(d1, c, b.x, acc1, esum1, sT, k3ff);
+        v2_tail<Q>(d0, c, a.x, acc0);
+        v2_tail<Q>(d1, c, b.x, acc1);
+        v2_renorm(acc0[NA - 2], esum0);
+        v2_renorm(acc1[NA - 2], esum1);
     }
 }
 
@@ -731,7 +734,6 @@ pass2_kernel(PassArgs P) {
             const double tj = g->exp_t[e];
             sT->exp_t[e] = __hiloint2double(__double2hiint(tj) - e * 4096, __double2loint(tj));
         }
-        for (int e = tid; e < 512; e += V2_THREADS) sT->log_rl[e] = make_double2(g->log_rc[e], g->log_lrc[e]);
     }
     const uint32_t sT_addr = sbase + L::TAB;
     const uint32_t sXI_addr = sbase + L::XI + (uint32_t)tl * 16u;
@@ -747,8 +749,9 @@ pass2_kernel(PassArgs P) {
     double acc0[NA], acc1[NA];
 #pragma unroll
     for (int n = 0; n < NA; ++n) { acc0[n] = 0.0; acc1[n] = 0.0; }
-    unsigned esum0 = 0, esum1 = 0; int nrec = 0;   // wrapping sums of the biased exponents of u1 = 1 + exp(eta); the true sum
-                                          // (<= 52 per record, < 2^25 records per thread) fits and survives the wrap
+    unsigned esum0 = 0, esum1 = 0; int nren = 0;   // wrapping sums of the biased exponents taken out of the running products
+                                          // of u1 = 1 + exp(eta); the true sum (<= 53 per record, < 2^25 records per thread) fits
+    if (MODE == MODE_IRLS_FULL) { acc0[NA - 2] = 1.0; acc1[NA - 2] = 1.0; }
     bool may_clamp = false;
     if (MODE == MODE_IRLS_FULL) {         // can any record of this attribute tile reach R's |eta| > 30 clamps?
         double b0 = fabs(beta0[0]) + fabs(beta0[1]) * P.dmax[a0 + 2 * tl];
@@ -822,8 +825,8 @@ pass2_kernel(PassArgs P) {
             int ms = (int)(rmid - rc);                      // first miss record of this chunk
             ms = ms < 0 ? 0 : (ms > n ? n : ms);
             if constexpr (MODE == MODE_IRLS_FULL) {
-                if (may_clamp) v2_range<Q, DIFF, NSL, true>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1, esum0, esum1, nrec);
-                else v2_range<Q, DIFF, NSL, false>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1, esum0, esum1, nrec);
+                if (may_clamp) v2_range<Q, DIFF, NSL, true>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1, esum0, esum1, nren);
+                else v2_range<Q, DIFF, NSL, false>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1, esum0, esum1, nren);
             } else if constexpr (MODE == MODE_LM) {
                 m2_range<MODE_LM, Q, DIFF, 0, NSL>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc0, acc1);
             } else {
@@ -833,8 +836,8 @@ pass2_kernel(PassArgs P) {
         }
     }
     if (MODE == MODE_IRLS_FULL) {                          // integer exponent sums -> log(u1) total
-        acc0[NA - 2] = fma((double)(int)(esum0 - 1023u * (unsigned)nrec), c_k[4], acc0[NA - 2]);
-        acc1[NA - 2] = fma((double)(int)(esum1 - 1023u * (unsigned)nrec), c_k[4], acc1[NA - 2]);
+        acc0[NA - 2] = fma((double)(int)(esum0 - 1023u * (unsigned)nren), c_k[4], log(acc0[NA - 2]));
+        acc1[NA - 2] = fma((double)(int)(esum1 - 1023u * (unsigned)nren), c_k[4], log(acc1[NA - 2]));
     }
     if (MODE == MODE_SIGN) {                               // (hits, misses) -> (S d, S d*s)
         const double h0 = acc0[0], m0 = acc0[2], h1 = acc1[0], m1 = acc1[2];

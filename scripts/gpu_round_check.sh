@@ -1,9 +1,15 @@
+# One GPU-box visit: parity tests, bench line, ncu launch list + full capture of the dominant kernels.  Usage (from the
+# repo root): gpurun --timeout 1500 -- 'bash scripts/gpu_round_check.sh <tag>'
 cd $GRAFT_REPO_ROOT
+TAG=${1:-x}
 mkdir -p gpurun_out
-(time python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_r1d.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_r1d.log
-tail -5 gpurun_out/pytest_r1d.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_cfg4_r1d.json 2> gpurun_out/bench_cfg4_r1d.err; echo "bench rc=$?"
-python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-variants > gpurun_out/plain_d.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1d.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-variants > gpurun_out/ncu_d1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:pass2_kernel -c 3 -o gpurun_out/prof_pass2_r1d -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-variants > gpurun_out/ncu_d2.log 2>&1
+(time python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$TAG.log
+tail -5 gpurun_out/pytest_$TAG.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_cfg4_$TAG.json 2> gpurun_out/bench_cfg4_$TAG.err; echo "bench rc=$?"
+python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-variants > gpurun_out/plain_$TAG.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-variants > gpurun_out/ncu_${TAG}_1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:pass2_kernel -c 3 -o gpurun_out/prof_pass2_$TAG -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-variants > gpurun_out/ncu_${TAG}_2.log 2>&1
+if [ "$2" = "cfg5" ]; then
+python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline --no-variants > gpurun_out/bench_cfg5_1gpu_$TAG.json 2> gpurun_out/bench_cfg5_1gpu_$TAG.err; echo "cfg5 rc=$?"
+fi
 echo done

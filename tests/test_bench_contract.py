@@ -36,7 +36,7 @@ def test_gpu_arm_line():
     assert BASE_KEYS | {"roofline", "clocks", "stages"} <= set(d)
     assert d["n_gpus"] == 1 and d["value"] > 0 and d["gpu_launches"] > 0 and d["higher_is_better"] is True
     r = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and 0 < r["frac"] < 1.5
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and 0 < r["frac"] < 1.0
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 1024 * 2048 * 8 and e["d2h_bytes_per_step"] == 2048 * 64
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
