@@ -392,8 +392,8 @@ def main():
                         "peak": hbm_peak, "unit": "GB/s",
                         "frac": (alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9) / hbm_peak if km["pass_full_ms"] > 0 else None}}
     dist_adds = float(p) * N * (N - 1)          # 2 DADD per element pair over the lower triangle (symmetric mode)
-    if world > 1:
-        dist_adds = 2.0 * float(p) * info["rows"][1] * N        # rectangle per rank
+    if world > 1:                                               # balanced: ~half of the rank's rectangle (the rest arrives over NVLink)
+        dist_adds = (1.0 if os.environ.get("NPDRB_NO_BALANCED") != "1" else 2.0) * float(p) * info["rows"][1] * N
     stage = {"distance_ms": sm["distance"], "neighbors_ms": sm["neighbors"], "prepare_ms": sm["prepare"], "regress_ms": sm["regress"],
              "irls_full_passes": passes, "pass_first_ms": km["pass_first_ms"],
              "distance_fp64_add_frac": (dist_adds / (sm["distance"] * 1e-3) / 1e12) / peak["dadd_tflops"] if sm["distance"] > 0 else None}
@@ -411,7 +411,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "description": wl["desc"], "N": N, "p": p, "q": q, "pairs_M": M,
                        "regression": "binomial", "nbd": "multisurf", "metric": "manhattan", "seed": SEED,
-                       "parallelism": f"rows/{world} (distance+neighbours) -> all-gather pairs -> attrs/{world} (regression)",
+                       "parallelism": f"rows/{world} (distance+neighbours" + (", symmetric halves swapped in one all-to-all" if world > 1 else "")
+                                      + f") -> all-gather pairs -> attrs/{world} (regression)",
                        "l2": "inputs (X = %.0f MB per GPU) exceed the 126 MB L2; no flush needed" % (N * p * 8 / 1e6)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "stages": stage, "fp64_peak_measured": peak, "variants": variants,

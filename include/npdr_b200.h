@@ -11,6 +11,8 @@
  *   npdrb_nearest_neighbors  <- nearestNeighbors    R/nearestNeighbors.R:153-285 (+ get_Ri_nearest :622-634,
  *                                                    uniqueNeighbors :572-583, knnVec :603-607)
  *   npdrb_nearest_neighbors_hitmiss <- nearestNeighborsSeparateHitMiss   R/nearestNeighbors.R:318-551
+ *   npdrb_distances2         <- npdrDistances2      R/npdrLearner.R:323-339 (flexclust::dist2)
+ *   npdrb_nearest_neighbors2 <- nearestNeighbors2   R/npdrLearner.R:378-482 (+ get_Ri_nearest R/nearestNeighbors.R:622-634)
  *   npdrb_knn_surf           <- knnSURF             R/utils.R:12-18
  *   npdrb_regress            <- the regression loop + diffRegression   R/npdr.R:391-430, 18-71
  *   npdrb_npdr               <- npdr() between argument parsing and order()/p.adjust()
@@ -141,6 +143,16 @@ int npdrb_diff(npdrb_ctx *ctx, const double *a, const double *b, int64_t n, int3
 /* N x N distance matrix (column-major, symmetric, zero diagonal) from N x p attributes */
 int npdrb_distances(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, int32_t metric, int32_t fast_euclidean,
                     double *D_out);
+/* npdrDistances2: m1 x m2 matrix (column-major) of distances between the rows of X1 (m1 x p) and of X2 (m2 x p).
+ * metric: MANHATTAN, EUCLIDEAN or ALLELE_SHARING_MANHATTAN (both matrices halved first). */
+int npdrb_distances2(npdrb_ctx *ctx, const double *X1, int64_t m1, const double *X2, int64_t m2, int64_t p, int32_t metric,
+                     double *D_out);
+/* nearestNeighbors2: for every instance of X2 (test) its neighbours among the instances of X1 (train).
+ * The reference returns a list of m2 integer vectors; here: offsets (m2 + 1, malloc'ed) into idx (M train indices,
+ * 1-based, malloc'ed).  sd_vec (length m2) may be NULL; radius_out (length m2) may be NULL (surf / multisurf). */
+int npdrb_nearest_neighbors2(npdrb_ctx *ctx, const double *X1, int64_t m1, const double *X2, int64_t m2, int64_t p,
+                             int32_t nbd_method, int32_t nbd_metric, const double *sd_vec, double sd_frac, int64_t k,
+                             int64_t **offsets, int32_t **idx, int64_t *M, double *radius_out);
 int64_t npdrb_knn_surf(int64_t m_samples, double sd_frac);
 /* nearestNeighbors: X is N x p attributes, or the N x N distance matrix when nbd_metric == PRECOMPUTED.
  * sd_vec (length N) may be NULL.  radius_out (length N) may be NULL; filled for surf/multisurf. */
@@ -180,6 +192,16 @@ int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t 
 /* rows [row0, row0+nrows) of the distance matrix against all N instances (nrows == N: symmetric mode) */
 int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
 /* adopt a precomputed distance block (device, nrows x N row-major = the columns Ri of a symmetric D) */
+/* Balanced symmetric distances for `world` row blocks (row_starts: world + 1 instance bounds, multiples of 128 except the
+ * last = N): this rank computes its diagonal square and a checkerboard half of every off-diagonal square (~N^2/(2 world)
+ * instance pairs instead of N^2/world); the other half arrives from the peers: _balanced_counts gives the per-peer message
+ * sizes in doubles, _balanced_pack fills a device send buffer (peers in rank order), the host runs an all-to-all
+ * (NCCL over NVLink), _balanced_unpack drops the received tiles into the block.  Bit-identical to the unsharded matrix. */
+int npdrb_session_distances_balanced(npdrb_session *s, int32_t metric, int32_t fast_euclidean, const int64_t *row_starts,
+                                     int32_t rank, int32_t world);
+int npdrb_session_balanced_counts(npdrb_session *s, int64_t *send_doubles, int64_t *recv_doubles);   /* length world each */
+int npdrb_session_balanced_pack(npdrb_session *s, double *d_send);
+int npdrb_session_balanced_unpack(npdrb_session *s, const double *d_recv);
 int npdrb_session_set_device_distances(npdrb_session *s, const double *dD, int64_t ldd, int64_t row0, int64_t nrows);
 int npdrb_session_set_sd_vec(npdrb_session *s, const double *sd_vec_host);   /* user sd.vec, length N */
 /* neighbour lists for the owned rows; *M_local = number of pairs found */

@@ -67,6 +67,9 @@ SIGNATURES = {
     "npdrb_release_cache": (C.c_int, [_vp]),
     "npdrb_diff": (C.c_int, [_vp, _dp, _dp, _i64, _i32, C.c_double, _dp]),
     "npdrb_distances": (C.c_int, [_vp, _dp, _i64, _i64, _i32, _i32, _dp]),
+    "npdrb_distances2": (C.c_int, [_vp, _dp, _i64, _dp, _i64, _i64, _i32, _dp]),
+    "npdrb_nearest_neighbors2": (C.c_int, [_vp, _dp, _i64, _dp, _i64, _i64, _i32, _i32, _dp, C.c_double, _i64,
+                                           C.POINTER(C.POINTER(_i64)), C.POINTER(_ip), C.POINTER(_i64), _dp]),
     "npdrb_knn_surf": (_i64, [_i64, C.c_double]),
     "npdrb_nearest_neighbors": (C.c_int, [_vp, _dp, _i64, _i64, _i32, _i32, _dp, C.c_double, _i64, _i32,
                                           C.POINTER(_ip), C.POINTER(_ip), C.POINTER(_i64), C.POINTER(_i64),
@@ -82,6 +85,10 @@ SIGNATURES = {
     "npdrb_session_set_device_inputs": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "npdrb_session_distances": (C.c_int, [_vp, _i32, _i32, _i64, _i64]),
     "npdrb_session_set_device_distances": (C.c_int, [_vp, _vp, _i64, _i64, _i64]),
+    "npdrb_session_distances_balanced": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i64), _i32, _i32]),
+    "npdrb_session_balanced_counts": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "npdrb_session_balanced_pack": (C.c_int, [_vp, _vp]),
+    "npdrb_session_balanced_unpack": (C.c_int, [_vp, _vp]),
     "npdrb_session_set_sd_vec": (C.c_int, [_vp, _dp]),
     "npdrb_session_neighbors": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "npdrb_session_neighbors_hitmiss": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
@@ -239,6 +246,23 @@ class Session:
         nrows = self.N if nrows is None else nrows
         check(load().npdrb_session_distances(self.handle, METRIC[metric], int(bool(fast_euclidean)), int(row0), int(nrows)))
         self.nrows = int(nrows)
+
+    def distances_balanced(self, metric, row_starts, rank):
+        """This rank's share of the symmetric matrix (diagonal square + half of every off-diagonal square);
+        -> (send_counts, recv_counts) in doubles per peer for the all-to-all that completes the block."""
+        world = len(row_starts) - 1
+        rs = (_i64 * (world + 1))(*[int(v) for v in row_starts])
+        check(load().npdrb_session_distances_balanced(self.handle, METRIC[metric], 0, rs, int(rank), world))
+        self.nrows = int(row_starts[rank + 1] - row_starts[rank])
+        sc, rc = (_i64 * world)(), (_i64 * world)()
+        check(load().npdrb_session_balanced_counts(self.handle, sc, rc))
+        return list(sc), list(rc)
+
+    def balanced_pack(self, d_send):
+        check(load().npdrb_session_balanced_pack(self.handle, _vp(d_send)))
+
+    def balanced_unpack(self, d_recv):
+        check(load().npdrb_session_balanced_unpack(self.handle, _vp(d_recv)))
 
     def set_device_distances(self, dD, ldd, row0, nrows):
         check(load().npdrb_session_set_device_distances(self.handle, _vp(dD), int(ldd), int(row0), int(nrows)))

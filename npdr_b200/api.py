@@ -9,6 +9,8 @@ the p-value / ordering / p.adjust residue in `rstats` (it stays in R in the R de
   npdrDistances      R/nearestNeighbors.R:63-101
   nearestNeighbors   R/nearestNeighbors.R:153-285
   nearestNeighborsSeparateHitMiss   R/nearestNeighbors.R:318-551
+  npdrDistances2     R/npdrLearner.R:323-339
+  nearestNeighbors2  R/npdrLearner.R:378-482
   uniqueNeighbors    R/nearestNeighbors.R:572-583
   knnVec             R/nearestNeighbors.R:603-607
   knnSURF            R/utils.R:12-18
@@ -114,6 +116,46 @@ def npdrDistances(attr_mat, metric="manhattan", fast_dist=False, device=0, fast_
     D = np.empty((N, N), order="F")
     check(_lib.load().npdrb_distances(context(device).handle, dptr(X), N, p, METRIC[metric], int(bool(fast_euclidean)), dptr(D)))
     return D
+
+
+def npdrDistances2(attr_mat1, attr_mat2, metric="manhattan", device=0):
+    """R/npdrLearner.R:323-339 -- m1 x m2 distances between the rows of two attribute matrices (flexclust::dist2).
+    As in the reference, any metric other than 'euclidean' / 'allele-sharing-manhattan' means manhattan."""
+    X1, _ = _as_matrix(attr_mat1)
+    X2, _ = _as_matrix(attr_mat2)
+    if X1.shape[1] != X2.shape[1]:
+        raise ValueError("attr.mat1 and attr.mat2 must have the same attributes (columns)")
+    m = metric if metric in ("euclidean", "allele-sharing-manhattan") else "manhattan"
+    D = np.empty((X1.shape[0], X2.shape[0]), order="F")
+    check(_lib.load().npdrb_distances2(context(device).handle, dptr(X1), X1.shape[0], dptr(X2), X2.shape[0], X1.shape[1], METRIC[m], dptr(D)))
+    return D
+
+
+def nearestNeighbors2(attr_mat1, attr_mat2, nbd_method="multisurf", nbd_metric="manhattan", sd_vec=None, sd_frac=0.5,
+                      dopar_nn=False, k=0, device=0, return_info=False):
+    """R/npdrLearner.R:378-482 -- for every instance of attr_mat2 (test) its neighbours among the instances of attr_mat1
+    (train): a list of m2 integer arrays of 1-based train indices (relieff: nearest first, the k + 1 nearest because a
+    test instance has no zero self-distance to drop; surf / multisurf: ascending index)."""
+    if nbd_method not in NBD:
+        raise ValueError(f"unknown nbd.method {nbd_method!r}")
+    X1, _ = _as_matrix(attr_mat1)
+    X2, _ = _as_matrix(attr_mat2)
+    if X1.shape[1] != X2.shape[1]:
+        raise ValueError("attr.mat1 and attr.mat2 must have the same attributes (columns)")
+    m1, m2 = X1.shape[0], X2.shape[0]
+    m = nbd_metric if nbd_metric in ("euclidean", "allele-sharing-manhattan") else "manhattan"
+    sv = f64(sd_vec) if sd_vec is not None else None
+    if sv is not None and sv.size != m2:
+        raise ValueError("sd.vec must have one entry per instance of attr.mat2")
+    off = C.POINTER(C.c_int64)(); idx = C.POINTER(C.c_int32)(); M = C.c_int64()
+    radius = np.full(m2, np.nan)
+    check(_lib.load().npdrb_nearest_neighbors2(context(device).handle, dptr(X1), m1, dptr(X2), m2, X1.shape[1], NBD[nbd_method], METRIC[m],
+                                          dptr(sv), float(sd_frac), int(k), C.byref(off), C.byref(idx), C.byref(M), dptr(radius)))
+    offsets = np.ctypeslib.as_array(off, shape=(m2 + 1,)).copy()
+    _lib.load().npdrb_free(C.cast(off, C.c_void_p))
+    nn = _lib.take_int_array(idx, M.value)
+    out = [nn[offsets[i]:offsets[i + 1]] for i in range(m2)]
+    return (out, {"radius": radius, "offsets": offsets}) if return_info else out
 
 
 def _nearest(X, nbd_method, nbd_metric, sd_vec, sd_frac, k, unique, device):

@@ -337,6 +337,23 @@ int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_eucli
     return nb_distances(s, metric, fast_euclidean, row0, nrows);
 }
 
+int npdrb_session_distances_balanced(npdrb_session *s, int32_t metric, int32_t fast_euclidean, const int64_t *row_starts,
+                                     int32_t rank, int32_t world) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_distances_balanced(s, metric, fast_euclidean, row_starts, rank, world);
+}
+int npdrb_session_balanced_counts(npdrb_session *s, int64_t *send_doubles, int64_t *recv_doubles) {
+    return nb_balanced_counts(s, send_doubles, recv_doubles);
+}
+int npdrb_session_balanced_pack(npdrb_session *s, double *d_send) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_balanced_pack(s, d_send);
+}
+int npdrb_session_balanced_unpack(npdrb_session *s, const double *d_recv) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_balanced_unpack(s, d_recv);
+}
+
 int npdrb_session_set_device_distances(npdrb_session *s, const double *dD, int64_t ldd, int64_t row0, int64_t nrows) {
     if (ldd < s->N || row0 < 0 || nrows < 1 || row0 + nrows > s->N) { npdrb_set_error("set_device_distances: bad block"); return NPDRB_EINVAL; }
     if (s->own_D) cudaFree(s->dD);
@@ -503,6 +520,103 @@ int npdrb_distances(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, int32
     int rc = npdrb_session_upload(s, X, nullptr, nullptr);
     if (!rc) rc = nb_distances(s, metric, fast_euclidean, 0, N);
     if (!rc) rc = npdrb_session_copy_distances(s, D_out);     // symmetric: row-major block == column-major matrix
+    npdrb_session_destroy(s);
+    return rc;
+}
+
+// X2 (m2 x p, host, column-major) -> device copy with the leading dimension padded like the session's X
+static int upload_padded(npdrb_ctx *ctx, const double *X, int64_t m, int64_t p, double **dX_out, int64_t *ld_out) {
+    const int64_t ld = nb_round_up(m, 16);
+    double *d = nullptr;
+    NB_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)ld * (size_t)p));
+    if (ld != m) NB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)ld * (size_t)p, ctx->stream));
+    NB_CUDA(cudaMemcpy2DAsync(d, sizeof(double) * (size_t)ld, X, sizeof(double) * (size_t)m, sizeof(double) * (size_t)m, (size_t)p,
+                              cudaMemcpyHostToDevice, ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    int rc = check_finite(ctx, d, ld * p, "the attribute matrix");
+    if (rc) { cudaFree(d); return rc; }
+    *dX_out = d; *ld_out = ld;
+    return NPDRB_OK;
+}
+
+// distances block of a rectangular problem: rows = X2 instances, columns = X1 instances (session N = m1)
+static int rect_block(npdrb_session *s, const double *X1, const double *X2, int64_t m2, int32_t metric) {
+    npdrb_ctx *ctx = s->ctx;
+    const int64_t m1 = s->N, p = s->p;
+    int32_t base_metric = metric;
+    std::vector<double> h1, h2;
+    if (metric == NPDRB_METRIC_ALLELE_SHARING_MANHATTAN) {          // attr.mat / 2 on both sides (R/npdrLearner.R:330-332)
+        h1.resize((size_t)m1 * p); h2.resize((size_t)m2 * p);
+        for (size_t i = 0; i < h1.size(); ++i) h1[i] = X1[i] / 2.0;
+        for (size_t i = 0; i < h2.size(); ++i) h2[i] = X2[i] / 2.0;
+        X1 = h1.data(); X2 = h2.data();
+        base_metric = NPDRB_METRIC_MANHATTAN;
+    } else if (metric != NPDRB_METRIC_MANHATTAN && metric != NPDRB_METRIC_EUCLIDEAN) {
+        npdrb_set_error("distances2: metric must be manhattan, euclidean or allele-sharing-manhattan");
+        return NPDRB_EINVAL;
+    }
+    NB_CHECK(npdrb_session_upload(s, X1, nullptr, nullptr));
+    double *dX2 = nullptr; int64_t ld2 = 0;
+    NB_CHECK(upload_padded(ctx, X2, m2, p, &dX2, &ld2));
+    if (s->own_D) cudaFree(s->dD);
+    s->ldd = nb_round_up(m1, 2);
+    s->dD = nullptr;
+    cudaError_t e = cudaMalloc(&s->dD, sizeof(double) * (size_t)m2 * (size_t)s->ldd);
+    if (e != cudaSuccess) { cudaFree(dX2); npdrb_set_error("distances2: out of device memory"); return NPDRB_ENOMEM; }
+    s->own_D = true; s->row0 = 0; s->nrows = m2; s->rect = true;
+    int rc = nb_distances2(ctx, s->dX, s->ldx, m1, dX2, ld2, m2, p, base_metric, 0, s->dD, s->ldd);
+    cudaFree(dX2);
+    return rc;
+}
+
+int npdrb_distances2(npdrb_ctx *ctx, const double *X1, int64_t m1, const double *X2, int64_t m2, int64_t p, int32_t metric,
+                     double *D_out) {
+    if (!ctx) { npdrb_set_error("npdrb_distances2: null context (no device)"); return NPDRB_ENODEVICE; }
+    if (m2 < 1) { npdrb_set_error("npdrb_distances2: empty second matrix"); return NPDRB_EINVAL; }
+    npdrb_session *s = nullptr;
+    NB_CHECK(npdrb_session_create(ctx, m1, p, 0, &s));
+    int rc = rect_block(s, X1, X2, m2, metric);
+    // block row i (X2 instance) holds the m1 distances to X1's instances = column i of the m1 x m2 column-major result
+    if (!rc) {
+        cudaError_t e = cudaMemcpy2DAsync(D_out, sizeof(double) * (size_t)m1, s->dD, sizeof(double) * (size_t)s->ldd,
+                                          sizeof(double) * (size_t)m1, (size_t)m2, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { npdrb_set_error("npdrb_distances2: %s", cudaGetErrorString(e)); rc = NPDRB_ECUDA; }
+    }
+    npdrb_session_destroy(s);
+    return rc;
+}
+
+int npdrb_nearest_neighbors2(npdrb_ctx *ctx, const double *X1, int64_t m1, const double *X2, int64_t m2, int64_t p,
+                             int32_t nbd_method, int32_t nbd_metric, const double *sd_vec, double sd_frac, int64_t k,
+                             int64_t **offsets, int32_t **idx, int64_t *M, double *radius_out) {
+    if (!ctx) { npdrb_set_error("npdrb_nearest_neighbors2: null context (no device)"); return NPDRB_ENODEVICE; }
+    if (m2 < 1) { npdrb_set_error("npdrb_nearest_neighbors2: empty second matrix"); return NPDRB_EINVAL; }
+    npdrb_session *s = nullptr;
+    NB_CHECK(npdrb_session_create(ctx, m1, p, 0, &s));
+    int rc = rect_block(s, X1, X2, m2, nbd_metric);
+    if (!rc && sd_vec) {                                             // one sd per X2 instance
+        cudaError_t e = cudaMalloc(&s->d_sd_vec, sizeof(double) * (size_t)m2);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_sd_vec, sd_vec, sizeof(double) * (size_t)m2, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { npdrb_set_error("npdrb_nearest_neighbors2: %s", cudaGetErrorString(e)); rc = NPDRB_ECUDA; }
+    }
+    int64_t Ml = 0, ne = 0;
+    if (!rc) rc = nb_neighbors(s, nbd_method, sd_frac, k, &Ml, &ne);
+    if (!rc) {
+        *offsets = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m2 + 1));
+        *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(Ml > 0 ? Ml : 1));
+        if (!*offsets || !*idx) { npdrb_set_error("out of host memory"); rc = NPDRB_ENOMEM; }
+    }
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(*offsets, s->d_rowptr, sizeof(int64_t) * (size_t)(m2 + 1), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && Ml > 0) e = cudaMemcpyAsync(*idx, s->dNNL, sizeof(int32_t) * (size_t)Ml, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && radius_out && nbd_method != NPDRB_NBD_RELIEFF)
+            e = cudaMemcpyAsync(radius_out, s->d_radius, sizeof(double) * (size_t)m2, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { npdrb_set_error("npdrb_nearest_neighbors2: %s", cudaGetErrorString(e)); rc = NPDRB_ECUDA; }
+        *M = Ml;
+    }
     npdrb_session_destroy(s);
     return rc;
 }

@@ -85,6 +85,8 @@ struct npdrb_session {
     double *dC = nullptr; bool own_C = false;                            // N x q, ld N
     // distance block: nrows x N, row-major with leading dim ldd (row r = column row0+r of the symmetric D)
     double *dD = nullptr; int64_t ldd = 0; int64_t row0 = 0, nrows = 0; bool own_D = false;
+    std::vector<int64_t> bal_tile_starts; int bal_rank = -1;            // partition of the last balanced distance pass
+    bool rect = false;                                                   // rows are a second instance set (nearestNeighbors2)
     double *d_sd_vec = nullptr;                                          // optional user sd.vec (length N)
     double *d_radius = nullptr;                                          // owned rows
     double *d_radius2 = nullptr;                                         // owned rows: miss radius (separate hit/miss neighbourhoods)
@@ -110,6 +112,13 @@ struct npdrb_session {
 
 // stage implementations (one .cu each)
 int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
+int nb_distances_balanced(npdrb_session *s, int32_t metric, int32_t fast_euclidean, const int64_t *row_starts, int32_t rank,
+                          int32_t world);
+int nb_balanced_counts(npdrb_session *s, int64_t *send_doubles, int64_t *recv_doubles);
+int nb_balanced_pack(npdrb_session *s, double *d_send);
+int nb_balanced_unpack(npdrb_session *s, const double *d_recv);
+int nb_distances2(npdrb_ctx *ctx, const double *dX1, int64_t ld1, int64_t m1, const double *dX2, int64_t ld2, int64_t m2,
+                  int64_t p, int32_t metric, int32_t fast_euclidean, double *dD, int64_t ldd);
 int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local, int64_t *n_empty);
 int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local, int64_t *n_empty);
 int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_unique);

@@ -82,25 +82,24 @@ __device__ __forceinline__ void accumulate(double &acc, double a, double b) {
     else acc = __fma_rn(d, d, acc);
 }
 
-// tile index -> (it, jt)
-__device__ __forceinline__ void tile_coords(int64_t t, int symmetric, int n_jt, int &it, int &jt) {
-    if (symmetric) {
-        int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((int64_t)(r + 1) * (r + 2) / 2 <= t) ++r;
-        while ((int64_t)r * (r + 1) / 2 > t) --r;
-        it = r;
-        jt = (int)(t - (int64_t)r * (r + 1) / 2);
-    } else {
-        it = (int)(t / n_jt);
-        jt = (int)(t % n_jt);
-    }
-}
+// The host hands the kernel an explicit tile list: .x = row tile (relative to row0), .y = column tile, bit 30 of .y set
+// when the tile's transpose also belongs to this block (symmetric matrix: D[j, i] = D[i, j] bit for bit, since
+// |a - b| = |b - a| and (a - b)^2 = (b - a)^2 exactly).  Three list shapes are used (build_tiles below):
+//   full symmetric matrix  : tiles on or below the diagonal, mirrored              (one device)
+//   row block, every column: no mirroring                                         (row-sharded, or rectangular A x B)
+//   balanced row block     : the block's own diagonal square (lower half, mirrored) plus HALF of every off-diagonal
+//                            square by a parity rule; the owner of the other half sends its tiles over NVLink
+//                            (pack/unpack kernels below) -- every device computes ~N^2/(2G) pairs instead of N^2/G.
+constexpr int TILE_MIRROR = 1 << 30;
 
 // D block layout: Dout[(i - row0) * ldd + j] for owned rows i in [row0, row0 + nrows), all j in [0, N).
+// same_ab: the row and column operands come from the same matrix (tile i0 == j0 is then a diagonal tile and is
+// loaded once); otherwise tmapA describes the row-side matrix and tmapB the column-side one (npdrDistances2).
 template <int MODE>
 __global__ void __launch_bounds__(DTHREADS, 1)
-dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t p, int64_t row0, int64_t nrows,
-                int symmetric, int64_t n_tiles, int n_jt, double *__restrict__ Dout, int64_t ldd) {
+dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapB, int same_ab,
+                int64_t Nrows_total, int64_t N, int64_t p, int64_t row0, int64_t nrows,
+                const int2 *__restrict__ tiles, int64_t n_tiles, double *__restrict__ Dout, int64_t ldd) {
     extern __shared__ unsigned char smem_raw[];
     // explicit 32-bit shared-window addresses (keeps every access an LDS / SYNCS, never a generic LD)
     constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * sizeof(double);
@@ -122,11 +121,12 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t p, 
     uint32_t g = 0;                                                // chunks consumed so far (all tiles)
 
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        int it, jt;
-        tile_coords(t, symmetric, n_jt, it, jt);
+        const int2 tc = tiles[t];
+        const int it = tc.x, jt = tc.y & (TILE_MIRROR - 1);
+        const bool mirror = (tc.y & TILE_MIRROR) != 0;
         const int i0 = (int)row0 + it * TM;                        // global instance index of the tile's first row
         const int j0 = jt * TN;
-        const bool diag = (i0 == j0);
+        const bool diag = same_ab && (i0 == j0);
         const uint32_t tx_bytes = (uint32_t)(STAGE_DOUBLES * sizeof(double)) * (diag ? 1u : 2u);
 
         // prologue: fill STAGES-1 stages (all threads passed the __syncthreads that ended the previous tile)
@@ -135,7 +135,7 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t p, 
                 int s = (int)((g + c) % STAGES);
                 mbar_expect_tx(full + 8 * s, tx_bytes);
                 tma_load_2d(sA + s * STAGE_BYTES, &tmap, i0, c * BK, full + 8 * s);
-                if (!diag) tma_load_2d(sB + s * STAGE_BYTES, &tmap, j0, c * BK, full + 8 * s);
+                if (!diag) tma_load_2d(sB + s * STAGE_BYTES, &tmapB, j0, c * BK, full + 8 * s);
             }
         }
 
@@ -152,7 +152,7 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t p, 
                 int s = (int)((g + cn) % STAGES);
                 mbar_expect_tx(full + 8 * s, tx_bytes);
                 tma_load_2d(sA + s * STAGE_BYTES, &tmap, i0, cn * BK, full + 8 * s);
-                if (!diag) tma_load_2d(sB + s * STAGE_BYTES, &tmap, j0, cn * BK, full + 8 * s);
+                if (!diag) tma_load_2d(sB + s * STAGE_BYTES, &tmapB, j0, cn * BK, full + 8 * s);
             }
             const uint32_t gc = g + (uint32_t)c;
             const int s = (int)(gc % STAGES);
@@ -187,9 +187,9 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int64_t p, 
                 const int64_t j = (int64_t)j0 + (cc >> 1) * 32 + tx * 2 + (cc & 1);
                 double v = acc[r][cc];
                 if (MODE == MODE_EUCLID_EXACT || MODE == MODE_EUCLID_FMA) v = sqrt(v);
-                if (i < row0 + nrows && i < N && j < N) {
+                if (i < row0 + nrows && i < Nrows_total && j < N) {
                     Dout[(i - row0) * ldd + j] = v;
-                    if (symmetric && !diag) Dout[j * ldd + i] = v;      // row0 == 0 in symmetric mode
+                    if (mirror && !diag && j >= row0 && j < row0 + nrows) Dout[(j - row0) * ldd + i] = v;
                 }
             }
         }
@@ -290,20 +290,63 @@ int make_tensor_map(CUtensorMap *map, const double *X, int64_t N, int64_t p, int
     return NPDRB_OK;
 }
 
+// Which device computes tile (I, J) of a symmetric matrix whose tile rows are partitioned over ranks (I and J owned by
+// different ranks)?  The owner of the smaller tile index when I + J is even, the owner of the larger one otherwise:
+// every off-diagonal square is split checkerboard-fashion between its two owners.
+inline bool balanced_row_owner_computes(int I, int J) { return ((I < J) == (((I + J) & 1) == 0)); }
+
+struct TilePlan {
+    std::vector<int2> tiles;       // what this block computes
+};
+
+// list shapes: 0 = full symmetric, 1 = row block x all columns, 2 = balanced row block (tile_starts: G + 1 tile-row bounds)
+int build_tiles(int shape, int64_t row0, int64_t nrows, int64_t ncols, const std::vector<int64_t> *tile_starts, int rank,
+                TilePlan &plan) {
+    const int n_it = (int)nb_cdiv(nrows, TM), n_jt = (int)nb_cdiv(ncols, TN);
+    const int it0 = (int)(row0 / TM);
+    plan.tiles.clear();
+    if (shape == 0) {
+        for (int it = 0; it < n_it; ++it)
+            for (int jt = 0; jt <= it; ++jt) plan.tiles.push_back(make_int2(it, jt | TILE_MIRROR));
+    } else if (shape == 1) {
+        for (int it = 0; it < n_it; ++it)
+            for (int jt = 0; jt < n_jt; ++jt) plan.tiles.push_back(make_int2(it, jt));
+    } else {
+        const int a = (int)(*tile_starts)[rank], b = (int)(*tile_starts)[rank + 1];
+        if (a != it0 || b - a != n_it) { npdrb_set_error("balanced distances: row block does not match the partition"); return NPDRB_EINVAL; }
+        for (int I = a; I < b; ++I)
+            for (int J = 0; J < n_jt; ++J) {
+                if (J >= a && J < b) { if (J <= I) plan.tiles.push_back(make_int2(I - a, J | TILE_MIRROR)); }
+                else if (balanced_row_owner_computes(I, J)) plan.tiles.push_back(make_int2(I - a, J));
+            }
+    }
+    return NPDRB_OK;
+}
+
 template <int MODE>
-int launch_tma(npdrb_session *s, const double *X, int64_t row0, int64_t nrows, int symmetric) {
-    npdrb_ctx *ctx = s->ctx;
-    CUtensorMap map;
-    NB_CHECK(make_tensor_map(&map, X, s->N, s->p, s->ldx));
-    const int n_it = (int)nb_cdiv(nrows, TM), n_jt = (int)nb_cdiv(s->N, TN);
-    const int64_t n_tiles = symmetric ? (int64_t)n_it * (n_it + 1) / 2 : (int64_t)n_it * n_jt;
+int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const double *XB, int64_t NB, int64_t ldB, int64_t p,
+               int64_t row0, int64_t nrows, const TilePlan &plan, double *dD, int64_t ldd) {
+    CUtensorMap mapA, mapB;
+    NB_CHECK(make_tensor_map(&mapA, XA, NA, p, ldA));
+    NB_CHECK(make_tensor_map(&mapB, XB, NB, p, ldB));
+    const int64_t n_tiles = (int64_t)plan.tiles.size();
+    if (n_tiles == 0) return NPDRB_OK;
+    int2 *d_tiles = nullptr;
+    NB_CUDA(cudaMalloc(&d_tiles, sizeof(int2) * (size_t)n_tiles));
+    NB_CUDA(cudaMemcpyAsync(d_tiles, plan.tiles.data(), sizeof(int2) * (size_t)n_tiles, cudaMemcpyHostToDevice, ctx->stream));
     NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
     int grid = (int)((n_tiles < ctx->sm_count) ? n_tiles : ctx->sm_count);
     if (grid < 1) grid = 1;
-    dist_tma_kernel<MODE><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(map, s->N, s->p, row0, nrows, symmetric, n_tiles,
-                                                                      n_jt, s->dD, s->ldd);
+    dist_tma_kernel<MODE><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(mapA, mapB, XA == XB ? 1 : 0, NA, NB, p, row0, nrows,
+                                                                      d_tiles, n_tiles, dD, ldd);
     NB_LAUNCH_CHECK(ctx);
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));        // the pinned-less H2D source (plan.tiles) must outlive the copy
+    cudaFree(d_tiles);
     return NPDRB_OK;
+}
+template <int MODE>
+int launch_tma(npdrb_session *s, const double *X, int64_t row0, int64_t nrows, const TilePlan &plan) {
+    return launch_tma<MODE>(s->ctx, X, s->N, s->ldx, X, s->N, s->ldx, s->p, row0, nrows, plan, s->dD, s->ldd);
 }
 
 template <int MODE>
@@ -314,9 +357,46 @@ int launch_simple(npdrb_session *s, const double *X, int64_t row0, int64_t nrows
     return NPDRB_OK;
 }
 
-}  // namespace
+// pack: tile (x = local row tile, y = column tile) of this block, TRANSPOSED, into buf[tile][c][r] (128 x 128 doubles)
+__global__ void __launch_bounds__(256)
+pack_tiles_kernel(const double *__restrict__ D, int64_t ldd, int64_t nrows, int64_t N, const int2 *__restrict__ desc,
+                  double *__restrict__ buf) {
+    __shared__ double sm[32][33];
+    const int2 d = desc[blockIdx.x];
+    double *out = buf + (size_t)blockIdx.x * TM * TN;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+    for (int sb = 0; sb < 16; ++sb) {
+        const int r0 = (sb >> 2) * 32, c0 = (sb & 3) * 32;
+        for (int rr = ty; rr < 32; rr += 8) {
+            const int64_t row = (int64_t)d.x * TM + r0 + rr, col = (int64_t)d.y * TN + c0 + tx;
+            sm[rr][tx] = (row < nrows && col < N) ? D[row * ldd + col] : 0.0;
+        }
+        __syncthreads();
+        for (int cc = ty; cc < 32; cc += 8) out[(size_t)(c0 + cc) * TM + r0 + tx] = sm[tx][cc];
+        __syncthreads();
+    }
+}
+// unpack: buf[tile][c][r] -> D[(x * 128 + c) * ldd + y * 128 + r]   (x = local row tile, y = column tile of THIS block)
+__global__ void __launch_bounds__(256)
+unpack_tiles_kernel(double *__restrict__ D, int64_t ldd, int64_t nrows, int64_t N, const int2 *__restrict__ desc,
+                    const double *__restrict__ buf) {
+    const int2 d = desc[blockIdx.x];
+    const double *in = buf + (size_t)blockIdx.x * TM * TN;
+    for (int e = threadIdx.x; e < TM * TN; e += 256) {
+        const int c = e >> 7, r = e & 127;
+        const int64_t row = (int64_t)d.x * TM + c, col = (int64_t)d.y * TN + r;
+        if (row < nrows && col < N) D[row * ldd + col] = in[e];
+    }
+}
 
-int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows) {
+int metric_mode(int32_t metric, int32_t fast_euclidean) {
+    const bool euclid = (metric == NPDRB_METRIC_EUCLIDEAN || metric == NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN);
+    return metric == NPDRB_METRIC_HAMMING ? MODE_HAMMING
+         : !euclid ? MODE_MANHATTAN : (fast_euclidean ? MODE_EUCLID_FMA : MODE_EUCLID_EXACT);
+}
+
+int dist_core(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows, int shape,
+              const std::vector<int64_t> *tile_starts, int rank) {
     npdrb_ctx *ctx = s->ctx;
     if (!s->dX) { npdrb_set_error("distances: no attribute matrix in the session"); return NPDRB_EINVAL; }
     if ((metric < 0 || metric > NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN) && metric != NPDRB_METRIC_HAMMING) {
@@ -325,7 +405,6 @@ int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64
     }
     if (row0 < 0 || nrows < 1 || row0 + nrows > s->N) { npdrb_set_error("distances: bad row block"); return NPDRB_EINVAL; }
     if (row0 % TM != 0) { npdrb_set_error("distances: row0 must be a multiple of %d", TM); return NPDRB_EINVAL; }
-    const int symmetric = (row0 == 0 && nrows == s->N) ? 1 : 0;
 
     if (s->dD && s->own_D && (s->nrows != nrows)) { cudaFree(s->dD); s->dD = nullptr; }
     if (!s->dD || !s->own_D) {
@@ -343,11 +422,9 @@ int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64
         NB_LAUNCH_CHECK(ctx);
         X = s->dXs;
     }
-    const bool euclid = (metric == NPDRB_METRIC_EUCLIDEAN || metric == NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN);
-    const int mode = metric == NPDRB_METRIC_HAMMING ? MODE_HAMMING
-                   : !euclid ? MODE_MANHATTAN : (fast_euclidean ? MODE_EUCLID_FMA : MODE_EUCLID_EXACT);
+    const int mode = metric_mode(metric, fast_euclidean);
     const char *kenv = getenv("NPDRB_DIST_KERNEL");
-    const bool simple = kenv && strcmp(kenv, "simple") == 0;
+    const bool simple = kenv && strcmp(kenv, "simple") == 0 && shape != 2;
     int rc;
     if (simple) {
         rc = mode == MODE_MANHATTAN ? launch_simple<MODE_MANHATTAN>(s, X, row0, nrows)
@@ -355,10 +432,12 @@ int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64
            : mode == MODE_EUCLID_EXACT ? launch_simple<MODE_EUCLID_EXACT>(s, X, row0, nrows)
                                        : launch_simple<MODE_EUCLID_FMA>(s, X, row0, nrows);
     } else {
-        rc = mode == MODE_MANHATTAN ? launch_tma<MODE_MANHATTAN>(s, X, row0, nrows, symmetric)
-           : mode == MODE_HAMMING ? launch_tma<MODE_HAMMING>(s, X, row0, nrows, symmetric)
-           : mode == MODE_EUCLID_EXACT ? launch_tma<MODE_EUCLID_EXACT>(s, X, row0, nrows, symmetric)
-                                       : launch_tma<MODE_EUCLID_FMA>(s, X, row0, nrows, symmetric);
+        TilePlan plan;
+        NB_CHECK(build_tiles(shape, row0, nrows, s->N, tile_starts, rank, plan));
+        rc = mode == MODE_MANHATTAN ? launch_tma<MODE_MANHATTAN>(s, X, row0, nrows, plan)
+           : mode == MODE_HAMMING ? launch_tma<MODE_HAMMING>(s, X, row0, nrows, plan)
+           : mode == MODE_EUCLID_EXACT ? launch_tma<MODE_EUCLID_EXACT>(s, X, row0, nrows, plan)
+                                       : launch_tma<MODE_EUCLID_FMA>(s, X, row0, nrows, plan);
     }
     NB_CHECK(rc);
     NB_CUDA(cudaEventRecord(s->ev[1], ctx->stream));
@@ -367,4 +446,99 @@ int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64
     NB_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
     s->ms_distance = ms;
     return NPDRB_OK;
+}
+
+// tiles exchanged with the other ranks after a balanced distance pass, in the canonical order both sides enumerate:
+// peer h ascending; within a peer the SENDER's row tile ascending, then its column tile ascending
+int exchange_lists(npdrb_session *s, std::vector<int2> &send, std::vector<int2> &recv, std::vector<int64_t> &send_cnt,
+                   std::vector<int64_t> &recv_cnt) {
+    if (s->bal_rank < 0) { npdrb_set_error("balanced exchange: run npdrb_session_distances_balanced first"); return NPDRB_EINVAL; }
+    const std::vector<int64_t> &ts = s->bal_tile_starts;
+    const int G = (int)ts.size() - 1, g = s->bal_rank;
+    const int a = (int)ts[g], b = (int)ts[g + 1];
+    send.clear(); recv.clear(); send_cnt.assign(G, 0); recv_cnt.assign(G, 0);
+    for (int h = 0; h < G; ++h) {
+        if (h == g) continue;
+        const int c = (int)ts[h], d = (int)ts[h + 1];
+        for (int I = a; I < b; ++I)                // I send what I computed in the square (my rows, h's columns) ...
+            for (int J = c; J < d; ++J)
+                if (balanced_row_owner_computes(I, J)) { send.push_back(make_int2(I - a, J)); send_cnt[h] += (int64_t)TM * TN; }
+        for (int J = c; J < d; ++J)                // ... and receive what h computed there, transposed into my rows
+            for (int I = a; I < b; ++I)
+                if (balanced_row_owner_computes(J, I)) { recv.push_back(make_int2(I - a, J)); recv_cnt[h] += (int64_t)TM * TN; }
+    }
+    return NPDRB_OK;
+}
+
+int run_tile_copy(npdrb_session *s, const std::vector<int2> &desc, double *buf, bool pack) {
+    npdrb_ctx *ctx = s->ctx;
+    if (desc.empty()) return NPDRB_OK;
+    int2 *d_desc = nullptr;
+    NB_CUDA(cudaMalloc(&d_desc, sizeof(int2) * desc.size()));
+    NB_CUDA(cudaMemcpyAsync(d_desc, desc.data(), sizeof(int2) * desc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (pack) pack_tiles_kernel<<<(unsigned)desc.size(), 256, 0, ctx->stream>>>(s->dD, s->ldd, s->nrows, s->N, d_desc, buf);
+    else unpack_tiles_kernel<<<(unsigned)desc.size(), 256, 0, ctx->stream>>>(s->dD, s->ldd, s->nrows, s->N, d_desc, buf);
+    NB_LAUNCH_CHECK(ctx);
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_desc);
+    return NPDRB_OK;
+}
+
+}  // namespace
+
+int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows) {
+    const int symmetric = (row0 == 0 && nrows == s->N) ? 1 : 0;
+    s->bal_rank = -1;
+    return dist_core(s, metric, fast_euclidean, row0, nrows, symmetric ? 0 : 1, nullptr, 0);
+}
+
+// Balanced symmetric distances over `world` row blocks (row_starts: world + 1 instance bounds, tile aligned).  After
+// this call the block holds the tiles this rank computed; nb_balanced_pack / all-to-all / nb_balanced_unpack complete it.
+int nb_distances_balanced(npdrb_session *s, int32_t metric, int32_t fast_euclidean, const int64_t *row_starts, int32_t rank,
+                          int32_t world) {
+    if (!row_starts || world < 1 || rank < 0 || rank >= world) { npdrb_set_error("balanced distances: bad partition"); return NPDRB_EINVAL; }
+    std::vector<int64_t> ts((size_t)world + 1);
+    for (int r = 0; r <= world; ++r) {
+        if (row_starts[r] % TM != 0 && row_starts[r] != s->N) { npdrb_set_error("balanced distances: row bounds must be multiples of %d", TM); return NPDRB_EINVAL; }
+        ts[r] = nb_cdiv(row_starts[r], TM);
+    }
+    if (row_starts[0] != 0 || row_starts[world] != s->N) { npdrb_set_error("balanced distances: partition must cover 0..N"); return NPDRB_EINVAL; }
+    const int64_t row0 = row_starts[rank], nrows = row_starts[rank + 1] - row0;
+    if (nrows < 1) { npdrb_set_error("balanced distances: empty row block"); return NPDRB_EINVAL; }
+    NB_CHECK(dist_core(s, metric, fast_euclidean, row0, nrows, 2, &ts, rank));
+    s->bal_tile_starts = ts; s->bal_rank = rank;
+    return NPDRB_OK;
+}
+
+int nb_balanced_counts(npdrb_session *s, int64_t *send_doubles, int64_t *recv_doubles) {
+    std::vector<int2> sd, rv; std::vector<int64_t> sc, rc;
+    NB_CHECK(exchange_lists(s, sd, rv, sc, rc));
+    for (size_t h = 0; h < sc.size(); ++h) { send_doubles[h] = sc[h]; recv_doubles[h] = rc[h]; }
+    return NPDRB_OK;
+}
+int nb_balanced_pack(npdrb_session *s, double *d_send) {
+    std::vector<int2> sd, rv; std::vector<int64_t> sc, rc;
+    NB_CHECK(exchange_lists(s, sd, rv, sc, rc));
+    return run_tile_copy(s, sd, d_send, true);
+}
+int nb_balanced_unpack(npdrb_session *s, const double *d_recv) {
+    std::vector<int2> sd, rv; std::vector<int64_t> sc, rc;
+    NB_CHECK(exchange_lists(s, sd, rv, sc, rc));
+    return run_tile_copy(s, rv, (double *)d_recv, false);
+}
+
+// Rectangular distances (npdrDistances2, R/npdrLearner.R:323-339): rows = instances of X2 (m2), columns = instances of
+// X1 (m1); dD is m2 x ldd row-major, i.e. column i of the reference's m1 x m2 matrix is row i here.
+int nb_distances2(npdrb_ctx *ctx, const double *dX1, int64_t ld1, int64_t m1, const double *dX2, int64_t ld2, int64_t m2,
+                  int64_t p, int32_t metric, int32_t fast_euclidean, double *dD, int64_t ldd) {
+    if (metric != NPDRB_METRIC_MANHATTAN && metric != NPDRB_METRIC_EUCLIDEAN) {
+        npdrb_set_error("distances2: metric must be manhattan or euclidean (allele-sharing is a pre-scaling by the caller)");
+        return NPDRB_EINVAL;
+    }
+    TilePlan plan;
+    NB_CHECK(build_tiles(1, 0, m2, m1, nullptr, 0, plan));
+    const int mode = metric_mode(metric, fast_euclidean);
+    return mode == MODE_MANHATTAN ? launch_tma<MODE_MANHATTAN>(ctx, dX2, m2, ld2, dX1, m1, ld1, p, 0, m2, plan, dD, ldd)
+         : mode == MODE_EUCLID_EXACT ? launch_tma<MODE_EUCLID_EXACT>(ctx, dX2, m2, ld2, dX1, m1, ld1, p, 0, m2, plan, dD, ldd)
+                                     : launch_tma<MODE_EUCLID_FMA>(ctx, dX2, m2, ld2, dX1, m1, ld1, p, 0, m2, plan, dD, ldd);
 }

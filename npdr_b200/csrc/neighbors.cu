@@ -15,6 +15,9 @@ namespace {
 // One lane per owned row; a warp walks 32 rows through 32x32 transposed tiles so that global
 // reads stay coalesced while every lane runs its own strictly sequential extended-precision sums.
 // PASSES: 1 = colSums only (user sd.vec), 3 = colSums + two-pass var().
+// RECT (nearestNeighbors2, R/npdrLearner.R:446-450): the rows are a second instance set, so there is no own distance to
+// skip, the statistics run over all N entries, and the mean is colMeans() (long-double sum / n, rounded once).
+template <bool RECT>
 __global__ void __launch_bounds__(128)
 radius_multisurf_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t row0, int64_t nrows,
                         double sd_frac, const double *__restrict__ sd_vec, double *__restrict__ radius) {
@@ -25,7 +28,7 @@ radius_multisurf_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, in
     const int64_t r = rbase + lane;             // local row
     const int64_t g = row0 + r;                 // global instance (its own distance is skipped)
     const bool valid = r < nrows;
-    const int64_t nobs = N - 1;
+    const int64_t nobs = RECT ? N : N - 1;
 
     xf80 S = xf_zero(), T = xf_zero(), XM = xf_zero();
     const int n_pass = sd_vec ? 1 : 3;
@@ -40,7 +43,7 @@ radius_multisurf_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, in
             if (valid) {
                 const int lim = (int)((N - c0 < 32) ? (N - c0) : 32);
                 for (int cc = 0; cc < lim; ++cc) {
-                    if (c0 + cc == g) continue;
+                    if (!RECT && c0 + cc == g) continue;
                     xf80 x = xf_from_double(tile[w][lane][cc]);
                     if (pass == 0) acc = xf_add(acc, x);
                     else if (pass == 1) acc = xf_add(acc, xf_sub(x, T));
@@ -58,6 +61,10 @@ radius_multisurf_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, in
     double sdv;
     if (sd_vec) sdv = sd_vec[g];
     else sdv = sqrt(xf_to_double(xf_div(XM, xf_from_int(nobs - 1))));
+    if (RECT) {                                  // colMeans(dist.mat) - sd.frac * sd.vec
+        radius[r] = __dsub_rn(xf_to_double(xf_div(S, xf_from_int(nobs))), __dmul_rn(sd_frac, sdv));
+        return;
+    }
     // Ri.radius = colSums(dist.mat)/(N-1) - sd.frac*sd.vec   (R/nearestNeighbors.R:246), plain double ops
     radius[r] = __dsub_rn(__ddiv_rn(colsum, (double)(N - 1)), __dmul_rn(sd_frac, sdv));
 }
@@ -86,6 +93,39 @@ __global__ void surf_radius_serial_kernel(const double *__restrict__ D, int64_t 
     const double var = xf_to_double(xf_div(sum, xf_from_int(nu - 1)));
     const double num_pair = __ddiv_rn(__dmul_rn((double)N, (double)(N - 1)), 2.0);
     out[0] = __dsub_rn(__ddiv_rn(total, __dmul_rn(2.0, num_pair)), __dmul_rn(sd_frac, sqrt(var)));
+}
+
+// nearestNeighbors2 SURF radius (R/npdrLearner.R:439-444): mean(dist.mat) - sd.frac * sd(dist.mat) over all nrows x N
+// entries in storage order (column-major m1 x m2 in R = row-major here).  mean(): long-double sum / n plus one
+// correction pass; sd(): sqrt(var(as.double(x))) = cov_complete1's two-pass mean and the sum of squared deviations.
+__global__ void surf_rect_serial_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t nrows, double sd_frac,
+                                        double *__restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int64_t n = N * nrows;
+    xf80 s = xf_zero();
+    for (int64_t r = 0; r < nrows; ++r) for (int64_t j = 0; j < N; ++j) s = xf_add(s, xf_from_double(D[r * ldd + j]));
+    xf80 m = xf_div(s, xf_from_int(n));
+    xf80 t = xf_zero();
+    for (int64_t r = 0; r < nrows; ++r) for (int64_t j = 0; j < N; ++j) t = xf_add(t, xf_sub(xf_from_double(D[r * ldd + j]), m));
+    const xf80 mean_ld = xf_add(m, xf_div(t, xf_from_int(n)));     // mean() and cov_complete1 compute the same two passes
+    const double mean_d = xf_to_double(mean_ld);
+    const xf80 xm = xf_from_double(mean_d);
+    xf80 ss = xf_zero();
+    for (int64_t r = 0; r < nrows; ++r)
+        for (int64_t j = 0; j < N; ++j) { xf80 d = xf_sub(xf_from_double(D[r * ldd + j]), xm); ss = xf_add(ss, xf_mul(d, d)); }
+    const double var = xf_to_double(xf_div(ss, xf_from_int(n - 1)));
+    out[0] = __dsub_rn(mean_d, __dmul_rn(sd_frac, sqrt(var)));
+}
+// large blocks: per-row sums (pass 0) / sums of squared deviations (pass 1) in double, combined on the host
+__global__ void rect_row_moment_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t nrows, int pass, double mean,
+                                       double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nrows) return;
+    double a = 0;
+    for (int64_t j = lane; j < N; j += 32) { double v = D[r * ldd + j]; if (pass == 0) a += v; else { v -= mean; a += v * v; } }
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[r] = a;
 }
 
 // Large N (or row blocks): per-row moments (sum over all j, sum and sum of squares over j > global row)
@@ -676,6 +716,31 @@ static int surf_radius(npdrb_session *s, double sd_frac, double *d_rad_scalar) {
     double radius;
     if (s->have_surf_radius) {
         radius = s->surf_radius;
+    } else if (s->rect) {
+        const int64_t nrows = s->nrows;
+        if (N * nrows <= (1ll << 18)) {
+            surf_rect_serial_kernel<<<1, 32, 0, ctx->stream>>>(s->dD, s->ldd, N, nrows, sd_frac, d_rad_scalar);
+            NB_LAUNCH_CHECK(ctx);
+            return NPDRB_OK;
+        }
+        // large blocks: parallel moments (a few ulp from R's sequential long-double chains)
+        double *d_m = nullptr;
+        NB_CUDA(cudaMalloc(&d_m, sizeof(double) * (size_t)nrows));
+        std::vector<double> h((size_t)nrows);
+        long double tot = 0, ss = 0;
+        rect_row_moment_kernel<<<(unsigned)nb_cdiv(nrows, 8), 256, 0, ctx->stream>>>(s->dD, s->ldd, N, nrows, 0, 0.0, d_m);
+        NB_LAUNCH_CHECK(ctx);
+        NB_CUDA(cudaMemcpyAsync(h.data(), d_m, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (double v : h) tot += v;
+        const double mean = (double)(tot / (long double)(N * nrows));
+        rect_row_moment_kernel<<<(unsigned)nb_cdiv(nrows, 8), 256, 0, ctx->stream>>>(s->dD, s->ldd, N, nrows, 1, mean, d_m);
+        NB_LAUNCH_CHECK(ctx);
+        NB_CUDA(cudaMemcpyAsync(h.data(), d_m, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (double v : h) ss += v;
+        cudaFree(d_m);
+        radius = mean - sd_frac * sqrt((double)(ss / (long double)(N * nrows - 1)));
     } else if (s->nrows != N) {
         npdrb_set_error("surf on a row block needs npdrb_session_set_surf_radius (combine npdrb_session_surf_partial across ranks)");
         return NPDRB_EINVAL;
@@ -708,8 +773,9 @@ int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k
 
     if (s->dRiL) { cudaFree(s->dRiL); s->dRiL = nullptr; }
     if (s->dNNL) { cudaFree(s->dNNL); s->dNNL = nullptr; }
-    if (!s->d_radius) NB_CUDA(cudaMalloc(&s->d_radius, sizeof(double) * (size_t)N));
-    if (!s->d_rowptr) NB_CUDA(cudaMalloc(&s->d_rowptr, sizeof(int64_t) * (size_t)(N + 2)));
+    const int64_t nmax = N > nrows ? N : nrows;                 // rectangular blocks may have more rows than columns
+    if (!s->d_radius) NB_CUDA(cudaMalloc(&s->d_radius, sizeof(double) * (size_t)nmax));
+    if (!s->d_rowptr) NB_CUDA(cudaMalloc(&s->d_rowptr, sizeof(int64_t) * (size_t)(nmax + 2)));
     int64_t *d_counts = nullptr, *d_nempty = nullptr;
     NB_CUDA(cudaMalloc(&d_counts, sizeof(int64_t) * (size_t)nrows));
     NB_CUDA(cudaMalloc(&d_nempty, sizeof(int64_t)));
@@ -741,8 +807,12 @@ int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k
     } else {
         int scalar = 0;
         if (nbd_method == NPDRB_NBD_MULTISURF) {
-            radius_multisurf_kernel<<<(unsigned)nb_cdiv(nrows, 128), 128, 0, ctx->stream>>>(
-                s->dD, s->ldd, N, s->row0, nrows, sd_frac, s->d_sd_vec, s->d_radius);
+            if (s->rect)
+                radius_multisurf_kernel<true><<<(unsigned)nb_cdiv(nrows, 128), 128, 0, ctx->stream>>>(
+                    s->dD, s->ldd, N, s->row0, nrows, sd_frac, s->d_sd_vec, s->d_radius);
+            else
+                radius_multisurf_kernel<false><<<(unsigned)nb_cdiv(nrows, 128), 128, 0, ctx->stream>>>(
+                    s->dD, s->ldd, N, s->row0, nrows, sd_frac, s->d_sd_vec, s->d_radius);
             NB_LAUNCH_CHECK(ctx);
         } else {
             scalar = 1;

@@ -1,8 +1,11 @@
 """Sharding NPDR's hot path over the GPUs of one node (one process per GPU, torch.distributed).
 
 The path has two embarrassingly parallel stages joined by ONE exchange:
-  A+B  distances + neighbour lists : row-block sharded (rank g owns instances I_g, computes D[I_g, :]);
-       multiSURF radii are per-row, so no reduction is needed; SURF needs two scalar all-reduces.
+  A+B  distances + neighbour lists : row-block sharded (rank g owns instances I_g and needs D[I_g, :]).  D is
+       symmetric, so each rank computes its diagonal square and a checkerboard HALF of every off-diagonal square and
+       the halves are swapped in one all-to-all over NVLink (packed, transposed 128 x 128 tiles): ~N^2/(2G) instance
+       pairs per rank instead of N^2/G, bit-identical to the unsharded matrix.  multiSURF radii are per-row, so no
+       reduction is needed; SURF needs two scalar all-reduces.
   X    all-gather of the variable-length (Ri, NN) segments -- concatenation in rank order IS the
        reference's order, because segments are contiguous in Ri.
   C    regression : attribute-column sharded, every rank holds the full pair list; statistics are
@@ -11,6 +14,8 @@ The path has two embarrassingly parallel stages joined by ONE exchange (SURVEY 8
 `Engine` is the per-rank compute interface; `GpuEngine` drives libnpdr_b200 sessions.  The collective
 plumbing below only sees torch tensors, so it is exercised on CPU with the gloo backend in tests/.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -79,6 +84,28 @@ def all_gather_varlen(t, group=None):
     return torch.cat([b[:c] for b, c in zip(bufs, counts)]), counts
 
 
+def exchange_balanced(engine, parts, rank, nbd_metric, group=None):
+    """Row block of the symmetric distance matrix with the work split evenly over the ranks.  Each rank computes its
+    diagonal square and a checkerboard half of every off-diagonal square (engine.balanced_local), packs the tiles its
+    peers need (transposed, peers in rank order), ONE all-to-all (NCCL over NVLink) swaps the halves, and
+    engine.balanced_unpack drops the received tiles into the block.  Ranks without rows join with empty messages."""
+    world = len(parts)
+    live = [g for g, (_, n) in enumerate(parts) if n > 0]
+    row_starts = [parts[g][0] for g in live] + [parts[live[-1]][0] + parts[live[-1]][1]]
+    send_counts, recv_counts = [0] * world, [0] * world
+    mine = rank in live
+    if mine:
+        sc, rc = engine.balanced_local(row_starts, live.index(rank), nbd_metric)
+        for j, g in enumerate(live):
+            send_counts[g], recv_counts[g] = int(sc[j]), int(rc[j])
+    n_send, n_recv = sum(send_counts), sum(recv_counts)
+    send = engine.balanced_pack(n_send) if mine else torch.empty(1, dtype=torch.float64, device=engine.device)
+    recv = torch.empty(max(n_recv, 1), dtype=torch.float64, device=engine.device)
+    dist.all_to_all_single(recv[:n_recv], send[:n_send], recv_counts, send_counts, group=group)
+    if mine:
+        engine.balanced_unpack(recv, n_recv)
+
+
 def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numeric-abs", nbd_method="multisurf",
                  nbd_metric="manhattan", knn=0, msurf_sd_frac=0.5, covar_diff_type=(), neighbor_sampling="none",
                  group=None, separate_hitmiss_nbds=False):
@@ -91,6 +118,8 @@ def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numer
 
     if nbd_method == "surf" and separate_hitmiss_nbds and world > 1:
         raise NotImplementedError("surf hit/miss radii need the whole distance matrix on one device")
+    if world > 1 and hasattr(engine, "balanced_local") and os.environ.get("NPDRB_NO_BALANCED") != "1":
+        exchange_balanced(engine, partition_rows(N, world), rank, nbd_metric, group)    # collective: every rank calls it
     if nbd_method == "surf" and world > 1:
         # one global mean / sd: two scalar all-reduces (R/nearestNeighbors.R:234-241)
         m0 = torch.tensor(engine.surf_partial(row0, nrows, nbd_metric, 0.0) if nrows else [0.0] * 4, dtype=torch.float64, device=dev)
@@ -156,6 +185,24 @@ class GpuEngine(Engine):
         if self._metric_done != key:
             self.session.distances(nbd_metric, False, row0, nrows)
             self._metric_done = key
+
+    # balanced symmetric distances: the three per-rank primitives exchange_balanced() drives
+    def balanced_local(self, row_starts, index, nbd_metric):
+        self._bal_key = (row_starts[index], row_starts[index + 1] - row_starts[index], nbd_metric)
+        return self.session.distances_balanced(nbd_metric, row_starts, index)
+
+    def balanced_pack(self, n_send):
+        send = torch.empty(max(n_send, 1), dtype=torch.float64, device=self.device)
+        if n_send:
+            self.session.balanced_pack(send.data_ptr())
+        torch.cuda.synchronize(self.device)          # the library's stream has finished packing
+        return send
+
+    def balanced_unpack(self, recv, n_recv):
+        torch.cuda.synchronize(self.device)
+        if n_recv:
+            self.session.balanced_unpack(recv.data_ptr())
+        self._metric_done = self._bal_key
 
     def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k, hitmiss=False):
         self._ensure_distances(row0, nrows, nbd_metric)

@@ -279,6 +279,103 @@ int orc_neighbors(const double *D, int64_t N, int method, int64_t k, const doubl
     return ORC_OK;
 }
 
+/* ------------------------------------------------ npdrDistances2 / nearestNeighbors2 (R/npdrLearner.R:323-482) */
+static double r_mean(const double *x, int64_t n);
+/* npdrDistances2, R/npdrLearner.R:323-339 -> flexclust::dist2(x, y, method) (third-party, unvendored and unpinned:
+ * DESCRIPTION Suggests flexclust).  dist2 is flexclust's two-matrix generalisation of stats::dist and is restated with
+ * dist()'s arithmetic: plain double accumulation over k = 0..p-1 in order, euclidean = sqrt(sum dev*dev).
+ * metric: MANHATTAN, EUCLIDEAN, or ALLELE_SHARING_MANHATTAN (= both matrices / 2, then manhattan, :330-332).
+ * D: m1 x m2 column-major (rows = instances of X1, columns = instances of X2), as the reference returns it. */
+int orc_distances2(const double *X1, int64_t m1, const double *X2, int64_t m2, int64_t p, int metric, double *D) {
+    if (metric != ORC_METRIC_MANHATTAN && metric != ORC_METRIC_EUCLIDEAN && metric != ORC_METRIC_ALLELE_SHARING_MANHATTAN)
+        return ORC_EINVAL;
+    const int euclid = metric == ORC_METRIC_EUCLIDEAN;
+    const double scale = metric == ORC_METRIC_ALLELE_SHARING_MANHATTAN ? 2.0 : 1.0;
+    double *T1 = (double *)malloc(sizeof(double) * (size_t)m1 * (size_t)p), *T2 = (double *)malloc(sizeof(double) * (size_t)m2 * (size_t)p);
+    if (!T1 || !T2) { free(T1); free(T2); return ORC_ENOMEM; }
+    for (int64_t k = 0; k < p; ++k) {
+        for (int64_t i = 0; i < m1; ++i) T1[i * p + k] = X1[k * m1 + i] / scale;
+        for (int64_t i = 0; i < m2; ++i) T2[i * p + k] = X2[k * m2 + i] / scale;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < m2; ++j) {
+        const double *xj = T2 + j * p;
+        for (int64_t i = 0; i < m1; ++i) {
+            const double *xi = T1 + i * p;
+            double dist = 0.0;
+            if (euclid) { for (int64_t k = 0; k < p; ++k) { double dev = xi[k] - xj[k]; dist += dev * dev; } dist = sqrt(dist); }
+            else { for (int64_t k = 0; k < p; ++k) { double dev = fabs(xi[k] - xj[k]); dist += dev; } }
+            D[j * m1 + i] = dist;
+        }
+    }
+    free(T1); free(T2);
+    return ORC_OK;
+}
+
+/* nearestNeighbors2 radii, R/npdrLearner.R:439-450.  D is the m1 x m2 matrix of orc_distances2.
+ *  surf:      radius = mean(dist.mat) - sd.frac * sd(dist.mat), replicated m2 times.  mean(): long-double two-pass over all
+ *             m1*m2 entries in storage order; sd(<matrix>) = sqrt(var(as.double(x))) -> r_var on the flattened matrix.
+ *  multisurf: sd.vec[i] = sd(dist.mat[, i]) (all m1 entries: a test instance has no self distance);
+ *             radius = colMeans(dist.mat) - sd.frac * sd.vec; colMeans: long-double sum / m1, rounded once. */
+int orc_radius2(const double *D, int64_t m1, int64_t m2, int method, double sd_frac, const double *sd_vec_in, double *radius) {
+    if (method == ORC_NBD_SURF) {
+        const double r = r_mean(D, m1 * m2) - sd_frac * sqrt(r_var(D, m1 * m2, -1));
+        for (int64_t c = 0; c < m2; ++c) radius[c] = r;
+        return ORC_OK;
+    }
+    if (method != ORC_NBD_MULTISURF) return ORC_EINVAL;
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < m2; ++c) {
+        const double *col = D + c * m1;
+        const double sdv = sd_vec_in ? sd_vec_in[c] : sqrt(r_var(col, m1, -1));
+        long double s = 0.0L;
+        for (int64_t i = 0; i < m1; ++i) s += col[i];
+        s /= m1;
+        radius[c] = (double)s - sd_frac * sdv;
+    }
+    return ORC_OK;
+}
+
+/* nearestNeighbors2 selection, R/npdrLearner.R:421-433,470-478 -> get_Ri_nearest (R/nearestNeighbors.R:622-634) on
+ * column Ri of the m1 x m2 matrix: the same dplyr verbs as nearestNeighbors, but no row is the test instance itself,
+ * so relieff's slice_min(n = k + 1) keeps k + 1 training instances (and boundary ties) unless a distance is exactly 0.
+ * Returns CSR: offsets[m2 + 1] (caller-allocated), idx malloc'ed here (1-based training indices). */
+int orc_neighbors2(const double *D, int64_t m1, int64_t m2, int method, int64_t k, const double *radius,
+                   int64_t *offsets, int32_t **idx_out) {
+    int64_t cap = 1024, M = 0;
+    int32_t *NN = (int32_t *)malloc(sizeof(int32_t) * cap);
+    dj_t *buf = (dj_t *)malloc(sizeof(dj_t) * (size_t)(m1 > 0 ? m1 : 1));
+    if (!NN || !buf) return ORC_ENOMEM;
+    for (int64_t c = 0; c < m2; ++c) {
+        const double *col = D + c * m1;
+        offsets[c] = M;
+        if (method == ORC_NBD_RELIEFF) {
+            for (int64_t j = 0; j < m1; ++j) { buf[j].d = col[j]; buf[j].j = (int32_t)j; }
+            qsort(buf, (size_t)m1, sizeof(dj_t), cmp_dj);
+            int64_t n = k + 1;
+            if (n > m1) n = m1;
+            if (n <= 0) continue;
+            const double cut = buf[n - 1].d;
+            for (int64_t t = 0; t < m1 && buf[t].d <= cut; ++t) {
+                if (!(buf[t].d > 0)) continue;
+                if (M == cap) { cap *= 2; NN = realloc(NN, sizeof(int32_t) * cap); if (!NN) return ORC_ENOMEM; }
+                NN[M++] = buf[t].j + 1;
+            }
+        } else {
+            const double r = radius[c];
+            for (int64_t j = 0; j < m1; ++j)
+                if ((col[j] < r) && (col[j] > 0)) {
+                    if (M == cap) { cap *= 2; NN = realloc(NN, sizeof(int32_t) * cap); if (!NN) return ORC_ENOMEM; }
+                    NN[M++] = (int32_t)(j + 1);
+                }
+        }
+    }
+    offsets[m2] = M;
+    free(buf);
+    *idx_out = NN;
+    return ORC_OK;
+}
+
 /* nearestNeighborsSeparateHitMiss, R/nearestNeighbors.R:318-551 (npdr(separate.hitmiss.nbds = TRUE), R/npdr.R:215-251).
  * Same distance matrix; hit and miss neighbourhoods are formed separately and listed hits first, then misses.
  *  multisurf (:483-500): per Ri, radius_hit = mean(d[hits, not self]) - sd.frac*sd(same), radius_miss likewise over misses

@@ -224,3 +224,38 @@ def regress_attrs(X, Ri, NN, ydiff, cdiff=None, attr_diff_type="numeric-abs", re
                                  C.c_int(REG[regression_type]), _d(out))
     assert rc == 0, rc
     return out
+
+
+def distances2(X1, X2, metric="manhattan"):
+    """npdrDistances2 (R/npdrLearner.R:323-339): m1 x m2 matrix, rows = instances of X1, columns = instances of X2."""
+    X1 = _f64(np.asarray(X1, dtype=np.float64)); X2 = _f64(np.asarray(X2, dtype=np.float64))
+    m = metric if metric in ("euclidean", "allele-sharing-manhattan") else "manhattan"
+    D = np.empty((X1.shape[0], X2.shape[0]), order="F")
+    rc = lib().orc_distances2(_d(X1), C.c_int64(X1.shape[0]), _d(X2), C.c_int64(X2.shape[0]), C.c_int64(X1.shape[1]),
+                              C.c_int(METRIC[m]), _d(D))
+    assert rc == 0
+    return D
+
+
+def nearest_neighbors2(X1, X2, nbd_method="multisurf", nbd_metric="manhattan", sd_vec=None, sd_frac=0.5, k=0):
+    """nearestNeighbors2 (R/npdrLearner.R:378-482) -> (list of m2 int32 arrays of 1-based X1 indices, radius, D)."""
+    D = distances2(X1, X2, nbd_metric)
+    m1, m2 = D.shape
+    radius = np.full(m2, np.nan)
+    if nbd_method == "relieff":
+        if k == 0:
+            k = int(lib().orc_knn_surf(C.c_int64(m1), C.c_double(sd_frac)))       # R/npdrLearner.R:413-418
+    else:
+        sv = _f64(np.asarray(sd_vec, dtype=np.float64)) if sd_vec is not None else None
+        rc = lib().orc_radius2(_d(D), C.c_int64(m1), C.c_int64(m2), C.c_int(NBD[nbd_method]), C.c_double(sd_frac),
+                               _d(sv) if sv is not None else None, _d(radius))
+        assert rc == 0
+    off = np.zeros(m2 + 1, dtype=np.int64)
+    idx = _ip()
+    rc = lib().orc_neighbors2(_d(D), C.c_int64(m1), C.c_int64(m2), C.c_int(NBD[nbd_method]), C.c_int64(k), _d(radius),
+                              off.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(idx))
+    assert rc == 0
+    M = int(off[-1])
+    nn = np.ctypeslib.as_array(idx, shape=(max(M, 1),))[:M].copy()
+    lib().orc_free(C.cast(idx, C.c_void_p))
+    return [nn[off[i]:off[i + 1]] for i in range(m2)], radius, D

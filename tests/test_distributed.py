@@ -68,6 +68,100 @@ class OracleEngine:
         return st, nu, ri.size
 
 
+class BalancedOracleEngine(OracleEngine):
+    """Numpy mirror of the balanced-distance primitives of libnpdr_b200 (distance.cu: build_tiles / exchange_lists /
+    pack / unpack), so the all-to-all plumbing of exchange_balanced() runs under gloo on CPU."""
+    T = 128
+
+    @staticmethod
+    def _row_owner_computes(I, J):
+        return (I < J) == ((I + J) % 2 == 0)
+
+    def balanced_local(self, row_starts, index, nbd_metric):
+        T = self.T
+        Dfull = self.O.distances(self.X, nbd_metric)
+        N = Dfull.shape[0]
+        ts = [-(-r // T) for r in row_starts]
+        a, b = ts[index], ts[index + 1]
+        self.r0, self.r1 = row_starts[index], row_starts[index + 1]
+        self.block = np.full((self.r1 - self.r0, N), np.nan)            # NaN = not computed here
+        self.send_tiles, self.recv_tiles, sc, rc = [], [], [], []
+        n_jt = -(-N // T)
+        for I in range(a, b):
+            for J in range(n_jt):
+                own = a <= J < b
+                if own or self._row_owner_computes(I, J):
+                    i0, i1 = I * T, min((I + 1) * T, self.r1)
+                    j0, j1 = J * T, min((J + 1) * T, N)
+                    self.block[i0 - self.r0:i1 - self.r0, j0:j1] = Dfull[i0:i1, j0:j1]
+        for h in range(len(ts) - 1):
+            if h == index:
+                sc.append(0); rc.append(0); continue
+            c, d = ts[h], ts[h + 1]
+            snd = [(I, J) for I in range(a, b) for J in range(c, d) if self._row_owner_computes(I, J)]
+            rcv = [(I, J) for J in range(c, d) for I in range(a, b) if self._row_owner_computes(J, I)]
+            self.send_tiles += snd; self.recv_tiles += rcv
+            sc.append(len(snd) * T * T); rc.append(len(rcv) * T * T)
+        return sc, rc
+
+    def balanced_pack(self, n_send):
+        T = self.T
+        N = self.block.shape[1]
+        out = np.zeros((len(self.send_tiles), T, T))
+        for t, (I, J) in enumerate(self.send_tiles):                     # tile (I, J) transposed: buf[t][c][r]
+            i0, i1 = I * T - self.r0, min((I + 1) * T, self.r1) - self.r0
+            j0, j1 = J * T, min((J + 1) * T, N)
+            out[t, :j1 - j0, :i1 - i0] = self.block[i0:i1, j0:j1].T
+        assert out.size == n_send
+        return torch.from_numpy(out.reshape(-1)) if n_send else torch.zeros(1, dtype=torch.float64)
+
+    def balanced_unpack(self, recv, n_recv):
+        T = self.T
+        N = self.block.shape[1]
+        buf = recv[:n_recv].numpy().reshape(-1, T, T)
+        for t, (I, J) in enumerate(self.recv_tiles):                     # rows I (mine), columns J (the sender's rows)
+            i0, i1 = I * T - self.r0, min((I + 1) * T, self.r1) - self.r0
+            j0, j1 = J * T, min((J + 1) * T, N)
+            self.block[i0:i1, j0:j1] = buf[t, :i1 - i0, :j1 - j0]
+
+
+def _worker_balanced(rank, world, port, N, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import sys
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from npdr_b200.distributed import exchange_balanced, partition_rows
+    rng = np.random.default_rng(5)
+    X = np.asfortranarray(rng.normal(size=(N, 6)))
+    eng = BalancedOracleEngine(X, None, None)
+    parts = partition_rows(N, world)
+    exchange_balanced(eng, parts, rank, "manhattan")
+    ok = True
+    if parts[rank][1] > 0:
+        D = eng.O.distances(X, "manhattan")
+        ok = bool(np.array_equal(eng.block, D[parts[rank][0]:parts[rank][0] + parts[rank][1], :]))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N", [(2, 300), (3, 700), (4, 300)])
+def test_balanced_distance_exchange_gloo(world, N):
+    """exchange_balanced(): every rank ends with its full row block although it computed only half of the off-diagonal
+    squares; (4, 300) has a rank without rows, which still joins the all-to-all."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_balanced, args=(r, world, port, N, q)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    res = dict(q.get(timeout=240) for _ in range(world))
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    assert all(res[r] for r in range(world)), res
+
+
 def _case(seed=0):
     rng = np.random.default_rng(seed)
     N, p = 300, 37

@@ -472,3 +472,120 @@ def test_medium_scale_properties(nb, oracle):
     assert np.all(np.diff(nn)[same] > 0)
     assert np.all(D[nn - 1, ri - 1] < r[ri - 1]) and np.all(D[nn - 1, ri - 1] > 0)
     assert set(out["att"][:5]) == {"1", "2", "3", "4", "5"}        # the planted effects rank first
+
+
+# ---------------------------------------------------------------- npdrDistances2 / nearestNeighbors2 (R/npdrLearner.R:323-482)
+@pytest.mark.parametrize("shape", [(100, 37, 50), (130, 257, 19), (3, 5, 2), (300, 129, 1000)])
+@pytest.mark.parametrize("metric", ["manhattan", "euclidean", "allele-sharing-manhattan"])
+def test_distances2_bit_exact(nb, oracle, shape, metric):
+    m1, m2, p = shape
+    rng = np.random.default_rng(m1 + m2 + p)
+    if metric == "allele-sharing-manhattan":
+        X1 = rng.integers(0, 3, size=(m1, p)).astype(float); X2 = rng.integers(0, 3, size=(m2, p)).astype(float)
+    else:
+        X1 = rng.normal(size=(m1, p)); X2 = rng.normal(size=(m2, p))
+    D = nb.npdrDistances2(X1, X2, metric)
+    assert D.shape == (m1, m2)
+    assert np.array_equal(D, oracle.distances2(X1, X2, metric))
+    if metric == "manhattan":                                   # the reference's quirk: unknown metric names mean manhattan
+        assert np.array_equal(nb.npdrDistances2(X1, X2, "hamming"), D)
+
+
+def test_distances2_of_a_matrix_with_itself_is_dist(nb, oracle):
+    X = np.random.default_rng(3).normal(size=(150, 40))
+    assert np.array_equal(nb.npdrDistances2(X, X), oracle.distances(X, "manhattan"))
+
+
+@pytest.mark.parametrize("method", ["multisurf", "surf", "relieff"])
+@pytest.mark.parametrize("kind", ["normal", "snp", "dups", "wide"])
+def test_nearest_neighbors2_bit_exact(nb, oracle, method, kind):
+    rng = np.random.default_rng(len(method) * 7 + len(kind))
+    m1, m2, p = (90, 41, 30) if kind != "wide" else (35, 300, 12)      # wide: more test than training instances
+    if kind == "snp":                                            # integer data: exact ties in distance and at the cut
+        X1 = rng.integers(0, 3, size=(m1, p)).astype(float); X2 = rng.integers(0, 3, size=(m2, p)).astype(float)
+    else:
+        X1 = rng.normal(size=(m1, p)); X2 = rng.normal(size=(m2, p))
+    if kind == "dups":                                           # test instances identical to training instances: d == 0 is dropped
+        X2[:5] = X1[10:15]
+    metric = "manhattan" if kind != "wide" else "euclidean"
+    got, info = nb.nearestNeighbors2(X1, X2, method, metric, return_info=True)
+    exp, radius, _ = oracle.nearest_neighbors2(X1, X2, method, metric)
+    assert len(got) == m2
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b)
+    if method != "relieff":
+        if method == "surf" and m1 * m2 > (1 << 18):
+            np.testing.assert_allclose(info["radius"], radius, rtol=1e-14)
+        else:
+            assert np.array_equal(info["radius"], radius)
+    elif kind == "normal":
+        assert all(len(a) == oracle.lib().orc_knn_surf(m1, 0.5) + 1 for a in got)   # k + 1: no self to drop
+
+
+def test_nearest_neighbors2_options(nb, oracle):
+    rng = np.random.default_rng(77)
+    X1 = rng.normal(size=(120, 25)); X2 = rng.normal(size=(33, 25))
+    sd = np.abs(rng.normal(size=33)) + 0.5
+    got = nb.nearestNeighbors2(X1, X2, "multisurf", "manhattan", sd_vec=sd, sd_frac=0.3)
+    exp, _, _ = oracle.nearest_neighbors2(X1, X2, "multisurf", "manhattan", sd_vec=sd, sd_frac=0.3)
+    assert all(np.array_equal(a, b) for a, b in zip(got, exp))
+    got = nb.nearestNeighbors2(X1, X2, "relieff", "manhattan", k=7)
+    exp, _, _ = oracle.nearest_neighbors2(X1, X2, "relieff", "manhattan", k=7)
+    assert all(np.array_equal(a, b) for a, b in zip(got, exp)) and all(len(a) == 8 for a in got)
+    with pytest.raises(ValueError):
+        nb.nearestNeighbors2(X1, X2[:, :5])
+    with pytest.raises(ValueError):
+        nb.nearestNeighbors2(X1, X2, "nope")
+
+
+# ---------------------------------------------------------------- balanced symmetric distances across row blocks
+@pytest.mark.parametrize("N,world", [(300, 2), (1000, 3), (1300, 8), (640, 4), (300, 8)])
+@pytest.mark.parametrize("metric", ["manhattan", "euclidean"])
+def test_balanced_distance_blocks_equal_full(nb, oracle, N, world, metric):
+    """Every rank computes its diagonal square + a checkerboard half of each off-diagonal square; the all-to-all of the
+    packed (transposed) tiles completes the blocks.  Emulated on one device: the routing is done with numpy."""
+    import torch
+    from npdr_b200 import _lib
+    from npdr_b200.distributed import partition_rows
+    rng = np.random.default_rng(N + world)
+    p = 24
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    D = oracle.distances(X, metric)
+    ctx = _lib.context(0)
+    parts = partition_rows(N, world)
+    row_starts = [r0 for r0, _ in parts] + [N]
+    live = [g for g in range(world) if parts[g][1] > 0]
+    if len(live) < world:                                        # trailing empty blocks: the partition passed down covers live ranks
+        row_starts = [parts[g][0] for g in live] + [N]
+    sess, send_bufs, counts = [], [], []
+    n_tiles_total = 0
+    for gi, g in enumerate(live):
+        s = _lib.Session(ctx, N, p, 0)
+        s.upload(X)
+        sc, rc = s.distances_balanced(metric, row_starts, gi)
+        buf = torch.zeros(max(sum(sc), 1), dtype=torch.float64, device="cuda")
+        s.balanced_pack(buf.data_ptr())
+        torch.cuda.synchronize()
+        sess.append(s); send_bufs.append(buf.cpu().numpy()); counts.append((sc, rc))
+        n_tiles_total += sum(sc) // (128 * 128)
+    W = len(live)
+    for gi in range(W):                                          # what all_to_all_single would deliver to rank gi
+        sc, rc = counts[gi]
+        pieces = []
+        for h in range(W):
+            sch = counts[h][0]
+            off = sum(sch[:gi])
+            pieces.append(send_bufs[h][off:off + sch[gi]])
+            assert sch[gi] == rc[h]
+        recv = torch.from_numpy(np.concatenate(pieces) if sum(rc) else np.zeros(1)).cuda()
+        sess[gi].balanced_unpack(recv.data_ptr())
+        torch.cuda.synchronize()
+        r0, r1 = row_starts[gi], row_starts[gi + 1]
+        assert np.array_equal(sess[gi].copy_distances(), D[r0:r1, :])
+    # each off-diagonal tile pair crossed the wire exactly once
+    T = -(-N // 128)
+    tb = [-(-r // 128) for r in row_starts]
+    cross = sum((tb[a + 1] - tb[a]) * (tb[b + 1] - tb[b]) for a in range(W) for b in range(a + 1, W))
+    assert n_tiles_total == cross and T == tb[-1]
+    for s in sess:
+        s.close()

@@ -183,3 +183,33 @@ def test_diff_regression_quirk3(oracle):
     Xc = np.column_stack([np.ones(ri.size), cd])
     b, *_ = np.linalg.lstsq(Xc, yd, rcond=None)
     assert int(out2[1, 7]) & 1 and abs(out2[1, 0] - b[1]) < 1e-10 and abs(out2[1, 2] - b[0]) < 1e-10
+
+
+def test_rectangular_distances_and_neighbors2_against_numpy(oracle):
+    """npdrDistances2 / nearestNeighbors2 (R/npdrLearner.R:323-482): oracle vs an independent numpy statement."""
+    from scipy.spatial.distance import cdist
+    rng = np.random.default_rng(11)
+    X1 = rng.normal(size=(60, 9)); X2 = rng.normal(size=(17, 9))
+    np.testing.assert_allclose(oracle.distances2(X1, X2, "manhattan"), cdist(X1, X2, "cityblock"), rtol=1e-13)
+    np.testing.assert_allclose(oracle.distances2(X1, X2, "euclidean"), cdist(X1, X2, "euclidean"), rtol=1e-13)
+    np.testing.assert_allclose(oracle.distances2(X1, X2, "allele-sharing-manhattan"), cdist(X1 / 2, X2 / 2, "cityblock"), rtol=1e-13)
+    assert np.array_equal(oracle.distances2(X1, X2, "anything-else"), oracle.distances2(X1, X2, "manhattan"))
+    D = cdist(X1, X2, "cityblock")
+    # multisurf: colMeans - sd.frac * sd(column), all m1 entries; strict `<`, `> 0`, ascending index
+    nn, r, _ = oracle.nearest_neighbors2(X1, X2, "multisurf")
+    r_np = D.mean(0) - 0.5 * D.std(0, ddof=1)
+    np.testing.assert_allclose(r, r_np, rtol=1e-13)
+    for i in range(17):
+        assert np.array_equal(nn[i], 1 + np.flatnonzero((D[:, i] < r[i]) & (D[:, i] > 0)))
+    # surf: one radius from all m1 * m2 entries
+    nn, r, _ = oracle.nearest_neighbors2(X1, X2, "surf")
+    np.testing.assert_allclose(r, np.full(17, D.mean() - 0.5 * D.std(ddof=1)), rtol=1e-13)
+    # relieff: k + 1 nearest (no self distance), nearest first
+    k = int(oracle.lib().orc_knn_surf(60, 0.5))
+    nn, _, _ = oracle.nearest_neighbors2(X1, X2, "relieff")
+    for i in range(17):
+        assert np.array_equal(nn[i], 1 + np.argsort(D[:, i], kind="stable")[:k + 1])
+    # a test instance that IS a training instance: its zero distance is filtered, leaving k
+    X2[0] = X1[5]
+    nn, _, _ = oracle.nearest_neighbors2(X1, X2, "relieff")
+    assert len(nn[0]) == k and 6 not in nn[0]
