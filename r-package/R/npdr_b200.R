@@ -13,6 +13,21 @@ npdrDistances <- function(attr.mat, metric = "manhattan", fast.dist = FALSE) {
   .Call("C_npdrb_distances", unname(as.matrix(attr.mat)) + 0, .metric_code[[metric]], PACKAGE = "npdrb200")
 }
 
+# R/npdrLearner.R:323-339 (flexclust::dist2): any metric other than euclidean / allele-sharing-manhattan means manhattan
+npdrDistances2 <- function(attr.mat1, attr.mat2, metric = "manhattan") {
+  m <- if (metric %in% c("euclidean", "allele-sharing-manhattan")) metric else "manhattan"
+  .Call("C_npdrb_distances2", unname(as.matrix(attr.mat1)) + 0, unname(as.matrix(attr.mat2)) + 0, .metric_code[[m]],
+        PACKAGE = "npdrb200")
+}
+
+# R/npdrLearner.R:378-482: list (one element per row of attr.mat2) of neighbour row indices in attr.mat1
+nearestNeighbors2 <- function(attr.mat1, attr.mat2, nbd.method = "multisurf", nbd.metric = "manhattan", sd.vec = NULL,
+                              sd.frac = 0.5, dopar.nn = FALSE, k = 0) {
+  m <- if (nbd.metric %in% c("euclidean", "allele-sharing-manhattan")) nbd.metric else "manhattan"
+  .Call("C_npdrb_nearest_neighbors2", unname(as.matrix(attr.mat1)) + 0, unname(as.matrix(attr.mat2)) + 0,
+        .nbd_code[[nbd.method]], .metric_code[[m]], sd.vec, sd.frac, k, PACKAGE = "npdrb200")
+}
+
 nearestNeighbors <- function(attr.mat, nbd.method = "multisurf", nbd.metric = "manhattan", sd.vec = NULL,
                              sd.frac = 0.5, k = 0, neighbor.sampling = "none", att_to_remove = c(),
                              fast.dist = FALSE, dopar.nn = FALSE) {

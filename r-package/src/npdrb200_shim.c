@@ -2,7 +2,7 @@
  * npdrb200_shim.c -- thin .Call shim between R and libnpdr_b200.so (include/npdr_b200.h).
  *
  * NOT compiled in the build container (no R headers there); it is the binding a maintainer adds to the
- * reference package.  Plain R C API (no Rcpp dependency needed for five entry points).  Rules followed:
+ * reference package.  Plain R C API (no Rcpp dependency needed for seven entry points).  Rules followed:
  * inputs (SEXP payloads) are never written; native buffers are copied into R-allocated vectors and freed with
  * npdrb_free(); errors are turned into Rf_error() only after native resources are released.
  */
@@ -106,7 +106,44 @@ SEXP C_npdrb_unireg(SEXP X, SEXP y, SEXP C, SEXP reg) {
     return stats;
 }
 
+/* .Call("C_npdrb_distances2", X1, X2, metric) -> m1 x m2 matrix     (npdrDistances2, R/npdrLearner.R:323) */
+SEXP C_npdrb_distances2(SEXP X1, SEXP X2, SEXP metric) {
+    const int *d1 = INTEGER(Rf_getAttrib(X1, R_DimSymbol)), *d2 = INTEGER(Rf_getAttrib(X2, R_DimSymbol));
+    if (d1[1] != d2[1]) Rf_error("npdr_b200: attr.mat1 and attr.mat2 must have the same number of columns");
+    SEXP D = PROTECT(Rf_allocMatrix(REALSXP, d1[0], d2[0]));
+    int rc = npdrb_distances2(ctx_get(), REAL(X1), d1[0], REAL(X2), d2[0], d1[1], Rf_asInteger(metric), REAL(D));
+    UNPROTECT(1);
+    if (rc) Rf_error("npdr_b200: %s", npdrb_last_error());
+    return D;
+}
+
+/* .Call("C_npdrb_nearest_neighbors2", X1, X2, nbd.method, nbd.metric, sd.vec|NULL, sd.frac, k)
+ *   -> list of nrow(X2) integer vectors of X1 row indices           (nearestNeighbors2, R/npdrLearner.R:378) */
+SEXP C_npdrb_nearest_neighbors2(SEXP X1, SEXP X2, SEXP method, SEXP metric, SEXP sd_vec, SEXP sd_frac, SEXP k) {
+    const int *d1 = INTEGER(Rf_getAttrib(X1, R_DimSymbol)), *d2 = INTEGER(Rf_getAttrib(X2, R_DimSymbol));
+    if (d1[1] != d2[1]) Rf_error("npdr_b200: attr.mat1 and attr.mat2 must have the same number of columns");
+    int64_t *off = NULL, M = 0;
+    int32_t *idx = NULL;
+    int rc = npdrb_nearest_neighbors2(ctx_get(), REAL(X1), d1[0], REAL(X2), d2[0], d1[1], Rf_asInteger(method),
+                                      Rf_asInteger(metric), Rf_isNull(sd_vec) ? NULL : REAL(sd_vec), Rf_asReal(sd_frac),
+                                      (int64_t)Rf_asReal(k), &off, &idx, &M, NULL);
+    if (rc) Rf_error("npdr_b200: %s", npdrb_last_error());
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, d2[0]));
+    for (int i = 0; i < d2[0]; ++i) {
+        const int64_t n = off[i + 1] - off[i];
+        SEXP v = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)n));
+        if (n) memcpy(INTEGER(v), idx + off[i], sizeof(int) * (size_t)n);
+        SET_VECTOR_ELT(out, i, v);
+        UNPROTECT(1);
+    }
+    npdrb_free(off); npdrb_free(idx);
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
+    {"C_npdrb_distances2", (DL_FUNC)&C_npdrb_distances2, 3},
+    {"C_npdrb_nearest_neighbors2", (DL_FUNC)&C_npdrb_nearest_neighbors2, 7},
     {"C_npdrb_distances", (DL_FUNC)&C_npdrb_distances, 2},
     {"C_npdrb_nearest_neighbors", (DL_FUNC)&C_npdrb_nearest_neighbors, 7},
     {"C_npdrb_npdr", (DL_FUNC)&C_npdrb_npdr, 5},
