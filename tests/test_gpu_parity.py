@@ -589,3 +589,63 @@ def test_balanced_distance_blocks_equal_full(nb, oracle, N, world, metric):
     assert n_tiles_total == cross and T == tb[-1]
     for s in sess:
         s.close()
+
+
+# ---------------------------------------------------------------- BASELINE config 4 at full size (4,000 x 20,000)
+def test_cfg4_full_size_properties(nb, oracle):
+    """The bench workload itself (same generator, same seed): size-independent invariants on the full run, bit-exact
+    distances / radii / pair list against the oracle at full size, oracle regression parity on 12 attributes over ALL
+    6.3 M pairs (the oracle cannot regress 20,000 attributes in seconds), shard and work-saving invariances."""
+    import torch
+    import bench
+    from npdr_b200 import _lib
+    from npdr_b200.distributed import GpuEngine, npdr_sharded
+    dev = torch.device("cuda", 0)
+    data = bench.make_data(bench.WORKLOADS["cfg4"], 1, dev)
+    N, p = data["N"], data["p"]
+    assert (N, p) == (4000, 20000)
+    eng = GpuEngine(device_index=0, dX=data["dX"], ldx=data["ldx"], dy=data["dy"], dC=None, N=N, p=p, q=0)
+    stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, ())
+    s = eng.session
+    M = info["n_pairs"]
+    ri, nn = s.copy_pairs(M)
+    D = s.copy_distances()
+    r = s.copy_radius()
+    # distance matrix: symmetric bit for bit, zero diagonal, positive elsewhere
+    assert np.array_equal(D, D.T) and not D.diagonal().any() and (D[~np.eye(N, dtype=bool)] > 0).all()
+    # pair list: no self pairs, grouped by ascending Ri, ascending NN inside a group, exactly the entries under the radius
+    assert np.all(ri != nn) and np.all(np.diff(ri) >= 0) and np.all(np.diff(nn)[np.diff(ri) == 0] > 0)
+    sel = (D < r[:, None]) & (D > 0)
+    assert M == int(sel.sum()) and np.array_equal(np.flatnonzero(sel.ravel()), (ri - 1).astype(np.int64) * N + (nn - 1))
+    assert abs(M / (N * (N - 1)) - 0.3085) < 0.09                 # multiSURF expectation (N-1)(1-Phi(.5)) per instance, loosely
+    # bit-exact against the oracle at full size: all 8.0e6 distances (1.6e11 element pairs, ~20 s on the host cores),
+    # the long-double multiSURF radii and the complete pair list
+    X = data["dX"][:, :N].T.cpu().numpy()                         # (N, p) view of the column-major device matrix
+    D_exp = oracle.distances(np.asfortranarray(X), "manhattan")
+    assert np.array_equal(D, D_exp)
+    r_exp, _ = oracle.radius_multisurf(D_exp, 0.5)
+    assert np.array_equal(r, r_exp)
+    ri_exp, nn_exp, _ = oracle.neighbors(D_exp, "multisurf", radius=r_exp)
+    assert np.array_equal(ri, ri_exp) and np.array_equal(nn, nn_exp)
+    del D_exp
+    # regression: oracle parity on 12 attributes over all M pairs (functional + background columns)
+    sl = np.r_[0:4, 1000:1004, 19996:20000]
+    yh = data["dy"].cpu().numpy()
+    exp = oracle.regress_attrs(np.asfortranarray(X[:, sl]), ri, nn, oracle.pair_diffs(yh, ri, nn, "match-mismatch"))
+    _stats_close(stats[sl], exp, RTOL_IRLS, "cfg4 full size")
+    assert np.array_equal(stats[sl, 6], exp[:, 6])                 # IRLS iteration counts
+    # attribute sharding and the exact work-saving devices do not change a bit / stay within the IRLS bar
+    part = s.regress(1000, 2500, "binomial")
+    assert np.array_equal(part, stats[1000:3500])
+    os.environ["NPDRB_NO_SPECULATE"] = "1"; os.environ["NPDRB_NO_FOLD"] = "1"
+    try:
+        s2 = _lib.Session(_lib.context(0), N, p, 0)
+        s2.set_device_inputs(data["dX"].data_ptr(), data["ldx"], data["dy"].data_ptr(), 0)
+        s2.import_pairs_host(ri, nn)
+        plain = s2.regress(0, 512, "binomial")
+        s2.close()
+    finally:
+        os.environ.pop("NPDRB_NO_SPECULATE"); os.environ.pop("NPDRB_NO_FOLD")
+    _stats_close(stats[:512], plain, 1e-9, "work saving on/off")
+    assert np.array_equal(stats[:512, 6], plain[:, 6]) and np.array_equal(stats[:512, 7], plain[:, 7])
+    eng.close()
