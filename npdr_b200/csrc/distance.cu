@@ -20,7 +20,8 @@
 namespace {
 
 constexpr int TM = 128;       // tile rows (i)
-constexpr int TN = 128;       // tile cols (j)
+constexpr int TN = 128;       // tile cols (j) of the wide kernel; the narrow variant uses 64 (twice the tiles: fills the SMs of
+                              // a row block that has fewer than ~2 waves of 128 x 128 tiles)
 constexpr int BK = 16;        // attributes per pipeline stage
 constexpr int STAGES = 4;
 constexpr int DTHREADS = 256;
@@ -95,7 +96,7 @@ constexpr int TILE_MIRROR = 1 << 30;
 // D block layout: Dout[(i - row0) * ldd + j] for owned rows i in [row0, row0 + nrows), all j in [0, N).
 // same_ab: the row and column operands come from the same matrix (tile i0 == j0 is then a diagonal tile and is
 // loaded once); otherwise tmapA describes the row-side matrix and tmapB the column-side one (npdrDistances2).
-template <int MODE>
+template <int MODE, int TNV>
 __global__ void __launch_bounds__(DTHREADS, 1)
 dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapB, int same_ab,
                 int64_t Nrows_total, int64_t N, int64_t p, int64_t row0, int64_t nrows,
@@ -103,9 +104,11 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     extern __shared__ unsigned char smem_raw[];
     // explicit 32-bit shared-window addresses (keeps every access an LDS / SYNCS, never a generic LD)
     constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * sizeof(double);
+    constexpr uint32_t STAGE_BYTES_B = BK * TNV * sizeof(double);
+    constexpr int NC = TNV / 16;                                   // accumulator columns per thread (8 or 4)
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t sA = base;                                      // [STAGES][BK][TM]
-    const uint32_t sB = base + STAGES * STAGE_BYTES;               // [STAGES][BK][TN]
+    const uint32_t sB = base + STAGES * STAGE_BYTES;               // [STAGES][BK][TNV]
     const uint32_t full = base + 2 * STAGES * STAGE_BYTES;         // STAGES mbarriers
 
     const int tid = threadIdx.x;
@@ -125,9 +128,9 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const int it = tc.x, jt = tc.y & (TILE_MIRROR - 1);
         const bool mirror = (tc.y & TILE_MIRROR) != 0;
         const int i0 = (int)row0 + it * TM;                        // global instance index of the tile's first row
-        const int j0 = jt * TN;
-        const bool diag = same_ab && (i0 == j0);
-        const uint32_t tx_bytes = (uint32_t)(STAGE_DOUBLES * sizeof(double)) * (diag ? 1u : 2u);
+        const int j0 = jt * TNV;
+        const bool diag = same_ab && (j0 >= i0) && (j0 + TNV <= i0 + TM);     // the column range lies inside the row range: one load
+        const uint32_t tx_bytes = STAGE_BYTES + (diag ? 0u : STAGE_BYTES_B);
 
         // prologue: fill STAGES-1 stages (all threads passed the __syncthreads that ended the previous tile)
         if (tid == 0) {
@@ -135,15 +138,15 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 int s = (int)((g + c) % STAGES);
                 mbar_expect_tx(full + 8 * s, tx_bytes);
                 tma_load_2d(sA + s * STAGE_BYTES, &tmap, i0, c * BK, full + 8 * s);
-                if (!diag) tma_load_2d(sB + s * STAGE_BYTES, &tmapB, j0, c * BK, full + 8 * s);
+                if (!diag) tma_load_2d(sB + s * STAGE_BYTES_B, &tmapB, j0, c * BK, full + 8 * s);
             }
         }
 
-        double acc[8][8];
+        double acc[8][NC];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+            for (int c = 0; c < NC; ++c) acc[r][c] = 0.0;
 
         for (int c = 0; c < n_chunks; ++c) {
             // refill the stage freed by the previous iteration
@@ -152,27 +155,31 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 int s = (int)((g + cn) % STAGES);
                 mbar_expect_tx(full + 8 * s, tx_bytes);
                 tma_load_2d(sA + s * STAGE_BYTES, &tmap, i0, cn * BK, full + 8 * s);
-                if (!diag) tma_load_2d(sB + s * STAGE_BYTES, &tmapB, j0, cn * BK, full + 8 * s);
+                if (!diag) tma_load_2d(sB + s * STAGE_BYTES_B, &tmapB, j0, cn * BK, full + 8 * s);
             }
             const uint32_t gc = g + (uint32_t)c;
             const int s = (int)(gc % STAGES);
             mbar_wait(full + 8 * s, (gc / STAGES) & 1u);
             const uint32_t As = sA + s * STAGE_BYTES + ty * 16;
-            const uint32_t Bs = (diag ? sA : sB) + s * STAGE_BYTES + tx * 16;
+            const uint32_t Bs = (diag ? sA + s * STAGE_BYTES + (uint32_t)(j0 - i0) * 8u : sB + s * STAGE_BYTES_B) + tx * 16;
+            const uint32_t bstride = diag ? (uint32_t)(TM * 8) : (uint32_t)(TNV * 8);
 #pragma unroll 4
             for (int kk = 0; kk < BK; ++kk) {
-                double a[8], b[8];
+                double a[8], b[NC];
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     double2 av = lds_v2(As + kk * (TM * 8) + h * 256);
-                    double2 bv = lds_v2(Bs + kk * (TN * 8) + h * 256);
                     a[2 * h] = av.x; a[2 * h + 1] = av.y;
+                }
+#pragma unroll
+                for (int h = 0; h < NC / 2; ++h) {
+                    double2 bv = lds_v2(Bs + kk * bstride + h * 256);
                     b[2 * h] = bv.x; b[2 * h + 1] = bv.y;
                 }
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) accumulate<MODE>(acc[r][cc], a[r], b[cc]);
+                    for (int cc = 0; cc < NC; ++cc) accumulate<MODE>(acc[r][cc], a[r], b[cc]);
             }
             __syncthreads();                                       // stage s is free for the refill of the next iteration
         }
@@ -183,7 +190,7 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         for (int r = 0; r < 8; ++r) {
             const int64_t i = (int64_t)i0 + (r >> 1) * 32 + ty * 2 + (r & 1);
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
+            for (int cc = 0; cc < NC; ++cc) {
                 const int64_t j = (int64_t)j0 + (cc >> 1) * 32 + tx * 2 + (cc & 1);
                 double v = acc[r][cc];
                 if (MODE == MODE_EUCLID_EXACT || MODE == MODE_EUCLID_FMA) v = sqrt(v);
@@ -263,7 +270,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tensor_map(CUtensorMap *map, const double *X, int64_t N, int64_t p, int64_t ldx) {
+int make_tensor_map(CUtensorMap *map, const double *X, int64_t N, int64_t p, int64_t ldx, int box_rows = TM) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void *ptr = nullptr;
@@ -277,7 +284,7 @@ int make_tensor_map(CUtensorMap *map, const double *X, int64_t N, int64_t p, int
     }
     cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)p};
     cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(double)};
-    cuuint32_t box[2] = {(cuuint32_t)TM, (cuuint32_t)BK};
+    cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)BK};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)X, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -297,30 +304,45 @@ inline bool balanced_row_owner_computes(int I, int J) { return ((I < J) == (((I 
 
 struct TilePlan {
     std::vector<int2> tiles;       // what this block computes
+    int tn = TN;                   // tile width the list was built for
 };
 
 // list shapes: 0 = full symmetric, 1 = row block x all columns, 2 = balanced row block (tile_starts: G + 1 tile-row bounds)
+// tn: tile width (128 or 64); ownership rules are stated on 128 x 128 squares, each square is 128 / tn column tiles.
 int build_tiles(int shape, int64_t row0, int64_t nrows, int64_t ncols, const std::vector<int64_t> *tile_starts, int rank,
-                TilePlan &plan) {
-    const int n_it = (int)nb_cdiv(nrows, TM), n_jt = (int)nb_cdiv(ncols, TN);
+                int tn, TilePlan &plan) {
+    const int n_it = (int)nb_cdiv(nrows, TM), n_J = (int)nb_cdiv(ncols, TM), sub = TM / tn;
     const int it0 = (int)(row0 / TM);
     plan.tiles.clear();
+    plan.tn = tn;
+    auto push = [&](int it, int J, int flag) {
+        for (int h = 0; h < sub; ++h)
+            if ((int64_t)(J * sub + h) * tn < ncols) plan.tiles.push_back(make_int2(it, (J * sub + h) | flag));
+    };
     if (shape == 0) {
         for (int it = 0; it < n_it; ++it)
-            for (int jt = 0; jt <= it; ++jt) plan.tiles.push_back(make_int2(it, jt | TILE_MIRROR));
+            for (int J = 0; J <= it; ++J) push(it, J, TILE_MIRROR);
     } else if (shape == 1) {
         for (int it = 0; it < n_it; ++it)
-            for (int jt = 0; jt < n_jt; ++jt) plan.tiles.push_back(make_int2(it, jt));
+            for (int J = 0; J < n_J; ++J) push(it, J, 0);
     } else {
         const int a = (int)(*tile_starts)[rank], b = (int)(*tile_starts)[rank + 1];
         if (a != it0 || b - a != n_it) { npdrb_set_error("balanced distances: row block does not match the partition"); return NPDRB_EINVAL; }
         for (int I = a; I < b; ++I)
-            for (int J = 0; J < n_jt; ++J) {
-                if (J >= a && J < b) { if (J <= I) plan.tiles.push_back(make_int2(I - a, J | TILE_MIRROR)); }
-                else if (balanced_row_owner_computes(I, J)) plan.tiles.push_back(make_int2(I - a, J));
+            for (int J = 0; J < n_J; ++J) {
+                if (J >= a && J < b) { if (J <= I) push(I - a, J, TILE_MIRROR); }
+                else if (balanced_row_owner_computes(I, J)) push(I - a, J, 0);
             }
     }
     return NPDRB_OK;
+}
+
+// 128 x 64 tiles when the block has fewer than two waves of 128 x 128 tiles (NPDRB_DIST_TILE=64|128 forces a shape)
+int pick_tile_width(int64_t n_squares, int sm_count) {
+    const char *e = getenv("NPDRB_DIST_TILE");
+    if (e && atoi(e) == 64) return 64;
+    if (e && atoi(e) == 128) return 128;
+    return n_squares < 2 * (int64_t)sm_count ? 64 : 128;
 }
 
 template <int MODE>
@@ -328,17 +350,23 @@ int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const 
                int64_t row0, int64_t nrows, const TilePlan &plan, double *dD, int64_t ldd) {
     CUtensorMap mapA, mapB;
     NB_CHECK(make_tensor_map(&mapA, XA, NA, p, ldA));
-    NB_CHECK(make_tensor_map(&mapB, XB, NB, p, ldB));
+    NB_CHECK(make_tensor_map(&mapB, XB, NB, p, ldB, plan.tn));
     const int64_t n_tiles = (int64_t)plan.tiles.size();
     if (n_tiles == 0) return NPDRB_OK;
     int2 *d_tiles = nullptr;
     NB_CUDA(cudaMalloc(&d_tiles, sizeof(int2) * (size_t)n_tiles));
     NB_CUDA(cudaMemcpyAsync(d_tiles, plan.tiles.data(), sizeof(int2) * (size_t)n_tiles, cudaMemcpyHostToDevice, ctx->stream));
-    NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
     int grid = (int)((n_tiles < ctx->sm_count) ? n_tiles : ctx->sm_count);
     if (grid < 1) grid = 1;
-    dist_tma_kernel<MODE><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(mapA, mapB, XA == XB ? 1 : 0, NA, NB, p, row0, nrows,
-                                                                      d_tiles, n_tiles, dD, ldd);
+    if (plan.tn == 64) {
+        NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
+        dist_tma_kernel<MODE, 64><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(mapA, mapB, XA == XB ? 1 : 0, NA, NB, p, row0, nrows,
+                                                                              d_tiles, n_tiles, dD, ldd);
+    } else {
+        NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
+        dist_tma_kernel<MODE, TN><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(mapA, mapB, XA == XB ? 1 : 0, NA, NB, p, row0, nrows,
+                                                                              d_tiles, n_tiles, dD, ldd);
+    }
     NB_LAUNCH_CHECK(ctx);
     NB_CUDA(cudaStreamSynchronize(ctx->stream));        // the pinned-less H2D source (plan.tiles) must outlive the copy
     cudaFree(d_tiles);
@@ -433,7 +461,9 @@ int dist_core(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t 
                                        : launch_simple<MODE_EUCLID_FMA>(s, X, row0, nrows);
     } else {
         TilePlan plan;
-        NB_CHECK(build_tiles(shape, row0, nrows, s->N, tile_starts, rank, plan));
+        NB_CHECK(build_tiles(shape, row0, nrows, s->N, tile_starts, rank, TN, plan));
+        const int tn = pick_tile_width((int64_t)plan.tiles.size(), ctx->sm_count);
+        if (tn != TN) NB_CHECK(build_tiles(shape, row0, nrows, s->N, tile_starts, rank, tn, plan));
         rc = mode == MODE_MANHATTAN ? launch_tma<MODE_MANHATTAN>(s, X, row0, nrows, plan)
            : mode == MODE_HAMMING ? launch_tma<MODE_HAMMING>(s, X, row0, nrows, plan)
            : mode == MODE_EUCLID_EXACT ? launch_tma<MODE_EUCLID_EXACT>(s, X, row0, nrows, plan)
@@ -536,7 +566,9 @@ int nb_distances2(npdrb_ctx *ctx, const double *dX1, int64_t ld1, int64_t m1, co
         return NPDRB_EINVAL;
     }
     TilePlan plan;
-    NB_CHECK(build_tiles(1, 0, m2, m1, nullptr, 0, plan));
+    NB_CHECK(build_tiles(1, 0, m2, m1, nullptr, 0, TN, plan));
+    const int tn = pick_tile_width((int64_t)plan.tiles.size(), ctx->sm_count);
+    if (tn != TN) NB_CHECK(build_tiles(1, 0, m2, m1, nullptr, 0, tn, plan));
     const int mode = metric_mode(metric, fast_euclidean);
     return mode == MODE_MANHATTAN ? launch_tma<MODE_MANHATTAN>(ctx, dX2, m2, ld2, dX1, m1, ld1, p, 0, m2, plan, dD, ldd)
          : mode == MODE_EUCLID_EXACT ? launch_tma<MODE_EUCLID_EXACT>(ctx, dX2, m2, ld2, dX1, m1, ld1, p, 0, m2, plan, dD, ldd)

@@ -174,6 +174,7 @@ class GpuEngine(Engine):
             self.session.upload(X, y, C)
         else:
             self._keep = (dX, dy, dC)
+            torch.cuda.synchronize(self.device)      # the producers of the adopted tensors ran on torch's streams, the library has its own
             self.session.set_device_inputs(dX.data_ptr(), ldx, dy.data_ptr(), dC.data_ptr() if dC is not None else 0)
         self._metric_done = None
 

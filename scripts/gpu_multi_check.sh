@@ -3,8 +3,10 @@
 cd $GRAFT_REPO_ROOT
 TAG=${1:-x}; N=${2:-2}
 mkdir -p gpurun_out
+if [ -z "$SKIP_TESTS" ]; then
 (time python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$TAG.log
 tail -5 gpurun_out/pytest_$TAG.log
+fi
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 bench.py --gpus $N "${@:2}"; }
 run 29511 --steps 3 --warmup 3 --no-variants > gpurun_out/bench_cfg4_n${N}_$TAG.json 2> gpurun_out/bench_cfg4_n${N}_$TAG.err; echo "bench balanced rc=$?"
 NPDRB_NO_BALANCED=1 run 29512 --steps 3 --warmup 3 --no-variants --no-e2e > gpurun_out/bench_cfg4_n${N}_${TAG}_nobal.json 2> gpurun_out/bench_cfg4_n${N}_${TAG}_nobal.err; echo "bench unbalanced rc=$?"
