@@ -250,15 +250,22 @@ def main():
         eng.close()
         return stats, info, km, sm, passes
 
-    # host copies for the end-to-end arm (pinned; rank 0 only -- the other ranks receive X over NVLink)
+    # host copies for the end-to-end arm (pinned).  One GPU: the whole matrix goes through the host-buffer C ABI.  Several
+    # GPUs: every rank holds the pinned host copy of ITS attribute columns, uploads them over its own PCIe link and the
+    # shards are all-gathered over NVLink (a single host thread would feed the G devices the same way); y / covariates
+    # come from rank 0.  When p does not divide evenly rank 0 uploads everything and broadcasts.
     hX = hy = hC = hXt = None
     e2e_dev = None
-    if not args.no_e2e and rank == 0:
-        hXt = torch.empty((p, N), dtype=torch.float64, pin_memory=True)
-        hXt.copy_(data["dX"][:, :N])
-        hX = hXt.numpy().T                                       # (N, p) Fortran-ordered view of pinned memory
-        hy = data["dy"].cpu().numpy()
-        hC = np.asfortranarray(data["dC"].cpu().numpy().T) if q else None
+    shard_upload = world > 1 and p % world == 0
+    if not args.no_e2e and (rank == 0 or shard_upload):
+        a0, na = (0, p) if not shard_upload else (rank * (p // world), p // world)
+        hXt = torch.empty((na, N), dtype=torch.float64, pin_memory=True)
+        hXt.copy_(data["dX"][a0:a0 + na, :N])
+        if world == 1:
+            hX = hXt.numpy().T                                   # (N, p) Fortran-ordered view of pinned memory
+        if rank == 0:
+            hy = data["dy"].cpu().numpy()
+            hC = np.asfortranarray(data["dC"].cpu().numpy().T) if q else None
     if not args.no_e2e and world > 1:
         e2e_dev = dict(dX=torch.zeros((p, data["ldx"]), dtype=torch.float64, device=device),
                        dy=torch.zeros(N, dtype=torch.float64, device=device),
@@ -270,13 +277,19 @@ def main():
         if world == 1:
             eng = GpuEngine(X=hX, y=hy, C=hC, device_index=local_rank)   # host-buffer C ABI: H2D upload inside
         else:
-            # rank 0 uploads the host buffers once and broadcasts them over NVLink (NCCL); every rank then shards
-            if rank == 0:
+            if shard_upload:                                     # own columns over the own PCIe link, then NVLink all-gather
+                na = p // world
+                mine = e2e_dev["dX"][rank * na:(rank + 1) * na]
+                mine[:, :N].copy_(hXt, non_blocking=True)
+                dist.all_gather_into_tensor(e2e_dev["dX"], mine)
+            elif rank == 0:
                 e2e_dev["dX"][:, :N].copy_(hXt, non_blocking=True)
+            if rank == 0:
                 e2e_dev["dy"].copy_(hy_t, non_blocking=True)
                 if q:
                     e2e_dev["dC"].copy_(hC_t, non_blocking=True)
-            dist.broadcast(e2e_dev["dX"], 0)
+            if not shard_upload:
+                dist.broadcast(e2e_dev["dX"], 0)
             dist.broadcast(e2e_dev["dy"], 0)
             if q:
                 dist.broadcast(e2e_dev["dC"], 0)
@@ -337,7 +350,9 @@ def main():
         e2e = {"value": float(p) * M / (ms_e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e,
                "h2d_bytes_per_step": int(N * p * 8 + N * 8 + N * q * 8), "d2h_bytes_per_step": int(p * 8 * 8),
                "note": ("host-buffer C-ABI path: pinned X/y(/C) uploaded and statistics read back every step" if world == 1 else
-                        "rank 0 uploads pinned X/y(/C) and broadcasts over NVLink (NCCL) every step; statistics read back on rank 0")}
+                        ("every rank uploads its pinned attribute columns over its own PCIe link, NCCL all-gather over NVLink; y(/C) from "
+                         "rank 0; statistics read back on rank 0" if shard_upload else
+                         "rank 0 uploads pinned X/y(/C) and broadcasts over NVLink (NCCL) every step; statistics read back on rank 0"))}
 
     if rank != 0:
         if world > 1:
