@@ -49,10 +49,10 @@ def f_bin(q):
 
 def fp64_instr(q):
     """FP64 instructions the v2 IRLS pass kernel EXECUTES per attribute x record evaluation (SASS count):
-    12 (diff, range reduction, exp polynomial, 1+t, reciprocal, weight, deviance product) + 2(k-1) (eta, w*x) +
-    k(k+1)/2 (X'WX) + k (score), k = 2 + q: 19 at q = 0, 32 at q = 2."""
+    11 (diff 1, range reduction 3, degree-2 exp polynomial 2, 1+t 1, reciprocal 2, weight 1, deviance product 1) +
+    2(k-1) (eta, w*x) + k(k+1)/2 (X'WX) + k (score), k = 2 + q: 18 at q = 0, 31 at q = 2."""
     k = 2 + q
-    return 12 + 2 * (k - 1) + k * (k + 1) // 2 + k
+    return 11 + 2 * (k - 1) + k * (k + 1) // 2 + k
 
 
 def gen_columns(gen, N, ncols, col0, p_total, n_func, f, g, sgn, device, dtype):
@@ -391,15 +391,15 @@ def main():
                 "launches": n_full, "avg_launch_ms": km["pass_full_ms"] / n_full,
                 "fp64_instr_per_eval": fp64_instr(q), "evals_per_launch_avg": km["evals_pass_full"] / n_full,
                 "note": "achieved = attribute x record evaluations per launch x FP64 instructions the kernel executes per evaluation "
-                        "(19 at q = 0, 32 at q = 2; SASS count, DESIGN.md 4) x 2 flops per issue slot / CUDA-event launch time, against "
+                        "(18 at q = 0, 31 at q = 2; SASS count, DESIGN.md 4) x 2 flops per issue slot / CUDA-event launch time, against "
                         "the measured DFMA peak: frac is the FP64 pipe's issue-slot utilisation (ncu sm__pipe_fp64_cycles_active agrees). "
-                        "records = pairs after folding mutual (i,j)/(j,i) pairs into one weight-2 record.  The kernel also issues 12.5 "
+                        "records = pairs after folding mutual (i,j)/(j,i) pairs into one weight-2 record.  The kernel also issues 10.6 "
                         "(q = 0) / 13.5 (q = 2) non-FP64 instructions per evaluation; an FP64 warp instruction holds the dispatch "
-                        "port for 2 cycles, so the issue-limited ceiling of this mix is 38/50.5 = 75 % (q = 0), 64/77.5 = 83 % (q = 2)",
+                        "port for 2 cycles, so the issue-limited ceiling of this mix is 36/46.6 = 77 % (q = 0), 62/75.5 = 82 % (q = 2)",
                 "canonical": {"flops_per_eval_iteration": f_bin(q), "achieved": canon,
                               "frac": canon / peak["dfma_tflops"] if peak["dfma_tflops"] else None,
                               "note": "SURVEY 8d's canonical count (exp = log = 20, reciprocal = 8 flops): exceeds 1 because the kernel "
-                                      "spends 7 FP64 instructions on exp, 2 on the reciprocal and replaces the per-record log by a running "
+                                      "spends 6 FP64 instructions on exp, 2 on the reciprocal and replaces the per-record log by a running "
                                       "product (one multiply per record, one log per thread)"},
                 "records_per_pair": km["records"] / max(info["n_pairs_used"], 1),
                 "share_of_step": km["pass_full_ms"] / ms_step,

@@ -231,7 +231,7 @@ struct PassArgs {
     const double *beta;            // [KMAX][nattr_pad] current coefficients (IRLS_FULL)
     const unsigned char *tile_active;  // per attribute tile, or NULL
     const nb_tables *tables;       // device copy of the exp/log tables (v1 kernel)
-    const nb_tables512 *tables512; // exp 256 / log 512 tables (v2 kernel)
+    const nb_tables1024 *tables1024; // 1024-entry exp table (v2 kernel)
     const double *dmax;            // [nattr_pad] bound on the attribute diff (v2 IRLS pass: clamp pre-check)
     double cmax[NPDRB_MAX_COVARS]; // bounds on the covariate diffs
     int diff_type;
@@ -415,24 +415,24 @@ pass_kernel(PassArgs P) {
 //   * table indices are formed directly as byte offsets from the high word (2 integer ops each);
 //   * reciprocal: rcp.approx (2^-23) + ONE Newton step (2^-46 ~ 1.4e-14); exp / log are the trimmed
 //     nb_exp_fast / nb_log_ge1_fast recurrences (dmath.cuh carries the error budget and the host test).
-// The v2 kernel carries the linear predictor in units of ln2/256: s = eta * 256/ln2 (the coefficients are pre-scaled
+// The v2 kernel carries the linear predictor in units of ln2/1024: s = eta * 1024/ln2 (the coefficients are pre-scaled
 // when they are loaded), so k = rint(s) and the reduced argument frac = s - k (exact) need no multiplication, and
-// exp(eta) = 2^(k/256) * exp(frac * ln2/256) with the ln2/256 powers folded into the polynomial coefficients.  The
-// shared table image stores 2^(j/256) with j * 4096 pre-subtracted from its high word, so one IMAD (k * 4096 + high
-// word) applies the 2^(k >> 8) scale without masking k
-// (nb_one_plus_exp256 / nb_log_mant512 in dmath.cuh are the host-tested statements of the same recurrences).
-#define NB_C NB_LN2_256
+// exp(eta) = 2^(k/1024) * exp(frac * ln2/1024) with an economised degree-2 polynomial (1.6e-12 relative; 1024 table
+// entries buy one FMA per evaluation over the degree-3 / 256-entry form).  The shared table image stores 2^(j/1024) with
+// j * 1024 pre-subtracted from its high word, so one IMAD (k * 1024 + high word) applies the 2^(k >> 10) scale without
+// masking k (nb_one_plus_exp1024 in dmath.cuh is the host-tested statement of the same recurrence).
+#define NB_C NB_LN2_1024
 __constant__ double c_k[10] = {
     6755399441055744.0,                                                  // 0     1.5 * 2^52 (round-to-integer magic)
-    NB_C * NB_C * NB_C / 6.0, NB_C * NB_C / 2.0, NB_C,                   // 1..3  exp polynomial in frac
-    NB_LN2, 1.0 / 3.0, -0.5,                                             // 4..6  ln2; log1p polynomial
-    NB_LOG_INV_EPS * NB_256_OVER_LN2,                                    // 7     log(1/DBL_EPSILON) in units of ln2/256
-    30.0 * NB_256_OVER_LN2,                                              // 8     clamp threshold in the same units
-    NB_256_OVER_LN2                                                      // 9
+    0.0, NB_EXP2_C2, NB_EXP2_C1,                                         // 1..3  exp polynomial in frac (degree 2)
+    NB_LN2, 1.0 / 3.0, -0.5,                                             // 4..6  ln2; (unused)
+    NB_LOG_INV_EPS * NB_1024_OVER_LN2,                                   // 7     log(1/DBL_EPSILON) in units of ln2/1024
+    30.0 * NB_1024_OVER_LN2,                                             // 8     clamp threshold in the same units
+    NB_1024_OVER_LN2                                                     // 9
 };
 
 struct nb_tables2 {                 // shared-memory image used by v2
-    double exp_t[256];              // 2^(j/256)
+    double exp_t[1024];             // 2^(j/1024), high words pre-biased
 };
 
 constexpr int V2_TPS = TA / 2;      // threads per slice (64)
@@ -441,19 +441,18 @@ constexpr int V2_TPS = TA / 2;      // threads per slice (64)
 __host__ __device__ constexpr int v2_nslice(int mode, int q) { return (mode == MODE_IRLS_FULL && q >= 2) ? 6 : 8; }
 constexpr int V2_RCHUNK = 512;      // records per staged chunk (two buffers)
 
-// u = 1 + exp(eta) (dmath.cuh: nb_one_plus_exp256 is the host-tested statement of the same recurrence)
-__device__ __forceinline__ double v2_u1_fast(double sv, uint32_t sT) {             // sv = eta * 256/ln2, |eta| < 30
+// u = 1 + exp(eta) (dmath.cuh: nb_one_plus_exp1024 is the host-tested statement of the same recurrence)
+__device__ __forceinline__ double v2_u1_fast(double sv, uint32_t sT) {             // sv = eta * 1024/ln2, |eta| < 30
     const double tt = sv + c_k[0];
-    const int ki = __double2loint(tt);                           // rint(eta * 256/ln2)
+    const int ki = __double2loint(tt);                           // rint(eta * 1024/ln2)
     const double kf = tt - c_k[0];
     const double fr = sv - kf;                                   // exact, |fr| <= 1/2
-    double qq = fma(fr, c_k[1], c_k[2]);
-    qq = fma(qq, fr, c_k[3]);
-    qq = fma(qq, fr, 1.0);                                       // exp(fr * ln2/256)
+    double qq = fma(fr, c_k[2], c_k[3]);
+    qq = fma(qq, fr, 1.0);                                       // exp(fr * ln2/1024)
     double tj;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x7F8)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x1FF8)));
     int thi;
-    asm("mad.lo.s32 %0, %1, 4096, %2;" : "=r"(thi) : "r"(ki), "r"(__double2hiint(tj)));    // * 2^(k >> 8) (entry is pre-biased by -j * 4096)
+    asm("mad.lo.s32 %0, %1, 1024, %2;" : "=r"(thi) : "r"(ki), "r"(__double2hiint(tj)));    // * 2^(k >> 10) (entry is pre-biased by -j * 1024)
     return fma(__hiloint2double(thi, __double2loint(tj)), qq, 1.0);
 }
 // logit linkinv with R's clamps (stats family.c): eta < -30 -> DBL_EPSILON, eta > 30 -> 1/DBL_EPSILON.
@@ -523,11 +522,17 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
     // m_begin is even and slices are an even number of records long: record pairs are fetched with one 8-byte load.
     const int len = m_end - m_begin, per = (((len + NSL - 1) / NSL) + 1) & ~1;
     const int m_lo = m_begin + slice * per, m_hi = (m_lo + per < m_end) ? (m_lo + per) : m_end;
-    if (m_hi > m_lo) nren += (m_hi - m_lo + 1) >> 1;             // one renormalisation per loop trip (+ one for an odd tail)
+    // renormalisations of the running products: q = 0 once per FOUR records (the product of four factors < 2^54 and a
+    // mantissa stays below 2^217), otherwise once per two; plus one for a leftover pair and one for an odd tail
+    constexpr int UNR = (Q == 0) ? 2 : 1;
+    if (m_hi > m_lo) {
+        const int ln = m_hi - m_lo;
+        nren += (UNR == 2) ? (ln >> 2) + ((ln & 2) >> 1) + (ln & 1) : (ln + 1) >> 1;
+    }
     uint32_t io_prev = 0xFFFFFFFFu;
     double xi0 = 0.0, xi1 = 0.0;                                 // cached I row (two attributes)
     int m = m_lo;
-    for (; m + 1 < m_hi; m += 2) {
+    auto two_records = [&](int m) {
         uint32_t ra, rb;                                         // (il << 10) | (jl << 26) | y: byte offsets of the two rows
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ra), "=r"(rb) : "r"(sREC_addr + 4u * m));
         const uint32_t ioa = ra & 0xFC00u, iob = rb & 0xFC00u;
@@ -557,7 +562,7 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         if (CHECK) {                                             // !CHECK: the CTA proved |eta| < 30 for all its records up front
             const int hmax = max(max(__double2hiint(ea0) & 0x7fffffff, __double2hiint(ea1) & 0x7fffffff),
                                  max(__double2hiint(eb0) & 0x7fffffff, __double2hiint(eb1) & 0x7fffffff));
-            fast = hmax < 0x40C5A380;                            // |s| < 11079 < 30 * 256/ln2 (= 11079.9) for all four
+            fast = hmax < 0x40E5A380;                            // |s| < 44316 < 30 * 1024/ln2 (= 44319.6) for all four
         }
         if (fast) {
             ta0 = v2_u1_fast(ea0, sT); ta1 = v2_u1_fast(ea1, sT);
@@ -573,8 +578,26 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         v2_tail<Q>(da1, ca, ta1, acc1);
         v2_tail<Q>(db0, cb, tb0, acc0);
         v2_tail<Q>(db1, cb, tb1, acc1);
-        v2_renorm(acc0[NA - 2], esum0);
-        v2_renorm(acc1[NA - 2], esum1);
+    };
+    if (UNR == 2) {
+        for (; m + 3 < m_hi; m += 4) {
+            two_records(m);
+            two_records(m + 2);
+            v2_renorm(acc0[NA - 2], esum0);
+            v2_renorm(acc1[NA - 2], esum1);
+        }
+        if (m + 1 < m_hi) {
+            two_records(m);
+            v2_renorm(acc0[NA - 2], esum0);
+            v2_renorm(acc1[NA - 2], esum1);
+            m += 2;
+        }
+    } else {
+        for (; m + 1 < m_hi; m += 2) {
+            two_records(m);
+            v2_renorm(acc0[NA - 2], esum0);
+            v2_renorm(acc1[NA - 2], esum1);
+        }
     }
     if (m < m_hi) {                                              // odd tail: one record
         uint32_t r;
@@ -729,10 +752,10 @@ pass2_kernel(PassArgs P) {
 
     if (MODE == MODE_IRLS_FULL) {   // table image
         nb_tables2 *sT = (nb_tables2 *)(smem_raw + L::TAB);
-        const nb_tables512 *g = P.tables512;
-        for (int e = tid; e < 256; e += V2_THREADS) {          // high word pre-biased by -j * 4096 (see v2_u1_fast)
+        const nb_tables1024 *g = P.tables1024;
+        for (int e = tid; e < 1024; e += V2_THREADS) {         // high word pre-biased by -j * 1024 (see v2_u1_fast)
             const double tj = g->exp_t[e];
-            sT->exp_t[e] = __hiloint2double(__double2hiint(tj) - e * 4096, __double2loint(tj));
+            sT->exp_t[e] = __hiloint2double(__double2hiint(tj) - e * 1024, __double2loint(tj));
         }
     }
     const uint32_t sT_addr = sbase + L::TAB;
@@ -742,7 +765,7 @@ pass2_kernel(PassArgs P) {
     if (MODE == MODE_IRLS_FULL) {
 #pragma unroll
         for (int r = 0; r < K; ++r) {
-            beta0[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl] * c_k[9];         // units of ln2/256
+            beta0[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl] * c_k[9];         // units of ln2/1024
             beta1[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1] * c_k[9];
         }
     }
@@ -1206,19 +1229,19 @@ int dmalloc(T **p, size_t n) {
 }
 
 nb_tables *g_tables_dev[64] = {nullptr};
-nb_tables512 *g_tables512_dev[64] = {nullptr};
+nb_tables1024 *g_tables1024_dev[64] = {nullptr};
 
-int get_tables512(npdrb_ctx *ctx, const nb_tables512 **out) {
-    if (!g_tables512_dev[ctx->device & 63]) {
-        static const nb_tables512 host_tables = NB_TABLES512_STATIC_INIT;
-        nb_tables512 *d = nullptr;
-        cudaError_t e = (cudaMalloc)((void **)&d, sizeof(nb_tables512));       // lives as long as the process: not from the cache
-        if (e != cudaSuccess) { npdrb_set_error("cudaMalloc(tables512): %s", cudaGetErrorString(e)); return NPDRB_ENOMEM; }
-        NB_CUDA(cudaMemcpyAsync(d, &host_tables, sizeof(nb_tables512), cudaMemcpyHostToDevice, ctx->stream));
+int get_tables1024(npdrb_ctx *ctx, const nb_tables1024 **out) {
+    if (!g_tables1024_dev[ctx->device & 63]) {
+        static const nb_tables1024 host_tables = NB_TABLES1024_STATIC_INIT;
+        nb_tables1024 *d = nullptr;
+        cudaError_t e = (cudaMalloc)((void **)&d, sizeof(nb_tables1024));       // lives as long as the process: not from the cache
+        if (e != cudaSuccess) { npdrb_set_error("cudaMalloc(tables1024): %s", cudaGetErrorString(e)); return NPDRB_ENOMEM; }
+        NB_CUDA(cudaMemcpyAsync(d, &host_tables, sizeof(nb_tables1024), cudaMemcpyHostToDevice, ctx->stream));
         NB_CUDA(cudaStreamSynchronize(ctx->stream));
-        g_tables512_dev[ctx->device & 63] = d;
+        g_tables1024_dev[ctx->device & 63] = d;
     }
-    *out = g_tables512_dev[ctx->device & 63];
+    *out = g_tables1024_dev[ctx->device & 63];
     return NPDRB_OK;
 }
 
@@ -1567,9 +1590,9 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     NB_CUDA(cudaMemsetAsync(d_iters, 0, sizeof(int) * nattr_pad, ctx->stream));
 
     const nb_tables *d_tab = nullptr;
-    const nb_tables512 *d_tab512 = nullptr;
+    const nb_tables1024 *d_tab1024 = nullptr;
     NB_CHECK(get_tables(ctx, &d_tab));
-    NB_CHECK(get_tables512(ctx, &d_tab512));
+    NB_CHECK(get_tables1024(ctx, &d_tab1024));
 
     SolveArgs S;
     memset(&S, 0, sizeof(S));
@@ -1609,7 +1632,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         PassArgs P;
         memset(&P, 0, sizeof(P));
         P.XT = s->dXT; P.ldt = s->ldt; P.N = N; P.nattr = (int)nattr; P.nattr_pad = (int)nattr_pad;
-        P.beta = d_beta; P.tile_active = tile_active; P.tables = d_tab; P.tables512 = d_tab512; P.diff_type = diff_type;
+        P.beta = d_beta; P.tile_active = tile_active; P.tables = d_tab; P.tables1024 = d_tab1024; P.diff_type = diff_type;
         P.dmax = d_dmax;
         for (int c = 0; c < NPDRB_MAX_COVARS; ++c) P.cmax[c] = S.cmax[c];
         double *pp = d_part;

@@ -6,6 +6,7 @@
 static const nb_tables T = NB_TABLES_STATIC_INIT;
 static const nb_tables256 T2 = NB_TABLES256_STATIC_INIT;
 static const nb_tables512 T3 = NB_TABLES512_STATIC_INIT;
+static const nb_tables1024 T4 = NB_TABLES1024_STATIC_INIT;
 int main() {
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(-30.0, 30.0);
@@ -77,6 +78,17 @@ int main() {
     h_bias /= (double)n_bias;
     printf("v3: max_rel_err(1+exp)=%.3e max_log_err(rel to max(1,log))=%.3e mean_log_err=%.3e\n", h_u, h_log, h_bias);
     if (!(h_u < 2e-13 && h_log < 3e-13 && fabs(h_bias) < 6e-14)) return 1;
+    // v4 exp used by pass2_kernel<IRLS_FULL>: 1024-entry table, economised degree-2 polynomial
+    double k_u = 0;
+    for (int it = 0; it < 4000000; ++it) {
+        double eta = (it < 2000000) ? U(rng) : U(rng) / 30.0;
+        double u = nb_one_plus_exp1024(eta * NB_1024_OVER_LN2, T4.exp_t);
+        long double ue = 1.0L + expl((long double)eta);
+        double rel = (double)fabsl(((long double)u - ue) / ue);
+        if (rel > k_u) k_u = rel;
+    }
+    printf("v4: max_rel_err(1+exp)=%.3e\n", k_u);
+    if (!(k_u < 1.8e-12)) return 1;
     return !(max_rel_exp < 4e-16 && max_abs_log < 8e-15 && max_rel_log < 1e-15 && fr_exp < 6e-14 && fa_log < 2e-15 &&
              g_exp < 2e-13 && g_log < 8e-15);
 }
