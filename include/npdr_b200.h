@@ -185,6 +185,9 @@ int npdrb_unireg(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const do
 int npdrb_session_create(npdrb_ctx *ctx, int64_t N, int64_t p, int32_t q, npdrb_session **s);
 void npdrb_session_destroy(npdrb_session *s);
 /* copy host inputs in (pinned staging + async copies on the context stream); C may be NULL when q == 0 */
+/* A matrix of 64 MB or more is uploaded as 8 column slabs on a second stream; the distance kernel starts on the first
+ * slab while the others cross PCIe (bit-identical results).  X must therefore stay valid until the first call that
+ * consumes it (distances / neighbours / regress) has returned.  NPDRB_NO_PIPELINED_UPLOAD=1 restores one blocking copy. */
 int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, const double *C);
 /* or adopt device buffers: dX column-major with leading dimension ldx >= N (ldx % 2 == 0), dy[N], dC N x q (ld N) */
 int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy,

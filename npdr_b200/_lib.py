@@ -237,6 +237,7 @@ class Session:
         Xa = f64(X) if X is not None else None
         ya = f64(y) if y is not None else None
         Ca = f64(C_) if C_ is not None else None
+        self._host = (Xa, ya, Ca)       # a large X is uploaded in slabs that are still in flight when this call returns
         check(load().npdrb_session_upload(self.handle, dptr(Xa), dptr(ya), dptr(Ca)))
 
     def set_device_inputs(self, dX=0, ldx=0, dy=0, dC=0):

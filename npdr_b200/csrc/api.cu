@@ -125,6 +125,16 @@ int check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what) {
 
 }  // namespace
 
+int nb_check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what) { return check_finite(ctx, d, n, what); }
+
+int nb_wait_upload(npdrb_session *s) {
+    if (s->n_slabs_pending == 0) return NPDRB_OK;
+    npdrb_ctx *ctx = s->ctx;
+    for (int i = 0; i < s->n_slabs_pending; ++i) NB_CUDA(cudaStreamWaitEvent(ctx->stream, s->slab_ev[(size_t)i], 0));
+    s->n_slabs_pending = 0;
+    return check_finite(ctx, s->dX, s->ldx * s->p, "the attribute matrix");
+}
+
 extern "C" {
 
 const char *npdrb_version(void) { return "npdr_b200 0.1.0 (sm_100a)"; }
@@ -202,6 +212,7 @@ void npdrb_destroy(npdrb_ctx *ctx) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         cache_release_device(ctx->device);
     }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -271,6 +282,8 @@ int npdrb_session_create(npdrb_ctx *ctx, int64_t N, int64_t p, int32_t q, npdrb_
 void npdrb_session_destroy(npdrb_session *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
+    if (s->ctx->copy_stream) cudaStreamSynchronize(s->ctx->copy_stream);
+    for (cudaEvent_t e : s->slab_ev) if (e) cudaEventDestroy(e);
     cudaStreamSynchronize(s->ctx->stream);
     if (s->own_X) cudaFree(s->dX);
     cudaFree(s->dXs);
@@ -298,8 +311,37 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
             s->own_X = true;
             if (s->ldx != N) NB_CUDA(cudaMemsetAsync(s->dX, 0, sizeof(double) * (size_t)s->ldx * (size_t)p, ctx->stream));
         }
-        NB_CUDA(cudaMemcpy2DAsync(s->dX, sizeof(double) * (size_t)s->ldx, X, sizeof(double) * (size_t)N,
-                                  sizeof(double) * (size_t)N, (size_t)p, cudaMemcpyHostToDevice, ctx->stream));
+        // Large matrices travel as column slabs on a second stream: the distance kernel starts on slab 0 while the rest
+        // is still crossing PCIe (it accumulates attribute ranges in order, so the result is bit-identical).  The host
+        // buffer must stay valid until the first call that consumes X returns.
+        const int64_t bytes = (int64_t)sizeof(double) * N * p;
+        const char *np_ = getenv("NPDRB_NO_PIPELINED_UPLOAD");
+        const int n_slabs = (bytes >= (64ll << 20) && !(np_ && np_[0] == '1')) ? 8 : 1;
+        if (n_slabs > 1) {
+            if (!ctx->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (cudaEvent_t e : s->slab_ev) cudaEventDestroy(e);
+            s->slab_ev.assign((size_t)n_slabs, nullptr);
+            s->slab_cols = nb_round_up(nb_cdiv(p, n_slabs), 16);
+            cudaEvent_t ready;                              // the memset / previous users of dX on the main stream come first
+            NB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            NB_CUDA(cudaEventRecord(ready, ctx->stream));
+            NB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+            cudaEventDestroy(ready);
+            int used = 0;
+            for (int i = 0; i < n_slabs; ++i) {
+                const int64_t c0 = (int64_t)i * s->slab_cols, c1 = (c0 + s->slab_cols < p) ? c0 + s->slab_cols : p;
+                if (c0 >= p) break;
+                NB_CUDA(cudaMemcpy2DAsync(s->dX + c0 * s->ldx, sizeof(double) * (size_t)s->ldx, X + c0 * N, sizeof(double) * (size_t)N,
+                                          sizeof(double) * (size_t)N, (size_t)(c1 - c0), cudaMemcpyHostToDevice, ctx->copy_stream));
+                NB_CUDA(cudaEventCreateWithFlags(&s->slab_ev[(size_t)i], cudaEventDisableTiming));
+                NB_CUDA(cudaEventRecord(s->slab_ev[(size_t)i], ctx->copy_stream));
+                used = i + 1;
+            }
+            s->n_slabs_pending = used;
+        } else {
+            NB_CUDA(cudaMemcpy2DAsync(s->dX, sizeof(double) * (size_t)s->ldx, X, sizeof(double) * (size_t)N,
+                                      sizeof(double) * (size_t)N, (size_t)p, cudaMemcpyHostToDevice, ctx->stream));
+        }
         s->xt_attr0 = -1; s->xt_nattr = 0;
     }
     if (y) {
@@ -313,7 +355,7 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
         s->streams_valid = false;
     }
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (X) NB_CHECK(check_finite(ctx, s->dX, s->ldx * p, "the attribute matrix"));
+    if (X && s->n_slabs_pending == 0) NB_CHECK(check_finite(ctx, s->dX, s->ldx * p, "the attribute matrix"));
     if (y) NB_CHECK(check_finite(ctx, s->dy, N, "the outcome"));
     if (C && s->q > 0) NB_CHECK(check_finite(ctx, s->dC, N * s->q, "the covariates"));
     return NPDRB_OK;
@@ -321,6 +363,7 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
 
 int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy, const double *dC) {
     if (dX) {
+        if (s->n_slabs_pending) { cudaStreamSynchronize(s->ctx->copy_stream); s->n_slabs_pending = 0; }
         if (ldx < s->N || (ldx & 1)) { npdrb_set_error("set_device_inputs: ldx must be even and >= N"); return NPDRB_EINVAL; }
         if (((uintptr_t)dX) & 15) { npdrb_set_error("set_device_inputs: dX must be 16-byte aligned"); return NPDRB_EINVAL; }
         if (s->own_X) cudaFree(s->dX);
@@ -556,6 +599,7 @@ static int rect_block(npdrb_session *s, const double *X1, const double *X2, int6
         return NPDRB_EINVAL;
     }
     NB_CHECK(npdrb_session_upload(s, X1, nullptr, nullptr));
+    NB_CHECK(nb_wait_upload(s));
     double *dX2 = nullptr; int64_t ld2 = 0;
     NB_CHECK(upload_padded(ctx, X2, m2, p, &dX2, &ld2));
     if (s->own_D) cudaFree(s->dD);

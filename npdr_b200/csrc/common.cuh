@@ -54,6 +54,7 @@ struct npdrb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // host->device slabs of a large X travel here while the distance kernel consumes earlier ones
     int sm_count = 148;
     int64_t launches = 0;
     size_t smem_optin = 0;
@@ -81,6 +82,9 @@ struct npdrb_session {
     // inputs
     double *dX = nullptr; int64_t ldx = 0; bool own_X = false;          // column-major, N x p, leading dim ldx
     double *dXs = nullptr;                                               // pre-scaled copy for scaled metrics
+    // pipelined upload (npdrb_session_upload of a large X): column slabs in flight on ctx->copy_stream; slab i covers
+    // attributes [i * slab_cols, ...) and is complete once slab_ev[i] has fired.  nb_wait_upload() joins them.
+    std::vector<cudaEvent_t> slab_ev; int64_t slab_cols = 0; int n_slabs_pending = 0;
     double *dy = nullptr; bool own_y = false;
     double *dC = nullptr; bool own_C = false;                            // N x q, ld N
     // distance block: nrows x N, row-major with leading dim ldd (row r = column row0+r of the symmetric D)
@@ -111,6 +115,8 @@ struct npdrb_session {
 };
 
 // stage implementations (one .cu each)
+int nb_wait_upload(npdrb_session *s);     // main stream waits for every slab; NA/NaN/Inf check of X (NPDRB_EDATA)
+int nb_check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what);
 int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
 int nb_distances_balanced(npdrb_session *s, int32_t metric, int32_t fast_euclidean, const int64_t *row_starts, int32_t rank,
                           int32_t world);

@@ -100,7 +100,11 @@ template <int MODE, int TNV>
 __global__ void __launch_bounds__(DTHREADS, 1)
 dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapB, int same_ab,
                 int64_t Nrows_total, int64_t N, int64_t p, int64_t row0, int64_t nrows,
-                const int2 *__restrict__ tiles, int64_t n_tiles, double *__restrict__ Dout, int64_t ldd) {
+                const int2 *__restrict__ tiles, int64_t n_tiles, double *__restrict__ Dout, int64_t ldd,
+                int chunk_lo, int chunk_hi, int resume, int finalize) {
+    // Attribute range [chunk_lo, chunk_hi) * BK of this launch.  resume: the accumulators start from the partial sums a
+    // previous launch left in Dout (same per-element order k = 0..p-1, so slab-wise launches are bit-identical to one
+    // launch); finalize: last range -- euclidean takes its square root only then.
     extern __shared__ unsigned char smem_raw[];
     // explicit 32-bit shared-window addresses (keeps every access an LDS / SYNCS, never a generic LD)
     constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * sizeof(double);
@@ -120,7 +124,7 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     }
     __syncthreads();
 
-    const int n_chunks = (int)((p + BK - 1) / BK);
+    const int n_chunks = chunk_hi - chunk_lo;
     uint32_t g = 0;                                                // chunks consumed so far (all tiles)
 
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -137,16 +141,21 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             for (int c = 0; c < STAGES - 1 && c < n_chunks; ++c) {
                 int s = (int)((g + c) % STAGES);
                 mbar_expect_tx(full + 8 * s, tx_bytes);
-                tma_load_2d(sA + s * STAGE_BYTES, &tmap, i0, c * BK, full + 8 * s);
-                if (!diag) tma_load_2d(sB + s * STAGE_BYTES_B, &tmapB, j0, c * BK, full + 8 * s);
+                tma_load_2d(sA + s * STAGE_BYTES, &tmap, i0, (chunk_lo + c) * BK, full + 8 * s);
+                if (!diag) tma_load_2d(sB + s * STAGE_BYTES_B, &tmapB, j0, (chunk_lo + c) * BK, full + 8 * s);
             }
         }
 
         double acc[8][NC];
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 8; ++r) {
+            const int64_t i = (int64_t)i0 + (r >> 1) * 32 + ty * 2 + (r & 1);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) acc[r][c] = 0.0;
+            for (int c = 0; c < NC; ++c) {
+                const int64_t j = (int64_t)j0 + (c >> 1) * 32 + tx * 2 + (c & 1);
+                acc[r][c] = (resume && i < row0 + nrows && i < Nrows_total && j < N) ? Dout[(i - row0) * ldd + j] : 0.0;
+            }
+        }
 
         for (int c = 0; c < n_chunks; ++c) {
             // refill the stage freed by the previous iteration
@@ -154,8 +163,8 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 int cn = c + STAGES - 1;
                 int s = (int)((g + cn) % STAGES);
                 mbar_expect_tx(full + 8 * s, tx_bytes);
-                tma_load_2d(sA + s * STAGE_BYTES, &tmap, i0, cn * BK, full + 8 * s);
-                if (!diag) tma_load_2d(sB + s * STAGE_BYTES_B, &tmapB, j0, cn * BK, full + 8 * s);
+                tma_load_2d(sA + s * STAGE_BYTES, &tmap, i0, (chunk_lo + cn) * BK, full + 8 * s);
+                if (!diag) tma_load_2d(sB + s * STAGE_BYTES_B, &tmapB, j0, (chunk_lo + cn) * BK, full + 8 * s);
             }
             const uint32_t gc = g + (uint32_t)c;
             const int s = (int)(gc % STAGES);
@@ -193,7 +202,7 @@ dist_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             for (int cc = 0; cc < NC; ++cc) {
                 const int64_t j = (int64_t)j0 + (cc >> 1) * 32 + tx * 2 + (cc & 1);
                 double v = acc[r][cc];
-                if (MODE == MODE_EUCLID_EXACT || MODE == MODE_EUCLID_FMA) v = sqrt(v);
+                if ((MODE == MODE_EUCLID_EXACT || MODE == MODE_EUCLID_FMA) && finalize) v = sqrt(v);
                 if (i < row0 + nrows && i < Nrows_total && j < N) {
                     Dout[(i - row0) * ldd + j] = v;
                     if (mirror && !diag && j >= row0 && j < row0 + nrows) Dout[(j - row0) * ldd + i] = v;
@@ -351,7 +360,8 @@ int pick_tile_width(int64_t n_squares, int sm_count) {
 
 template <int MODE>
 int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const double *XB, int64_t NB, int64_t ldB, int64_t p,
-               int64_t row0, int64_t nrows, const TilePlan &plan, double *dD, int64_t ldd) {
+               int64_t row0, int64_t nrows, const TilePlan &plan, double *dD, int64_t ldd,
+               const std::vector<cudaEvent_t> *slab_ev = nullptr, int n_slabs = 0, int64_t slab_cols = 0) {
     CUtensorMap mapA, mapB;
     NB_CHECK(make_tensor_map(&mapA, XA, NA, p, ldA));
     NB_CHECK(make_tensor_map(&mapB, XB, NB, p, ldB, plan.tn));
@@ -362,23 +372,41 @@ int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const 
     NB_CUDA(cudaMemcpyAsync(d_tiles, plan.tiles.data(), sizeof(int2) * (size_t)n_tiles, cudaMemcpyHostToDevice, ctx->stream));
     int grid = (int)((n_tiles < ctx->sm_count) ? n_tiles : ctx->sm_count);
     if (grid < 1) grid = 1;
-    if (plan.tn == 64) {
-        NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
-        dist_tma_kernel<MODE, 64><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(mapA, mapB, XA == XB ? 1 : 0, NA, NB, p, row0, nrows,
-                                                                              d_tiles, n_tiles, dD, ldd);
-    } else {
-        NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
-        dist_tma_kernel<MODE, TN><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(mapA, mapB, XA == XB ? 1 : 0, NA, NB, p, row0, nrows,
-                                                                              d_tiles, n_tiles, dD, ldd);
+    NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
+    NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
+    // one launch over all attributes, or one per uploaded column slab as it arrives (pipelined npdrb_session_upload)
+    const int n_chunks = (int)nb_cdiv(p, BK);
+    const int n_launch = (slab_ev && n_slabs > 1) ? n_slabs : 1;
+    for (int l = 0; l < n_launch; ++l) {
+        int c_lo = 0, c_hi = n_chunks;
+        if (n_launch > 1) {
+            NB_CUDA(cudaStreamWaitEvent(ctx->stream, (*slab_ev)[(size_t)l], 0));
+            c_lo = (int)(l * slab_cols / BK);
+            c_hi = (int)nb_cdiv((l + 1) * slab_cols < p ? (l + 1) * slab_cols : p, BK);
+        }
+        const int acc = l > 0, fin = l == n_launch - 1;
+        if (plan.tn == 64)
+            dist_tma_kernel<MODE, 64><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(mapA, mapB, XA == XB ? 1 : 0, NA, NB, p, row0, nrows,
+                                                                                  d_tiles, n_tiles, dD, ldd, c_lo, c_hi, acc, fin);
+        else
+            dist_tma_kernel<MODE, TN><<<grid, DTHREADS, DIST_SMEM, ctx->stream>>>(mapA, mapB, XA == XB ? 1 : 0, NA, NB, p, row0, nrows,
+                                                                                  d_tiles, n_tiles, dD, ldd, c_lo, c_hi, acc, fin);
+        NB_LAUNCH_CHECK(ctx);
     }
-    NB_LAUNCH_CHECK(ctx);
     NB_CUDA(cudaStreamSynchronize(ctx->stream));        // the pinned-less H2D source (plan.tiles) must outlive the copy
     cudaFree(d_tiles);
     return NPDRB_OK;
 }
 template <int MODE>
 int launch_tma(npdrb_session *s, const double *X, int64_t row0, int64_t nrows, const TilePlan &plan) {
-    return launch_tma<MODE>(s->ctx, X, s->N, s->ldx, X, s->N, s->ldx, s->p, row0, nrows, plan, s->dD, s->ldd);
+    const bool slabs = s->n_slabs_pending > 1 && X == s->dX;
+    int rc = launch_tma<MODE>(s->ctx, X, s->N, s->ldx, X, s->N, s->ldx, s->p, row0, nrows, plan, s->dD, s->ldd,
+                              slabs ? &s->slab_ev : nullptr, slabs ? s->n_slabs_pending : 0, s->slab_cols);
+    if (rc == NPDRB_OK && slabs) {                     // every slab has been waited for on the main stream
+        s->n_slabs_pending = 0;
+        rc = nb_check_finite(s->ctx, s->dX, s->ldx * s->p, "the attribute matrix");
+    }
+    return rc;
 }
 
 template <int MODE>
@@ -448,6 +476,10 @@ int dist_core(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t 
 
     NB_CUDA(cudaEventRecord(s->ev[0], ctx->stream));
     const double *X = s->dX;
+    const char *kenv0 = getenv("NPDRB_DIST_KERNEL");
+    if ((metric >= NPDRB_METRIC_ALLELE_SHARING_MANHATTAN && metric <= NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN) ||
+        (kenv0 && strcmp(kenv0, "simple") == 0))
+        NB_CHECK(nb_wait_upload(s));                    // pre-scaling / the diagnostic kernel need the whole matrix
     if (metric >= NPDRB_METRIC_ALLELE_SHARING_MANHATTAN && metric <= NPDRB_METRIC_RELIEF_SCALED_EUCLIDEAN) {
         if (!s->dXs) NB_CUDA(cudaMalloc(&s->dXs, sizeof(double) * (size_t)s->ldx * (size_t)s->p));
         prescale_kernel<<<(unsigned)s->p, 256, 0, ctx->stream>>>(s->dX, s->ldx, s->N, metric, s->dXs);

@@ -1461,6 +1461,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     const int q = s->q;
     const int64_t N = s->N;
     if (!s->dX || !s->dy) { npdrb_set_error("regress: inputs not set"); return NPDRB_EINVAL; }
+    NB_CHECK(nb_wait_upload(s));
     if (q > 0 && !s->dC) { npdrb_set_error("regress: covariates missing"); return NPDRB_EINVAL; }
     if (!s->dRi || s->M <= 0) { npdrb_set_error("regress: empty pair list"); return NPDRB_EINVAL; }
     if (attr0 < 0 || nattr < 1 || attr0 + nattr > s->p) { npdrb_set_error("regress: bad attribute range"); return NPDRB_EINVAL; }

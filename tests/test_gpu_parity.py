@@ -676,3 +676,26 @@ def test_cfg4_full_size_properties(nb, oracle):
     _stats_close(stats[:512], plain, 1e-9, "work saving on/off")
     assert np.array_equal(stats[:512, 6], plain[:, 6]) and np.array_equal(stats[:512, 7], plain[:, 7])
     eng.close()
+
+
+def test_pipelined_upload_distances_bit_exact(nb, oracle, monkeypatch):
+    """X >= 64 MB travels as column slabs on a second stream while the distance kernel accumulates the slabs that have
+    arrived: bit-identical to the one-launch result and to the oracle; NA input is still rejected."""
+    rng = np.random.default_rng(91)
+    N, p = 1100, 8000                                            # 70 MB
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    for metric in ("manhattan", "euclidean"):
+        D = nb.npdrDistances(X, metric)
+        assert np.array_equal(D, oracle.distances(X, metric))
+        monkeypatch.setenv("NPDRB_NO_PIPELINED_UPLOAD", "1")
+        assert np.array_equal(nb.npdrDistances(X, metric), D)
+        monkeypatch.delenv("NPDRB_NO_PIPELINED_UPLOAD")
+    y = (rng.random(N) < 0.5).astype(float)
+    out, info = nb.npdr(y, X[:, :8000], return_info=True)        # the whole path behind a pipelined upload
+    ri, nn, _, _ = oracle.nearest_neighbors(X)
+    assert np.array_equal(info["Ri"], ri) and np.array_equal(info["NN"], nn)
+    X[700, 7999] = np.nan                                        # last slab
+    with pytest.raises(nb.NpdrB200Error):
+        nb.npdrDistances(X, "manhattan")
+    with pytest.raises(nb.NpdrB200Error):
+        nb.npdr(y, X)
