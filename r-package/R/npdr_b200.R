@@ -28,6 +28,50 @@ nearestNeighbors2 <- function(attr.mat1, attr.mat2, nbd.method = "multisurf", nb
         .nbd_code[[nbd.method]], .metric_code[[m]], sd.vec, sd.frac, k, PACKAGE = "npdrb200")
 }
 
+# R/nearestNeighbors.R:15-40
+npdrDiff <- function(a, b, diff.type = "manhattan", norm.fac = 1) {
+  diff.type <- match.arg(diff.type, c("manhattan", "numeric-abs", "numeric-sqr", "allele-sharing", "match-mismatch", "correlation-data"))
+  if (diff.type == "correlation-data") stop("npdr_b200: correlation-data is not accelerated")
+  .Call("C_npdrb_diff", as.numeric(a), as.numeric(b), .diff_code[[diff.type]], norm.fac, PACKAGE = "npdrb200")
+}
+
+# R/utils.R:12-18
+knnSURF <- function(m.samples, sd.frac = .5) {
+  erf <- function(x) 2 * pnorm(x * sqrt(2)) - 1
+  floor((m.samples - 1) * (1 - erf(sd.frac / sqrt(2))) / 2)
+}
+
+# R/utils.R:66-157: per-column lm / glm of the outcome on the raw attribute (+ covariates); the rounding, p.adjust and sort stay in R
+uniReg <- function(outcome, dataset, regression.type = "lm", padj.method = "fdr", covars = "none") {
+  if (length(outcome) == 1) {
+    pheno.vec <- dataset[, outcome]
+    attr.mat <- dataset[, setdiff(if (is.character(outcome)) colnames(dataset) else seq_len(ncol(dataset)), outcome), drop = FALSE]
+  } else {
+    pheno.vec <- outcome
+    attr.mat <- dataset
+  }
+  y <- if (regression.type == "lm") as.numeric(pheno.vec) else as.numeric(as.factor(pheno.vec)) - 1
+  C <- if (length(covars) > 1) as.matrix(covars) + 0 else NULL
+  s <- t(.Call("C_npdrb_unireg", unname(as.matrix(attr.mat)) + 0, y, C, .reg_code[[regression.type]], PACKAGE = "npdrb200"))
+  pval <- if (regression.type == "lm") 2 * pt(-abs(s[, 2]), s[, 5]) else 2 * pnorm(-abs(s[, 2]))
+  padj <- p.adjust(pval, method = padj.method)
+  betas <- cbind(beta = s[, 1], beta.Z.att = s[, 2], pval = pval, p.adj = padj)
+  betas <- apply(betas, 2, function(v) as.numeric(format(v, digits = 5)))       # R/utils.R:143-146
+  row.names(betas) <- colnames(attr.mat)
+  betas[order(betas[, "pval"], decreasing = FALSE), , drop = FALSE]
+}
+
+# R/nearestNeighbors.R:318-551 (npdr(separate.hitmiss.nbds = TRUE))
+nearestNeighborsSeparateHitMiss <- function(attr.mat, pheno.vec, nbd.method = "relieff", nbd.metric = "manhattan",
+                                            sd.frac = 0.5, k = 0, neighbor.sampling = "none", att_to_remove = c(),
+                                            fast.dist = FALSE, dopar.nn = FALSE) {
+  X <- as.matrix(attr.mat)
+  if (length(att_to_remove)) X <- X[, setdiff(colnames(X), att_to_remove), drop = FALSE]
+  r <- .Call("C_npdrb_nearest_neighbors_hitmiss", unname(X) + 0, as.numeric(as.character(pheno.vec)), .nbd_code[[nbd.method]],
+             .metric_code[[nbd.metric]], sd.frac, k, neighbor.sampling == "unique", PACKAGE = "npdrb200")
+  data.frame(Ri_idx = r$Ri_idx, NN_idx = r$NN_idx)
+}
+
 nearestNeighbors <- function(attr.mat, nbd.method = "multisurf", nbd.metric = "manhattan", sd.vec = NULL,
                              sd.frac = 0.5, k = 0, neighbor.sampling = "none", att_to_remove = c(),
                              fast.dist = FALSE, dopar.nn = FALSE) {

@@ -2,7 +2,7 @@
  * npdrb200_shim.c -- thin .Call shim between R and libnpdr_b200.so (include/npdr_b200.h).
  *
  * NOT compiled in the build container (no R headers there); it is the binding a maintainer adds to the
- * reference package.  Plain R C API (no Rcpp dependency needed for seven entry points).  Rules followed:
+ * reference package.  Plain R C API (no Rcpp dependency needed for eight entry points).  Rules followed:
  * inputs (SEXP payloads) are never written; native buffers are copied into R-allocated vectors and freed with
  * npdrb_free(); errors are turned into Rf_error() only after native resources are released.
  */
@@ -141,7 +141,31 @@ SEXP C_npdrb_nearest_neighbors2(SEXP X1, SEXP X2, SEXP method, SEXP metric, SEXP
     return out;
 }
 
+/* .Call("C_npdrb_nearest_neighbors_hitmiss", X, pheno, nbd.method, nbd.metric, sd.frac, k, unique)
+ *   -> list(Ri_idx, NN_idx, n_unique, radius_hit, radius_miss)      (nearestNeighborsSeparateHitMiss, R/nearestNeighbors.R:318) */
+SEXP C_npdrb_nearest_neighbors_hitmiss(SEXP X, SEXP pheno, SEXP method, SEXP metric, SEXP sd_frac, SEXP k, SEXP uniq) {
+    SEXP dim = Rf_getAttrib(X, R_DimSymbol);
+    const R_xlen_t N = INTEGER(dim)[0], p = INTEGER(dim)[1];
+    int32_t *Ri = NULL, *NN = NULL;
+    int64_t M = 0, nu = 0;
+    SEXP rh = PROTECT(Rf_allocVector(REALSXP, N)), rm = PROTECT(Rf_allocVector(REALSXP, N));
+    int rc = npdrb_nearest_neighbors_hitmiss(ctx_get(), REAL(X), N, p, REAL(pheno), Rf_asInteger(method), Rf_asInteger(metric),
+                                             Rf_asReal(sd_frac), (int64_t)Rf_asReal(k), Rf_asLogical(uniq), &Ri, &NN, &M, &nu,
+                                             REAL(rh), REAL(rm));
+    if (rc) { UNPROTECT(2); Rf_error("npdr_b200: %s", npdrb_last_error()); }
+    SEXP ri = PROTECT(Rf_allocVector(INTSXP, M)), nn = PROTECT(Rf_allocVector(INTSXP, M));
+    if (M) { memcpy(INTEGER(ri), Ri, sizeof(int) * (size_t)M); memcpy(INTEGER(nn), NN, sizeof(int) * (size_t)M); }
+    npdrb_free(Ri); npdrb_free(NN);
+    const char *names[] = {"Ri_idx", "NN_idx", "n_unique", "radius_hit", "radius_miss", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
+    SET_VECTOR_ELT(out, 0, ri); SET_VECTOR_ELT(out, 1, nn); SET_VECTOR_ELT(out, 2, Rf_ScalarReal((double)nu));
+    SET_VECTOR_ELT(out, 3, rh); SET_VECTOR_ELT(out, 4, rm);
+    UNPROTECT(5);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
+    {"C_npdrb_nearest_neighbors_hitmiss", (DL_FUNC)&C_npdrb_nearest_neighbors_hitmiss, 7},
     {"C_npdrb_distances2", (DL_FUNC)&C_npdrb_distances2, 3},
     {"C_npdrb_nearest_neighbors2", (DL_FUNC)&C_npdrb_nearest_neighbors2, 7},
     {"C_npdrb_distances", (DL_FUNC)&C_npdrb_distances, 2},

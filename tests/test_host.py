@@ -139,3 +139,19 @@ def test_row_and_attr_partitions():
             for (r0, n), (r1, _) in zip(parts, parts[1:]):
                 assert r0 + n == r1 and (n == 0 or r0 % 128 == 0)
     assert partition_attrs(10, 4) == [(0, 3), (3, 3), (6, 2), (8, 2)]
+
+
+def test_r_shim_compiles_against_api_stub():
+    """R is absent from the image, so the .Call shim cannot be built; it is at least type-checked against a stub of the
+    R C API it uses and against include/npdr_b200.h (every C entry point it binds exists with that signature)."""
+    import subprocess
+    stub = os.path.join(ROOT, "tests", "cpu", "r_api_stub")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", stub, "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "r-package", "src", "npdrb200_shim.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    shim = open(os.path.join(ROOT, "r-package", "src", "npdrb200_shim.c")).read()
+    wrapper = open(os.path.join(ROOT, "r-package", "R", "npdr_b200.R")).read()
+    import re
+    registered = set(re.findall(r'\{"(C_npdrb_\w+)"', shim))
+    called = set(re.findall(r'\.Call\("(C_npdrb_\w+)"', wrapper))
+    assert called <= registered and len(registered) >= 8, (called - registered)
