@@ -17,6 +17,7 @@
  *   npdrb_regress            <- the regression loop + diffRegression   R/npdr.R:391-430, 18-71
  *   npdrb_npdr               <- npdr() between argument parsing and order()/p.adjust()
  *                                                    R/npdr.R:256-270, 299-345, 391-430
+ *   npdrb_npdr_multi         <- the same on several GPUs from one process (the R session's multi-GPU entry point)
  *   npdrb_unireg             <- uniReg's per-column fits   R/utils.R:66-157
  *
  * What stays on the R side (per BASELINE north_star): argument parsing, factor coding,
@@ -176,6 +177,12 @@ int npdrb_regress(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const i
 /* the whole path on one device */
 int npdrb_npdr(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
                const npdrb_opts *opts, npdrb_result *res);
+/* The whole path on n_devices GPUs of one node from ONE host process (what an R session calls: one host thread per
+ * device for the duration of the call).  devices: CUDA ordinals or NULL for 0..n_devices-1.  Row blocks of the distance /
+ * neighbour stage, symmetric distance halves pulled from the peers over NVLink, full pair list on every device, attribute
+ * columns of the regression; same options, same result layout and the same pair list (bit for bit) as npdrb_npdr. */
+int npdrb_npdr_multi(int32_t n_devices, const int32_t *devices, const double *X, int64_t N, int64_t p, const double *y,
+                     const double *C, const npdrb_opts *opts, npdrb_result *res);
 /* uniReg: univariate lm/glm of y on each raw column (+ covariates C as additional regressors) */
 int npdrb_unireg(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
                  int32_t q, int32_t regression_type, double *stats_out);

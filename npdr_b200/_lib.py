@@ -78,6 +78,7 @@ SIGNATURES = {
                                                   C.POINTER(_ip), C.POINTER(_ip), C.POINTER(_i64), C.POINTER(_i64), _dp, _dp]),
     "npdrb_regress": (C.c_int, [_vp, _dp, _i64, _i64, _ip, _ip, _i64, _dp, _dp, _i32, _ip, _i32, _i32, _dp]),
     "npdrb_npdr": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, C.POINTER(Opts), C.POINTER(Result)]),
+    "npdrb_npdr_multi": (C.c_int, [_i32, _ip, _dp, _i64, _i64, _dp, _dp, C.POINTER(Opts), C.POINTER(Result)]),
     "npdrb_unireg": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, _i32, _i32, _dp]),
     "npdrb_session_create": (C.c_int, [_vp, _i64, _i64, _i32, C.POINTER(_vp)]),
     "npdrb_session_destroy": (None, [_vp]),

@@ -380,7 +380,7 @@ def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-a
          padj_method="bonferroni", verbose=False, use_glmnet=False, glmnet_alpha=1, glmnet_lower=0,
          glmnet_lam="lambda.1se", rm_attr_from_dist=(), neighbor_sampling="none", separate_hitmiss_nbds=False,
          corr_attr_names=None, fast_reg=False, fast_dist=False, dopar_nn=False, dopar_reg=False, unique_dof=False,
-         external_dist=None, device=0, return_info=False, k=None):
+         external_dist=None, device=0, return_info=False, k=None, n_gpus=1, devices=None):
     """Nearest-neighbour Projected-Distance Regression (R/npdr.R:151-634), default (non-glmnet) branch.
 
     Same formals as the reference (dots -> underscores); `k` is accepted as an alias of `knn` because R's
@@ -435,7 +435,11 @@ def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-a
         o.return_pairs = int(bool(return_info))
         o.separate_hitmiss_nbds = int(bool(separate_hitmiss_nbds))
         res = _lib.Result()
-        check(L.npdrb_npdr(ctx.handle, dptr(X), N, p, dptr(f64(y)), dptr(Cm), C.byref(o), C.byref(res)))
+        if (n_gpus and int(n_gpus) > 1) or devices is not None:   # one host process, one thread per device (what R would call)
+            devs = np.ascontiguousarray(np.arange(int(n_gpus)) if devices is None else devices, dtype=np.int32)
+            check(L.npdrb_npdr_multi(int(devs.size), iptr(devs), dptr(X), N, p, dptr(f64(y)), dptr(Cm), C.byref(o), C.byref(res)))
+        else:
+            check(L.npdrb_npdr(ctx.handle, dptr(X), N, p, dptr(f64(y)), dptr(Cm), C.byref(o), C.byref(res)))
         stats = np.ctypeslib.as_array(res.stats, shape=(p, STATS_PER_ATTR)).copy()
         num_pairs, num_unique, n_used = res.n_pairs, res.n_unique_pairs, res.n_pairs_used
         k_ave = res.k_ave_empirical

@@ -1,0 +1,274 @@
+// multi.cu -- the whole path on several GPUs of one node, driven from ONE host process (npdrb_npdr_multi).
+//
+// This is what an R session uses: R is single threaded and cannot be launched once per GPU, so the `.Call` spawns one host
+// thread per device for the duration of the call.  The partitioning is the one of npdr_b200/distributed.py:
+//   rows/G      distances + neighbour lists; D is symmetric, so each device computes its diagonal square and a
+//               checkerboard half of every off-diagonal square and PULLS the other half from its peers' packed send
+//               buffers over NVLink (cudaMemcpyPeerAsync), then unpacks (distance.cu: nb_distances_balanced / pack / unpack);
+//   exchange    every device pulls the peers' (Ri, NN) segments into its copy of the full list (rank order = reference order);
+//   attrs/G     regression of the device's attribute columns; statistics land in the caller's p x 8 array.
+// No data-path reduction: distances, radii and pair lists are bit-identical to the one-device run.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_ROWS = 128;      // row blocks start on distance-tile boundaries
+
+struct Barrier {
+    std::mutex mu; std::condition_variable cv; int n, waiting = 0; unsigned gen = 0;
+    explicit Barrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+struct Worker {
+    int dev = 0;
+    npdrb_ctx *ctx = nullptr;
+    npdrb_session *s = nullptr;
+    int rc = NPDRB_OK;
+    char err[600] = "";
+    int64_t row0 = 0, nrows = 0, attr0 = 0, nattr = 0;
+    int live = -1;                                   // index among the devices that own rows, or -1
+    double *d_send = nullptr;
+    std::vector<int64_t> send_cnt, recv_cnt;         // doubles per live peer
+    int64_t M_local = 0, n_empty = 0, n_unique = 0;
+    double surf0[4] = {0, 0, 0, 0}, surf1[4] = {0, 0, 0, 0};
+    int32_t irls_passes = 0;
+    double ms_distance = 0, ms_neighbors = 0, ms_prepare = 0, ms_regress = 0;
+};
+
+struct Shared {
+    int G = 0;
+    std::vector<Worker> w;
+    std::vector<int> live_devs;                      // worker indices that own rows
+    std::vector<int64_t> row_starts;                 // live + 1 bounds
+    std::atomic<int> failed{0};
+    Barrier *bar = nullptr;
+    const double *X = nullptr, *y = nullptr, *C = nullptr;
+    int64_t N = 0, p = 0;
+    const npdrb_opts *o = nullptr;
+    double *stats = nullptr;                         // p x 8, host
+    int64_t k = 0;
+    int64_t M_total = 0;
+};
+
+void fail(Shared &S, Worker &w, int rc) {
+    w.rc = rc;
+    snprintf(w.err, sizeof(w.err), "device %d: %s", w.dev, npdrb_last_error());
+    S.failed.store(1);
+}
+#define STEP(call) do { if (!S.failed.load() && w.rc == NPDRB_OK) { int rc__ = (call); if (rc__ != NPDRB_OK) fail(S, w, rc__); } } while (0)
+#define CU(call) ([&]() -> int { cudaError_t e__ = (call); if (e__ != cudaSuccess) { npdrb_set_error("%s: %s", #call, cudaGetErrorString(e__)); return NPDRB_ECUDA; } return NPDRB_OK; }())
+
+void run_worker(Shared &S, int g) {
+    Worker &w = S.w[(size_t)g];
+    const npdrb_opts &o = *S.o;
+    const int W = (int)S.live_devs.size();
+    STEP(CU(cudaSetDevice(w.dev)));
+    STEP(npdrb_create(w.dev, &w.ctx));
+    if (w.ctx) {
+        for (int h = 0; h < S.G; ++h)                // NVLink peer access (already-enabled / unsupported are not errors)
+            if (S.w[(size_t)h].dev != w.dev) { cudaDeviceEnablePeerAccess(S.w[(size_t)h].dev, 0); cudaGetLastError(); }
+    }
+    STEP(npdrb_session_create(w.ctx, S.N, S.p, o.n_covars, &w.s));
+    STEP(npdrb_session_upload(w.s, S.X, S.y, S.C));  // every device over its own PCIe link, in parallel
+    // ---- phase 1: this device's share of the distance matrix, packed halves for the peers
+    if (w.live >= 0) {
+        if (W == 1) STEP(nb_distances(w.s, o.nbd_metric, o.fast_euclidean, 0, S.N));
+        else {
+            STEP(nb_distances_balanced(w.s, o.nbd_metric, o.fast_euclidean, S.row_starts.data(), w.live, W));
+            w.send_cnt.assign((size_t)W, 0); w.recv_cnt.assign((size_t)W, 0);
+            STEP(nb_balanced_counts(w.s, w.send_cnt.data(), w.recv_cnt.data()));
+            int64_t ns = 0;
+            for (int64_t c : w.send_cnt) ns += c;
+            STEP(CU(cudaMalloc(&w.d_send, sizeof(double) * (size_t)(ns > 0 ? ns : 1))));
+            if (ns > 0) STEP(nb_balanced_pack(w.s, w.d_send));
+        }
+        if (w.s) w.ms_distance = w.s->ms_distance;
+    }
+    S.bar->wait();
+    if (S.failed.load()) return;
+    // ---- phase 2: pull the halves the peers computed for my rows, unpack
+    double *d_recv = nullptr;
+    if (w.live >= 0 && W > 1) {
+        int64_t nr = 0;
+        for (int64_t c : w.recv_cnt) nr += c;
+        STEP(CU(cudaMalloc(&d_recv, sizeof(double) * (size_t)(nr > 0 ? nr : 1))));
+        int64_t roff = 0;
+        for (int h = 0; h < W; ++h) {
+            const int64_t n = w.recv_cnt[(size_t)h];
+            if (n == 0) continue;
+            const Worker &peer = S.w[(size_t)S.live_devs[(size_t)h]];
+            int64_t soff = 0;                        // my segment inside the peer's send buffer (peers in rank order)
+            for (int t = 0; t < w.live; ++t) soff += peer.send_cnt[(size_t)t];
+            STEP(CU(cudaMemcpyPeerAsync(d_recv + roff, w.dev, peer.d_send + soff, peer.dev, sizeof(double) * (size_t)n, w.ctx->stream)));
+            roff += n;
+        }
+        STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
+    }
+    S.bar->wait();                                   // every pull has completed: send buffers can go
+    if (w.d_send) { cudaFree(w.d_send); w.d_send = nullptr; }
+    if (S.failed.load()) { if (d_recv) cudaFree(d_recv); return; }
+    if (w.live >= 0 && W > 1) {
+        int64_t nr = 0;
+        for (int64_t c : w.recv_cnt) nr += c;
+        if (nr > 0) STEP(nb_balanced_unpack(w.s, d_recv));
+        cudaFree(d_recv);
+    }
+    // ---- SURF on row blocks: one global mean / sd from per-block moments (R/nearestNeighbors.R:234-241)
+    const bool surf_multi = (o.nbd_method == NPDRB_NBD_SURF) && W > 1;
+    if (surf_multi) {
+        if (w.live >= 0) STEP(npdrb_session_surf_partial(w.s, 0.0, w.surf0));
+        S.bar->wait();
+        if (S.failed.load()) return;
+        double m0[4] = {0, 0, 0, 0};
+        for (int h : S.live_devs) for (int t = 0; t < 4; ++t) m0[t] += S.w[(size_t)h].surf0[t];
+        const double mean_u = m0[1] / m0[2];
+        if (w.live >= 0) STEP(npdrb_session_surf_partial(w.s, mean_u, w.surf1));
+        S.bar->wait();
+        if (S.failed.load()) return;
+        double m1[4] = {0, 0, 0, 0};
+        for (int h : S.live_devs) for (int t = 0; t < 4; ++t) m1[t] += S.w[(size_t)h].surf1[t];
+        const double num_pair = (double)S.N * (double)(S.N - 1) / 2.0;
+        const double radius = m0[0] / (2.0 * num_pair) - o.msurf_sd_frac * sqrt(m1[3] / (m1[2] - 1.0));
+        if (w.live >= 0) STEP(npdrb_session_set_surf_radius(w.s, radius));
+    }
+    // ---- phase 3: neighbour lists of my rows
+    if (w.live >= 0) {
+        if (o.separate_hitmiss_nbds) STEP(nb_neighbors_hitmiss(w.s, o.nbd_method, o.msurf_sd_frac, S.k, &w.M_local, &w.n_empty));
+        else STEP(nb_neighbors(w.s, o.nbd_method, o.msurf_sd_frac, S.k, &w.M_local, &w.n_empty));
+        if (w.s) w.ms_neighbors = w.s->ms_neighbors;
+    }
+    S.bar->wait();
+    if (S.failed.load()) return;
+    // ---- phase 4: the full pair list on every device (segments in rank order = reference order)
+    int64_t M = 0;
+    for (int h : S.live_devs) M += S.w[(size_t)h].M_local;
+    int32_t *dRi = nullptr, *dNN = nullptr;
+    if (M > 0 && w.nattr > 0) {
+        STEP(CU(cudaMalloc(&dRi, sizeof(int32_t) * (size_t)M)));
+        STEP(CU(cudaMalloc(&dNN, sizeof(int32_t) * (size_t)M)));
+        int64_t off = 0;
+        for (int h : S.live_devs) {
+            const Worker &peer = S.w[(size_t)h];
+            if (peer.M_local > 0) {
+                STEP(CU(cudaMemcpyPeerAsync(dRi + off, w.dev, peer.s->dRiL, peer.dev, sizeof(int32_t) * (size_t)peer.M_local, w.ctx->stream)));
+                STEP(CU(cudaMemcpyPeerAsync(dNN + off, w.dev, peer.s->dNNL, peer.dev, sizeof(int32_t) * (size_t)peer.M_local, w.ctx->stream)));
+            }
+            off += peer.M_local;
+        }
+        STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
+    }
+    S.bar->wait();                                   // every device has its copy: the local segments may be reused
+    if (S.failed.load()) { if (dRi) cudaFree(dRi); if (dNN) cudaFree(dNN); return; }
+    if (g == 0) S.M_total = M;
+    // ---- phase 5: regression of my attribute columns
+    if (M > 0 && w.nattr > 0) {
+        STEP(npdrb_session_import_pairs(w.s, dRi, dNN, M));
+        if (w.s) w.s->own_pairs = true;              // the session frees the list
+        STEP(nb_unique_pairs(w.s, o.neighbor_sampling_unique, &w.n_unique));
+        STEP(nb_regress(w.s, w.attr0, w.nattr, o.regression_type, o.attr_diff_type, o.covar_diff_type,
+                        S.stats + (size_t)w.attr0 * NPDRB_STATS_PER_ATTR, &w.irls_passes));
+        if (w.s) { w.ms_prepare = w.s->ms_prepare; w.ms_regress = w.s->ms_regress; }
+    }
+}
+
+}  // namespace
+
+extern "C" int npdrb_npdr_multi(int32_t n_devices, const int32_t *devices, const double *X, int64_t N, int64_t p, const double *y,
+                                const double *C, const npdrb_opts *o, npdrb_result *res) {
+    if (!o || !res) { npdrb_set_error("npdrb_npdr_multi: null opts/result"); return NPDRB_EINVAL; }
+    memset(res, 0, sizeof(*res));
+    if (n_devices < 1 || n_devices > 64) { npdrb_set_error("npdrb_npdr_multi: 1..64 devices"); return NPDRB_EINVAL; }
+    if (o->nbd_metric == NPDRB_METRIC_PRECOMPUTED) { npdrb_set_error("npdrb_npdr_multi: precomputed distances are a one-device path"); return NPDRB_EINVAL; }
+    if (o->nbd_method == NPDRB_NBD_SURF && o->separate_hitmiss_nbds && n_devices > 1) {
+        npdrb_set_error("npdrb_npdr_multi: surf hit/miss radii need the whole distance matrix on one device");
+        return NPDRB_EINVAL;
+    }
+    for (int a = 0; a < n_devices; ++a)
+        for (int b = a + 1; b < n_devices; ++b)
+            if (devices && devices[a] == devices[b]) { npdrb_set_error("npdrb_npdr_multi: device %d listed twice", devices[a]); return NPDRB_EINVAL; }
+    Shared S;
+    S.G = n_devices; S.X = X; S.y = y; S.C = C; S.N = N; S.p = p; S.o = o;
+    S.w.resize((size_t)n_devices);
+    S.k = o->knn;
+    if (o->nbd_method == NPDRB_NBD_RELIEFF && S.k <= 0) S.k = npdrb_knn_surf(N, o->msurf_sd_frac);
+    // row blocks (tile aligned, trailing devices may be empty) and attribute blocks, as distributed.py partitions them
+    const int64_t n_tiles = nb_cdiv(N, TILE_ROWS);
+    int64_t t0 = 0, a0 = 0;
+    for (int g = 0; g < n_devices; ++g) {
+        Worker &w = S.w[(size_t)g];
+        w.dev = devices ? devices[g] : g;
+        const int64_t nt = n_tiles / n_devices + (g < n_tiles % n_devices ? 1 : 0);
+        w.row0 = (t0 * TILE_ROWS < N) ? t0 * TILE_ROWS : N;
+        const int64_t row1 = ((t0 + nt) * TILE_ROWS < N) ? (t0 + nt) * TILE_ROWS : N;
+        w.nrows = row1 - w.row0;
+        t0 += nt;
+        if (w.nrows > 0) { w.live = (int)S.live_devs.size(); S.live_devs.push_back(g); S.row_starts.push_back(w.row0); }
+        w.attr0 = a0;
+        w.nattr = p / n_devices + (g < p % n_devices ? 1 : 0);
+        a0 += w.nattr;
+    }
+    S.row_starts.push_back(N);
+    res->stats = (double *)malloc(sizeof(double) * (size_t)p * NPDRB_STATS_PER_ATTR);
+    if (!res->stats) { npdrb_set_error("out of host memory"); return NPDRB_ENOMEM; }
+    S.stats = res->stats;
+    Barrier bar(n_devices);
+    S.bar = &bar;
+    const auto wall0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int g = 1; g < n_devices; ++g) th.emplace_back(run_worker, std::ref(S), g);
+    run_worker(S, 0);
+    for (auto &t : th) t.join();
+    const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+
+    int rc = NPDRB_OK;
+    for (const Worker &w : S.w)
+        if (w.rc != NPDRB_OK && rc == NPDRB_OK) { rc = w.rc; npdrb_set_error("%s", w.err); }
+    if (rc == NPDRB_OK && S.M_total <= 0) { npdrb_set_error("npdr: no neighbour pairs found"); rc = NPDRB_EDATA; }
+    if (rc == NPDRB_OK && o->return_pairs) {
+        const Worker *src = nullptr;
+        for (const Worker &w : S.w) if (w.s && w.s->dRi && w.s->M > 0) { src = &w; break; }
+        if (src) {
+            cudaSetDevice(src->dev);
+            res->Ri = (int32_t *)malloc(sizeof(int32_t) * (size_t)src->s->M);
+            res->NN = (int32_t *)malloc(sizeof(int32_t) * (size_t)src->s->M);
+            if (!res->Ri || !res->NN) { npdrb_set_error("out of host memory"); rc = NPDRB_ENOMEM; }
+            else rc = npdrb_session_copy_pairs(src->s, res->Ri, res->NN);
+        }
+    }
+    if (rc == NPDRB_OK) {
+        int64_t ne = 0;
+        for (const Worker &w : S.w) {
+            ne += w.n_empty;
+            if (w.ms_distance > res->ms_distance) res->ms_distance = w.ms_distance;
+            if (w.ms_neighbors > res->ms_neighbors) res->ms_neighbors = w.ms_neighbors;
+            if (w.ms_prepare > res->ms_prepare) res->ms_prepare = w.ms_prepare;
+            if (w.ms_regress > res->ms_regress) res->ms_regress = w.ms_regress;
+            if (w.irls_passes > res->irls_passes) res->irls_passes = w.irls_passes;
+        }
+        const Worker &w0 = S.w[0];
+        res->n_attr = p; res->n_pairs = S.M_total; res->n_unique_pairs = w0.n_unique;
+        res->n_pairs_used = (w0.s ? w0.s->M : S.M_total);
+        res->n_empty = ne; res->knn_used = (o->nbd_method == NPDRB_NBD_RELIEFF) ? S.k : 0;
+        res->k_ave_empirical = (N - ne) > 0 ? (double)S.M_total / (double)(N - ne) : 0.0;
+        res->ms_total = wall_ms;                     // host wall clock around the G device threads
+    }
+    for (Worker &w : S.w) {
+        if (w.ctx) cudaSetDevice(w.dev);
+        if (w.s) npdrb_session_destroy(w.s);
+        if (w.ctx) npdrb_destroy(w.ctx);
+    }
+    if (rc != NPDRB_OK) npdrb_result_release(res);
+    return rc;
+}

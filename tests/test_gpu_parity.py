@@ -699,3 +699,52 @@ def test_pipelined_upload_distances_bit_exact(nb, oracle, monkeypatch):
         nb.npdrDistances(X, "manhattan")
     with pytest.raises(nb.NpdrB200Error):
         nb.npdr(y, X)
+
+
+# ---------------------------------------------------------------- in-process multi-GPU driver (npdrb_npdr_multi)
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3"])
+def test_npdr_multi_driver_one_device(nb, name):
+    """npdrb_npdr_multi with a single device: the threaded driver itself (partition, phases, result assembly)."""
+    case = load_case(name)
+    kw = dict(regression_type=case["regression_type"], nbd_method=case["nbd_method"], nbd_metric=case["nbd_metric"],
+              covars=case["C"] if case["C"] is not None else "none", covar_diff_type=case["covar_diff_type"] or "match-mismatch",
+              return_info=True)
+    out1, info1 = nb.npdr(case["y"], case["X"], **kw)
+    out2, info2 = nb.npdr(case["y"], case["X"], devices=[0], **kw)
+    assert np.array_equal(info1["Ri"], info2["Ri"]) and np.array_equal(info1["NN"], info2["NN"])
+    assert np.array_equal(info1["stats"], info2["stats"], equal_nan=True)
+    assert list(out1["att"]) == list(out2["att"])
+    for f in ("n_pairs", "n_unique_pairs", "n_pairs_used", "n_empty", "knn_used"):
+        assert info1[f] == info2[f], f
+
+
+@pytest.mark.parametrize("method,hitmiss", [("multisurf", False), ("surf", False), ("relieff", False), ("multisurf", True)])
+def test_npdr_multi_driver_two_devices(nb, oracle, method, hitmiss):
+    """Two GPUs from one process: pair list bit-identical to the oracle, statistics within the IRLS bar."""
+    if _n_devices() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(33)
+    N, p = 700, 300                                              # 6 row tiles -> 3 + 3; ragged last tile
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    y = (rng.random(N) < 0.5).astype(float)
+    X[:, :4] += 0.7 * y[:, None]
+    Cv = np.asfortranarray(np.column_stack([rng.integers(0, 2, N).astype(float), rng.normal(40, 10, N).round()]))
+    out, info = nb.npdr(y, X, "binomial", "numeric-abs", method, "manhattan", covars=Cv,
+                        covar_diff_type=("match-mismatch", "numeric-abs"), separate_hitmiss_nbds=hitmiss, n_gpus=2, return_info=True)
+    if hitmiss:
+        ri, nn, _, _, _ = oracle.nearest_neighbors_hitmiss(X, y, method)
+    else:
+        ri, nn, _, _ = oracle.nearest_neighbors(X, method)
+    if method == "surf":                                         # radius from combined moments: a boundary pair may differ
+        assert abs(info["n_pairs"] - ri.size) <= 2
+        return
+    assert np.array_equal(info["Ri"], ri) and np.array_equal(info["NN"], nn)
+    cd = np.column_stack([oracle.pair_diffs(Cv[:, 0], ri, nn, "match-mismatch"), oracle.pair_diffs(Cv[:, 1], ri, nn, "numeric-abs")])
+    exp = oracle.regress_attrs(X, ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"), cd)
+    _stats_close(info["stats"], exp, RTOL_IRLS, f"multi {method}")
+    assert set(out["att"][:4]) == {"1", "2", "3", "4"}
