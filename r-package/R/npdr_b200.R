@@ -107,7 +107,8 @@ npdr <- function(outcome, dataset, regression.type = "binomial", attr.diff.type 
   io <- c(.reg_code[[regression.type]], .diff_code[[attr.diff.type]], .nbd_code[[nbd.method]], .metric_code[[nbd.metric]],
           as.integer(knn), ncov, as.integer(neighbor.sampling == "unique"), as.integer(separate.hitmiss.nbds),
           .diff_code[covar.diff.type])
-  r <- .Call("C_npdrb_npdr", unname(X) + 0, y, C, as.integer(io), msurf.sd.frac, PACKAGE = "npdrb200")
+  r <- .Call("C_npdrb_npdr", unname(X) + 0, y, C, as.integer(io), msurf.sd.frac,
+             as.integer(getOption("npdr_b200.gpus", 1L)), PACKAGE = "npdrb200")   # > 1: all GPUs of the node, driven in-process
   s <- t(r$stats)                                               # p x 8: beta_a, stat_a, beta_0, stat_0, df, r2|dev, iters, flags
   res.df <- if (unique.dof) r$n_unique_pairs - 2 else s[, 5]    # R/npdr.R:419-423
   pval.att <- pt(s[, 2], res.df, lower.tail = FALSE)            # R/npdr.R:55

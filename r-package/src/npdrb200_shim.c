@@ -54,9 +54,9 @@ SEXP C_npdrb_nearest_neighbors(SEXP X, SEXP method, SEXP metric, SEXP sd_vec, SE
     return out;
 }
 
-/* .Call("C_npdrb_npdr", X, y, C|NULL, opts(integer/real vector)) -> list(stats = p x 8 (row-major -> t()), counters)
+/* .Call("C_npdrb_npdr", X, y, C|NULL, opts(integer vector), sd.frac, n.gpus) -> list(stats = p x 8 (row-major -> t()), counters)
  * the whole path between argument parsing and order()/p.adjust()    (R/npdr.R:256-430) */
-SEXP C_npdrb_npdr(SEXP X, SEXP y, SEXP C, SEXP iopts, SEXP sd_frac) {
+SEXP C_npdrb_npdr(SEXP X, SEXP y, SEXP C, SEXP iopts, SEXP sd_frac, SEXP n_gpus) {
     SEXP dim = Rf_getAttrib(X, R_DimSymbol);
     const R_xlen_t N = INTEGER(dim)[0], p = INTEGER(dim)[1];
     npdrb_opts o;
@@ -67,7 +67,9 @@ SEXP C_npdrb_npdr(SEXP X, SEXP y, SEXP C, SEXP iopts, SEXP sd_frac) {
     for (int c = 0; c < o.n_covars && c < NPDRB_MAX_COVARS; ++c) o.covar_diff_type[c] = io[8 + c];
     o.msurf_sd_frac = Rf_asReal(sd_frac);
     npdrb_result res;
-    int rc = npdrb_npdr(ctx_get(), REAL(X), N, p, REAL(y), Rf_isNull(C) ? NULL : REAL(C), &o, &res);
+    const int ng = Rf_asInteger(n_gpus);            /* options(npdr_b200.gpus = 8): one host thread per device inside the call */
+    int rc = ng > 1 ? npdrb_npdr_multi(ng, NULL, REAL(X), N, p, REAL(y), Rf_isNull(C) ? NULL : REAL(C), &o, &res)
+                    : npdrb_npdr(ctx_get(), REAL(X), N, p, REAL(y), Rf_isNull(C) ? NULL : REAL(C), &o, &res);
     if (rc) Rf_error("npdr_b200: %s", npdrb_last_error());
     SEXP stats = PROTECT(Rf_allocMatrix(REALSXP, NPDRB_STATS_PER_ATTR, (int)p));     /* 8 x p, column = attribute */
     memcpy(REAL(stats), res.stats, sizeof(double) * (size_t)p * NPDRB_STATS_PER_ATTR);
@@ -170,7 +172,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_npdrb_nearest_neighbors2", (DL_FUNC)&C_npdrb_nearest_neighbors2, 7},
     {"C_npdrb_distances", (DL_FUNC)&C_npdrb_distances, 2},
     {"C_npdrb_nearest_neighbors", (DL_FUNC)&C_npdrb_nearest_neighbors, 7},
-    {"C_npdrb_npdr", (DL_FUNC)&C_npdrb_npdr, 5},
+    {"C_npdrb_npdr", (DL_FUNC)&C_npdrb_npdr, 6},
     {"C_npdrb_diff", (DL_FUNC)&C_npdrb_diff, 4},
     {"C_npdrb_unireg", (DL_FUNC)&C_npdrb_unireg, 4},
     {NULL, NULL, 0}};
