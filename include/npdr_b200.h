@@ -183,6 +183,7 @@ int npdrb_npdr(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const doub
  * columns of the regression; same options, same result layout and the same pair list (bit for bit) as npdrb_npdr. */
 int npdrb_npdr_multi(int32_t n_devices, const int32_t *devices, const double *X, int64_t N, int64_t p, const double *y,
                      const double *C, const npdrb_opts *opts, npdrb_result *res);
+void npdrb_multi_shutdown(void);                   /* releases the per-device contexts npdrb_npdr_multi keeps between calls */
 /* uniReg: univariate lm/glm of y on each raw column (+ covariates C as additional regressors) */
 int npdrb_unireg(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
                  int32_t q, int32_t regression_type, double *stats_out);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "npdrb_regress": (C.c_int, [_vp, _dp, _i64, _i64, _ip, _ip, _i64, _dp, _dp, _i32, _ip, _i32, _i32, _dp]),
     "npdrb_npdr": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, C.POINTER(Opts), C.POINTER(Result)]),
     "npdrb_npdr_multi": (C.c_int, [_i32, _ip, _dp, _i64, _i64, _dp, _dp, C.POINTER(Opts), C.POINTER(Result)]),
+    "npdrb_multi_shutdown": (None, []),
     "npdrb_unireg": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, _i32, _i32, _dp]),
     "npdrb_session_create": (C.c_int, [_vp, _i64, _i64, _i32, C.POINTER(_vp)]),
     "npdrb_session_destroy": (None, [_vp]),

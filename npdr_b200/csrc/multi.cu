@@ -62,6 +62,18 @@ struct Shared {
     int64_t M_total = 0;
 };
 
+// One context per device for the life of the process: the device-memory cache (api.cu) then survives between calls, which
+// saves ~200 ms of cudaMalloc / cudaFree per call and device.  npdrb_multi_shutdown() releases them.
+std::mutex g_ctx_mu;
+npdrb_ctx *g_ctx[64] = {nullptr};
+int get_ctx(int dev, npdrb_ctx **out) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (dev < 0 || dev >= 64) { npdrb_set_error("device %d out of range", dev); return NPDRB_ENODEVICE; }
+    if (!g_ctx[dev]) NB_CHECK(npdrb_create(dev, &g_ctx[dev]));
+    *out = g_ctx[dev];
+    return NPDRB_OK;
+}
+
 void fail(Shared &S, Worker &w, int rc) {
     w.rc = rc;
     snprintf(w.err, sizeof(w.err), "device %d: %s", w.dev, npdrb_last_error());
@@ -75,13 +87,40 @@ void run_worker(Shared &S, int g) {
     const npdrb_opts &o = *S.o;
     const int W = (int)S.live_devs.size();
     STEP(CU(cudaSetDevice(w.dev)));
-    STEP(npdrb_create(w.dev, &w.ctx));
+    STEP(get_ctx(w.dev, &w.ctx));
+    STEP(CU(cudaSetDevice(w.dev)));
     if (w.ctx) {
         for (int h = 0; h < S.G; ++h)                // NVLink peer access (already-enabled / unsupported are not errors)
             if (S.w[(size_t)h].dev != w.dev) { cudaDeviceEnablePeerAccess(S.w[(size_t)h].dev, 0); cudaGetLastError(); }
     }
     STEP(npdrb_session_create(w.ctx, S.N, S.p, o.n_covars, &w.s));
-    STEP(npdrb_session_upload(w.s, S.X, S.y, S.C));  // every device over its own PCIe link, in parallel
+    if (S.G == 1) {
+        STEP(npdrb_session_upload(w.s, S.X, S.y, S.C));
+    } else {
+        // every device uploads ITS attribute columns over its own PCIe link (1/G of the matrix), then pulls the other
+        // columns from its peers over NVLink: G x less host traffic than G full uploads
+        STEP(npdrb_session_upload(w.s, nullptr, S.y, S.C));
+        const int64_t ldx = nb_round_up(S.N, 16);
+        double *dX = nullptr;
+        STEP(CU(cudaMalloc(&dX, sizeof(double) * (size_t)ldx * (size_t)S.p)));
+        if (dX && ldx != S.N) STEP(CU(cudaMemsetAsync(dX, 0, sizeof(double) * (size_t)ldx * (size_t)S.p, w.ctx->stream)));
+        if (dX && w.nattr > 0)
+            STEP(CU(cudaMemcpy2DAsync(dX + w.attr0 * ldx, sizeof(double) * (size_t)ldx, S.X + w.attr0 * S.N, sizeof(double) * (size_t)S.N,
+                                      sizeof(double) * (size_t)S.N, (size_t)w.nattr, cudaMemcpyHostToDevice, w.ctx->stream)));
+        STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
+        if (w.s && dX) { w.s->dX = dX; w.s->ldx = ldx; w.s->own_X = true; }
+        else if (dX) cudaFree(dX);
+        S.bar->wait();
+        if (S.failed.load()) return;
+        for (int h = 0; h < S.G; ++h) {
+            const Worker &peer = S.w[(size_t)h];
+            if (h == g || peer.nattr == 0) continue;
+            STEP(CU(cudaMemcpyPeerAsync(w.s->dX + peer.attr0 * ldx, w.dev, peer.s->dX + peer.attr0 * ldx, peer.dev,
+                                        sizeof(double) * (size_t)ldx * (size_t)peer.nattr, w.ctx->stream)));
+        }
+        STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
+        STEP(nb_check_finite(w.ctx, w.s ? w.s->dX : nullptr, ldx * S.p, "the attribute matrix"));
+    }
     // ---- phase 1: this device's share of the distance matrix, packed halves for the peers
     if (w.live >= 0) {
         if (W == 1) STEP(nb_distances(w.s, o.nbd_metric, o.fast_euclidean, 0, S.N));
@@ -266,9 +305,14 @@ extern "C" int npdrb_npdr_multi(int32_t n_devices, const int32_t *devices, const
     }
     for (Worker &w : S.w) {
         if (w.ctx) cudaSetDevice(w.dev);
-        if (w.s) npdrb_session_destroy(w.s);
-        if (w.ctx) npdrb_destroy(w.ctx);
+        if (w.s) npdrb_session_destroy(w.s);         // the contexts (and their memory caches) stay for the next call
     }
     if (rc != NPDRB_OK) npdrb_result_release(res);
     return rc;
+}
+
+extern "C" void npdrb_multi_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (int d = 0; d < 64; ++d)
+        if (g_ctx[d]) { npdrb_destroy(g_ctx[d]); g_ctx[d] = nullptr; }
 }

@@ -185,4 +185,5 @@ void R_init_npdrb200(DllInfo *dll) {
 void R_unload_npdrb200(DllInfo *dll) {
     (void)dll;
     if (g_ctx) { npdrb_destroy(g_ctx); g_ctx = NULL; }
+    npdrb_multi_shutdown();
 }
