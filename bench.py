@@ -9,8 +9,9 @@ IRLS) over one synthetic batch.  Workloads (BASELINE.json configs; synthetic sta
                   With --gpus N the attribute count grows to 20,000 x N (weak scaling: per-GPU work fixed).
   cfg5            20,000 x 50,000, binomial, multisurf, manhattan, 2 covariates (strong scaling: total fixed).
   small           1,024 x 2,048 (development).
-Sharding (N > 1, one process per GPU under torchrun): row blocks for distance+neighbours, one all-gather of
-the pair segments (NCCL), attribute columns for the regression, statistics gathered to rank 0.
+Sharding (N > 1, one process per GPU under torchrun): row blocks for distance+neighbours (symmetric halves of the
+distance matrix swapped in one NCCL all-to-all), one all-gather of the pair segments, attribute columns for the
+regression, statistics gathered to rank 0.
 
 `value` is p*M / step time with inputs resident in HBM; `e2e` is the same metric through the host-buffer API
 (H2D of X, y inside the timed region, D2H of the statistics).  `roofline` describes the dominant kernel

@@ -57,7 +57,7 @@ def main():
     ms = 1e3 * sum(times) / len(times)
     print(json.dumps({"driver": "npdrb_npdr_multi (one host process, one thread per device)", "workload": args.workload,
                       "n_gpus": args.gpus, "N": N, "p": p, "q": q, "pairs_M": info["n_pairs"], "ms_per_call": ms,
-                      "evals_per_s": float(p) * info["n_pairs"] / (ms * 1e-3), "h2d_bytes_per_device": int(N * p * 8),
+                      "evals_per_s": float(p) * info["n_pairs"] / (ms * 1e-3), "h2d_bytes_per_device": int(N * p * 8 // args.gpus) if args.gpus > 1 else int(N * p * 8),
                       "stages_max_over_devices": info, "timing": "host wall clock around the call, host buffers in / statistics out"}))
 
 
