@@ -13,10 +13,13 @@
  * container.  The only known-answer vectors the reference's own tests hold for
  * this path are the five npdrDiff expectations
  * (tests/testthat/test-nearestNeighbors.R:1-12); those are pinned
- * (tests/test_oracle.py).  Distances, radii, neighbour lists and regression
- * statistics are restated from the published base-R / LINPACK algorithms and
- * cross-checked against independent numpy/scipy implementations, but are
- * otherwise **parity unpinned**.
+ * (tests/test_oracle.py).  The lm.fit / glm.fit / summary.* restatement is
+ * additionally pinned to what R itself prints for four models on datasets::mtcars
+ * (coefficients, standard errors, R^2, deviance, Fisher scoring iterations;
+ * tests/golden/r_published_kats.py).  Distances, radii and neighbour lists (and
+ * the regression statistics beyond those known answers) are restated from the
+ * published base-R / LINPACK / dplyr algorithms and cross-checked against
+ * independent numpy/scipy implementations, but are otherwise **parity unpinned**.
  *
  * Each function cites the reference file:line it follows.  Plain C, `long double`
  * is x87 80-bit on x86-64 Linux = R's LDOUBLE.  Build: see oracle/Makefile

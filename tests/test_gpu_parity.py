@@ -748,3 +748,30 @@ def test_npdr_multi_driver_two_devices(nb, oracle, method, hitmiss):
     exp = oracle.regress_attrs(X, ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"), cd)
     _stats_close(info["stats"], exp, RTOL_IRLS, f"multi {method}")
     assert set(out["att"][:4]) == {"1", "2", "3", "4"}
+
+
+def test_gpu_solvers_reproduce_published_r_output(nb, oracle):
+    """The mtcars known answers R prints (tests/golden/r_published_kats.py) through the GPU regression path: every
+    predictor of each model takes the attribute slot once (the others ride as covariates)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import r_published_kats as K
+    from npdr_b200 import _lib
+    from npdr_b200._lib import REG, check, dptr, f64
+    for name, (yv, cols, fam, coef_p, se_p, extra) in K.KATS.items():
+        for lead in range(len(cols)):
+            order = [lead] + [c for c in range(len(cols)) if c != lead]
+            X = np.asfortranarray(cols[order[0]].reshape(-1, 1))
+            Cm = np.asfortranarray(np.column_stack([cols[c] for c in order[1:]])) if len(cols) > 1 else None
+            out = np.empty((1, 8))
+            check(_lib.load().npdrb_unireg(_lib.context(0).handle, dptr(X), yv.size, 1, dptr(f64(yv)), dptr(Cm), len(cols) - 1,
+                                           REG[fam], dptr(out)))
+            beta, stat, beta0, stat0, df, r2dev, iters, flags = out[0]
+            assert K.printed_close(beta, coef_p[1 + lead]), (name, lead, beta)
+            assert K.printed_close(beta0, coef_p[0]), (name, beta0)
+            assert K.printed_close(beta / stat, se_p[1 + lead]) and K.printed_close(beta0 / stat0, se_p[0]), (name, "se")
+            assert df == extra["df"] and flags == 0
+            if fam == "lm":
+                assert K.printed_close(r2dev, extra["r_squared"])
+            else:
+                assert K.printed_close(r2dev, extra["deviance"]) and iters == extra["iters"], (name, r2dev, iters)

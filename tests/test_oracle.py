@@ -6,7 +6,9 @@ import numpy as np
 import pytest
 from scipy.spatial.distance import cdist
 
-from conftest import GOLDEN, load_case, oracle_run
+import sys
+
+from conftest import GOLDEN, ROOT, load_case, oracle_run
 
 
 # ---- the reference's only pinned vectors: tests/testthat/test-nearestNeighbors.R:1-12 ----
@@ -213,3 +215,23 @@ def test_rectangular_distances_and_neighbors2_against_numpy(oracle):
     X2[0] = X1[5]
     nn, _, _ = oracle.nearest_neighbors2(X1, X2, "relieff")
     assert len(nn[0]) == k and 6 not in nn[0]
+
+
+def test_lm_glm_restatement_reproduces_published_r_output(oracle):
+    """External pin: summary(lm) / summary(glm(binomial)) outputs that R prints for datasets::mtcars
+    (tests/golden/r_published_kats.py) -- coefficients, standard errors, R^2 / residual deviance, residual df and the
+    number of Fisher scoring iterations."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import r_published_kats as K
+    for name, (yv, cols, fam, coef_p, se_p, extra) in K.KATS.items():
+        design = np.asfortranarray(np.column_stack([np.ones(yv.size)] + cols))
+        coef, se, info = (oracle.lm if fam == "lm" else oracle.glm_binomial)(design, yv)
+        for v, pr in zip(coef, coef_p):
+            assert K.printed_close(v, pr), (name, "coef", v, pr)
+        for v, pr in zip(se, se_p):
+            assert K.printed_close(v, pr), (name, "se", v, pr)
+        assert info["df_resid"] == extra["df"]
+        if fam == "lm":
+            assert K.printed_close(info["r_squared"], extra["r_squared"]), name
+        else:
+            assert K.printed_close(info["deviance"], extra["deviance"]) and info["iters"] == extra["iters"] and info["converged"], name
