@@ -25,14 +25,6 @@ struct nb_tables {
 
 #define NB_TABLES_STATIC_INIT { NB_EXP_TABLE_INIT, NB_LOG_RC_TABLE_INIT, NB_LOG_LRC_TABLE_INIT, NB_LOG_ELN2_TABLE_INIT }
 
-struct nb_tables256 {
-    double exp_t[256];     // 2^(j/256)
-    double log_rc[256];    // ~1/centre of mantissa bin i of width 1/256 (24 significant bits)
-    double log_lrc[256];   // -log(log_rc[i])
-    double log_eln2[64];   // e * ln2
-};
-#define NB_TABLES256_STATIC_INIT { NB_EXP256_TABLE_INIT, NB_LOG256_RC_TABLE_INIT, NB_LOG256_LRC_TABLE_INIT, NB_LOG_ELN2_TABLE_INIT }
-
 NB_HD uint64_t nb_d2u(double d) {
 #if defined(__CUDA_ARCH__)
     return (uint64_t)__double_as_longlong(d);
@@ -91,126 +83,12 @@ NB_HD double nb_log_ge1(double u, const double* __restrict__ log_rc, const doubl
     return (log_eln2[e & 63] + log_lrc[i]) + p;   // & 63: a NaN/Inf argument must not index out of the table
 }
 
-// ---- trimmed variants used by the IRLS pass kernel --------------------------------------------
-// exp: the r^5/120 term is dropped (relative error <= 4.2e-14); log: the f^6/6 term is dropped
-// (absolute error <= 6.5e-16).  Both are far below what a 1e-8 deviance criterion and a 1e-6 parity bar
-// can see, and each saves one FP64 instruction per attribute x pair x iteration on the binding pipe.
-// The device kernel evaluates the same recurrences with its coefficients in constant memory.
-NB_HD double nb_exp_fast(double eta, const double* __restrict__ exp_t) {
-    const double magic = 6755399441055744.0;
-    double t = nb_fma(eta, NB_64_OVER_LN2, magic);
-    int32_t ki = (int32_t)(uint32_t)nb_d2u(t);
-    double kf = t - magic;
-    double r = nb_fma(kf, -NB_LN2_64_HI, eta);
-    r = nb_fma(kf, -NB_LN2_64_LO, r);
-    double r2 = r * r;
-    double q = nb_fma(r, 1.0 / 24.0, 1.0 / 6.0);
-    q = nb_fma(q, r, 0.5);
-    q = nb_fma(q, r2, r);
-    double tj = exp_t[ki & 63];
-    double v = nb_fma(tj, q, tj);
-    uint64_t b = nb_d2u(v);
-    uint32_t hi = (uint32_t)(b >> 32) + ((uint32_t)ki << 14 & 0xFFF00000u);   // += (ki >> 6) << 20 on the high word
-    return nb_u2d(((uint64_t)hi << 32) | (b & 0xFFFFFFFFull));
-}
-
-NB_HD double nb_log_ge1_fast(double u, const double* __restrict__ log_rc, const double* __restrict__ log_lrc,
-                             const double* __restrict__ log_eln2) {
-    uint64_t b = nb_d2u(u);
-    int32_t e = (int32_t)(b >> 52) - 1023;
-    int32_t i = (int32_t)((b >> 45) & 127);
-    double m = nb_u2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
-    double f = nb_fma(m, log_rc[i], -1.0);
-    double p = nb_fma(f, 0.2, -0.25);
-    p = nb_fma(p, f, 1.0 / 3.0);
-    p = nb_fma(p, f, -0.5);
-    double f2 = f * f;
-    p = nb_fma(p, f2, f);
-    return (log_eln2[e & 63] + log_lrc[i]) + p;
-}
-
-// ---- 256-entry variants (what pass2_kernel<IRLS_FULL> evaluates) -------------------------------
-// The linear predictor is carried in units of ln2/256 (sv = eta * 256/ln2): k = rint(sv), frac = sv - k is exact,
-// exp(eta) = 2^(k/256) * exp(frac * ln2/256) with a degree-3 polynomial (dropped term <= (ln2/512)^4/24 = 1.4e-13
-// relative); log(u), u >= 1: 256 mantissa bins, degree-4 log1p (dropped term <= 2^-45/5 = 5.7e-15 absolute).
-NB_HD double nb_exp_fast256(double sv, const double* __restrict__ exp_t) {
-    const double magic = 6755399441055744.0;
-    const double c = NB_LN2_256;
-    double tt = sv + magic;
-    int32_t ki = (int32_t)(uint32_t)nb_d2u(tt);
-    double kf = tt - magic;
-    double fr = sv - kf;
-    double qq = nb_fma(fr, c * c * c / 6.0, c * c / 2.0);
-    qq = nb_fma(qq, fr, c);
-    qq = qq * fr;
-    double tj = exp_t[ki & 255];
-    double v = nb_fma(tj, qq, tj);
-    uint64_t b = nb_d2u(v);
-    uint32_t hi = (uint32_t)(b >> 32) + (((uint32_t)ki & 0xFFFFFF00u) << 12);    // += (ki >> 8) << 20
-    return nb_u2d(((uint64_t)hi << 32) | (b & 0xFFFFFFFFull));
-}
-
-NB_HD double nb_log_ge1_fast256(double u, const double* __restrict__ log_rc, const double* __restrict__ log_lrc,
-                                const double* __restrict__ log_eln2) {
-    uint64_t b = nb_d2u(u);
-    int32_t e = (int32_t)(b >> 52) - 1023;
-    int32_t i = (int32_t)((b >> 44) & 255);
-    double m = nb_u2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
-    double f = nb_fma(m, log_rc[i], -1.0);
-    double p = nb_fma(f, -0.25, 1.0 / 3.0);
-    p = nb_fma(p, f, -0.5);
-    p = nb_fma(p, f * f, f);
-    return (log_eln2[e & 63] + log_lrc[i]) + p;
-}
-
-
-// ---- v3 variants (what pass2_kernel<IRLS_FULL> evaluates now) ---------------------------------
-// One FP64 instruction less on each side of the reciprocal:
-//  * u = 1 + exp(eta) directly: the polynomial returns exp(frac*ln2/256) (not exp - 1), the 2^(k>>8) scale is applied to
-//    the table value (integer add on its high word) and one FMA forms 1 + T_j * poly.  Relative error of the exp part:
-//    dropped term (ln2/512)^4/24 = 1.4e-13 plus one extra rounding (1.1e-16).
-//  * log(u), u >= 1: 512 mantissa bins (|f| <= 2^-10 + 2^-24), degree-3 log1p (dropped term <= f^4/4 = 2.3e-13
-//    absolute, mean 4.6e-14), the table term is folded into the final FMA and the exponent e is returned as an integer:
-//    the kernel sums e in an integer register and multiplies by ln2 once per work item (no e*ln2 table, no FP64 add).
-struct nb_tables512 {
-    double exp_t[256];     // 2^(j/256)
-    double log_rc[512];    // ~1/centre of mantissa bin i of width 1/512 (24 significant bits)
-    double log_lrc[512];   // -log(log_rc[i])
-};
-#define NB_TABLES512_STATIC_INIT { NB_EXP256_TABLE_INIT, NB_LOG512_RC_TABLE_INIT, NB_LOG512_LRC_TABLE_INIT }
-
-NB_HD double nb_one_plus_exp256(double sv, const double* __restrict__ exp_t) {      // sv = eta * 256/ln2, |eta| < 30
-    const double magic = 6755399441055744.0;
-    const double c = NB_LN2_256;
-    double tt = sv + magic;
-    int32_t ki = (int32_t)(uint32_t)nb_d2u(tt);
-    double kf = tt - magic;
-    double fr = sv - kf;
-    double qq = nb_fma(fr, c * c * c / 6.0, c * c / 2.0);
-    qq = nb_fma(qq, fr, c);
-    qq = nb_fma(qq, fr, 1.0);
-    uint32_t j = (uint32_t)ki & 255u;
-    uint64_t b = nb_d2u(exp_t[j]);
-    uint32_t hi = ((uint32_t)(b >> 32) - j * 4096u) + (uint32_t)ki * 4096u;      // the kernel's table image holds the first term
-    double tjs = nb_u2d(((uint64_t)hi << 32) | (b & 0xFFFFFFFFull));
-    return nb_fma(tjs, qq, 1.0);
-}
-
-NB_HD double nb_log_mant512(double u, const double* __restrict__ log_rc, const double* __restrict__ log_lrc, int32_t* e) {
-    uint64_t b = nb_d2u(u);
-    *e = (int32_t)(b >> 52) - 1023;
-    int32_t i = (int32_t)((b >> 43) & 511);
-    double m = nb_u2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
-    double f = nb_fma(m, log_rc[i], -1.0);
-    double s = f + log_lrc[i];
-    double p = nb_fma(f, 1.0 / 3.0, -0.5);
-    return nb_fma(p, f * f, s);                               // log(u) = e*ln2 + this
-}
-
-// ---- v4 exp (what pass2_kernel<IRLS_FULL> evaluates now): 1024 table entries, degree-2 polynomial ----------------
+// ---- exp of the v2 IRLS pass kernel (pass2_kernel<IRLS_FULL>): 1024 table entries, degree-2 polynomial --------------
+// (the v1 kernel, used for more than two covariates, evaluates nb_exp / nb_log_ge1 above)
 // eta in units of ln2/1024: k = rint(s), frac = s - k (exact, |frac| <= 1/2), x = frac * ln2/1024, |x| <= h = ln2/2048.
 // exp(x) ~ 1 + (1 + h^2/8) x + x^2/2: the linear coefficient absorbs the Chebyshev-economised cubic term, leaving
-// max |error| = h^3/24 + h^4/192 = 1.6e-12 relative -- one FMA less per evaluation than the degree-3 / 256-entry form.
+// max |error| = h^3/24 + h^4/192 = 1.6e-12 relative -- one FMA less per evaluation than a degree-3 / 256-entry form.
+// The kernel needs no per-record log: the deviance is accumulated as a running product (regress.cu: v2_tail / v2_renorm).
 struct nb_tables1024 { double exp_t[1024]; };
 #define NB_TABLES1024_STATIC_INIT { NB_EXP1024_TABLE_INIT }
 #define NB_EXP2_C1 (NB_LN2_1024 * (1.0 + (NB_LN2_1024 * 0.5) * (NB_LN2_1024 * 0.5) / 8.0))

@@ -403,18 +403,18 @@ pass_kernel(PassArgs P) {
 }
 
 // ------------------------------------------------------------------ IRLS pass kernel, v2 (q <= 2)
-// Same arithmetic as pass_kernel<MODE_IRLS_FULL>, restructured for the FP64 issue port (ncu on v1: 94 warp
-// instructions per evaluation, only 38 of them FP64; 68 % issue-active, "wait" = dependency stalls on top):
-//   * each thread owns TWO adjacent attributes: one LDS.128 per instance row, one record fetch and one
-//     covariate fetch per pair for both, and two independent dependency chains the scheduler can interleave
-//     (the rare |eta| > 30 clamp is a single warp-level branch around the exp only, so the chains stay straight-line);
-//   * records are ordered hits-then-misses inside each tile (tile_mid), so y is a compile-time constant of the
-//     loop: no select, and w*z = w*eta - mu (hit) or w*eta + (1 - mu) (miss) costs one FMA;
-//   * record fields are pre-shifted into byte offsets when the chunk is staged;
-//   * polynomial coefficients come from constant memory (constant-bank operands, no IMAD.MOV/UMOV);
-//   * table indices are formed directly as byte offsets from the high word (2 integer ops each);
-//   * reciprocal: rcp.approx (2^-23) + ONE Newton step (2^-46 ~ 1.4e-14); exp / log are the trimmed
-//     nb_exp_fast / nb_log_ge1_fast recurrences (dmath.cuh carries the error budget and the host test).
+// Same statistics as pass_kernel<MODE_IRLS_FULL>, restructured for the FP64 issue port (an FP64 warp
+// instruction holds the dispatch port for 2 cycles, so cycles per evaluation ~ 2 * FP64 + other instructions):
+//   * each thread owns TWO adjacent attributes: one LDS.128 per instance row, one record fetch and one covariate fetch
+//     per pair for both; two records are in flight, i.e. four independent exp -> reciprocal chains per thread;
+//   * records are ordered hits-then-misses inside each tile and the accumulation is outcome independent: the score is
+//     X'(1 - mu) over ALL records plus the hit/miss moments of the closed-form first pass (no per-record select);
+//   * record fields are pre-shifted into byte offsets when the chunk is staged; record pairs come in one 8-byte load;
+//   * constants come from constant memory (constant-bank operands, no IMAD.MOV/UMOV);
+//   * u = 1 + exp(eta) in 7 FP64 instructions (table + economised degree-2 polynomial, below), reciprocal = rcp.approx +
+//     ONE Newton step (1.4e-14), weight = (1-mu) - (1-mu)^2, deviance = running product of u (v2_tail / v2_renorm);
+//   * R's |eta| > 30 clamps are ruled out per work item from bounds on |x.beta| (may_clamp), so the common path carries no
+//     per-record check.
 // The v2 kernel carries the linear predictor in units of ln2/1024: s = eta * 1024/ln2 (the coefficients are pre-scaled
 // when they are loaded), so k = rint(s) and the reduced argument frac = s - k (exact) need no multiplication, and
 // exp(eta) = 2^(k/1024) * exp(frac * ln2/1024) with an economised degree-2 polynomial (1.6e-12 relative; 1024 table
@@ -425,7 +425,7 @@ pass_kernel(PassArgs P) {
 __constant__ double c_k[10] = {
     6755399441055744.0,                                                  // 0     1.5 * 2^52 (round-to-integer magic)
     0.0, NB_EXP2_C2, NB_EXP2_C1,                                         // 1..3  exp polynomial in frac (degree 2)
-    NB_LN2, 1.0 / 3.0, -0.5,                                             // 4..6  ln2; (unused)
+    NB_LN2, 0.0, 0.0,                                                    // 4     ln2 (5, 6 unused)
     NB_LOG_INV_EPS * NB_1024_OVER_LN2,                                   // 7     log(1/DBL_EPSILON) in units of ln2/1024
     30.0 * NB_1024_OVER_LN2,                                             // 8     clamp threshold in the same units
     NB_1024_OVER_LN2                                                     // 9
