@@ -416,7 +416,7 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        N_s, p_s = (1500, 256) if wl_name != "small" else (512, 128)
+        N_s, p_s = (2000, 512) if wl_name != "small" else (512, 128)      # ~10 s of host work on the box's 16 cores
         ev, dt, thr, M_s = cpu_oracle_sample(wl_name, N_s, p_s, q)
         cpu_baseline = {"value": ev / dt, "unit": "evals/s", "cores": thr, "kind": "port", "seconds": dt,
                         "sample": f"first {N_s} instances x {p_s} attributes of the {wl_name} recipe (M={M_s} pairs), all stages, "
