@@ -124,6 +124,12 @@ class BalancedOracleEngine(OracleEngine):
             j0, j1 = J * T, min((J + 1) * T, N)
             self.block[i0:i1, j0:j1] = buf[t, :i1 - i0, :j1 - j0]
 
+    def neighbors_block(self, row0, nrows, nbd_method, nbd_metric, sd_frac, k, hitmiss=False):
+        # inside npdr_sharded(): the exchanged block must be this rank's rows of the full matrix before it is used
+        assert self.block is not None and (self.r0, self.r1) == (row0, row0 + nrows)
+        assert np.array_equal(self.block, self._dist(nbd_metric)[row0:row0 + nrows, :])
+        return super().neighbors_block(row0, nrows, nbd_method, nbd_metric, sd_frac, k, hitmiss)
+
 
 def _worker_balanced(rank, world, port, N, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -171,14 +177,14 @@ def _case(seed=0):
     return X, y, C
 
 
-def _worker(rank, world, port, method, q, hitmiss=False):
+def _worker(rank, world, port, method, q, hitmiss=False, balanced=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import sys
     sys.path.insert(0, ROOT)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from npdr_b200.distributed import npdr_sharded
     X, y, C = _case()
-    eng = OracleEngine(X, y, C)
+    eng = (BalancedOracleEngine if balanced else OracleEngine)(X, y, C)
     stats, info = npdr_sharded(eng, X.shape[0], X.shape[1], "binomial", "numeric-abs", method, "manhattan", 0, 0.5,
                                ("match-mismatch", "numeric-abs"), separate_hitmiss_nbds=hitmiss)
     if rank == 0:
@@ -192,14 +198,15 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("world,method,hitmiss", [(2, "multisurf", False), (3, "multisurf", False), (2, "surf", False),
-                                                  (2, "relieff", False), (2, "multisurf", True)])
-def test_sharded_equals_unsharded(world, method, hitmiss):
+@pytest.mark.parametrize("world,method,hitmiss,balanced", [(2, "multisurf", False, False), (3, "multisurf", False, True),
+                                                           (2, "surf", False, True), (2, "relieff", False, False),
+                                                           (2, "multisurf", True, True)])
+def test_sharded_equals_unsharded(world, method, hitmiss, balanced):
     from oracle import oracle as O
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, method, q, hitmiss)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, method, q, hitmiss, balanced)) for r in range(world)]
     for p_ in procs:
         p_.start()
     stats, info = q.get(timeout=240)
