@@ -155,3 +155,18 @@ def test_r_shim_compiles_against_api_stub():
     registered = set(re.findall(r'\{"(C_npdrb_\w+)"', shim))
     called = set(re.findall(r'\.Call\("(C_npdrb_\w+)"', wrapper))
     assert called <= registered and len(registered) >= 8, (called - registered)
+
+
+def test_c_caller_links_and_fails_loudly_without_gpu():
+    """examples/npdr_c_abi.c: a plain C program links against the shared library through include/npdr_b200.h alone and,
+    on a machine without a B200, stops with NPDRB_ENODEVICE (exit 2) -- on the GPU box it runs the path (exit 0)."""
+    import subprocess
+    exe = "/tmp/npdr_c_abi_test"
+    lib_dir = os.path.join(ROOT, "npdr_b200")
+    subprocess.check_call(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "npdr_c_abi.c"),
+                           "-L", lib_dir, "-lnpdr_b200", f"-Wl,-rpath,{lib_dir}", "-lm", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if gpu_available():
+        assert r.returncode == 0 and "pairs" in r.stdout, r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
