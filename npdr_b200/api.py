@@ -11,6 +11,7 @@ the p-value / ordering / p.adjust residue in `rstats` (it stays in R in the R de
   nearestNeighborsSeparateHitMiss   R/nearestNeighbors.R:318-551
   npdrDistances2     R/npdrLearner.R:323-339
   nearestNeighbors2  R/npdrLearner.R:378-482
+  npdrLearner        R/npdrLearner.R:204-292 (host-side vote on nearestNeighbors2)
   uniqueNeighbors    R/nearestNeighbors.R:572-583
   knnVec             R/nearestNeighbors.R:603-607
   knnSURF            R/utils.R:12-18
@@ -156,6 +157,72 @@ def nearestNeighbors2(attr_mat1, attr_mat2, nbd_method="multisurf", nbd_metric="
     nn = _lib.take_int_array(idx, M.value)
     out = [nn[offsets[i]:offsets[i + 1]] for i in range(m2)]
     return (out, {"radius": radius, "offsets": offsets}) if return_info else out
+
+
+def _r_levels(values):
+    """levels(as.factor(x)): sorted unique values as strings -- numbers sort numerically, everything else as strings."""
+    vals = list(dict.fromkeys(np.asarray(values).tolist()))
+    try:
+        return [str(int(v)) if float(v) == int(float(v)) else repr(float(v)) for v in sorted(vals, key=float)]
+    except (TypeError, ValueError):
+        return sorted(str(v) for v in vals)
+
+
+def _learner_codes(values):
+    """R/npdrLearner.R:208-229 -- class levels that look numeric are used as numbers, other levels become 1, 2, ... in
+    level order.  -> (codes float array, levels as strings, numeric_looking)."""
+    lv = _r_levels(values)
+    as_str = [str(int(v)) if isinstance(v, (int, np.integer)) or (isinstance(v, (float, np.floating)) and float(v) == int(v))
+              else str(v) for v in np.asarray(values).tolist()]
+    try:
+        num = [float(l) for l in lv]
+        lut = dict(zip(lv, num))
+        return np.array([lut[a] if a in lut else float(a) for a in as_str]), lv, True
+    except ValueError:
+        lut = {l: float(i + 1) for i, l in enumerate(lv)}
+        return np.array([lut[a] for a in as_str]), lv, False
+
+
+def _knn_vote(train_codes, neighbor_lists):
+    """R/npdrLearner.R:267-276 -- table(train.pheno[nbs]) %>% which.max %>% names %>% as.numeric: the most frequent class
+    among the neighbours, ties going to the smallest class code (table() sorts its names, which.max takes the first
+    maximum).  An empty neighbourhood predicts NaN (the reference's sapply() would return a ragged list there)."""
+    pred = np.full(len(neighbor_lists), np.nan)
+    for i, nbs in enumerate(neighbor_lists):
+        if len(nbs) == 0:
+            continue
+        vals, counts = np.unique(train_codes[np.asarray(nbs, dtype=np.int64) - 1], return_counts=True)
+        pred[i] = vals[np.argmax(counts)]
+    return pred
+
+
+def npdrLearner(train_outcome, train_data, test_outcome, test_data, nbd_method="relieff", nbd_metric="manhattan",
+                msurf_sd_frac=0.5, dopar_nn=False, knn=0, device=0):
+    """R/npdrLearner.R:204-292 -- nearest-neighbour classifier on NPDR neighbourhoods: every test instance takes the
+    majority class of its nearestNeighbors2() neighbours in the training set (GPU), the vote and the bookkeeping are host
+    side.  Returns the reference's list: train_nbs_of_test, actual, confusion (predicted x actual counts), prediction,
+    accuracy.  `prediction` is mapped back to the original labels exactly as the reference's replace() loop does it
+    (codes equal to a level INDEX are replaced, R/npdrLearner.R:279-283 -- with numeric-looking levels such as -1 / 1 that
+    relabels class 1 as the first level; `prediction.codes` holds the untouched numeric prediction).  With separate
+    outcome vectors the reference stops at that loop (its level table is undefined); here the codes are returned."""
+    Xtr, _, ptr = _split_outcome(train_outcome, train_data)
+    Xte, _, pte = _split_outcome(test_outcome, test_data)
+    named = np.ndim(train_outcome) == 0 and np.ndim(test_outcome) == 0
+    tr_codes, _, _ = _learner_codes(ptr) if np.ndim(train_outcome) == 0 else (np.asarray(ptr, dtype=np.float64), None, True)
+    te_codes, te_levels, _ = _learner_codes(pte) if np.ndim(test_outcome) == 0 else (np.asarray(pte, dtype=np.float64), None, True)
+    nbs = nearestNeighbors2(Xtr, Xte, nbd_method, nbd_metric, None, msurf_sd_frac, dopar_nn, knn, device)
+    codes = _knn_vote(tr_codes, nbs)
+    acc = float(np.sum(codes == te_codes) / te_codes.size)
+    actual = [str(v) for v in np.asarray(pte).tolist()] if named else [repr(v) for v in te_codes.tolist()]
+    pred = [("NA" if np.isnan(c) else (str(int(c)) if c == int(c) else repr(c))) for c in codes]
+    if named:
+        for i, lev in enumerate(te_levels, start=1):             # replace(test.predict, test.predict %in% i, org_test_levels[i])
+            pred = [lev if (q_ == str(i)) else q_ for q_ in pred]
+    conf = None
+    if pd is not None:
+        conf = pd.crosstab(pd.Series(pred, name="Test Predicted"), pd.Series(actual, name="Test Actual"))
+    return {"train_nbs_of_test": nbs, "actual": actual, "confusion": conf, "prediction": pred, "prediction.codes": codes,
+            "accuracy": acc}
 
 
 def _nearest(X, nbd_method, nbd_metric, sd_vec, sd_frac, k, unique, device):

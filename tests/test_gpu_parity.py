@@ -775,3 +775,27 @@ def test_gpu_solvers_reproduce_published_r_output(nb, oracle):
                 assert K.printed_close(r2dev, extra["r_squared"])
             else:
                 assert K.printed_close(r2dev, extra["deviance"]) and iters == extra["iters"], (name, r2dev, iters)
+
+
+def test_npdr_learner(nb, oracle):
+    """npdrLearner (R/npdrLearner.R:204-292): GPU neighbourhoods (nearestNeighbors2) + host-side majority vote."""
+    import pandas as pd
+    rng = np.random.default_rng(8)
+    def make(n):
+        y = np.where(rng.random(n) < 0.5, 1, -1)
+        X = rng.normal(size=(n, 20)); X[:, :4] += 0.9 * y[:, None]
+        df = pd.DataFrame(X, columns=[f"v{i}" for i in range(20)]); df["class"] = y
+        return df, X, y
+    tr, Xtr, ytr = make(150)
+    te, Xte, yte = make(60)
+    for method in ("relieff", "multisurf"):
+        out = nb.npdrLearner("class", tr, "class", te, nbd_method=method)
+        exp_nbs, _, _ = oracle.nearest_neighbors2(Xtr, Xte, method)
+        assert all(np.array_equal(a, b) for a, b in zip(out["train_nbs_of_test"], exp_nbs))
+        exp_pred = np.array([(-1.0 if (ytr[n - 1] == -1).sum() >= (ytr[n - 1] == 1).sum() else 1.0) if len(n) else np.nan for n in exp_nbs])
+        assert np.array_equal(out["prediction.codes"], exp_pred, equal_nan=True)
+        assert out["accuracy"] == np.mean(exp_pred == yte) and out["accuracy"] > 0.8
+        assert out["actual"] == [str(v) for v in yte] and out["confusion"].to_numpy().sum() == 60
+    # separate outcome vectors (the reference stops in its relabelling loop; here the codes come back)
+    out2 = nb.npdrLearner(ytr.astype(float), Xtr, yte.astype(float), Xte, nbd_method="relieff")
+    assert out2["accuracy"] == nb.npdrLearner("class", tr, "class", te)["accuracy"]

@@ -170,3 +170,16 @@ def test_c_caller_links_and_fails_loudly_without_gpu():
         assert r.returncode == 0 and "pairs" in r.stdout, r.stderr
     else:
         assert r.returncode == 2 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_npdr_learner_vote_and_level_coding():
+    """Host-side logic of npdrLearner (R/npdrLearner.R:208-229, 267-283): level coding and the majority vote."""
+    from npdr_b200 import api
+    codes, lv, numeric = api._learner_codes(np.array([1.0, -1.0, 1.0, -1.0]))
+    assert lv == ["-1", "1"] and numeric and codes.tolist() == [1.0, -1.0, 1.0, -1.0]
+    codes, lv, numeric = api._learner_codes(np.array(["MDD", "HC", "HC"]))
+    assert lv == ["HC", "MDD"] and not numeric and codes.tolist() == [2.0, 1.0, 1.0]          # levels become 1, 2 in level order
+    assert api._r_levels(np.array([10, 9, 9])) == ["9", "10"]                                  # numeric, not lexical
+    train = np.array([1.0, -1.0, 1.0, -1.0, -1.0])
+    pred = api._knn_vote(train, [np.array([1, 2, 3]), np.array([1, 2]), np.array([2, 4, 5, 1]), np.array([], dtype=np.int32)])
+    assert pred[:3].tolist() == [1.0, -1.0, -1.0] and np.isnan(pred[3])                         # tie -> smallest code (which.max of table())
