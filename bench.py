@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- NPDR hot-path benchmark (BASELINE.json metric: attr x neighbor-pair GLM evals/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg5|small] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg5|small] [--impl ours|reference] [--no-target]
 
 One "step" = one full pass of the hot path (distances -> multiSURF neighbour pairs -> per-attribute binomial
 IRLS) over one synthetic batch.  Workloads (BASELINE.json configs; synthetic stand-ins, seed 1618):
@@ -13,10 +13,16 @@ Sharding (N > 1, one process per GPU under torchrun): row blocks for distance+ne
 distance matrix swapped in one NCCL all-to-all), one all-gather of the pair segments, attribute columns for the
 regression, statistics gathered to rank 0.
 
-`value` is p*M / step time with inputs resident in HBM; `e2e` is the same metric through the host-buffer API
-(H2D of X, y inside the timed region, D2H of the statistics).  `roofline` describes the dominant kernel
-(the binomial IRLS pass kernel, FP64-issue bound) with CUDA-event launch durations; `cpu_baseline` /
-`--impl reference` time the CPU oracle (a restatement of the reference R algorithm; R itself cannot be installed).
+`value` is p*M / step time with inputs resident in HBM.  `e2e` is the same metric from PAGEABLE host buffers (what R
+holds) to the statistics back on the host: with one GPU it is ONE call of the C-ABI entry point the R shim binds,
+`npdrb_npdr`; with N GPUs under torchrun every rank uploads its attribute columns through the library's pinned staging
+ring and the path runs sharded over NCCL, and `e2e_inproc` is ONE call of `npdrb_npdr_multi` (one host process, one
+thread per device -- the R session's multi-GPU entry point) made by rank 0 while the other ranks idle.
+`multi_gpu_check` (N > 1) compares the N-rank result with a one-GPU run on rank 0: pair-list hash and the statistics of
+512 attributes.  `roofline` describes the dominant kernel (the binomial IRLS pass kernel, FP64-issue bound) with
+CUDA-event launch durations; `cpu_baseline` / `--impl reference` time the CPU oracle (a restatement of the reference R
+algorithm; R itself cannot be installed).  `target` is the same measurement on BASELINE's north-star configuration
+(cfg5: 20,000 x 50,000, q = 2, STRONG scaling: total work fixed) for 1 warm-up + 1 step at the same N.
 """
 import argparse
 import json
@@ -145,11 +151,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_sample(wl_name, N_s, p_s, q):
+def cpu_oracle_sample(wl_name, N_s, p_s, q, threads=None):
     """One pass of the hot path through the CPU oracle on a bounded sample (first N_s instances x p_s attributes of
     the same synthetic recipe, numpy generator).  -> (evals, seconds, threads, M)."""
     from oracle import oracle as O
     O.build()
+    if threads:
+        O.set_num_threads(threads)          # torchrun exports OMP_NUM_THREADS=1: ask for the host's cores explicitly
     rng = np.random.default_rng(SEED)
     f = rng.normal(size=(N_s, 1)); g = rng.normal(size=(N_s, 1))
     y = (rng.permutation(N_s) < N_s // 2).astype(float)
@@ -174,31 +182,358 @@ def cpu_oracle_sample(wl_name, N_s, p_s, q):
     return float(p_s) * ri.size, dt, O.num_threads(), int(ri.size)
 
 
+CPU_SAMPLE = {"cfg4": (2000, 512), "cfg5": (2000, 512), "small": (512, 128)}      # one sample for cpu_baseline AND --impl reference
+
+
+def workload_config(wl_name, world):
+    """The `config` object: static descriptors only, so the reference arm prints the identical object."""
+    wl = WORKLOADS[wl_name]
+    N, q = wl["N"], wl["q"]
+    p = wl["p_total"] or wl["p_per_gpu"] * world
+    return {"workload": wl_name, "description": wl["desc"], "N": N, "p": p, "q": q, "regression": "binomial",
+            "nbd": "multisurf", "metric": "manhattan", "seed": SEED,
+            "parallelism": f"rows/{world} (distance+neighbours" + (", symmetric halves swapped in one all-to-all" if world > 1 else "")
+                           + f") -> all-gather pairs -> attrs/{world} (regression)",
+            "l2": "inputs (X = %.0f MB per GPU) exceed the 126 MB L2; no flush needed" % (N * p * 8 / 1e6)}
+
+
 def run_reference(args, wl_name, wl):
-    """--impl reference: the CPU restatement of the reference path on the host cores, bounded sample per step."""
+    """--impl reference: the CPU restatement of the reference path on ALL host cores, bounded sample per step (the same
+    sample as the GPU arm's cpu_baseline leg).  Under torchrun rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    N_s, p_s = (1000, 256) if wl_name != "small" else (512, 128)
-    vals, secs, M = [], [], 0
+    N_s, p_s = CPU_SAMPLE[wl_name]
+    cores = os.cpu_count() or 1
+    vals, secs, M, thr = [], [], 0, 1
     for it in range(args.warmup + args.steps):
-        ev, dt, thr, M = cpu_oracle_sample(wl_name, N_s, p_s, wl["q"])
+        ev, dt, thr, M = cpu_oracle_sample(wl_name, N_s, p_s, wl["q"], threads=cores)
         if it >= args.warmup:
             vals.append(ev / dt); secs.append(dt)
     value = float(np.sum([v * s for v, s in zip(vals, secs)]) / np.sum(secs))
     sample = (f"first {N_s} instances x {p_s} attributes of the {wl_name} recipe (M={M} pairs), all stages, "
-              f"OpenMP over attributes (the reference's dopar.reg analogue)")
+              f"OpenMP over attributes (the reference's dopar.reg analogue), {thr} threads")
     line = {"impl": "reference", "metric": "npdr_attr_x_pair_glm_evals_per_s", "value": value, "unit": "evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
             "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "description": wl["desc"], "regression": "binomial", "nbd": "multisurf",
-                       "metric": "manhattan", "covariates": wl["q"]},
+            "config": workload_config(wl_name, args.gpus),
             "cpu_baseline": {"value": value, "unit": "evals/s", "cores": thr, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "CPU oracle = C restatement of the reference R algorithm (R cannot be installed here; the reference "
-                    "itself cannot allocate its dense M x p matrix at this workload, R/npdr.R:313)"}
+            "note": "CPU oracle = C restatement of the reference R algorithm (R cannot be installed here or on the GPU box; the "
+                    "reference itself cannot allocate its dense M x p matrix at this workload, R/npdr.R:313); each step is the "
+                    "bounded sample above, not the full workload"}
     print(json.dumps(line))
+
+
+class Bench:
+    """Everything one workload needs on this rank: synthetic data on the device, host copies for the end-to-end arms."""
+
+    def __init__(self, args, wl_name, rank, local_rank, world, device, ctx):
+        import torch
+        self.torch = torch
+        self.args, self.wl_name, self.wl = args, wl_name, WORKLOADS[wl_name]
+        self.rank, self.local_rank, self.world, self.device, self.ctx = rank, local_rank, world, device, ctx
+        self.data = make_data(self.wl, world, device)
+        self.N, self.p, self.q = self.data["N"], self.data["p"], self.data["q"]
+        self.cdt = self.data["covar_diff_type"]
+        torch.cuda.synchronize()
+        self._seq = 0
+
+    # ---- helpers
+    def barrier(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup):
+        import torch.distributed as dist
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        l0 = self.ctx.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.device)
+        launches = torch.tensor([self.ctx.launch_count() - l0], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        return float(ms.item()), int(launches.item()), out
+
+    # ---- resident arm (`value`)
+    def step_resident(self, pair_hash=False):
+        from npdr_b200.distributed import GpuEngine, npdr_sharded
+        d = self.data
+        eng = GpuEngine(device_index=self.local_rank, dX=d["dX"], ldx=d["ldx"], dy=d["dy"], dC=d["dC"], N=self.N, p=self.p, q=self.q)
+        stats, info = npdr_sharded(eng, self.N, self.p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, self.cdt,
+                                   pair_hash=pair_hash)
+        km = eng.session.kernel_ms(); sm = eng.session.stage_ms(); passes = eng.session.irls_passes
+        eng.close()
+        return stats, info, km, sm, passes
+
+    # ---- end-to-end arms: PAGEABLE host buffers in, statistics out
+    def prepare_host(self, inproc):
+        """Pageable numpy copies (what an R session holds): one GPU -> the whole matrix; torchrun -> this rank's attribute
+        columns; rank 0 additionally the whole matrix for the in-process multi-GPU call."""
+        torch, d, N, p, world, rank = self.torch, self.data, self.N, self.p, self.world, self.rank
+        self.hX = self.hXs = self.hy = self.hC = None
+        self.shard = world > 1 and p % world == 0
+        if world == 1 or (inproc and rank == 0):
+            self.hX = d["dX"][:, :N].cpu().numpy().T                   # (N, p) Fortran-ordered view of a pageable buffer
+        if world > 1:
+            if self.shard:
+                na = p // world
+                self.hXs = d["dX"][rank * na:(rank + 1) * na, :N].cpu().numpy().T
+            elif rank == 0 and self.hX is None:
+                self.hX = d["dX"][:, :N].cpu().numpy().T
+            self.e2e_dev = dict(dX=torch.zeros((p, d["ldx"]), dtype=torch.float64, device=self.device),
+                                dy=torch.zeros(N, dtype=torch.float64, device=self.device),
+                                dC=torch.zeros((self.q, N), dtype=torch.float64, device=self.device) if self.q else None)
+        if rank == 0 or world == 1:
+            self.hy = d["dy"].cpu().numpy()
+            self.hC = np.asfortranarray(d["dC"].cpu().numpy().T) if self.q else None
+
+    def step_e2e(self):
+        import torch.distributed as dist
+        import npdr_b200 as nb
+        from npdr_b200.distributed import GpuEngine, npdr_sharded
+        torch, N, p, q, rank, world = self.torch, self.N, self.p, self.q, self.rank, self.world
+        if world == 1:                                                   # ONE call of npdrb_npdr, exactly what the R shim does
+            stats, info = nb.npdr_stats(self.hX, self.hy, self.hC, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5,
+                                        self.cdt, device=self.local_rank)
+            return stats, info
+        dev = self.e2e_dev
+        if self.shard:                                                   # own columns over the own PCIe link, then NVLink all-gather
+            na = p // world
+            mine = dev["dX"][rank * na:(rank + 1) * na]
+            self.ctx.upload_columns(mine.data_ptr(), self.data["ldx"], self.hXs)
+            dist.all_gather_into_tensor(dev["dX"], mine)
+        elif rank == 0:
+            self.ctx.upload_columns(dev["dX"].data_ptr(), self.data["ldx"], self.hX)
+        if rank == 0:
+            dev["dy"].copy_(torch.from_numpy(self.hy))
+            if q:
+                dev["dC"].copy_(torch.from_numpy(np.ascontiguousarray(self.hC.T)))
+        if not self.shard:
+            dist.broadcast(dev["dX"], 0)
+        dist.broadcast(dev["dy"], 0)
+        if q:
+            dist.broadcast(dev["dC"], 0)
+        eng = GpuEngine(device_index=self.local_rank, dX=dev["dX"], ldx=self.data["ldx"], dy=dev["dy"], dC=dev["dC"], N=N, p=p, q=q)
+        stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, self.cdt)
+        eng.close()
+        return stats, info                                               # stats are host numpy on rank 0: D2H done
+
+    def run_inproc(self, steps, warmup):
+        """rank 0: `steps` calls of npdrb_npdr_multi on all `world` devices from its pageable host buffers; the other
+        ranks leave their GPUs idle and wait on the rendezvous store (an NCCL barrier would keep their SMs spinning).
+        -> (ms per call, host wall clock on rank 0; stats of the last call) on rank 0, (None, None) elsewhere."""
+        import torch.distributed as dist
+        import npdr_b200 as nb
+        self.barrier()
+        store = dist.distributed_c10d._get_default_store()
+        self._seq += 1
+        key = f"npdrb_inproc_{self.wl_name}_{self._seq}"
+        if self.rank != 0:
+            store.wait([key])
+            self.barrier()
+            return None, None
+        devs = list(range(self.world))
+        call = lambda: nb.npdr_stats(self.hX, self.hy, self.hC, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5,
+                                     self.cdt, devices=devs)
+        for _ in range(warmup):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            stats, info = call()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        store.set(key, b"1")
+        self.barrier()
+        return ms, (stats, info)
+
+    # ---- N ranks vs one GPU
+    def multi_gpu_check(self, stats_n, info_n, n_cmp=256):
+        """rank 0 re-runs the neighbour stage on ONE GPU (whole matrix) and the regression of the first and last n_cmp
+        attributes, and compares with what the N ranks produced: pair-list hash, statistics, IRLS iteration counts."""
+        from npdr_b200 import _lib
+        from npdr_b200.distributed import pair_list_hash
+        torch, d, N, p = self.torch, self.data, self.N, self.p
+        s = _lib.Session(self.ctx, N, p, self.q)
+        try:
+            torch.cuda.synchronize()
+            s.set_device_inputs(d["dX"].data_ptr(), d["ldx"], d["dy"].data_ptr(), d["dC"].data_ptr() if d["dC"] is not None else 0)
+            s.distances("manhattan", False, 0, N)
+            M, _ = s.neighbors("multisurf", 0.5, 0)
+            ri = torch.empty(M, dtype=torch.int32, device=self.device); nn = torch.empty(M, dtype=torch.int32, device=self.device)
+            s.copy_local_pairs_device(ri.data_ptr(), nn.data_ptr())
+            h1 = pair_list_hash(ri, nn)
+            s.import_pairs(ri.data_ptr(), nn.data_ptr(), M)
+            n_cmp = min(n_cmp, p // 2)
+            blocks = [(0, n_cmp), (p - n_cmp, n_cmp)]
+            ref = np.vstack([s.regress(a0, na, "binomial", "numeric-abs", self.cdt) for a0, na in blocks])
+        finally:
+            s.close()
+        got = np.vstack([stats_n[a0:a0 + na] for a0, na in blocks])
+        rel = 0.0
+        for col in (0, 1, 2, 3, 5):
+            scale = np.maximum(np.abs(ref[:, col]), 1e-3 * np.max(np.abs(ref[:, col])))
+            rel = max(rel, float(np.max(np.abs(got[:, col] - ref[:, col]) / scale)))
+        strong = np.abs(ref[:, 1]) > 1.0
+        rel_z = float(np.max(np.abs(got[strong, 1] - ref[strong, 1]) / np.abs(ref[strong, 1]))) if strong.any() else 0.0
+        return {"pair_list_hash_equal": bool(h1 == info_n["pair_hash"]), "n_pairs_1gpu": int(M), "n_pairs_ngpu": int(info_n["n_pairs"]),
+                "attrs_compared": int(ref.shape[0]), "max_rel_stat_diff": rel, "max_rel_diff_Z_where_absZ_gt_1": rel_z,
+                "irls_iterations_equal": bool(np.array_equal(got[:, 6], ref[:, 6])), "flags_equal": bool(np.array_equal(got[:, 7], ref[:, 7])),
+                "note": "N-rank result vs a one-GPU run on rank 0: order-sensitive 64-bit hash of the (Ri, NN) list; statistics of the "
+                        "first and last attributes (same sums in a different grouping: <= 1e-10 expected)"}
+
+    # ---- the whole measurement of this workload
+    def run(self, steps, warmup, variants=True, e2e=True, inproc=True, cpu_baseline=True, check=True):
+        args, world, rank, N, p, q, ctx = self.args, self.world, self.rank, self.N, self.p, self.q, self.ctx
+        wl_name, wl = self.wl_name, self.wl
+        sampler = ClockSampler(self.local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        ms_total, launches, (stats, info, km, sm, passes) = self.timed(self.step_resident, steps, warmup)
+        clocks = sampler.stop() if sampler else None
+        M = info["n_pairs"]
+        ms_step = ms_total / steps
+        out = {"value": float(p) * M / (ms_step * 1e-3), "ms_per_step": ms_step, "gpu_launches": launches, "clocks": clocks, "pairs_M": M}
+
+        # the same step with the two exact work-saving devices switched off (see DESIGN.md 4): every reference pair evaluated
+        # (no mutual-pair folding) and every IRLS iteration confirmed by its own pass (no guarded speculative convergence)
+        out["variants"] = {}
+        if variants:
+            for name, env in (("no_speculation", {"NPDRB_NO_SPECULATE": "1"}),
+                              ("no_speculation_no_folding", {"NPDRB_NO_SPECULATE": "1", "NPDRB_NO_FOLD": "1"})):
+                os.environ.update(env)
+                try:
+                    ms_v, _, (_, info_v, km_v, _, passes_v) = self.timed(self.step_resident, 2, 1)
+                finally:
+                    for k in env:
+                        os.environ.pop(k, None)
+                out["variants"][name] = {"value": float(p) * M / (ms_v / 2 * 1e-3), "ms_per_step": ms_v / 2, "irls_full_passes": passes_v,
+                                         "records_per_pair": km_v["records"] / max(info_v["n_pairs_used"], 1)}
+
+        out["multi_gpu_check"] = None
+        if check and world > 1:
+            stats_h, info_h, _, _, _ = self.step_resident(pair_hash=True)
+            self.barrier()
+            if rank == 0:
+                out["multi_gpu_check"] = self.multi_gpu_check(stats_h, info_h)
+            self.barrier()
+
+        out["e2e"] = out["e2e_inproc"] = None
+        if e2e:
+            self.prepare_host(inproc and world > 1)
+            e_steps = max(1, min(steps, 3))
+            ms_e, _, _ = self.timed(self.step_e2e, e_steps, 1 if steps > 1 else 0)
+            ms_e /= e_steps
+            h2d = int(N * p * 8 + N * 8 + N * q * 8)
+            out["e2e"] = {"value": float(p) * M / (ms_e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e,
+                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(p * 8 * 8), "host_memory": "pageable",
+                          "api": "npdrb_npdr (one C-ABI call, the entry point the R shim binds)" if world == 1 else
+                                 "torchrun: npdrb_upload_columns (pinned staging ring) + NCCL all-gather of X + npdrb_session_* sharded path",
+                          "note": ("pageable X/y(/C) in, statistics out, every step" if world == 1 else
+                                   ("every rank uploads its attribute columns from pageable memory over its own PCIe link, NCCL all-gather over "
+                                    "NVLink; y(/C) from rank 0; statistics read back on rank 0" if self.shard else
+                                    "rank 0 uploads pageable X/y(/C) and broadcasts over NVLink (NCCL) every step; statistics read back on rank 0"))}
+            if inproc and world > 1:
+                ms_i, res_i = self.run_inproc(e_steps, 1 if steps > 1 else 0)
+                if rank == 0:
+                    st_i, info_i = res_i
+                    agree = None
+                    if stats is not None:
+                        sc = np.maximum(np.abs(stats[:, 1]), 1.0)
+                        agree = float(np.max(np.abs(st_i[:, 1] - stats[:, 1]) / sc))
+                    out["e2e_inproc"] = {"value": float(p) * M / (ms_i * 1e-3), "unit": "evals/s", "ms_per_step": ms_i,
+                                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(p * 8 * 8), "host_memory": "pageable",
+                                         "api": f"npdrb_npdr_multi({world} devices): ONE host process, one thread per device",
+                                         "timer": "host wall clock on rank 0 around the call (all devices, uploads and read-back inside)",
+                                         "n_pairs": int(info_i["n_pairs"]), "max_diff_Z_vs_torchrun_arm": agree}
+            self.hX = self.hXs = None
+            self.e2e_dev = None
+
+        if rank != 0:
+            return None
+
+        # roofline of the dominant kernel (IRLS pass kernel), rank 0's launches of the last step
+        peak = ctx.fp64_peak()
+        n_full = max(int(km["n_pass_full"]), 1)
+        # issue-slot roofline: every FP64 instruction (DADD, DMUL or DFMA) takes one slot of the pipe whose peak the DFMA
+        # micro-benchmark measures as 2 flops per slot, so achieved = evaluations x executed FP64 instructions x 2 / time
+        flops = km["evals_pass_full"] * fp64_instr(q) * 2.0
+        achieved = flops / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
+        canon = km["evals_pass_full"] * f_bin(q) / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
+        hbm_peak = 6553.6
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        p_local = info["attrs"][1]
+        alg_bytes = n_full * (N * p_local * 8 + km["records"] * (4 + 8 * q) + p_local * 8 * 16)   # per pass: X slab once, record stream once, partials
+        traffic = traffic_src = None                  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+        for tf in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+                if tj["workload"] == wl_name and tj["n_gpus"] == world:
+                    traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+                    traffic_src = tj["source"]
+                    break
+            except Exception:
+                pass
+        out["roofline"] = {
+            "kernel": "IRLS pass kernel (binomial, npdr_b200/csrc/regress.cu)", "bound": "fp64",
+            "achieved": achieved, "peak": peak["dfma_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peak["dfma_tflops"] if peak["dfma_tflops"] else None, "traffic": traffic,
+            "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": alg_bytes / n_full,
+            "peak_source": "measured live by npdrb_measure_fp64_peak (DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
+            "launches": n_full, "avg_launch_ms": km["pass_full_ms"] / n_full,
+            "fp64_instr_per_eval": fp64_instr(q), "evals_per_launch_avg": km["evals_pass_full"] / n_full,
+            "note": "achieved = attribute x record evaluations per launch x FP64 instructions the kernel executes per evaluation "
+                    "(SASS count, DESIGN.md 4) x 2 flops per issue slot / CUDA-event launch time, against the measured DFMA peak: frac is "
+                    "the FP64 pipe's issue-slot utilisation (ncu sm__pipe_fp64_cycles_active agrees).  records = pairs after folding "
+                    "mutual (i,j)/(j,i) pairs into one weight-2 record.  An FP64 warp instruction holds the dispatch port for 2 cycles "
+                    "and nothing issues under it (scripts/dev/ubench_fp64.cu), so every non-FP64 instruction of the loop lowers the ceiling",
+            "canonical": {"flops_per_eval_iteration": f_bin(q), "achieved": canon,
+                          "frac": canon / peak["dfma_tflops"] if peak["dfma_tflops"] else None,
+                          "note": "SURVEY 8d's canonical count (exp = log = 20, reciprocal = 8 flops): exceeds 1 because the kernel "
+                                  "spends 6 FP64 instructions on exp, 2 on the reciprocal and replaces the per-record log by a running "
+                                  "product (one multiply per record, one log per thread)"},
+            "records_per_pair": km["records"] / max(info["n_pairs_used"], 1),
+            "share_of_step": km["pass_full_ms"] / ms_step,
+            "hbm": {"achieved": alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9 if km["pass_full_ms"] > 0 else 0.0,
+                    "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9) / hbm_peak if km["pass_full_ms"] > 0 else None}}
+        dist_adds = float(p) * N * (N - 1)          # 2 DADD per element pair over the lower triangle (symmetric mode)
+        if world > 1:                                               # balanced: ~half of the rank's rectangle (the rest arrives over NVLink)
+            dist_adds = (1.0 if os.environ.get("NPDRB_NO_BALANCED") != "1" else 2.0) * float(p) * info["rows"][1] * N
+        out["stages"] = {"distance_ms": sm["distance"], "neighbors_ms": sm["neighbors"], "prepare_ms": sm["prepare"], "regress_ms": sm["regress"],
+                         "irls_full_passes": passes, "pass_first_ms": km["pass_first_ms"],
+                         "distance_fp64_add_frac": (dist_adds / (sm["distance"] * 1e-3) / 1e12) / peak["dadd_tflops"] if sm["distance"] > 0 else None}
+        out["fp64_peak_measured"] = peak
+
+        out["cpu_baseline"] = None
+        if cpu_baseline and world == 1:
+            N_s, p_s = CPU_SAMPLE[wl_name]                              # ~10 s of host work on the box's 16 cores
+            ev, dt, thr, M_s = cpu_oracle_sample(wl_name, N_s, p_s, q, threads=os.cpu_count())
+            out["cpu_baseline"] = {"value": ev / dt, "unit": "evals/s", "cores": thr, "kind": "port", "seconds": dt,
+                                   "sample": f"first {N_s} instances x {p_s} attributes of the {wl_name} recipe (M={M_s} pairs), all stages, "
+                                             f"CPU oracle (C restatement of the reference R path), OpenMP over attributes"}
+        return out
+
+    def free(self):
+        self.data = None
+        self.torch.cuda.empty_cache()
+        self.ctx.release_cache()
 
 
 def main():
@@ -211,6 +546,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-target", action="store_true", help="skip the cfg5 (north-star) measurement appended to a cfg4 run")
+    ap.add_argument("--no-check", action="store_true", help="skip the N-rank vs one-GPU comparison")
     args = ap.parse_args()
     wl_name, wl = args.workload, WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -220,7 +557,6 @@ def main():
     import torch
     import torch.distributed as dist
     import npdr_b200 as nb
-    from npdr_b200.distributed import GpuEngine, npdr_sharded
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -235,207 +571,32 @@ def main():
     ctx = nb.context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)      # library work and torch events share one stream
 
-    data = make_data(wl, world, device)
-    N, p, q = data["N"], data["p"], data["q"]
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def one_step_resident():
-        eng = GpuEngine(device_index=local_rank, dX=data["dX"], ldx=data["ldx"], dy=data["dy"], dC=data["dC"], N=N, p=p, q=q)
-        stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, data["covar_diff_type"])
-        km = eng.session.kernel_ms(); sm = eng.session.stage_ms(); passes = eng.session.irls_passes
-        eng.close()
-        return stats, info, km, sm, passes
-
-    # host copies for the end-to-end arm (pinned).  One GPU: the whole matrix goes through the host-buffer C ABI.  Several
-    # GPUs: every rank holds the pinned host copy of ITS attribute columns, uploads them over its own PCIe link and the
-    # shards are all-gathered over NVLink (a single host thread would feed the G devices the same way); y / covariates
-    # come from rank 0.  When p does not divide evenly rank 0 uploads everything and broadcasts.
-    hX = hy = hC = hXt = None
-    e2e_dev = None
-    shard_upload = world > 1 and p % world == 0
-    if not args.no_e2e and (rank == 0 or shard_upload):
-        a0, na = (0, p) if not shard_upload else (rank * (p // world), p // world)
-        hXt = torch.empty((na, N), dtype=torch.float64, pin_memory=True)
-        hXt.copy_(data["dX"][a0:a0 + na, :N])
-        if world == 1:
-            hX = hXt.numpy().T                                   # (N, p) Fortran-ordered view of pinned memory
+    b = Bench(args, wl_name, rank, local_rank, world, device, ctx)
+    res = b.run(args.steps, args.warmup, variants=not args.no_variants, e2e=not args.no_e2e, cpu_baseline=not args.no_cpu_baseline,
+                check=not args.no_check)
+    b.free()
+    target = None
+    if wl_name == "cfg4" and not args.no_target:
+        # BASELINE's north-star configuration at the same N (strong scaling): 1 warm-up + 1 step of every arm
+        bt = Bench(args, "cfg5", rank, local_rank, world, device, ctx)
+        rt = bt.run(1, 1, variants=False, e2e=not args.no_e2e, cpu_baseline=False, check=not args.no_check)
+        bt.free()
         if rank == 0:
-            hy = data["dy"].cpu().numpy()
-            hC = np.asfortranarray(data["dC"].cpu().numpy().T) if q else None
-    if not args.no_e2e and world > 1:
-        e2e_dev = dict(dX=torch.zeros((p, data["ldx"]), dtype=torch.float64, device=device),
-                       dy=torch.zeros(N, dtype=torch.float64, device=device),
-                       dC=torch.zeros((q, N), dtype=torch.float64, device=device) if q else None)
-        hy_t = torch.from_numpy(hy).pin_memory() if rank == 0 else None
-        hC_t = torch.from_numpy(np.ascontiguousarray(hC.T)).pin_memory() if (rank == 0 and q) else None
+            target = {"metric": "npdr_attr_x_pair_glm_evals_per_s", "unit": "evals/s", "scaling": "strong", "steps": 1, "warmup": 1,
+                      "config": workload_config("cfg5", world), **rt}
 
-    def one_step_e2e():
-        if world == 1:
-            eng = GpuEngine(X=hX, y=hy, C=hC, device_index=local_rank)   # host-buffer C ABI: H2D upload inside
-        else:
-            if shard_upload:                                     # own columns over the own PCIe link, then NVLink all-gather
-                na = p // world
-                mine = e2e_dev["dX"][rank * na:(rank + 1) * na]
-                mine[:, :N].copy_(hXt, non_blocking=True)
-                dist.all_gather_into_tensor(e2e_dev["dX"], mine)
-            elif rank == 0:
-                e2e_dev["dX"][:, :N].copy_(hXt, non_blocking=True)
-            if rank == 0:
-                e2e_dev["dy"].copy_(hy_t, non_blocking=True)
-                if q:
-                    e2e_dev["dC"].copy_(hC_t, non_blocking=True)
-            if not shard_upload:
-                dist.broadcast(e2e_dev["dX"], 0)
-            dist.broadcast(e2e_dev["dy"], 0)
-            if q:
-                dist.broadcast(e2e_dev["dC"], 0)
-            eng = GpuEngine(device_index=local_rank, dX=e2e_dev["dX"], ldx=data["ldx"], dy=e2e_dev["dy"], dC=e2e_dev["dC"],
-                            N=N, p=p, q=q)
-        stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, data["covar_diff_type"])
-        eng.close()
-        return stats, info                                              # stats are host numpy on rank 0: D2H done
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        l0 = ctx.launch_count()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = None
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-        launches = torch.tensor([ctx.launch_count() - l0], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-        return float(ms.item()), int(launches.item()), out
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms_total, launches, (stats, info, km, sm, passes) = timed(one_step_resident, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
-    M = info["n_pairs"]
-    ms_step = ms_total / args.steps
-    value = float(p) * M / (ms_step * 1e-3)
-
-    # the same step with the two exact work-saving devices switched off: every reference pair evaluated
-    # (no mutual-pair folding) and every IRLS iteration confirmed by its own pass (no guarded speculative convergence)
-    variants = {}
-    if not args.no_variants:
-        for name, env in (("no_speculation", {"NPDRB_NO_SPECULATE": "1"}),
-                          ("no_speculation_no_folding", {"NPDRB_NO_SPECULATE": "1", "NPDRB_NO_FOLD": "1"})):
-            os.environ.update(env)
-            try:
-                ms_v, _, (_, info_v, km_v, _, passes_v) = timed(one_step_resident, 2, 1)
-            finally:
-                for k in env:
-                    os.environ.pop(k, None)
-            variants[name] = {"value": float(p) * M / (ms_v / 2 * 1e-3), "ms_per_step": ms_v / 2, "irls_full_passes": passes_v,
-                              "records_per_pair": km_v["records"] / max(info_v["n_pairs_used"], 1)}
-
-    e2e = None
-    if not args.no_e2e:
-        e_steps = max(1, min(args.steps, 3))
-        ms_e, _, _ = timed(one_step_e2e, e_steps, 1)
-        ms_e /= e_steps
-        e2e = {"value": float(p) * M / (ms_e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e,
-               "h2d_bytes_per_step": int(N * p * 8 + N * 8 + N * q * 8), "d2h_bytes_per_step": int(p * 8 * 8),
-               "note": ("host-buffer C-ABI path: pinned X/y(/C) uploaded and statistics read back every step" if world == 1 else
-                        ("every rank uploads its pinned attribute columns over its own PCIe link, NCCL all-gather over NVLink; y(/C) from "
-                         "rank 0; statistics read back on rank 0" if shard_upload else
-                         "rank 0 uploads pinned X/y(/C) and broadcasts over NVLink (NCCL) every step; statistics read back on rank 0"))}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # roofline of the dominant kernel (IRLS pass kernel), rank 0's launches of the last step
-    peak = ctx.fp64_peak()
-    n_full = max(int(km["n_pass_full"]), 1)
-    # issue-slot roofline: every FP64 instruction (DADD, DMUL or DFMA) takes one slot of the pipe whose peak the DFMA
-    # micro-benchmark measures as 2 flops per slot, so achieved = evaluations x executed FP64 instructions x 2 / time
-    flops = km["evals_pass_full"] * fp64_instr(q) * 2.0
-    achieved = flops / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
-    canon = km["evals_pass_full"] * f_bin(q) / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
-    hbm_peak = 6553.6
-    try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except Exception:
-        pass
-    p_local = info["attrs"][1]
-    alg_bytes = n_full * (N * p_local * 8 + km["records"] * (4 + 8 * q) + p_local * 8 * 16)   # per pass: X slab once, record stream once, partials
-    traffic = traffic_src = None                  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        if tj["workload"] == wl_name and tj["n_gpus"] == world:
-            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
-            traffic_src = tj["source"]
-    except Exception:
-        pass
-    roofline = {"kernel": "pass2_kernel<IRLS_FULL, q, diff> (binomial IRLS pass, npdr_b200/csrc/regress.cu)", "bound": "fp64",
-                "achieved": achieved, "peak": peak["dfma_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peak["dfma_tflops"] if peak["dfma_tflops"] else None, "traffic": traffic,
-                "traffic_unit": "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": alg_bytes / n_full,
-                "peak_source": "measured live by npdrb_measure_fp64_peak (DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
-                "launches": n_full, "avg_launch_ms": km["pass_full_ms"] / n_full,
-                "fp64_instr_per_eval": fp64_instr(q), "evals_per_launch_avg": km["evals_pass_full"] / n_full,
-                "note": "achieved = attribute x record evaluations per launch x FP64 instructions the kernel executes per evaluation "
-                        "(18 at q = 0, 31 at q = 2; SASS count, DESIGN.md 4) x 2 flops per issue slot / CUDA-event launch time, against "
-                        "the measured DFMA peak: frac is the FP64 pipe's issue-slot utilisation (ncu sm__pipe_fp64_cycles_active agrees). "
-                        "records = pairs after folding mutual (i,j)/(j,i) pairs into one weight-2 record.  The kernel also issues 10.6 "
-                        "(q = 0) / 13.5 (q = 2) non-FP64 instructions per evaluation; an FP64 warp instruction holds the dispatch "
-                        "port for 2 cycles, so the issue-limited ceiling of this mix is 36/46.6 = 77 % (q = 0), 62/75.5 = 82 % (q = 2)",
-                "canonical": {"flops_per_eval_iteration": f_bin(q), "achieved": canon,
-                              "frac": canon / peak["dfma_tflops"] if peak["dfma_tflops"] else None,
-                              "note": "SURVEY 8d's canonical count (exp = log = 20, reciprocal = 8 flops): exceeds 1 because the kernel "
-                                      "spends 6 FP64 instructions on exp, 2 on the reciprocal and replaces the per-record log by a running "
-                                      "product (one multiply per record, one log per thread)"},
-                "records_per_pair": km["records"] / max(info["n_pairs_used"], 1),
-                "share_of_step": km["pass_full_ms"] / ms_step,
-                "hbm": {"achieved": alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9 if km["pass_full_ms"] > 0 else 0.0,
-                        "peak": hbm_peak, "unit": "GB/s",
-                        "frac": (alg_bytes / (km["pass_full_ms"] * 1e-3) / 1e9) / hbm_peak if km["pass_full_ms"] > 0 else None}}
-    dist_adds = float(p) * N * (N - 1)          # 2 DADD per element pair over the lower triangle (symmetric mode)
-    if world > 1:                                               # balanced: ~half of the rank's rectangle (the rest arrives over NVLink)
-        dist_adds = (1.0 if os.environ.get("NPDRB_NO_BALANCED") != "1" else 2.0) * float(p) * info["rows"][1] * N
-    stage = {"distance_ms": sm["distance"], "neighbors_ms": sm["neighbors"], "prepare_ms": sm["prepare"], "regress_ms": sm["regress"],
-             "irls_full_passes": passes, "pass_first_ms": km["pass_first_ms"],
-             "distance_fp64_add_frac": (dist_adds / (sm["distance"] * 1e-3) / 1e12) / peak["dadd_tflops"] if sm["distance"] > 0 else None}
-
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        N_s, p_s = (2000, 512) if wl_name != "small" else (512, 128)      # ~10 s of host work on the box's 16 cores
-        ev, dt, thr, M_s = cpu_oracle_sample(wl_name, N_s, p_s, q)
-        cpu_baseline = {"value": ev / dt, "unit": "evals/s", "cores": thr, "kind": "port", "seconds": dt,
-                        "sample": f"first {N_s} instances x {p_s} attributes of the {wl_name} recipe (M={M_s} pairs), all stages, "
-                                  f"CPU oracle (C restatement of the reference R path), OpenMP over attributes"}
-
-    line = {"metric": "npdr_attr_x_pair_glm_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": wl["scaling"],
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "description": wl["desc"], "N": N, "p": p, "q": q, "pairs_M": M,
-                       "regression": "binomial", "nbd": "multisurf", "metric": "manhattan", "seed": SEED,
-                       "parallelism": f"rows/{world} (distance+neighbours" + (", symmetric halves swapped in one all-to-all" if world > 1 else "")
-                                      + f") -> all-gather pairs -> attrs/{world} (regression)",
-                       "l2": "inputs (X = %.0f MB per GPU) exceed the 126 MB L2; no flush needed" % (N * p * 8 / 1e6)},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "stages": stage, "fp64_peak_measured": peak, "variants": variants,
-            "work_saving": "exact: (i,j)/(j,i) pairs folded into one weight-2 record; the IRLS pass that would only confirm convergence "
-                           "is skipped when the Newton quadratic model + cubic remainder bound puts the next deviance change >= 10x "
-                           "below glm.fit's epsilon (same beta, se, iteration count); `variants` times the step without them"}
-    print(json.dumps(line))
+    if rank == 0:
+        line = {"metric": "npdr_attr_x_pair_glm_evals_per_s", "value": res["value"], "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": wl["scaling"],
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl_name, world),
+                "pairs_M": res["pairs_M"], "e2e": res["e2e"], "e2e_inproc": res["e2e_inproc"], "gpu_launches": res["gpu_launches"],
+                "clocks": res["clocks"], "roofline": res["roofline"], "cpu_baseline": res["cpu_baseline"], "stages": res["stages"],
+                "fp64_peak_measured": res["fp64_peak_measured"], "variants": res["variants"], "multi_gpu_check": res["multi_gpu_check"],
+                "target": target,
+                "work_saving": "exact: (i,j)/(j,i) pairs folded into one weight-2 record; the IRLS pass that would only confirm convergence "
+                               "is skipped when the Newton quadratic model + cubic remainder bound puts the next deviance change >= 10x "
+                               "below glm.fit's epsilon (same beta, se, iteration count); `variants` times the step without them"}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -133,6 +133,10 @@ int npdrb_synchronize(npdrb_ctx *ctx);
 int npdrb_measure_fp64_peak(npdrb_ctx *ctx, double *dfma_tflops, double *dadd_tflops);
 /* return the library's cached device memory on this device to the driver (buffers are otherwise kept for reuse) */
 int npdrb_release_cache(npdrb_ctx *ctx);
+/* Copy `ncols` contiguous host columns of `rows` doubles (src, column-major, leading dimension rows) to device memory
+ * (dst, leading dimension ld_dst doubles) and wait for it.  A pageable src (R's heap, numpy) goes through the context's
+ * pinned staging ring (see npdrb_session_upload); used by hosts that shard the upload of X by attribute columns. */
+int npdrb_upload_columns(npdrb_ctx *ctx, void *dst_device, int64_t ld_dst, const double *src_host, int64_t rows, int64_t ncols);
 /* number of this library's kernel launches since the context was created (bench.py's gpu_launches) */
 int64_t npdrb_launch_count(npdrb_ctx *ctx);
 
@@ -192,10 +196,14 @@ int npdrb_unireg(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const do
 
 int npdrb_session_create(npdrb_ctx *ctx, int64_t N, int64_t p, int32_t q, npdrb_session **s);
 void npdrb_session_destroy(npdrb_session *s);
-/* copy host inputs in (pinned staging + async copies on the context stream); C may be NULL when q == 0 */
-/* A matrix of 64 MB or more is uploaded as 8 column slabs on a second stream; the distance kernel starts on the first
- * slab while the others cross PCIe (bit-identical results).  X must therefore stay valid until the first call that
- * consumes it (distances / neighbours / regress) has returned.  NPDRB_NO_PIPELINED_UPLOAD=1 restores one blocking copy. */
+/* copy host inputs in; C may be NULL when q == 0.
+ * A matrix of 64 MB or more is uploaded as 8 column slabs on a second stream and the distance kernel starts on the first
+ * slab while the others cross PCIe (bit-identical results).  A pinned (cudaHostAlloc / cudaHostRegister) X is enqueued
+ * at once; a PAGEABLE X (R's heap) is staged slab by slab through the context's ring of three 32 MB pinned buffers
+ * (helper threads memcpy, async H2D), each slab right before the kernel that consumes it is launched, so the staging of
+ * slab i+1 runs under the kernel of slab i.  X must therefore stay valid until the first call that consumes it
+ * (distances / neighbours / regress) has returned.  NPDRB_NO_PIPELINED_UPLOAD=1 restores one blocking copy;
+ * NPDRB_STAGE_THREADS sets the number of copier threads (default 4). */
 int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, const double *C);
 /* or adopt device buffers: dX column-major with leading dimension ldx >= N (ldx % 2 == 0), dy[N], dC N x q (ld N) */
 int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy,
@@ -239,7 +247,10 @@ int npdrb_session_copy_distances(npdrb_session *s, double *D_host);         /* n
 /* the full pair list the regression will use (device pointers, e.g. the all-gathered segments) */
 int npdrb_session_import_pairs(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64_t M);
 int npdrb_session_import_pairs_host(npdrb_session *s, const int32_t *Ri, const int32_t *NN, int64_t M);
-/* uniqueNeighbors on the imported list: count, and optionally replace the list by its unique subset */
+/* uniqueNeighbors on the imported list: count, and optionally replace the list by its unique subset.
+ * Precondition (checked on the device, NPDRB_EINVAL otherwise): rows grouped by ascending Ri_idx, no ordered pair twice --
+ * the shape nearestNeighbors() emits; only then is "drop (i, j) when i > j and (j, i) is present" the reference's
+ * keep-the-first-occurrence rule (R/nearestNeighbors.R:576-582). */
 int npdrb_session_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_unique);
 /* regression over attribute columns [attr0, attr0+nattr); stats_out host, nattr x 8 row-major */
 int npdrb_session_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t regression_type,

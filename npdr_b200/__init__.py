@@ -7,7 +7,7 @@ or an sm_100 device is missing.
 from ._lib import NpdrB200Error, Context, Session, context  # noqa: F401
 from .api import (npdr, npdrDiff, npdrDistances, nearestNeighbors, nearestNeighborsSeparateHitMiss,  # noqa: F401
                   uniqueNeighbors, knnVec, knnSURF, diffRegression, uniReg, npdr_k_grid, vwok,
-                  npdrDistances2, nearestNeighbors2, npdrLearner)
+                  npdrDistances2, nearestNeighbors2, npdrLearner, npdr_stats)
 from . import rstats  # noqa: F401
 
 __version__ = "0.1.0"

@@ -65,6 +65,7 @@ SIGNATURES = {
     "npdrb_measure_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
     "npdrb_launch_count": (_i64, [_vp]),
     "npdrb_release_cache": (C.c_int, [_vp]),
+    "npdrb_upload_columns": (C.c_int, [_vp, _vp, _i64, _dp, _i64, _i64]),
     "npdrb_diff": (C.c_int, [_vp, _dp, _dp, _i64, _i32, C.c_double, _dp]),
     "npdrb_distances": (C.c_int, [_vp, _dp, _i64, _i64, _i32, _i32, _dp]),
     "npdrb_distances2": (C.c_int, [_vp, _dp, _i64, _dp, _i64, _i64, _i32, _dp]),
@@ -185,6 +186,11 @@ class Context:
 
     def launch_count(self):
         return int(load().npdrb_launch_count(self.handle))
+
+    def upload_columns(self, dst_device_ptr, ld_dst, src):
+        """Host columns (Fortran-ordered float64 [rows, ncols], pageable or pinned) -> device memory at dst_device_ptr."""
+        a = f64(src)
+        check(load().npdrb_upload_columns(self.handle, _vp(int(dst_device_ptr)), int(ld_dst), dptr(a), a.shape[0], a.shape[1]))
 
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()

@@ -442,6 +442,45 @@ def _split_outcome(outcome, dataset):
     return X, names, pheno
 
 
+def npdr_stats(X, y, Cm=None, regression_type="binomial", attr_diff_type="numeric-abs", nbd_method="multisurf",
+               nbd_metric="manhattan", knn=0, msurf_sd_frac=0.5, covar_diff_type=(), neighbor_sampling="none",
+               separate_hitmiss_nbds=False, return_pairs=False, device=0, devices=None):
+    """The C-ABI call an R `.Call` makes: npdrb_npdr (one device) or npdrb_npdr_multi (`devices`: CUDA ordinals, one host
+    thread per device inside the call) on HOST buffers -- column-major float64 X (N x p), coded outcome y, covariates Cm
+    (N x q) -- from upload to the p x 8 statistics (include/npdr_b200.h).  -> (stats [p, 8], info dict).  Everything
+    between npdr()'s argument parsing and its order()/p.adjust() (R/npdr.R:256-430)."""
+    L = _lib.load()
+    X = f64(X); N, p = X.shape
+    ya = f64(y)
+    Ca = f64(Cm) if Cm is not None else None
+    cdt = [covar_diff_type] if isinstance(covar_diff_type, str) else list(covar_diff_type)
+    o = _lib.Opts()
+    L.npdrb_opts_default(C.byref(o))
+    o.regression_type = REG[regression_type]; o.attr_diff_type = DIFF[attr_diff_type]
+    o.nbd_method = NBD[nbd_method]; o.nbd_metric = METRIC[nbd_metric]
+    o.knn = int(knn); o.msurf_sd_frac = float(msurf_sd_frac); o.n_covars = len(cdt) if Ca is not None else 0
+    for i, t in enumerate(cdt[:o.n_covars]):
+        o.covar_diff_type[i] = DIFF[t]
+    o.neighbor_sampling_unique = int(neighbor_sampling == "unique")
+    o.return_pairs = int(bool(return_pairs))
+    o.separate_hitmiss_nbds = int(bool(separate_hitmiss_nbds))
+    res = _lib.Result()
+    if devices is not None:
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        check(L.npdrb_npdr_multi(int(devs.size), iptr(devs), dptr(X), N, p, dptr(ya), dptr(Ca), C.byref(o), C.byref(res)))
+    else:
+        check(L.npdrb_npdr(context(device).handle, dptr(X), N, p, dptr(ya), dptr(Ca), C.byref(o), C.byref(res)))
+    stats = np.ctypeslib.as_array(res.stats, shape=(p, STATS_PER_ATTR)).copy()
+    info = {f: getattr(res, f) for f in ("n_pairs", "n_unique_pairs", "n_pairs_used", "k_ave_empirical", "n_empty",
+                                         "knn_used", "ms_h2d", "ms_distance", "ms_neighbors", "ms_prepare",
+                                         "ms_regress", "ms_total", "irls_passes")}
+    if return_pairs and res.n_pairs_used > 0:
+        info["Ri"] = np.ctypeslib.as_array(res.Ri, shape=(res.n_pairs_used,)).copy()
+        info["NN"] = np.ctypeslib.as_array(res.NN, shape=(res.n_pairs_used,)).copy()
+    L.npdrb_result_release(C.byref(res))
+    return stats, info
+
+
 def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-abs", nbd_method="multisurf",
          nbd_metric="manhattan", knn=0, msurf_sd_frac=0.5, covars="none", covar_diff_type="match-mismatch",
          padj_method="bonferroni", verbose=False, use_glmnet=False, glmnet_alpha=1, glmnet_lower=0,
@@ -491,32 +530,12 @@ def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-a
     if verbose:
         print("Finding nearest neighbor pairs.")
     if simple:
-        o = _lib.Opts()
-        L.npdrb_opts_default(C.byref(o))
-        o.regression_type = REG[regression_type]; o.attr_diff_type = DIFF[attr_diff_type]
-        o.nbd_method = NBD[nbd_method]; o.nbd_metric = METRIC[nbd_metric]
-        o.knn = int(knn); o.msurf_sd_frac = float(msurf_sd_frac); o.n_covars = q
-        for i, t in enumerate(cdt):
-            o.covar_diff_type[i] = DIFF[t]
-        o.neighbor_sampling_unique = int(neighbor_sampling == "unique")
-        o.return_pairs = int(bool(return_info))
-        o.separate_hitmiss_nbds = int(bool(separate_hitmiss_nbds))
-        res = _lib.Result()
+        devs = None
         if (n_gpus and int(n_gpus) > 1) or devices is not None:   # one host process, one thread per device (what R would call)
-            devs = np.ascontiguousarray(np.arange(int(n_gpus)) if devices is None else devices, dtype=np.int32)
-            check(L.npdrb_npdr_multi(int(devs.size), iptr(devs), dptr(X), N, p, dptr(f64(y)), dptr(Cm), C.byref(o), C.byref(res)))
-        else:
-            check(L.npdrb_npdr(ctx.handle, dptr(X), N, p, dptr(f64(y)), dptr(Cm), C.byref(o), C.byref(res)))
-        stats = np.ctypeslib.as_array(res.stats, shape=(p, STATS_PER_ATTR)).copy()
-        num_pairs, num_unique, n_used = res.n_pairs, res.n_unique_pairs, res.n_pairs_used
-        k_ave = res.k_ave_empirical
-        info = {f: getattr(res, f) for f in ("n_pairs", "n_unique_pairs", "n_pairs_used", "k_ave_empirical", "n_empty",
-                                             "knn_used", "ms_h2d", "ms_distance", "ms_neighbors", "ms_prepare",
-                                             "ms_regress", "ms_total", "irls_passes")}
-        if return_info and res.n_pairs_used > 0:
-            info["Ri"] = np.ctypeslib.as_array(res.Ri, shape=(res.n_pairs_used,)).copy()
-            info["NN"] = np.ctypeslib.as_array(res.NN, shape=(res.n_pairs_used,)).copy()
-        L.npdrb_result_release(C.byref(res))
+            devs = np.arange(int(n_gpus)) if devices is None else devices
+        stats, info = npdr_stats(X, y, Cm, regression_type, attr_diff_type, nbd_method, nbd_metric, knn, msurf_sd_frac, cdt,
+                                 neighbor_sampling, separate_hitmiss_nbds, return_pairs=bool(return_info), device=device, devices=devs)
+        num_pairs, num_unique, n_used, k_ave = info["n_pairs"], info["n_unique_pairs"], info["n_pairs_used"], info["k_ave_empirical"]
     else:
         # neighbours from a reduced attribute set or a user distance matrix, regression on all attributes
         if nbd_metric == "precomputed":

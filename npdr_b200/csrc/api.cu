@@ -2,8 +2,10 @@
 // host-buffer operator entry points that replace the reference's exported R functions.
 #include <math.h>
 #include <stdarg.h>
+#include <condition_variable>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include "common.cuh"
 
@@ -78,6 +80,123 @@ cudaError_t nb_cached_free(void *p) {
     return (cudaFree)(p);                                                     // not ours (should not happen)
 }
 
+// ------------------------------------------------------------------ pinned staging ring (pageable host sources)
+// R's heap is pageable: cudaMemcpyAsync from it is staged by the driver on the calling thread and does not overlap with
+// anything.  The ring gives a pageable source the behaviour of a pinned one: helper threads memcpy a chunk into one of
+// three pinned buffers, the chunk goes to the device asynchronously on the copy stream, and the buffer is reused once
+// its copy has completed.
+struct nb_stage_ring {
+    static constexpr int NBUF = 3;
+    size_t buf_bytes = (size_t)32 << 20;
+    void *buf[NBUF] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[NBUF] = {nullptr, nullptr, nullptr};
+    bool used[NBUF] = {false, false, false};
+    int next = 0;
+    // helper pool: piece t of the current job is copied by helper t (the caller copies piece 0)
+    int n_helpers = 0;
+    std::vector<std::thread> helpers;
+    std::mutex mu; std::condition_variable cv_go, cv_done;
+    unsigned gen = 0; int remaining = 0; bool stop = false;
+    char *job_dst = nullptr; const char *job_src = nullptr; size_t job_bytes = 0; int job_pieces = 1;
+
+    static void copy_piece(char *dst, const char *src, size_t bytes, int piece, int pieces) {
+        const size_t per = ((bytes / (size_t)pieces) + 4095) & ~(size_t)4095;
+        const size_t lo = per * (size_t)piece;
+        if (lo >= bytes) return;
+        const size_t n = (lo + per < bytes && piece + 1 < pieces) ? per : bytes - lo;
+        memcpy(dst + lo, src + lo, n);
+    }
+    void helper_main(int t) {
+        unsigned seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_go.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen;
+            char *d = job_dst; const char *sr = job_src; const size_t n = job_bytes; const int pcs = job_pieces;
+            lk.unlock();
+            if (t < pcs) copy_piece(d, sr, n, t, pcs);
+            lk.lock();
+            if (--remaining == 0) cv_done.notify_one();
+        }
+    }
+    void start(int helpers_wanted) {
+        n_helpers = helpers_wanted;
+        for (int t = 1; t <= n_helpers; ++t) helpers.emplace_back(&nb_stage_ring::helper_main, this, t);
+    }
+    void parallel_copy(void *dst, const void *src, size_t bytes) {
+        const int pieces = (bytes >= ((size_t)1 << 20)) ? n_helpers + 1 : 1;
+        if (pieces == 1) { memcpy(dst, src, bytes); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job_dst = (char *)dst; job_src = (const char *)src; job_bytes = bytes; job_pieces = pieces;
+            remaining = n_helpers; ++gen;
+        }
+        cv_go.notify_all();
+        copy_piece((char *)dst, (const char *)src, bytes, 0, pieces);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return remaining == 0; });
+    }
+    ~nb_stage_ring() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_go.notify_all();
+        for (auto &t : helpers) t.join();
+        for (int b = 0; b < NBUF; ++b) { if (buf[b]) cudaFreeHost(buf[b]); if (done[b]) cudaEventDestroy(done[b]); }
+    }
+};
+
+static int get_ring(npdrb_ctx *ctx, nb_stage_ring **out) {
+    if (!ctx->ring) {
+        nb_stage_ring *r = new nb_stage_ring();
+        for (int b = 0; b < nb_stage_ring::NBUF; ++b) {
+            cudaError_t e = cudaHostAlloc(&r->buf[b], r->buf_bytes, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->done[b], cudaEventDisableTiming);
+            if (e != cudaSuccess) { delete r; npdrb_set_error("pinned staging ring: %s", cudaGetErrorString(e)); return NPDRB_ENOMEM; }
+        }
+        int want = 3;                                     // + the calling thread = 4 copiers; NPDRB_STAGE_THREADS overrides
+        const char *e = getenv("NPDRB_STAGE_THREADS");
+        if (e && atoi(e) >= 1) want = atoi(e) - 1;
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw && want > (int)hw - 1) want = (int)hw - 1;
+        if (want > 15) want = 15;
+        r->start(want < 0 ? 0 : want);
+        ctx->ring = r;
+    }
+    *out = ctx->ring;
+    return NPDRB_OK;
+}
+
+int nb_staged_h2d(npdrb_ctx *ctx, double *dst, int64_t ld_dst, const double *src, int64_t rows, int64_t ncols) {
+    if (!ctx->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    const size_t col_bytes = sizeof(double) * (size_t)rows;
+    nb_stage_ring *r = nullptr;
+    NB_CHECK(get_ring(ctx, &r));
+    if (col_bytes > r->buf_bytes) {                       // a single column does not fit a ring buffer: let the driver stage it
+        NB_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)ld_dst, src, col_bytes, col_bytes, (size_t)ncols,
+                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+        return NPDRB_OK;
+    }
+    const int64_t cols_per_chunk = (int64_t)(r->buf_bytes / col_bytes);
+    for (int64_t c = 0; c < ncols; c += cols_per_chunk) {
+        const int64_t nc = (c + cols_per_chunk < ncols) ? cols_per_chunk : ncols - c;
+        const int b = r->next;
+        r->next = (b + 1) % nb_stage_ring::NBUF;
+        if (r->used[b]) NB_CUDA(cudaEventSynchronize(r->done[b]));
+        r->parallel_copy(r->buf[b], src + c * rows, col_bytes * (size_t)nc);
+        NB_CUDA(cudaMemcpy2DAsync(dst + c * ld_dst, sizeof(double) * (size_t)ld_dst, r->buf[b], col_bytes, col_bytes, (size_t)nc,
+                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+        NB_CUDA(cudaEventRecord(r->done[b], ctx->copy_stream));
+        r->used[b] = true;
+    }
+    return NPDRB_OK;
+}
+
+bool nb_host_pointer_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 namespace {
 
 __global__ void check_finite_kernel(const double *__restrict__ v, int64_t n, int *__restrict__ bad) {
@@ -127,11 +246,24 @@ int check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what) {
 
 int nb_check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what) { return check_finite(ctx, d, n, what); }
 
+int nb_issue_slab(npdrb_session *s, int slab) {
+    npdrb_ctx *ctx = s->ctx;
+    for (int i = s->n_slabs_issued; i <= slab && i < s->n_slabs_pending; ++i) {
+        const int64_t c0 = (int64_t)i * s->slab_cols, c1 = (c0 + s->slab_cols < s->p) ? c0 + s->slab_cols : s->p;
+        if (!s->hX_lazy) { npdrb_set_error("upload: slab %d has no host source", i); return NPDRB_EINVAL; }
+        NB_CHECK(nb_staged_h2d(ctx, s->dX + c0 * s->ldx, s->ldx, s->hX_lazy + c0 * s->N, s->N, c1 - c0));
+        NB_CUDA(cudaEventRecord(s->slab_ev[(size_t)i], ctx->copy_stream));
+        s->n_slabs_issued = i + 1;
+    }
+    return NPDRB_OK;
+}
+
 int nb_wait_upload(npdrb_session *s) {
     if (s->n_slabs_pending == 0) return NPDRB_OK;
     npdrb_ctx *ctx = s->ctx;
+    NB_CHECK(nb_issue_slab(s, s->n_slabs_pending - 1));
     for (int i = 0; i < s->n_slabs_pending; ++i) NB_CUDA(cudaStreamWaitEvent(ctx->stream, s->slab_ev[(size_t)i], 0));
-    s->n_slabs_pending = 0;
+    s->n_slabs_pending = 0; s->hX_lazy = nullptr;
     return check_finite(ctx, s->dX, s->ldx * s->p, "the attribute matrix");
 }
 
@@ -212,6 +344,8 @@ void npdrb_destroy(npdrb_ctx *ctx) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         cache_release_device(ctx->device);
     }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); }
+    delete ctx->ring;
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -233,6 +367,22 @@ int npdrb_synchronize(npdrb_ctx *ctx) {
 }
 
 int64_t npdrb_launch_count(npdrb_ctx *ctx) { return ctx->launches; }
+
+int npdrb_upload_columns(npdrb_ctx *ctx, void *dst_device, int64_t ld_dst, const double *src_host, int64_t rows, int64_t ncols) {
+    if (!ctx) { npdrb_set_error("npdrb_upload_columns: null context (no device)"); return NPDRB_ENODEVICE; }
+    if (!dst_device || !src_host || rows < 1 || ncols < 0 || ld_dst < rows) { npdrb_set_error("npdrb_upload_columns: bad arguments"); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(ctx->device));
+    if (ncols == 0) return NPDRB_OK;
+    if (nb_host_pointer_is_pinned(src_host)) {
+        NB_CUDA(cudaMemcpy2DAsync(dst_device, sizeof(double) * (size_t)ld_dst, src_host, sizeof(double) * (size_t)rows,
+                                  sizeof(double) * (size_t)rows, (size_t)ncols, cudaMemcpyHostToDevice, ctx->stream));
+        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return NPDRB_OK;
+    }
+    NB_CHECK(nb_staged_h2d(ctx, (double *)dst_device, ld_dst, src_host, rows, ncols));
+    NB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return NPDRB_OK;
+}
 
 int npdrb_measure_fp64_peak(npdrb_ctx *ctx, double *dfma_tflops, double *dadd_tflops) {
     NB_CUDA(cudaSetDevice(ctx->device));
@@ -327,17 +477,25 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
             NB_CUDA(cudaEventRecord(ready, ctx->stream));
             NB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
             cudaEventDestroy(ready);
+            // pinned source: every slab is enqueued now.  Pageable source: nothing is copied here -- nb_issue_slab()
+            // stages slab i through the pinned ring when its consumer is about to be launched (distance.cu), so the
+            // host-side memcpy of slab i+1 overlaps the kernel of slab i.
+            const bool pinned = nb_host_pointer_is_pinned(X);
             int used = 0;
             for (int i = 0; i < n_slabs; ++i) {
                 const int64_t c0 = (int64_t)i * s->slab_cols, c1 = (c0 + s->slab_cols < p) ? c0 + s->slab_cols : p;
                 if (c0 >= p) break;
-                NB_CUDA(cudaMemcpy2DAsync(s->dX + c0 * s->ldx, sizeof(double) * (size_t)s->ldx, X + c0 * N, sizeof(double) * (size_t)N,
-                                          sizeof(double) * (size_t)N, (size_t)(c1 - c0), cudaMemcpyHostToDevice, ctx->copy_stream));
                 NB_CUDA(cudaEventCreateWithFlags(&s->slab_ev[(size_t)i], cudaEventDisableTiming));
-                NB_CUDA(cudaEventRecord(s->slab_ev[(size_t)i], ctx->copy_stream));
+                if (pinned) {
+                    NB_CUDA(cudaMemcpy2DAsync(s->dX + c0 * s->ldx, sizeof(double) * (size_t)s->ldx, X + c0 * N, sizeof(double) * (size_t)N,
+                                              sizeof(double) * (size_t)N, (size_t)(c1 - c0), cudaMemcpyHostToDevice, ctx->copy_stream));
+                    NB_CUDA(cudaEventRecord(s->slab_ev[(size_t)i], ctx->copy_stream));
+                }
                 used = i + 1;
             }
             s->n_slabs_pending = used;
+            s->n_slabs_issued = pinned ? used : 0;
+            s->hX_lazy = pinned ? nullptr : X;
         } else {
             NB_CUDA(cudaMemcpy2DAsync(s->dX, sizeof(double) * (size_t)s->ldx, X, sizeof(double) * (size_t)N,
                                       sizeof(double) * (size_t)N, (size_t)p, cudaMemcpyHostToDevice, ctx->stream));
@@ -363,7 +521,7 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
 
 int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy, const double *dC) {
     if (dX) {
-        if (s->n_slabs_pending) { cudaStreamSynchronize(s->ctx->copy_stream); s->n_slabs_pending = 0; }
+        if (s->n_slabs_pending) { cudaStreamSynchronize(s->ctx->copy_stream); s->n_slabs_pending = 0; s->n_slabs_issued = 0; s->hX_lazy = nullptr; }
         if (ldx < s->N || (ldx & 1)) { npdrb_set_error("set_device_inputs: ldx must be even and >= N"); return NPDRB_EINVAL; }
         if (((uintptr_t)dX) & 15) { npdrb_set_error("set_device_inputs: dX must be 16-byte aligned"); return NPDRB_EINVAL; }
         if (s->own_X) cudaFree(s->dX);
@@ -636,6 +794,9 @@ int npdrb_nearest_neighbors2(npdrb_ctx *ctx, const double *X1, int64_t m1, const
                              int64_t **offsets, int32_t **idx, int64_t *M, double *radius_out) {
     if (!ctx) { npdrb_set_error("npdrb_nearest_neighbors2: null context (no device)"); return NPDRB_ENODEVICE; }
     if (m2 < 1) { npdrb_set_error("npdrb_nearest_neighbors2: empty second matrix"); return NPDRB_EINVAL; }
+    if (offsets) *offsets = nullptr;
+    if (idx) *idx = nullptr;
+    if (!offsets || !idx || !M) { npdrb_set_error("npdrb_nearest_neighbors2: null output pointer"); return NPDRB_EINVAL; }
     npdrb_session *s = nullptr;
     NB_CHECK(npdrb_session_create(ctx, m1, p, 0, &s));
     int rc = rect_block(s, X1, X2, m2, nbd_metric);
@@ -661,6 +822,7 @@ int npdrb_nearest_neighbors2(npdrb_ctx *ctx, const double *X1, int64_t m1, const
         if (e != cudaSuccess) { npdrb_set_error("npdrb_nearest_neighbors2: %s", cudaGetErrorString(e)); rc = NPDRB_ECUDA; }
         *M = Ml;
     }
+    if (rc) { free(*offsets); free(*idx); *offsets = nullptr; *idx = nullptr; }   // nothing is handed out on failure
     npdrb_session_destroy(s);
     return rc;
 }
@@ -669,9 +831,11 @@ static int pairs_to_host(npdrb_session *s, int32_t **Ri, int32_t **NN) {
     const int64_t M = s->M;
     *Ri = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
     *NN = (int32_t *)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
-    if (!*Ri || !*NN) { npdrb_set_error("out of host memory for %lld pairs", (long long)M); return NPDRB_ENOMEM; }
-    if (M > 0) NB_CHECK(npdrb_session_copy_pairs(s, *Ri, *NN));
-    return NPDRB_OK;
+    int rc = NPDRB_OK;
+    if (!*Ri || !*NN) { npdrb_set_error("out of host memory for %lld pairs", (long long)M); rc = NPDRB_ENOMEM; }
+    if (!rc && M > 0) rc = npdrb_session_copy_pairs(s, *Ri, *NN);
+    if (rc) { free(*Ri); free(*NN); *Ri = nullptr; *NN = nullptr; }              // nothing is handed out on failure
+    return rc;
 }
 
 // distances (or adoption of a precomputed matrix) + neighbours on one device; leaves the list imported in s

@@ -58,6 +58,7 @@ struct npdrb_ctx {
     int sm_count = 148;
     int64_t launches = 0;
     size_t smem_optin = 0;
+    struct nb_stage_ring *ring = nullptr; // pinned staging ring + memcpy helpers for pageable host sources (api.cu)
 };
 
 // One bucketed pair stream for the regression kernels (see regress.cu).
@@ -84,7 +85,11 @@ struct npdrb_session {
     double *dXs = nullptr;                                               // pre-scaled copy for scaled metrics
     // pipelined upload (npdrb_session_upload of a large X): column slabs in flight on ctx->copy_stream; slab i covers
     // attributes [i * slab_cols, ...) and is complete once slab_ev[i] has fired.  nb_wait_upload() joins them.
+    // A PAGEABLE host matrix (what R hands over) is not copied by npdrb_session_upload at all: hX_lazy keeps the caller's
+    // pointer and nb_issue_slab() stages slab i through the context's pinned ring (helper threads memcpy, async H2D) right
+    // before the consumer of slab i is launched, so the copy of slab i+1 runs under the distance kernel of slab i.
     std::vector<cudaEvent_t> slab_ev; int64_t slab_cols = 0; int n_slabs_pending = 0;
+    const double *hX_lazy = nullptr; int n_slabs_issued = 0;
     double *dy = nullptr; bool own_y = false;
     double *dC = nullptr; bool own_C = false;                            // N x q, ld N
     // distance block: nrows x N, row-major with leading dim ldd (row r = column row0+r of the symmetric D)
@@ -116,6 +121,12 @@ struct npdrb_session {
 
 // stage implementations (one .cu each)
 int nb_wait_upload(npdrb_session *s);     // main stream waits for every slab; NA/NaN/Inf check of X (NPDRB_EDATA)
+int nb_issue_slab(npdrb_session *s, int slab);   // make sure the H2D copy of column slab `slab` has been enqueued (slab_ev[slab] recorded)
+// staged host -> device copy of `ncols` contiguous columns of `rows` doubles (pageable source) through the context's pinned
+// ring on ctx->copy_stream; returns once every chunk has been ENQUEUED (the host source may not be touched until the
+// copy stream has drained, which the slab event / a stream synchronize guarantees to the callers)
+bool nb_host_pointer_is_pinned(const void *p);
+int nb_staged_h2d(npdrb_ctx *ctx, double *dst, int64_t ld_dst, const double *src, int64_t rows, int64_t ncols);
 int nb_check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what);
 int nb_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
 int nb_distances_balanced(npdrb_session *s, int32_t metric, int32_t fast_euclidean, const int64_t *row_starts, int32_t rank,

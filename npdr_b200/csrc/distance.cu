@@ -360,8 +360,12 @@ int pick_tile_width(int64_t n_squares, int sm_count) {
 
 template <int MODE>
 int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const double *XB, int64_t NB, int64_t ldB, int64_t p,
-               int64_t row0, int64_t nrows, const TilePlan &plan, double *dD, int64_t ldd,
-               const std::vector<cudaEvent_t> *slab_ev = nullptr, int n_slabs = 0, int64_t slab_cols = 0) {
+               int64_t row0, int64_t nrows, const TilePlan &plan, double *dD, int64_t ldd, npdrb_session *slab_s = nullptr) {
+    // slab_s: the session whose X is still arriving as column slabs (pipelined upload): one launch per slab, each issued
+    // right after its H2D copy has been enqueued (pageable sources are staged by this thread while the previous slab's
+    // kernel runs)
+    const int n_slabs = slab_s ? slab_s->n_slabs_pending : 0;
+    const int64_t slab_cols = slab_s ? slab_s->slab_cols : 0;
     CUtensorMap mapA, mapB;
     NB_CHECK(make_tensor_map(&mapA, XA, NA, p, ldA));
     NB_CHECK(make_tensor_map(&mapB, XB, NB, p, ldB, plan.tn));
@@ -376,11 +380,12 @@ int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const 
     NB_CUDA(cudaFuncSetAttribute(dist_tma_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM));
     // one launch over all attributes, or one per uploaded column slab as it arrives (pipelined npdrb_session_upload)
     const int n_chunks = (int)nb_cdiv(p, BK);
-    const int n_launch = (slab_ev && n_slabs > 1) ? n_slabs : 1;
+    const int n_launch = (n_slabs > 1) ? n_slabs : 1;
     for (int l = 0; l < n_launch; ++l) {
         int c_lo = 0, c_hi = n_chunks;
         if (n_launch > 1) {
-            NB_CUDA(cudaStreamWaitEvent(ctx->stream, (*slab_ev)[(size_t)l], 0));
+            NB_CHECK(nb_issue_slab(slab_s, l));
+            NB_CUDA(cudaStreamWaitEvent(ctx->stream, slab_s->slab_ev[(size_t)l], 0));
             c_lo = (int)(l * slab_cols / BK);
             c_hi = (int)nb_cdiv((l + 1) * slab_cols < p ? (l + 1) * slab_cols : p, BK);
         }
@@ -400,10 +405,9 @@ int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const 
 template <int MODE>
 int launch_tma(npdrb_session *s, const double *X, int64_t row0, int64_t nrows, const TilePlan &plan) {
     const bool slabs = s->n_slabs_pending > 1 && X == s->dX;
-    int rc = launch_tma<MODE>(s->ctx, X, s->N, s->ldx, X, s->N, s->ldx, s->p, row0, nrows, plan, s->dD, s->ldd,
-                              slabs ? &s->slab_ev : nullptr, slabs ? s->n_slabs_pending : 0, s->slab_cols);
+    int rc = launch_tma<MODE>(s->ctx, X, s->N, s->ldx, X, s->N, s->ldx, s->p, row0, nrows, plan, s->dD, s->ldd, slabs ? s : nullptr);
     if (rc == NPDRB_OK && slabs) {                     // every slab has been waited for on the main stream
-        s->n_slabs_pending = 0;
+        s->n_slabs_pending = 0; s->n_slabs_issued = 0; s->hX_lazy = nullptr;
         rc = nb_check_finite(s->ctx, s->dX, s->ldx * s->p, "the attribute matrix");
     }
     return rc;
@@ -465,6 +469,7 @@ int dist_core(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t 
     }
     if (row0 < 0 || nrows < 1 || row0 + nrows > s->N) { npdrb_set_error("distances: bad row block"); return NPDRB_EINVAL; }
     if (row0 % TM != 0) { npdrb_set_error("distances: row0 must be a multiple of %d", TM); return NPDRB_EINVAL; }
+    if (s->n_slabs_pending == 1) NB_CHECK(nb_wait_upload(s));     // a single pending slab: nothing to pipeline against
 
     if (s->dD && s->own_D && (s->nrows != nrows)) { cudaFree(s->dD); s->dD = nullptr; }
     if (!s->dD || !s->own_D) {

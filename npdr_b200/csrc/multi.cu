@@ -20,14 +20,18 @@ namespace {
 
 constexpr int TILE_ROWS = 128;      // row blocks start on distance-tile boundaries
 
+// Host barrier of the device threads.  wait() returns the value of `failed` as the LAST arriver saw it, so every thread
+// leaves the barrier with the same verdict: a thread that races ahead and fails in the next phase cannot make a slower
+// peer quit while the others still expect it at the following barrier (the exit decision is collective).
 struct Barrier {
-    std::mutex mu; std::condition_variable cv; int n, waiting = 0; unsigned gen = 0;
+    std::mutex mu; std::condition_variable cv; int n, waiting = 0; unsigned gen = 0; int verdict = 0;
     explicit Barrier(int n_) : n(n_) {}
-    void wait() {
+    int wait(const std::atomic<int> &failed) {
         std::unique_lock<std::mutex> lk(mu);
         const unsigned g = gen;
-        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        if (++waiting == n) { verdict = failed.load(); waiting = 0; ++gen; cv.notify_all(); }
         else cv.wait(lk, [&] { return gen != g; });
+        return verdict;                              // stable until all n threads have arrived at the NEXT barrier
     }
 };
 
@@ -104,14 +108,20 @@ void run_worker(Shared &S, int g) {
         double *dX = nullptr;
         STEP(CU(cudaMalloc(&dX, sizeof(double) * (size_t)ldx * (size_t)S.p)));
         if (dX && ldx != S.N) STEP(CU(cudaMemsetAsync(dX, 0, sizeof(double) * (size_t)ldx * (size_t)S.p, w.ctx->stream)));
-        if (dX && w.nattr > 0)
-            STEP(CU(cudaMemcpy2DAsync(dX + w.attr0 * ldx, sizeof(double) * (size_t)ldx, S.X + w.attr0 * S.N, sizeof(double) * (size_t)S.N,
-                                      sizeof(double) * (size_t)S.N, (size_t)w.nattr, cudaMemcpyHostToDevice, w.ctx->stream)));
+        if (dX && w.nattr > 0) {
+            if (nb_host_pointer_is_pinned(S.X)) {
+                STEP(CU(cudaMemcpy2DAsync(dX + w.attr0 * ldx, sizeof(double) * (size_t)ldx, S.X + w.attr0 * S.N, sizeof(double) * (size_t)S.N,
+                                          sizeof(double) * (size_t)S.N, (size_t)w.nattr, cudaMemcpyHostToDevice, w.ctx->stream)));
+            } else {                                 // pageable (R's heap): through this device's pinned ring, after the memset
+                STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
+                STEP(nb_staged_h2d(w.ctx, dX + w.attr0 * ldx, ldx, S.X + w.attr0 * S.N, S.N, w.nattr));
+                if (w.ctx && w.ctx->copy_stream) STEP(CU(cudaStreamSynchronize(w.ctx->copy_stream)));
+            }
+        }
         STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
         if (w.s && dX) { w.s->dX = dX; w.s->ldx = ldx; w.s->own_X = true; }
         else if (dX) cudaFree(dX);
-        S.bar->wait();
-        if (S.failed.load()) return;
+        if (S.bar->wait(S.failed)) return;
         for (int h = 0; h < S.G; ++h) {
             const Worker &peer = S.w[(size_t)h];
             if (h == g || peer.nattr == 0) continue;
@@ -135,8 +145,7 @@ void run_worker(Shared &S, int g) {
         }
         if (w.s) w.ms_distance = w.s->ms_distance;
     }
-    S.bar->wait();
-    if (S.failed.load()) return;
+    if (S.bar->wait(S.failed)) return;
     // ---- phase 2: pull the halves the peers computed for my rows, unpack
     double *d_recv = nullptr;
     if (w.live >= 0 && W > 1) {
@@ -155,9 +164,9 @@ void run_worker(Shared &S, int g) {
         }
         STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
     }
-    S.bar->wait();                                   // every pull has completed: send buffers can go
+    const int bad2 = S.bar->wait(S.failed);          // every pull has completed: send buffers can go
     if (w.d_send) { cudaFree(w.d_send); w.d_send = nullptr; }
-    if (S.failed.load()) { if (d_recv) cudaFree(d_recv); return; }
+    if (bad2) { if (d_recv) cudaFree(d_recv); return; }
     if (w.live >= 0 && W > 1) {
         int64_t nr = 0;
         for (int64_t c : w.recv_cnt) nr += c;
@@ -168,14 +177,12 @@ void run_worker(Shared &S, int g) {
     const bool surf_multi = (o.nbd_method == NPDRB_NBD_SURF) && W > 1;
     if (surf_multi) {
         if (w.live >= 0) STEP(npdrb_session_surf_partial(w.s, 0.0, w.surf0));
-        S.bar->wait();
-        if (S.failed.load()) return;
+        if (S.bar->wait(S.failed)) return;
         double m0[4] = {0, 0, 0, 0};
         for (int h : S.live_devs) for (int t = 0; t < 4; ++t) m0[t] += S.w[(size_t)h].surf0[t];
         const double mean_u = m0[1] / m0[2];
         if (w.live >= 0) STEP(npdrb_session_surf_partial(w.s, mean_u, w.surf1));
-        S.bar->wait();
-        if (S.failed.load()) return;
+        if (S.bar->wait(S.failed)) return;
         double m1[4] = {0, 0, 0, 0};
         for (int h : S.live_devs) for (int t = 0; t < 4; ++t) m1[t] += S.w[(size_t)h].surf1[t];
         const double num_pair = (double)S.N * (double)(S.N - 1) / 2.0;
@@ -188,8 +195,7 @@ void run_worker(Shared &S, int g) {
         else STEP(nb_neighbors(w.s, o.nbd_method, o.msurf_sd_frac, S.k, &w.M_local, &w.n_empty));
         if (w.s) w.ms_neighbors = w.s->ms_neighbors;
     }
-    S.bar->wait();
-    if (S.failed.load()) return;
+    if (S.bar->wait(S.failed)) return;
     // ---- phase 4: the full pair list on every device (segments in rank order = reference order)
     int64_t M = 0;
     for (int h : S.live_devs) M += S.w[(size_t)h].M_local;
@@ -208,8 +214,11 @@ void run_worker(Shared &S, int g) {
         }
         STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
     }
-    S.bar->wait();                                   // every device has its copy: the local segments may be reused
-    if (S.failed.load()) { if (dRi) cudaFree(dRi); if (dNN) cudaFree(dNN); return; }
+    if (S.bar->wait(S.failed)) {                     // every device has its copy: the local segments may be reused
+        if (dRi) cudaFree(dRi);
+        if (dNN) cudaFree(dNN);
+        return;
+    }
     if (g == 0) S.M_total = M;
     // ---- phase 5: regression of my attribute columns
     if (M > 0 && w.nattr > 0) {
@@ -234,7 +243,11 @@ extern "C" int npdrb_npdr_multi(int32_t n_devices, const int32_t *devices, const
         npdrb_set_error("npdrb_npdr_multi: surf hit/miss radii need the whole distance matrix on one device");
         return NPDRB_EINVAL;
     }
-    for (int a = 0; a < n_devices; ++a)
+    // NPDRB_MULTI_ALLOW_DUPLICATES=1 (tests): the same ordinal may be listed several times; the workers then share that
+    // device's context and stream (stream order keeps the memory cache's reuse rule valid) and "peer" copies are local.
+    const char *dup_env = getenv("NPDRB_MULTI_ALLOW_DUPLICATES");
+    const bool allow_dup = dup_env && dup_env[0] == '1';
+    for (int a = 0; a < n_devices && !allow_dup; ++a)
         for (int b = a + 1; b < n_devices; ++b)
             if (devices && devices[a] == devices[b]) { npdrb_set_error("npdrb_npdr_multi: device %d listed twice", devices[a]); return NPDRB_EINVAL; }
     Shared S;

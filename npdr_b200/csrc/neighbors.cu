@@ -378,9 +378,16 @@ __global__ void flag_dups_kernel(const int32_t *__restrict__ Ri, const int32_t *
             dup = (bits[b >> 5] >> (b & 31)) & 1u;
         }
         keep[m] = (uint8_t)!dup;
+        if (m > 0 && Ri[m] < Ri[m - 1]) atomicOr((unsigned *)(n_dup + 1), 1u);   // precondition: grouped by ascending Ri
     }
     unsigned mask = __ballot_sync(0xffffffffu, dup);
     if ((threadIdx.x & 31) == 0 && mask) atomicAdd(n_dup, (unsigned long long)__popc(mask));
+}
+__global__ void popcount_words_kernel(const unsigned *__restrict__ bits, size_t words, unsigned long long *__restrict__ out) {
+    unsigned long long c = 0;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) c += __popc(bits[w]);
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 // stable compaction of kept rows: per-block counts -> scan (host-free: reuse scan_counts_kernel) -> scatter
 __global__ void block_keep_count_kernel(const uint8_t *__restrict__ keep, int64_t M, int64_t *__restrict__ counts) {
@@ -1003,17 +1010,29 @@ int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_uniqu
     unsigned *d_bits = nullptr; uint8_t *d_keep = nullptr; unsigned long long *d_ndup = nullptr;
     NB_CUDA(cudaMalloc(&d_bits, sizeof(unsigned) * words));
     NB_CUDA(cudaMalloc(&d_keep, (size_t)M));
-    NB_CUDA(cudaMalloc(&d_ndup, sizeof(unsigned long long)));
+    NB_CUDA(cudaMalloc(&d_ndup, 3 * sizeof(unsigned long long)));      // [0] duplicates, [1] "not grouped by Ri" flag, [2] distinct ordered pairs
     NB_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned) * words, ctx->stream));
-    NB_CUDA(cudaMemsetAsync(d_ndup, 0, sizeof(unsigned long long), ctx->stream));
+    NB_CUDA(cudaMemsetAsync(d_ndup, 0, 3 * sizeof(unsigned long long), ctx->stream));
     const unsigned grid = (unsigned)nb_cdiv(M, 256);
     mark_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(s->dRi, s->dNN, M, N, d_bits);
     NB_LAUNCH_CHECK(ctx);
     flag_dups_kernel<<<grid, 256, 0, ctx->stream>>>(s->dRi, s->dNN, M, N, d_bits, d_keep, d_ndup);
     NB_LAUNCH_CHECK(ctx);
-    unsigned long long ndup = 0;
-    NB_CUDA(cudaMemcpyAsync(&ndup, d_ndup, sizeof(ndup), cudaMemcpyDeviceToHost, ctx->stream));
+    popcount_words_kernel<<<1024, 256, 0, ctx->stream>>>(d_bits, words, d_ndup + 2);
+    NB_LAUNCH_CHECK(ctx);
+    unsigned long long h3[3] = {0, 0, 0};
+    NB_CUDA(cudaMemcpyAsync(h3, d_ndup, sizeof(h3), cudaMemcpyDeviceToHost, ctx->stream));
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // The "i > j and (j, i) present" rule equals uniqueNeighbors' keep-the-first-occurrence (R/nearestNeighbors.R:576-582)
+    // only for lists grouped by ascending Ri_idx without repeated ordered pairs -- what nearestNeighbors() emits.  Anything
+    // else (a hand-made list through npdrb_session_import_pairs*) is rejected rather than answered differently from R.
+    if (h3[1] != 0 || (int64_t)h3[2] != M) {
+        cudaFree(d_bits); cudaFree(d_keep); cudaFree(d_ndup);
+        npdrb_set_error("unique_pairs: the pair list must be grouped by ascending Ri_idx and must not repeat an ordered pair "
+                        "(%lld rows, %llu distinct pairs%s)", (long long)M, h3[2], h3[1] ? ", Ri_idx decreases somewhere" : "");
+        return NPDRB_EINVAL;
+    }
+    const unsigned long long ndup = h3[0];
     const int64_t nu = M - (int64_t)ndup;
     if (n_unique) *n_unique = nu;
     if (keep_unique_only && ndup > 0) {

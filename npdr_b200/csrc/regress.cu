@@ -1495,7 +1495,8 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         int64_t n_miss = 0;
         bool folded = false;
         const char *nf = getenv("NPDRB_NO_FOLD");
-        if (!(nf && nf[0] == '1') && s->M >= 2) {
+        // (RAW = uniReg: the row is x[Ri], y[Ri] -- not symmetric in (i, j), so mutual pairs must not be folded)
+        if (!y_raw && !(nf && nf[0] == '1') && s->M >= 2) {
             // classify: one-directional (weight 1) / mutual with i<j (weight 2) / mutual reverse (dropped)
             const int64_t M = s->M;
             const size_t words = ((size_t)N * (size_t)N + 31) / 32;

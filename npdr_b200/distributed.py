@@ -106,11 +106,23 @@ def exchange_balanced(engine, parts, rank, nbd_metric, group=None):
         engine.balanced_unpack(recv, n_recv)
 
 
+def pair_list_hash(ri, nn):
+    """Order-sensitive 64-bit hash of a (Ri, NN) pair list held in torch tensors (wrapping int64 arithmetic): equal lists
+    <=> equal hashes for all practical purposes; used to assert that N ranks and one rank find the same list."""
+    if ri.numel() == 0:
+        return 0
+    i = ri.to(torch.int64); j = nn.to(torch.int64)
+    pos = torch.arange(1, ri.numel() + 1, dtype=torch.int64, device=ri.device)
+    h = (i * 1000003 + j * 7919 + 12345) * (pos * 2654435761 + 1)
+    h = h ^ (h >> 29)
+    return int(h.sum().item())
+
+
 def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numeric-abs", nbd_method="multisurf",
                  nbd_metric="manhattan", knn=0, msurf_sd_frac=0.5, covar_diff_type=(), neighbor_sampling="none",
-                 group=None, separate_hitmiss_nbds=False):
+                 group=None, separate_hitmiss_nbds=False, pair_hash=False):
     """Run the path sharded over the default process group.  Every rank returns
-    (stats [p, 8] on rank 0 else None, info dict)."""
+    (stats [p, 8] on rank 0 else None, info dict).  pair_hash: also return pair_list_hash() of the gathered list."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     row0, nrows = partition_rows(N, world)[rank]
@@ -150,6 +162,8 @@ def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numer
         st = torch.zeros((0, 8), dtype=torch.float64, device=dev); n_unique, n_used = -1, -1
     info = {"n_pairs": int(sum(counts)), "pair_counts": counts, "n_unique_pairs": n_unique, "n_pairs_used": n_used,
             "rows": (row0, nrows), "attrs": (attr0, nattr)}
+    if pair_hash:
+        info["pair_hash"] = pair_list_hash(ri_all, nn_all)
     if world == 1:
         return st.cpu().numpy(), info
     flat, fcounts = all_gather_varlen(st.reshape(-1), group)      # tiny: p x 8 doubles in total

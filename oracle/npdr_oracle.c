@@ -59,6 +59,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py's reference arm: use n host threads regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ npdrDiff */
 /* R/nearestNeighbors.R:15-40.  `manhattan` == `numeric-abs`. */
 static inline double diff1(double a, double b, int type, double norm_fac) {

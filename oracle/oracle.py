@@ -59,6 +59,12 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    """OpenMP threads of the oracle from now on (overrides OMP_NUM_THREADS, which torchrun sets to 1)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def diff(a, b, diff_type="numeric-abs", norm_fac=1.0):
     a = _f64(np.asarray(a, dtype=np.float64)); b = _f64(np.asarray(b, dtype=np.float64))
     if diff_type == "correlation-data":
