@@ -98,6 +98,7 @@ struct nb_stage_ring {
     std::mutex mu; std::condition_variable cv_go, cv_done;
     unsigned gen = 0; int remaining = 0; bool stop = false;
     char *job_dst = nullptr; const char *job_src = nullptr; size_t job_bytes = 0; int job_pieces = 1;
+    std::mutex api_mu;                // one staged copy at a time per ring (workers that share a context in the emulated multi-device mode)
 
     static void copy_piece(char *dst, const char *src, size_t bytes, int piece, int pieces) {
         const size_t per = ((bytes / (size_t)pieces) + 4095) & ~(size_t)4095;
@@ -145,7 +146,10 @@ struct nb_stage_ring {
     }
 };
 
+static std::mutex g_ring_mu;          // creation of a context's ring / copy stream
 static int get_ring(npdrb_ctx *ctx, nb_stage_ring **out) {
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    if (!ctx->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!ctx->ring) {
         nb_stage_ring *r = new nb_stage_ring();
         for (int b = 0; b < nb_stage_ring::NBUF; ++b) {
@@ -167,10 +171,10 @@ static int get_ring(npdrb_ctx *ctx, nb_stage_ring **out) {
 }
 
 int nb_staged_h2d(npdrb_ctx *ctx, double *dst, int64_t ld_dst, const double *src, int64_t rows, int64_t ncols) {
-    if (!ctx->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     const size_t col_bytes = sizeof(double) * (size_t)rows;
     nb_stage_ring *r = nullptr;
     NB_CHECK(get_ring(ctx, &r));
+    std::lock_guard<std::mutex> api_lk(r->api_mu);
     if (col_bytes > r->buf_bytes) {                       // a single column does not fit a ring buffer: let the driver stage it
         NB_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)ld_dst, src, col_bytes, col_bytes, (size_t)ncols,
                                   cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -468,7 +472,10 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
         const char *np_ = getenv("NPDRB_NO_PIPELINED_UPLOAD");
         const int n_slabs = (bytes >= (64ll << 20) && !(np_ && np_[0] == '1')) ? 8 : 1;
         if (n_slabs > 1) {
-            if (!ctx->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            {
+                std::lock_guard<std::mutex> lk(g_ring_mu);
+                if (!ctx->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            }
             for (cudaEvent_t e : s->slab_ev) cudaEventDestroy(e);
             s->slab_ev.assign((size_t)n_slabs, nullptr);
             s->slab_cols = nb_round_up(nb_cdiv(p, n_slabs), 16);

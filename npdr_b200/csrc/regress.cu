@@ -18,6 +18,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <math.h>
+#include <mutex>
 #include "common.cuh"
 #include "dmath.cuh"
 
@@ -1231,7 +1232,9 @@ int dmalloc(T **p, size_t n) {
 nb_tables *g_tables_dev[64] = {nullptr};
 nb_tables1024 *g_tables1024_dev[64] = {nullptr};
 
+std::mutex g_tables_mu;
 int get_tables1024(npdrb_ctx *ctx, const nb_tables1024 **out) {
+    std::lock_guard<std::mutex> lk(g_tables_mu);
     if (!g_tables1024_dev[ctx->device & 63]) {
         static const nb_tables1024 host_tables = NB_TABLES1024_STATIC_INIT;
         nb_tables1024 *d = nullptr;
@@ -1246,6 +1249,7 @@ int get_tables1024(npdrb_ctx *ctx, const nb_tables1024 **out) {
 }
 
 int get_tables(npdrb_ctx *ctx, const nb_tables **out) {
+    std::lock_guard<std::mutex> lk(g_tables_mu);
     if (!g_tables_dev[ctx->device & 63]) {
         static const nb_tables host_tables = NB_TABLES_STATIC_INIT;
         nb_tables *d = nullptr;

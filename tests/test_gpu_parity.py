@@ -723,31 +723,140 @@ def test_npdr_multi_driver_one_device(nb, name):
         assert info1[f] == info2[f], f
 
 
-@pytest.mark.parametrize("method,hitmiss", [("multisurf", False), ("surf", False), ("relieff", False), ("multisurf", True)])
-def test_npdr_multi_driver_two_devices(nb, oracle, method, hitmiss):
-    """Two GPUs from one process: pair list bit-identical to the oracle, statistics within the IRLS bar."""
-    if _n_devices() < 2:
-        pytest.skip("needs two GPUs")
+def _multi_devices(n, monkeypatch):
+    """Device list for an n-device in-process run: real ordinals when the box has them, otherwise device 0 listed n times
+    (NPDRB_MULTI_ALLOW_DUPLICATES: the workers share the device, every exchange still goes through the peer-copy path)."""
+    if _n_devices() >= n:
+        return list(range(n))
+    monkeypatch.setenv("NPDRB_MULTI_ALLOW_DUPLICATES", "1")
+    return [0] * n
+
+
+@pytest.mark.parametrize("method,hitmiss,ndev", [("multisurf", False, 2), ("surf", False, 2), ("relieff", False, 2), ("multisurf", True, 2),
+                                                 ("multisurf", False, 3), ("relieff", True, 3)])
+def test_npdr_multi_driver_two_devices(nb, oracle, method, hitmiss, ndev, monkeypatch):
+    """Several devices from one process (emulated on one GPU when the box has no more): pair list bit-identical to the
+    oracle, statistics within the IRLS bar."""
     rng = np.random.default_rng(33)
-    N, p = 700, 300                                              # 6 row tiles -> 3 + 3; ragged last tile
+    N, p = 700, 300                                              # 6 row tiles -> 3 + 3 (2 + 2 + 2); ragged last tile
     X = np.asfortranarray(rng.normal(size=(N, p)))
     y = (rng.random(N) < 0.5).astype(float)
     X[:, :4] += 0.7 * y[:, None]
     Cv = np.asfortranarray(np.column_stack([rng.integers(0, 2, N).astype(float), rng.normal(40, 10, N).round()]))
     out, info = nb.npdr(y, X, "binomial", "numeric-abs", method, "manhattan", covars=Cv,
-                        covar_diff_type=("match-mismatch", "numeric-abs"), separate_hitmiss_nbds=hitmiss, n_gpus=2, return_info=True)
+                        covar_diff_type=("match-mismatch", "numeric-abs"), separate_hitmiss_nbds=hitmiss,
+                        devices=_multi_devices(ndev, monkeypatch), return_info=True)
     if hitmiss:
         ri, nn, _, _, _ = oracle.nearest_neighbors_hitmiss(X, y, method)
     else:
         ri, nn, _, _ = oracle.nearest_neighbors(X, method)
-    if method == "surf":                                         # radius from combined moments: a boundary pair may differ
-        assert abs(info["n_pairs"] - ri.size) <= 2
-        return
     assert np.array_equal(info["Ri"], ri) and np.array_equal(info["NN"], nn)
     cd = np.column_stack([oracle.pair_diffs(Cv[:, 0], ri, nn, "match-mismatch"), oracle.pair_diffs(Cv[:, 1], ri, nn, "numeric-abs")])
     exp = oracle.regress_attrs(X, ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"), cd)
     _stats_close(info["stats"], exp, RTOL_IRLS, f"multi {method}")
     assert set(out["att"][:4]) == {"1", "2", "3", "4"}
+
+
+def test_npdr_multi_driver_error_paths_return(nb, monkeypatch):
+    """A failure inside one device thread ends the call with an error on every thread (no hang at a host barrier):
+    NaN input is detected after the column exchange, a single-level outcome in the regression phase."""
+    rng = np.random.default_rng(5)
+    N, p = 300, 64
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    y = (rng.random(N) < 0.5).astype(float)
+    devs = _multi_devices(2, monkeypatch)
+    Xbad = X.copy(order="F"); Xbad[17, 40] = np.nan
+    with pytest.raises(nb.NpdrB200Error):
+        nb.npdr(y, Xbad, devices=devs)
+    with pytest.raises(nb.NpdrB200Error):
+        nb.npdr(np.zeros(N), X, devices=devs)                    # every pair is a hit: glm has a single-level outcome
+    out = nb.npdr(y, X, devices=devs)                            # and the driver is still usable afterwards
+    assert len(out) == p
+
+
+# ---------------------------------------------------------------- BASELINE config 5 (20,000 x 50,000, q = 2): the north star
+CFG5_MEDIUM = dict(N=4000, p_per_gpu=None, p_total=512, q=2, pct_signals=0.01, scaling="strong", desc="cfg5 recipe at 4,000 x 512")
+
+
+def test_cfg5_recipe_medium_against_oracle(nb, oracle, monkeypatch):
+    """The cfg5 recipe (binomial, multisurf, manhattan, covariates sex -> match-mismatch and age -> numeric-abs) at
+    4,000 x 512, through npdrb_npdr from host buffers, FULLY against the oracle: pair list bit-exact, all 512 x 8
+    statistics within the IRLS bar with identical iteration counts; and the same call on two (emulated) devices."""
+    import torch
+    import bench
+    data = bench.make_data(CFG5_MEDIUM, 1, torch.device("cuda", 0))
+    N, p = data["N"], data["p"]
+    X = np.asfortranarray(data["dX"][:, :N].T.cpu().numpy())
+    y = data["dy"].cpu().numpy()
+    Cv = np.asfortranarray(data["dC"].T.cpu().numpy())
+    cdt = ("match-mismatch", "numeric-abs")
+    stats, info = nb.npdr_stats(X, y, Cv, covar_diff_type=cdt, return_pairs=True)
+    ri, nn, D, r = oracle.nearest_neighbors(X, "multisurf", "manhattan", 0.5)
+    assert np.array_equal(info["Ri"], ri) and np.array_equal(info["NN"], nn)
+    cd = np.column_stack([oracle.pair_diffs(Cv[:, c], ri, nn, cdt[c]) for c in range(2)])
+    exp = oracle.regress_attrs(X, ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"), cd)
+    _stats_close(stats, exp, RTOL_IRLS, "cfg5 recipe 4000 x 512")
+    strong = np.abs(exp[:, 1]) > 1.0                              # worst RELATIVE error where the statistic is not ~0
+    worst = np.max(np.abs(stats[strong, 1] - exp[strong, 1]) / np.abs(exp[strong, 1]))
+    assert worst < RTOL_IRLS, worst
+    stats2, info2 = nb.npdr_stats(X, y, Cv, covar_diff_type=cdt, return_pairs=True, devices=_multi_devices(2, monkeypatch))
+    assert np.array_equal(info2["Ri"], ri) and np.array_equal(info2["NN"], nn)
+    _stats_close(stats2, stats, 1e-8, "two devices vs one")       # other attribute ranges -> other chunking of the pair stream
+
+
+@pytest.mark.skipif(os.environ.get("NPDRB_SKIP_FULL_CFG5") == "1", reason="NPDRB_SKIP_FULL_CFG5=1")
+def test_cfg5_full_size_properties(nb, oracle):
+    """BASELINE's north-star configuration itself (bench generator, seed 1618; 20,000 x 50,000, q = 2, M = 1.66e8):
+    invariants of the full run, bit-exact oracle checks of what the oracle can do at this size (a 160-instance
+    sub-matrix of the distances in strict attribute order, ALL 20,000 long-double radii, the COMPLETE pair list), and
+    the oracle's IRLS on 4 attributes over all 1.66e8 pairs."""
+    import torch
+    import bench
+    from npdr_b200.distributed import GpuEngine, npdr_sharded
+    dev = torch.device("cuda", 0)
+    data = bench.make_data(bench.WORKLOADS["cfg5"], 1, dev)
+    torch.cuda.synchronize()
+    N, p, q = data["N"], data["p"], data["q"]
+    assert (N, p, q) == (20000, 50000, 2)
+    cdt = data["covar_diff_type"]
+    eng = GpuEngine(device_index=0, dX=data["dX"], ldx=data["ldx"], dy=data["dy"], dC=data["dC"], N=N, p=p, q=q)
+    stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, cdt)
+    s = eng.session
+    M = info["n_pairs"]
+    ri, nn = s.copy_pairs(M)
+    D = s.copy_distances()
+    r = s.copy_radius()
+    eng.close()
+    # distances: symmetric bit for bit, zero diagonal; a random 160 x 160 sub-matrix equals the oracle's strictly sequential sums
+    assert not D.diagonal().any()
+    for b0 in range(0, N, 2000):                                  # blockwise, to keep the temporaries small
+        assert np.array_equal(D[b0:b0 + 2000], D[:, b0:b0 + 2000].T)
+    sub = np.sort(np.random.default_rng(7).choice(N, 160, replace=False))
+    Xs = np.asfortranarray(data["dX"][:, :N].T[torch.as_tensor(sub, device=dev)].cpu().numpy())
+    assert np.array_equal(D[np.ix_(sub, sub)], oracle.distances(Xs, "manhattan"))
+    # radii: R's long-double colSums / sd over every row of the GPU's matrix; pair list: the complete selection, in order
+    r_exp, _ = oracle.radius_multisurf(D.T, 0.5)                  # D.T: the Fortran-ordered view of the symmetric matrix, no 3.2 GB copy
+    assert np.array_equal(r, r_exp)
+    ri_exp, nn_exp, _ = oracle.neighbors(D.T, "multisurf", radius=r_exp)
+    assert M == ri_exp.size and np.array_equal(ri, ri_exp) and np.array_equal(nn, nn_exp)
+    del ri_exp, nn_exp, D
+    assert np.all(ri != nn) and np.all(np.diff(ri) >= 0)
+    assert abs(M / (N * (N - 1)) - 0.3085) < 0.12
+    # statistics: finite, converged, and the functional (differential-correlation) attributes on top
+    assert np.isfinite(stats[:, :6]).all() and not stats[:, 7].any() and stats[:, 6].min() >= 2
+    top = np.argsort(-stats[:, 1])[:data["n_func"] // 2]
+    assert np.mean(top < data["n_func"]) > 0.9
+    # oracle IRLS (glm.fit restatement, QR) on 4 attributes over ALL pairs: two functional, two background columns
+    sl = np.array([1, data["n_func"] - 2, 30000, p - 1])
+    Xsl = np.asfortranarray(data["dX"][torch.as_tensor(sl, device=dev), :N].T.cpu().numpy())
+    yh = data["dy"].cpu().numpy(); Ch = data["dC"].T.cpu().numpy()
+    cd = np.column_stack([oracle.pair_diffs(np.ascontiguousarray(Ch[:, c]), ri, nn, cdt[c]) for c in range(2)])
+    oracle.set_num_threads(4)                                     # one M x 4 design matrix (5.3 GB) per thread
+    try:
+        exp = oracle.regress_attrs(Xsl, ri, nn, oracle.pair_diffs(yh, ri, nn, "match-mismatch"), cd)
+    finally:
+        oracle.set_num_threads(os.cpu_count() or 1)
+    _stats_close(stats[sl], exp, RTOL_IRLS, "cfg5 full size")
 
 
 def test_gpu_solvers_reproduce_published_r_output(nb, oracle):
