@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libnpdr_b200.so")
+SO_PATH = os.environ.get("NPDRB_LIB_PATH") or os.path.join(_HERE, "libnpdr_b200.so")   # override: A/B runs of two builds
 
 STATS_PER_ATTR = 8
 MAX_COVARS = 4

@@ -236,6 +236,7 @@ struct PassArgs {
     const double *dmax;            // [nattr_pad] bound on the attribute diff (v2 IRLS pass: clamp pre-check)
     double cmax[NPDRB_MAX_COVARS]; // bounds on the covariate diffs
     int diff_type;
+    int dbg;                       // development switches (NPDRB_V3_DBG)
 };
 
 template <int DIFF>
@@ -509,27 +510,56 @@ __device__ __forceinline__ void v2_renorm(double &prod, unsigned &esum) {
     prod = __hiloint2double(mhi, __double2loint(prod));
 }
 
+// Per-attribute constants of the q = 0 fast path ("folded intercept").  With s = b0 + b1 d (units of ln2/1024) the range
+// reduction k = rint(s), fr = s - k costs an FMA and three adds.  Split b0 = B0i + B0f (integer part, |B0f| <= 1/2) instead:
+//   tt = fma(b1, d, M + B0i)   = M + B0i + rint(b1 d) exactly (M = 1.5 * 2^52, ulp 1)  -> low word = the table index k
+//   kd = tt - (M + B0i)        = rint(b1 d)
+//   r1 = fma(b1, d, -kd)       in [-1/2, 1/2], exact up to one rounding
+//   exp(eta) = 2^(k/1024) * exp(B0f c) * exp(r1 c),  c = ln2/1024
+// and exp(B0f c) =: E0 is a per-attribute constant folded into the polynomial coefficients (p0, p1, p2) = E0 * (1, C1, C2).
+// Six FP64 instructions to u = 1 + exp(eta) instead of seven; the pass executes 17 FP64 instructions per evaluation.
+struct V2Fold { double b1, mb, p0, p1, p2; };
+__device__ __forceinline__ V2Fold v2_fold(double b0s, double b1s) {
+    V2Fold f;
+    const double b0i = rint(b0s), b0f = b0s - b0i;
+    const double e0 = exp(b0f * NB_C);
+    f.b1 = b1s; f.mb = c_k[0] + b0i; f.p0 = e0; f.p1 = e0 * c_k[3]; f.p2 = e0 * c_k[2];
+    return f;
+}
+__device__ __forceinline__ double v2_u1_fold(double d, const V2Fold &f, uint32_t sT) {
+    const double tt = fma(f.b1, d, f.mb);
+    const int ki = __double2loint(tt);
+    const double kd = tt - f.mb;
+    const double r1 = fma(f.b1, d, -kd);
+    double qq = fma(r1, f.p2, f.p1);
+    qq = fma(qq, r1, f.p0);
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(sT + (uint32_t)((ki << 3) & 0x1FF8)));
+    int thi;
+    asm("mad.lo.s32 %0, %1, 1024, %2;" : "=r"(thi) : "r"(ki), "r"(__double2hiint(tj)));
+    return fma(__hiloint2double(thi, __double2loint(tj)), qq, 1.0);
+}
+
 // records [m_begin, m_end) of the staged chunk, this thread's slice.  Two records x two attributes are in flight per
-// thread: four independent exp -> reciprocal -> log chains.
+// thread: four independent exp -> reciprocal chains (eight at q = 0, where two record pairs share one straight-line block:
+// predicated row reloads instead of branches keep it one basic block, which is what lets the scheduler interleave them).
+// The running products of u (deviance) are renormalised once per V2_RENORM records: without clamps |eta| < 30, so
+// u < 2^43.3 and 16 factors times a mantissa stay below 2^694.
+constexpr int V2_RENORM = 16;
 template <int Q, int DIFF, int NSL, bool CHECK>
 __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint32_t sREC_addr, uint32_t sCD_addr,
                                          uint32_t sXI_addr, uint32_t sXJ_addr, uint32_t sT, int diff_type,
-                                         const double (&beta0)[2 + Q], const double (&beta1)[2 + Q],
+                                         const double (&beta0)[2 + Q], const double (&beta1)[2 + Q], const V2Fold &f0, const V2Fold &f1,
                                          double (&acc0)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2],
                                          double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], unsigned &esum0, unsigned &esum1, int &nren) {
     constexpr int NA = (2 + Q) * (3 + Q) / 2 + (2 + Q) + 2;
+    constexpr bool FOLD = (Q == 0 && !CHECK);
     // each slice walks a CONTIGUOUS part of the range: records are in list order (grouped by Ri), so the I row
     // repeats for several records in a row and stays in registers (halves the shared-memory tile traffic).
     // m_begin is even and slices are an even number of records long: record pairs are fetched with one 8-byte load.
     const int len = m_end - m_begin, per = (((len + NSL - 1) / NSL) + 1) & ~1;
     const int m_lo = m_begin + slice * per, m_hi = (m_lo + per < m_end) ? (m_lo + per) : m_end;
-    // renormalisations of the running products: q = 0 once per FOUR records (the product of four factors < 2^54 and a
-    // mantissa stays below 2^217), otherwise once per two; plus one for a leftover pair and one for an odd tail
     constexpr int UNR = (Q == 0) ? 2 : 1;
-    if (m_hi > m_lo) {
-        const int ln = m_hi - m_lo;
-        nren += (UNR == 2) ? (ln >> 2) + ((ln & 2) >> 1) + (ln & 1) : (ln + 1) >> 1;
-    }
     uint32_t io_prev = 0xFFFFFFFFu;
     double xi0 = 0.0, xi1 = 0.0;                                 // cached I row (two attributes)
     int m = m_lo;
@@ -551,6 +581,16 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ca[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cb[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m) + 8u));
         }
+        double ta0, ta1, tb0, tb1;
+        if (FOLD) {                                              // q = 0, no clamps possible: folded intercept, 17 FP64 per evaluation
+            ta0 = v2_u1_fold(da0, f0, sT); ta1 = v2_u1_fold(da1, f1, sT);
+            tb0 = v2_u1_fold(db0, f0, sT); tb1 = v2_u1_fold(db1, f1, sT);
+            v2_tail<Q>(da0, ca, ta0, acc0);
+            v2_tail<Q>(da1, ca, ta1, acc1);
+            v2_tail<Q>(db0, cb, tb0, acc0);
+            v2_tail<Q>(db1, cb, tb1, acc1);
+            return;
+        }
         double ea0 = fma(beta0[1], da0, beta0[0]), ea1 = fma(beta1[1], da1, beta1[0]);
         double eb0 = fma(beta0[1], db0, beta0[0]), eb1 = fma(beta1[1], db1, beta1[0]);
 #pragma unroll
@@ -558,7 +598,6 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
             ea0 = fma(beta0[2 + u], ca[u], ea0); ea1 = fma(beta1[2 + u], ca[u], ea1);
             eb0 = fma(beta0[2 + u], cb[u], eb0); eb1 = fma(beta1[2 + u], cb[u], eb1);
         }
-        double ta0, ta1, tb0, tb1;
         bool fast = true;
         if (CHECK) {                                             // !CHECK: the CTA proved |eta| < 30 for all its records up front
             const int hmax = max(max(__double2hiint(ea0) & 0x7fffffff, __double2hiint(ea1) & 0x7fffffff),
@@ -580,26 +619,24 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         v2_tail<Q>(db0, cb, tb0, acc0);
         v2_tail<Q>(db1, cb, tb1, acc1);
     };
-    if (UNR == 2) {
-        for (; m + 3 < m_hi; m += 4) {
-            two_records(m);
-            two_records(m + 2);
-            v2_renorm(acc0[NA - 2], esum0);
-            v2_renorm(acc1[NA - 2], esum1);
+    auto renorm = [&]() {
+        v2_renorm(acc0[NA - 2], esum0);
+        v2_renorm(acc1[NA - 2], esum1);
+        ++nren;
+    };
+    constexpr int RN = CHECK ? 2 : V2_RENORM;                    // checked path: a factor can be 2^52, renormalise per pair
+    while (m + RN <= m_hi) {
+        if (UNR == 2 && !CHECK) {
+#pragma unroll 1
+            for (int i = 0; i < RN; i += 4) { two_records(m + i); two_records(m + i + 2); }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < RN; i += 2) two_records(m + i);
         }
-        if (m + 1 < m_hi) {
-            two_records(m);
-            v2_renorm(acc0[NA - 2], esum0);
-            v2_renorm(acc1[NA - 2], esum1);
-            m += 2;
-        }
-    } else {
-        for (; m + 1 < m_hi; m += 2) {
-            two_records(m);
-            v2_renorm(acc0[NA - 2], esum0);
-            v2_renorm(acc1[NA - 2], esum1);
-        }
+        m += RN;
+        renorm();
     }
+    for (; m + 1 < m_hi; m += 2) two_records(m);
     if (m < m_hi) {                                              // odd tail: one record
         uint32_t r;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));
@@ -620,9 +657,8 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         if (CHECK && (r & 1u)) { acc0[NA - 1] += a.y; acc1[NA - 1] += b.y; }
         v2_tail<Q>(d0, c, a.x, acc0);
         v2_tail<Q>(d1, c, b.x, acc1);
-        v2_renorm(acc0[NA - 2], esum0);
-        v2_renorm(acc1[NA - 2], esum1);
     }
+    renorm();
 }
 
 // Moment passes (lm pass / closed-form first IRLS pass).  MODE_LM: S(d), S(d^2), S(d*y), S(d*c_r) with y from the yv
@@ -770,6 +806,8 @@ pass2_kernel(PassArgs P) {
             beta1[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1] * c_k[9];
         }
     }
+    V2Fold f0 = {0, 0, 0, 0, 0}, f1 = {0, 0, 0, 0, 0};
+    if (MODE == MODE_IRLS_FULL && Q == 0) { f0 = v2_fold(beta0[0], beta0[1]); f1 = v2_fold(beta1[0], beta1[1]); }
     double acc0[NA], acc1[NA];
 #pragma unroll
     for (int n = 0; n < NA; ++n) { acc0[n] = 0.0; acc1[n] = 0.0; }
@@ -849,8 +887,8 @@ pass2_kernel(PassArgs P) {
             int ms = (int)(rmid - rc);                      // first miss record of this chunk
             ms = ms < 0 ? 0 : (ms > n ? n : ms);
             if constexpr (MODE == MODE_IRLS_FULL) {
-                if (may_clamp) v2_range<Q, DIFF, NSL, true>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1, esum0, esum1, nren);
-                else v2_range<Q, DIFF, NSL, false>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, acc0, acc1, esum0, esum1, nren);
+                if (may_clamp) v2_range<Q, DIFF, NSL, true>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, f0, f1, acc0, acc1, esum0, esum1, nren);
+                else v2_range<Q, DIFF, NSL, false>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta0, beta1, f0, f1, acc0, acc1, esum0, esum1, nren);
             } else if constexpr (MODE == MODE_LM) {
                 m2_range<MODE_LM, Q, DIFF, 0, NSL>(0, n, slice, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc0, acc1);
             } else {
@@ -881,6 +919,391 @@ pass2_kernel(PassArgs P) {
         double sacc = red[(0 * NA + n) * TA + a];
 #pragma unroll
         for (int sl = 1; sl < NSL; ++sl) sacc += red[(sl * NA + n) * TA + a];
+        A.partials[((int64_t)chunk * NA + n) * P.nattr_pad + a0 + a] = sacc;
+    }
+}
+
+// ------------------------------------------------------------------ pass kernels, v3 (q <= 2): FOUR attributes per thread
+// The issue-slot micro-benchmark (scripts/dev/ubench_fp64.cu) confirms the model of DESIGN.md 4: an FP64 instruction takes two
+// issue cycles and integer / LDS / MUFU instructions do NOT issue underneath it, so the only way to raise the FP64 pipe's
+// utilisation is to execute fewer non-FP64 instructions per evaluation.  v3 does that structurally:
+//   * a thread owns FOUR attributes -- lane l of a warp the attributes {2l, 2l+1, 64+2l, 64+2l+1} of the 128-attribute tile, so
+//     a row is fetched with two conflict-free LDS.128 -- and everything that is per RECORD (record word, row addresses, the
+//     I-row change test, covariate fetches, loop control) is paid once per four evaluations instead of once per two;
+//   * one warp = one pair slice (32 lanes x 4 attributes = the tile): record handling is warp-uniform, no divergence;
+//   * the I-row change test of two records is one LOP3 + one branch (rows change every ~16-25 records);
+//   * the running products of u = 1 + exp(eta) (deviance) are renormalised once per 16 records instead of every 2-4:
+//     without clamps |eta| < 30, so u < 2^43.3 and 16 factors times a mantissa stay below 2^694.
+// Per evaluation at q = 0: 18 FP64 + ~7.6 other instructions (v2: 18 + 10.6).
+constexpr int V3_APT = 4;                  // attributes per thread
+// pair slices = warps per CTA, as many as the register file allows: the q = 0 IRLS pass (two records x four attributes in
+// flight) fits 168 registers -> 12 warps; with covariates ~250 registers -> 8 warps; the moment passes 16 (12 at q = 2)
+__host__ __device__ constexpr int v3_nslice(int mode, int q) {
+    return mode == MODE_IRLS_FULL ? (q == 0 ? 12 : 8) : (q <= 1 ? 16 : 12);
+}
+constexpr int V3_RENORM = 16;              // records between renormalisations of the running products
+
+template <int MODE, int Q>
+struct V3Layout {
+    static constexpr int NCD = (MODE == MODE_LM) ? (Q + 1) : (Q > 0 ? Q : 0);       // double streams per record
+    static constexpr int NA = (MODE != MODE_IRLS_FULL) ? (3 + Q) : ((2 + Q) * (3 + Q) / 2 + (2 + Q) + 2);
+    static constexpr uint32_t XI = 0;
+    static constexpr uint32_t XJ = BI * TA * 8;                                      // two buffers of BJ*TA*8
+    static constexpr uint32_t REC = XJ + 2 * BJ * TA * 8;                            // two buffers
+    static constexpr uint32_t REC_BYTES = V2_RCHUNK * 4;
+    static constexpr uint32_t CD = REC + 2 * REC_BYTES;                              // two buffers
+    static constexpr uint32_t CD_BYTES = (NCD > 0 ? NCD : 1) * V2_RCHUNK * 8;
+    static constexpr uint32_t TAB = CD + 2 * CD_BYTES;
+    static constexpr uint32_t TOTAL = TAB + (MODE == MODE_IRLS_FULL ? sizeof(nb_tables2) : 0);
+    static constexpr int NSL = v3_nslice(MODE, Q);
+    static constexpr int THREADS = 32 * NSL;
+    static constexpr uint32_t RED = NSL * NA * TA * 8;
+    static constexpr uint32_t SMEM = TOTAL > RED ? TOTAL : RED;
+};
+
+// row of four attributes: {2l, 2l+1} at row + 16 l, {64+2l, 64+2l+1} at row + 512 + 16 l (addr already includes 16 l)
+__device__ __forceinline__ void v3_ld_row(uint32_t addr, double (&x)[4]) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+512];" : "=d"(x[2]), "=d"(x[3]) : "r"(addr));
+}
+
+// IRLS pass over records [m_lo, m_hi) of the staged chunk (this warp's slice).  NR records are in flight per step
+// (2 at q = 0, 1 with covariates: register budget); CHECK = the work item may reach R's |eta| > 30 clamps.
+template <int Q, int DIFF, bool CHECK>
+__device__ __forceinline__ void v3_irls_range(int m_lo, int m_hi, uint32_t sREC_addr, uint32_t sCD_addr, uint32_t sXI_addr,
+                                              uint32_t sXJ_addr, uint32_t sT, int diff_type, const double (&beta)[V3_APT][2 + Q],
+                                              double (&acc)[V3_APT][(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], unsigned (&esum)[V3_APT],
+                                              int &nren, int dbg = 0) {
+    constexpr int NA = (2 + Q) * (3 + Q) / 2 + (2 + Q) + 2;
+    constexpr int NR = (Q == 0 && !CHECK) ? 2 : 1;
+    if (m_lo >= m_hi) return;
+    uint32_t prev;                                               // previous record word (its I-row field is what matters)
+    double xi[V3_APT];
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(prev) : "r"(sREC_addr + 4u * m_lo));
+    v3_ld_row(sXI_addr + (prev & 0xFC00u), xi);                  // the range starts on the I row of its first record
+    auto renorm_all = [&]() {
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) v2_renorm(acc[k][NA - 2], esum[k]);
+        ++nren;
+    };
+    auto eta_of = [&](int k, double d, const double (&c)[Q > 0 ? Q : 1]) {
+        double e = fma(beta[k][1], d, beta[k][0]);
+#pragma unroll
+        for (int u = 0; u < Q; ++u) e = fma(beta[k][2 + u], c[u], e);
+        return e;
+    };
+    auto one_record = [&](int m) {                               // NR == 1 form (covariates, checked path, odd tails)
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));
+        double xj[V3_APT];
+        v3_ld_row(sXJ_addr + (r >> 16), xj);
+        if ((r ^ prev) & 0xFC00u) v3_ld_row(sXI_addr + (r & 0xFC00u), xi);
+        prev = r;
+        double c[Q > 0 ? Q : 1];
+#pragma unroll
+        for (int u = 0; u < Q; ++u) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c[u]) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
+        double d[V3_APT], u1[V3_APT];
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) d[k] = proj_diff<DIFF>(xi[k], xj[k], diff_type);
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) {
+            const double e = eta_of(k, d[k], c);
+            if (CHECK) {
+                const double2 v = v2_exp_clamped(e, sT);
+                u1[k] = v.x;
+                if (r & 1u) acc[k][NA - 1] += v.y;
+            } else {
+                u1[k] = v2_u1_fast(e, sT);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) v2_tail<Q>(d[k], c, u1[k], acc[k]);
+    };
+    auto two_records = [&](int m) {                              // q = 0, unchecked: eight exp -> reciprocal chains in flight
+        uint32_t ra, rb;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ra), "=r"(rb) : "r"(sREC_addr + 4u * m));
+        double ja[V3_APT], jb[V3_APT], da[V3_APT], db[V3_APT];
+        v3_ld_row(sXJ_addr + (ra >> 16), ja);
+        v3_ld_row(sXJ_addr + (rb >> 16), jb);
+        if (((ra ^ prev) | (rb ^ prev)) & 0xFC00u) {             // an I row changes here (every ~16-25 records)
+            if ((ra ^ rb) & 0xFC00u) { one_record(m); one_record(m + 1); return; }   // between the two records: one at a time
+            v3_ld_row(sXI_addr + (ra & 0xFC00u), xi);
+        }
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) { da[k] = proj_diff<DIFF>(xi[k], ja[k], diff_type); db[k] = proj_diff<DIFF>(xi[k], jb[k], diff_type); }
+        prev = rb;
+        const double c0[1] = {0.0};
+        double ua[V3_APT], ub[V3_APT];
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) { ua[k] = v2_u1_fast(fma(beta[k][1], da[k], beta[k][0]), sT); ub[k] = v2_u1_fast(fma(beta[k][1], db[k], beta[k][0]), sT); }
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) { v2_tail<0>(da[k], c0, ua[k], reinterpret_cast<double (&)[7]>(acc[k])); v2_tail<0>(db[k], c0, ub[k], reinterpret_cast<double (&)[7]>(acc[k])); }
+    };
+    int m = m_lo;
+    if (CHECK) {                                                 // rare: a factor can be 2^52, renormalise after every record
+        for (; m < m_hi; ++m) { one_record(m); renorm_all(); }
+        return;
+    }
+    if (NR == 2 && (dbg & 1)) {
+        for (; m < m_hi; ++m) { one_record(m); if (((m - m_lo) & 15) == 15) renorm_all(); }
+        renorm_all();
+        return;
+    }
+    if (NR == 2) {
+        if ((m & 1) && m < m_hi) { one_record(m); ++m; }         // 8-byte alignment of the record pairs
+        while (m + V3_RENORM <= m_hi) {
+#pragma unroll 2
+            for (int i = 0; i < V3_RENORM; i += 2) two_records(m + i);
+            m += V3_RENORM;
+            renorm_all();
+        }
+        for (; m + 1 < m_hi; m += 2) two_records(m);
+        if (m < m_hi) { one_record(m); ++m; }
+        renorm_all();
+    } else {
+        while (m + V3_RENORM <= m_hi) {
+#pragma unroll 2
+            for (int i = 0; i < V3_RENORM; ++i) one_record(m + i);
+            m += V3_RENORM;
+            renorm_all();
+        }
+        for (; m < m_hi; ++m) one_record(m);
+        renorm_all();
+    }
+}
+
+// moment passes, four attributes per thread, four records requested together (the loop is bound by the shared-memory pipe)
+template <int MODE, int Q, int DIFF, int Y>
+__device__ __forceinline__ void v3_moment_range(int m_lo, int m_hi, uint32_t sREC_addr, uint32_t sCD_addr, uint32_t sXI_addr,
+                                                uint32_t sXJ_addr, int diff_type, double (&acc)[V3_APT][3 + Q]) {
+    if (m_lo >= m_hi) return;
+    uint32_t prev;
+    double xi[V3_APT];
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(prev) : "r"(sREC_addr + 4u * m_lo));
+    v3_ld_row(sXI_addr + (prev & 0xFC00u), xi);                  // the range starts on the I row of its first record
+    auto consume = [&](uint32_t r, int m, const double (&xj)[V3_APT]) {
+        if ((r ^ prev) & 0xFC00u) v3_ld_row(sXI_addr + (r & 0xFC00u), xi);
+        prev = r;
+        double d[V3_APT];
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) d[k] = proj_diff<DIFF>(xi[k], xj[k], diff_type);
+        if (MODE == MODE_LM) {
+            double yv;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(yv) : "r"(sCD_addr + 8u * (Q * V2_RCHUNK + m)));
+#pragma unroll
+            for (int k = 0; k < V3_APT; ++k) { acc[k][0] += d[k]; acc[k][2] = fma(d[k], yv, acc[k][2]); }
+        } else {
+#pragma unroll
+            for (int k = 0; k < V3_APT; ++k) acc[k][Y == 0 ? 0 : 2] += d[k];
+        }
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) acc[k][1] = fma(d[k], d[k], acc[k][1]);
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+            double cu;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cu) : "r"(sCD_addr + 8u * (u * V2_RCHUNK + m)));
+#pragma unroll
+            for (int k = 0; k < V3_APT; ++k) acc[k][3 + u] = fma(d[k], cu, acc[k][3 + u]);
+        }
+    };
+    auto single = [&](int m) {
+        uint32_t r;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));
+        double xj[V3_APT];
+        v3_ld_row(sXJ_addr + (r >> 16), xj);
+        consume(r, m, xj);
+    };
+    int m = m_lo;
+    for (; m < m_hi && (m & 3); ++m) single(m);                  // peel to a 16-byte boundary of the record buffer
+    for (; m + 3 < m_hi; m += 4) {
+        uint32_t r[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sREC_addr + 4u * m));
+        double xj[4][V3_APT];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v3_ld_row(sXJ_addr + (r[k] >> 16), xj[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) consume(r[k], m + k, xj[k]);
+    }
+    for (; m < m_hi; ++m) single(m);
+}
+
+template <int MODE, int Q, int DIFF>
+__global__ void __launch_bounds__(V3Layout<MODE, Q>::THREADS, 1)
+pass3_kernel(PassArgs P) {
+    using L = V3Layout<MODE, Q>;
+    constexpr int K = 2 + Q;
+    constexpr int NA = L::NA;
+    constexpr int V3_NSL = L::NSL;
+    constexpr int V3_THREADS = L::THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    asm volatile("" : "+r"(sbase));                      // opaque: keep the window base in a register, not rematerialised
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, slice = tid >> 5;
+    // chunk index is the fast grid dimension: the CTAs resident at any moment share a few attribute tiles, whose XT slabs
+    // (N x 128 doubles each) then stay in L2 while every chunk of the pair stream sweeps over them
+    const int at = blockIdx.y;
+    const int sidx = ((int)blockIdx.x >= P.n_chunks0) ? 1 : 0;
+    const int chunk = (int)blockIdx.x - (sidx ? P.n_chunks0 : 0);
+    const StreamArgs &A = P.st[sidx];
+    if (MODE == MODE_IRLS_FULL && P.tile_active && !P.tile_active[at]) return;
+    const int64_t a0 = (int64_t)at * TA;
+    // local attribute index of this thread's k-th attribute
+    auto attr_of = [&](int k) { return (k >> 1) * 64 + 2 * lane + (k & 1); };
+
+    if (MODE == MODE_IRLS_FULL) {   // table image
+        nb_tables2 *sT = (nb_tables2 *)(smem_raw + L::TAB);
+        const nb_tables1024 *g = P.tables1024;
+        for (int e = tid; e < 1024; e += V3_THREADS) {         // high word pre-biased by -j * 1024 (see v2_u1_fast)
+            const double tj = g->exp_t[e];
+            sT->exp_t[e] = __hiloint2double(__double2hiint(tj) - e * 1024, __double2loint(tj));
+        }
+    }
+    const uint32_t sT_addr = sbase + L::TAB;
+    const uint32_t sXI_addr = sbase + L::XI + (uint32_t)lane * 16u;
+
+    double beta[V3_APT][K];
+    if (MODE == MODE_IRLS_FULL) {
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k)
+#pragma unroll
+            for (int r = 0; r < K; ++r) beta[k][r] = P.beta[(int64_t)r * P.nattr_pad + a0 + attr_of(k)] * c_k[9];      // units of ln2/1024
+    }
+    double acc[V3_APT][NA];
+#pragma unroll
+    for (int k = 0; k < V3_APT; ++k)
+#pragma unroll
+        for (int n = 0; n < NA; ++n) acc[k][n] = 0.0;
+    unsigned esum[V3_APT] = {0, 0, 0, 0};
+    int nren = 0;        // wrapping sums of the biased exponents taken out of the running products of u1 = 1 + exp(eta)
+    if (MODE == MODE_IRLS_FULL) {
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) acc[k][NA - 2] = 1.0;
+    }
+    bool may_clamp = false;
+    if (MODE == MODE_IRLS_FULL) {         // can any record of this attribute tile reach R's |eta| > 30 clamps?
+        bool over = false;
+        const double lim = c_k[8] * 0.999;
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) {
+            double b = fabs(beta[k][0]) + fabs(beta[k][1]) * P.dmax[a0 + attr_of(k)];
+#pragma unroll
+            for (int u = 0; u < Q; ++u) b += fabs(beta[k][2 + u]) * P.cmax[u];
+            over = over || !(b < lim);                           // NaN coefficients take the checked path
+        }
+        may_clamp = __syncthreads_or(over) != 0;
+    }
+
+    const int t_begin = A.chunk_tile[chunk], t_end = A.chunk_tile[chunk + 1];
+
+    // async stage of a [64][128] double tile (rows are TA contiguous doubles of XT, zero padded)
+    auto stage_tile = [&](uint32_t dst, int block) {
+        const double *g = P.XT + ((int64_t)block * 64) * P.ldt + a0;
+        for (int e = tid; e < 64 * TA / 2; e += V3_THREADS) {
+            const int row = e / (TA / 2), c2 = e % (TA / 2);
+            cp_async16(dst + (uint32_t)e * 16u, g + (int64_t)row * P.ldt + 2 * c2);
+        }
+    };
+    // async stage of records [rc, rc + n) (+ their covariate diffs / yv)
+    auto stage_records = [&](int buf, int64_t rc, int n) {
+        const uint32_t rdst = sbase + L::REC + buf * L::REC_BYTES, cdst = sbase + L::CD + buf * L::CD_BYTES;
+        for (int e = tid; e < n; e += V3_THREADS) {
+            cp_async4(rdst + 4u * e, A.rec + rc + e);
+#pragma unroll
+            for (int c = 0; c < Q; ++c) cp_async8(cdst + 8u * (c * V2_RCHUNK + e), A.cd[c] + rc + e);
+            if (MODE == MODE_LM) cp_async8(cdst + 8u * (Q * V2_RCHUNK + e), A.yv + rc + e);
+        }
+    };
+    auto first_chunk_len = [&](int t) -> int {
+        const int64_t len = A.tile_ptr[t + 1] - A.tile_ptr[t];
+        return (int)(len < V2_RCHUNK ? len : V2_RCHUNK);
+    };
+    // this warp's contiguous part of records [lo, hi): even length, so record pairs stay 8-byte aligned
+    auto slice_of = [&](int lo, int hi, int &s_lo, int &s_hi) {
+        const int len = hi - lo, per = (((len + V3_NSL - 1) / V3_NSL) + 3) & ~3;
+        s_lo = lo + slice * per;
+        s_hi = (s_lo + per < hi) ? (s_lo + per) : hi;
+        if (s_lo > hi) s_lo = hi;
+    };
+
+    int cur_ib = -1;
+    if (t_begin < t_end) {                                 // prologue: tile t_begin in flight
+        stage_tile(sbase + L::XJ, A.tile_jb[t_begin]);
+        stage_records(0, A.tile_ptr[t_begin], first_chunk_len(t_begin));
+        cp_async_commit();
+    }
+    for (int t = t_begin; t < t_end; ++t) {
+        const int buf = (t - t_begin) & 1;
+        const int ib = A.tile_ib[t];
+        const int64_t r0 = A.tile_ptr[t], r1 = A.tile_ptr[t + 1], rmid = A.tile_mid[t];
+        if (ib != cur_ib) {                                // new I block (once per row of tiles)
+            __syncthreads();                               // all threads are done with the previous tile's compute
+            stage_tile(sbase + L::XI, ib);
+            cp_async_commit();
+            cur_ib = ib;
+        }
+        cp_async_wait_all();
+        __syncthreads();                                   // tile t staged; previous tile's buffers are free
+        if (t + 1 < t_end) {                               // prefetch tile t+1 into the other buffers
+            stage_tile(sbase + L::XJ + (buf ^ 1) * (BJ * TA * 8), A.tile_jb[t + 1]);
+            stage_records(buf ^ 1, A.tile_ptr[t + 1], first_chunk_len(t + 1));
+            cp_async_commit();
+        }
+        const uint32_t sXJ_addr = sbase + L::XJ + buf * (BJ * TA * 8) + (uint32_t)lane * 16u;
+        const uint32_t sREC_addr = sbase + L::REC + buf * L::REC_BYTES;
+        const uint32_t sCD_addr = sbase + L::CD + buf * L::CD_BYTES;
+        for (int64_t rc = r0; rc < r1; rc += V2_RCHUNK) {
+            const int n = (int)((r1 - rc < V2_RCHUNK) ? (r1 - rc) : V2_RCHUNK);
+            if (rc != r0) {                                // rare: more than one record chunk in this tile
+                __syncthreads();                           // previous chunk consumed
+                stage_records(buf, rc, n);
+                cp_async_commit();
+                cp_async_wait_all();                       // (also completes the prefetch; correctness only)
+                __syncthreads();
+            }
+            int s_lo, s_hi;
+            if constexpr (MODE == MODE_IRLS_FULL) {
+                slice_of(0, n, s_lo, s_hi);
+                if (s_lo < s_hi) {
+                    if (may_clamp) v3_irls_range<Q, DIFF, true>(s_lo, s_hi, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta, acc, esum, nren);
+                    else v3_irls_range<Q, DIFF, false>(s_lo, s_hi, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, sT_addr, P.diff_type, beta, acc, esum, nren, P.dbg);
+                }
+            } else if constexpr (MODE == MODE_LM) {
+                slice_of(0, n, s_lo, s_hi);
+                v3_moment_range<MODE_LM, Q, DIFF, 0>(s_lo, s_hi, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc);
+            } else {
+                int ms = (int)(rmid - rc);                 // first miss record of this chunk
+                ms = ms < 0 ? 0 : (ms > n ? n : ms);
+                slice_of(0, ms, s_lo, s_hi);
+                v3_moment_range<MODE_SIGN, Q, DIFF, 0>(s_lo, s_hi, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc);
+                slice_of(ms, n, s_lo, s_hi);
+                v3_moment_range<MODE_SIGN, Q, DIFF, 1>(s_lo, s_hi, sREC_addr, sCD_addr, sXI_addr, sXJ_addr, P.diff_type, acc);
+            }
+        }
+    }
+    if (MODE == MODE_IRLS_FULL) {                          // integer exponent sums -> log(u1) total
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k)
+            acc[k][NA - 2] = fma((double)(int)(esum[k] - 1023u * (unsigned)nren), c_k[4], log(acc[k][NA - 2]));
+    }
+    if (MODE == MODE_SIGN) {                               // (hits, misses) -> (S d, S d*s)
+#pragma unroll
+        for (int k = 0; k < V3_APT; ++k) { const double h = acc[k][0], ms = acc[k][2]; acc[k][0] = h + ms; acc[k][2] = ms - h; }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    double *red = (double *)smem_raw;                      // [NSL][NA][TA]
+#pragma unroll
+    for (int k = 0; k < V3_APT; ++k)
+#pragma unroll
+        for (int n = 0; n < NA; ++n) red[(slice * NA + n) * TA + attr_of(k)] = acc[k][n];
+    __syncthreads();
+    for (int e = tid; e < NA * TA; e += V3_THREADS) {
+        const int n = e / TA, a = e % TA;
+        double sacc = red[(0 * NA + n) * TA + a];
+#pragma unroll
+        for (int sl = 1; sl < V3_NSL; ++sl) sacc += red[(sl * NA + n) * TA + a];
         A.partials[((int64_t)chunk * NA + n) * P.nattr_pad + a0 + a] = sacc;
     }
 }
@@ -1402,10 +1825,31 @@ int launch_pass2_t(npdrb_ctx *ctx, const PassArgs &P, int n_at, int n_chunks) {
     NB_LAUNCH_CHECK(ctx);
     return NPDRB_OK;
 }
-// v2 covers q <= 2 (shared memory: I tile + two J tiles + record buffers <= 227 KB); larger q uses the v1 kernel
+template <int MODE, int Q, int DIFF>
+int launch_pass3_t(npdrb_ctx *ctx, const PassArgs &P, int n_at, int n_chunks) {
+    const size_t smem = V3Layout<MODE, Q>::SMEM;
+    NB_CUDA(cudaFuncSetAttribute(pass3_kernel<MODE, Q, DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (n_at > 65535) { npdrb_set_error("regress: more than 65535 attribute tiles in one call; split the attribute range"); return NPDRB_EINVAL; }
+    dim3 grid((unsigned)n_chunks, (unsigned)n_at);
+    pass3_kernel<MODE, Q, DIFF><<<grid, V3Layout<MODE, Q>::THREADS, smem, ctx->stream>>>(P);
+    NB_LAUNCH_CHECK(ctx);
+    return NPDRB_OK;
+}
+bool use_v2_kernel() {
+    const char *e = getenv("NPDRB_PASS_KERNEL");
+    return e && strcmp(e, "v2") == 0;
+}
+// v2 / v3 cover q <= 2 (shared memory: I tile + two J tiles + record buffers <= 227 KB); larger q uses the v1 kernel
 template <int MODE>
 int launch_pass2(npdrb_ctx *ctx, int q, const PassArgs &P, int n_at, int n_chunks) {
     const bool ad = P.diff_type == NPDRB_DIFF_NUMERIC_ABS;
+    if (MODE != MODE_IRLS_FULL && !use_v2_kernel()) {        // moment passes: four attributes per thread (v3); IRLS pass: v2
+        switch (q) {
+        case 0: return ad ? launch_pass3_t<MODE, 0, 0>(ctx, P, n_at, n_chunks) : launch_pass3_t<MODE, 0, 1>(ctx, P, n_at, n_chunks);
+        case 1: return ad ? launch_pass3_t<MODE, 1, 0>(ctx, P, n_at, n_chunks) : launch_pass3_t<MODE, 1, 1>(ctx, P, n_at, n_chunks);
+        case 2: return ad ? launch_pass3_t<MODE, 2, 0>(ctx, P, n_at, n_chunks) : launch_pass3_t<MODE, 2, 1>(ctx, P, n_at, n_chunks);
+        }
+    }
     switch (q) {
     case 0: return ad ? launch_pass2_t<MODE, 0, 0>(ctx, P, n_at, n_chunks) : launch_pass2_t<MODE, 0, 1>(ctx, P, n_at, n_chunks);
     case 1: return ad ? launch_pass2_t<MODE, 1, 0>(ctx, P, n_at, n_chunks) : launch_pass2_t<MODE, 1, 1>(ctx, P, n_at, n_chunks);
@@ -1640,6 +2084,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         P.XT = s->dXT; P.ldt = s->ldt; P.N = N; P.nattr = (int)nattr; P.nattr_pad = (int)nattr_pad;
         P.beta = d_beta; P.tile_active = tile_active; P.tables = d_tab; P.tables1024 = d_tab1024; P.diff_type = diff_type;
         P.dmax = d_dmax;
+        { const char *dbg = getenv("NPDRB_V3_DBG"); P.dbg = dbg ? atoi(dbg) : 0; }
         for (int c = 0; c < NPDRB_MAX_COVARS; ++c) P.cmax[c] = S.cmax[c];
         double *pp = d_part;
         int total_chunks = 0;
