@@ -238,6 +238,15 @@ int npdrb_session_copy_radius2(npdrb_session *s, double *radius_host);      /* o
  *   sum_all/(2*num.pair) - sd.frac*sqrt(sumsq/(count-1))   with npdrb_session_set_surf_radius(). */
 int npdrb_session_surf_partial(npdrb_session *s, double centre, double *out4);
 int npdrb_session_set_surf_radius(npdrb_session *s, double radius);
+/* The pair list must be the reference's bit for bit, and R's radius is one sequential long-double chain over N^2 terms.
+ * Protocol for row blocks / large N: combine the partial moments (m0 at centre 0, m1 at centre m0[1]/m0[2]) into a radius
+ * and a rigorous bound eps on its distance from R's value (_from_moments); count the distances of every block inside
+ * [radius - eps, radius + eps] (_band_count); if the total is 0 every radius in the band selects the same pairs and the
+ * moment radius is used; otherwise gather the matrix on the host and replay R's chains exactly (_exact_host: D_host is the
+ * full symmetric N x N matrix, leading dimension ldd). */
+int npdrb_surf_radius_from_moments(const double *m0, const double *m1, int64_t N, double sd_frac, double *radius, double *eps);
+int npdrb_session_surf_band_count(npdrb_session *s, double lo, double hi, int64_t *count);
+int npdrb_surf_radius_exact_host(const double *D_host, int64_t ldd, int64_t N, double sd_frac, double *radius);
 /* device pointers to the local pair segment (int32, 1-based), valid until the next neighbours/import call */
 int npdrb_session_local_pairs(npdrb_session *s, const int32_t **dRi, const int32_t **dNN, int64_t *M_local);
 /* copy the local pair segment into caller-owned DEVICE buffers (e.g. torch tensors that NCCL will all-gather) */

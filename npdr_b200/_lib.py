@@ -98,6 +98,9 @@ SIGNATURES = {
     "npdrb_session_copy_radius2": (C.c_int, [_vp, _dp]),
     "npdrb_session_surf_partial": (C.c_int, [_vp, C.c_double, _dp]),
     "npdrb_session_set_surf_radius": (C.c_int, [_vp, C.c_double]),
+    "npdrb_surf_radius_from_moments": (C.c_int, [_dp, _dp, _i64, C.c_double, _dp, _dp]),
+    "npdrb_session_surf_band_count": (C.c_int, [_vp, C.c_double, C.c_double, C.POINTER(_i64)]),
+    "npdrb_surf_radius_exact_host": (C.c_int, [_dp, _i64, _i64, C.c_double, _dp]),
     "npdrb_session_local_pairs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "npdrb_session_copy_local_pairs_device": (C.c_int, [_vp, _vp, _vp]),
     "npdrb_session_copy_radius": (C.c_int, [_vp, _dp]),
@@ -210,6 +213,22 @@ def context(device=0):
     return ctx
 
 
+def surf_radius_from_moments(m0, m1, N, sd_frac):
+    """-> (radius, eps): SURF radius from combined partial moments and the bound on its distance from R's value."""
+    a = f64(np.asarray(m0, dtype=np.float64), "C"); b = f64(np.asarray(m1, dtype=np.float64), "C")
+    r, e = C.c_double(), C.c_double()
+    check(load().npdrb_surf_radius_from_moments(dptr(a), dptr(b), int(N), float(sd_frac), C.byref(r), C.byref(e)))
+    return r.value, e.value
+
+
+def surf_radius_exact_host(D, sd_frac):
+    """R's SURF radius replayed exactly on the host from the full symmetric distance matrix (numpy, any order)."""
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    r = C.c_double()
+    check(load().npdrb_surf_radius_exact_host(dptr(D), D.shape[1], D.shape[0], float(sd_frac), C.byref(r)))
+    return r.value
+
+
 def take_int_array(ptr, n):
     """Copy a library-malloc'ed int32 buffer into numpy and free it."""
     if n > 0:
@@ -303,6 +322,11 @@ class Session:
 
     def set_surf_radius(self, r):
         check(load().npdrb_session_set_surf_radius(self.handle, float(r)))
+
+    def surf_band_count(self, lo, hi):
+        n = _i64()
+        check(load().npdrb_session_surf_band_count(self.handle, float(lo), float(hi), C.byref(n)))
+        return n.value
 
     def local_pairs(self):
         a, b, M = _vp(), _vp(), _i64()

@@ -47,6 +47,7 @@ struct Worker {
     std::vector<int64_t> send_cnt, recv_cnt;         // doubles per live peer
     int64_t M_local = 0, n_empty = 0, n_unique = 0;
     double surf0[4] = {0, 0, 0, 0}, surf1[4] = {0, 0, 0, 0};
+    int64_t surf_band = 0;                           // distances of my block inside the SURF guard band
     int32_t irls_passes = 0;
     double ms_distance = 0, ms_neighbors = 0, ms_prepare = 0, ms_regress = 0;
 };
@@ -64,6 +65,8 @@ struct Shared {
     double *stats = nullptr;                         // p x 8, host
     int64_t k = 0;
     int64_t M_total = 0;
+    std::vector<double> hostD;                       // SURF exact replay: the gathered distance matrix
+    double surf_radius_exact = 0.0;
 };
 
 // One context per device for the life of the process: the device-memory cache (api.cu) then survives between calls, which
@@ -185,8 +188,27 @@ void run_worker(Shared &S, int g) {
         if (S.bar->wait(S.failed)) return;
         double m1[4] = {0, 0, 0, 0};
         for (int h : S.live_devs) for (int t = 0; t < 4; ++t) m1[t] += S.w[(size_t)h].surf1[t];
-        const double num_pair = (double)S.N * (double)(S.N - 1) / 2.0;
-        const double radius = m0[0] / (2.0 * num_pair) - o.msurf_sd_frac * sqrt(m1[3] / (m1[2] - 1.0));
+        // radius from the combined moments + guard band; if a distance of any block falls inside the band the blocks are
+        // gathered on the host and R's sequential long-double chains are replayed exactly (neighbors.cu)
+        double radius = 0.0, eps = 0.0;
+        STEP(npdrb_surf_radius_from_moments(m0, m1, S.N, o.msurf_sd_frac, &radius, &eps));
+        if (w.live >= 0) STEP(npdrb_session_surf_band_count(w.s, radius - eps, radius + eps, &w.surf_band));
+        if (S.bar->wait(S.failed)) return;
+        int64_t in_band = 0;
+        for (int h : S.live_devs) in_band += S.w[(size_t)h].surf_band;
+        const char *force = getenv("NPDRB_SURF_FORCE_EXACT");
+        if (in_band > 0 || (force && force[0] == '1')) {
+            if (g == S.live_devs[0]) S.hostD.assign((size_t)S.N * (size_t)S.N, 0.0);
+            if (S.bar->wait(S.failed)) return;
+            if (w.live >= 0) STEP(npdrb_session_copy_distances(w.s, S.hostD.data() + (size_t)w.row0 * (size_t)S.N));
+            if (S.bar->wait(S.failed)) return;
+            if (g == S.live_devs[0]) {
+                STEP(npdrb_surf_radius_exact_host(S.hostD.data(), S.N, S.N, o.msurf_sd_frac, &S.surf_radius_exact));
+                std::vector<double>().swap(S.hostD);
+            }
+            if (S.bar->wait(S.failed)) return;
+            radius = S.surf_radius_exact;
+        }
         if (w.live >= 0) STEP(npdrb_session_set_surf_radius(w.s, radius));
     }
     // ---- phase 3: neighbour lists of my rows

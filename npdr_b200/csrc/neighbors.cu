@@ -154,6 +154,68 @@ __global__ void surf_sumsq_kernel(const double *__restrict__ D, int64_t ldd, int
     if (lane == 0) out[r] = ss;
 }
 
+// ---- SURF, large N / row blocks: provably the reference's pair list -------------------------------------------------
+// R's radius is ONE sequential long-double chain over N^2 terms; it cannot be parallelised, but the pair list only depends on
+// which side of the radius every distance falls.  So: (1) radius r~ from parallel moments, with a rigorous bound eps on
+// |r~ - r_R| (npdrb_surf_radius_from_moments); (2) count the distances inside [r~ - eps, r~ + eps] (surf_band_count_kernel);
+// none -> every radius in the band, r_R included, selects the same pairs, done; (3) otherwise replay R's chains exactly on the
+// host (native x87 long double on x86-64, the software xf80 elsewhere) -- rare: the band is ~1e-10 wide relative to r.
+__global__ void surf_band_count_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t nrows, double lo, double hi,
+                                       unsigned long long *__restrict__ count) {
+    unsigned long long c = 0;
+    const int64_t total = nrows * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = D[(e / N) * ldd + (e % N)];
+        c += (v >= lo && v <= hi) ? 1u : 0u;
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+#if defined(__x86_64__) && defined(__LDBL_MANT_DIG__) && (__LDBL_MANT_DIG__ == 64)
+#define NB_HOST_X87 1
+#else
+#define NB_HOST_X87 0
+#endif
+// sum(dist.mat) / (2 num.pair) - sd.frac * sd(dist.mat[upper.tri(dist.mat)]) exactly as R evaluates it:
+// D is the full symmetric matrix on the host, element (i, c) at D[c * ldd + i].
+static double surf_radius_exact_host_impl(const double *D, int64_t ldd, int64_t N, double sd_frac) {
+    const int64_t nu = N * (N - 1) / 2;
+    double total, var;
+#if NB_HOST_X87
+    long double s = 0.0L;
+    for (int64_t c = 0; c < N; ++c) { const double *col = D + c * ldd; for (int64_t i = 0; i < N; ++i) s += col[i]; }
+    total = (double)s;
+    long double sum = 0.0L;
+    for (int64_t j = 0; j < N; ++j) { const double *col = D + j * ldd; for (int64_t i = 0; i < j; ++i) sum += col[i]; }
+    long double tmp = sum / (long double)nu;
+    sum = 0.0L;
+    for (int64_t j = 0; j < N; ++j) { const double *col = D + j * ldd; for (int64_t i = 0; i < j; ++i) sum += (col[i] - tmp); }
+    tmp = tmp + sum / (long double)nu;
+    const long double xm = (double)tmp;
+    sum = 0.0L;
+    for (int64_t j = 0; j < N; ++j) { const double *col = D + j * ldd; for (int64_t i = 0; i < j; ++i) { const long double d = col[i] - xm; sum += d * d; } }
+    var = (double)(sum / (long double)(nu - 1));
+#else
+    xf80 s = xf_zero();
+    for (int64_t c = 0; c < N; ++c) for (int64_t i = 0; i < N; ++i) s = xf_add(s, xf_from_double(D[c * ldd + i]));
+    total = xf_to_double(s);
+    xf80 sum = xf_zero();
+    for (int64_t j = 0; j < N; ++j) for (int64_t i = 0; i < j; ++i) sum = xf_add(sum, xf_from_double(D[j * ldd + i]));
+    xf80 tmp = xf_div(sum, xf_from_int(nu));
+    sum = xf_zero();
+    for (int64_t j = 0; j < N; ++j) for (int64_t i = 0; i < j; ++i) sum = xf_add(sum, xf_sub(xf_from_double(D[j * ldd + i]), tmp));
+    tmp = xf_add(tmp, xf_div(sum, xf_from_int(nu)));
+    const xf80 xm = xf_from_double(xf_to_double(tmp));
+    sum = xf_zero();
+    for (int64_t j = 0; j < N; ++j)
+        for (int64_t i = 0; i < j; ++i) { xf80 d = xf_sub(xf_from_double(D[j * ldd + i]), xm); sum = xf_add(sum, xf_mul(d, d)); }
+    var = xf_to_double(xf_div(sum, xf_from_int(nu - 1)));
+#endif
+    const double num_pair = (double)N * (double)(N - 1) / 2.0;
+    return total / (2.0 * num_pair) - sd_frac * sqrt(var);
+}
+
 // ---------------------------------------------------------------- threshold selection (surf / multisurf)
 __global__ void count_threshold_kernel(const double *__restrict__ D, int64_t ldd, int64_t N, int64_t nrows,
                                        const double *__restrict__ radius, int radius_is_scalar,
@@ -692,6 +754,47 @@ int nb_diff_vectors(npdrb_ctx *ctx, const double *da, const double *db, int64_t 
     return NPDRB_OK;
 }
 
+extern "C" int npdrb_surf_radius_exact_host(const double *D_host, int64_t ldd, int64_t N, double sd_frac, double *radius) {
+    if (!D_host || !radius || N < 3 || ldd < N) { npdrb_set_error("npdrb_surf_radius_exact_host: bad arguments"); return NPDRB_EINVAL; }
+    *radius = surf_radius_exact_host_impl(D_host, ldd, N, sd_frac);
+    return NPDRB_OK;
+}
+
+// radius from the combined partial moments of npdrb_session_surf_partial (m0: centre 0, m1: centre = m0[1]/m0[2]) and a
+// rigorous bound on its distance from R's value.  R side: three sequential x87 chains of <= N^2 non-negative terms, each
+// with relative error <= n 2^-64, plus a handful of double roundings; this side: per-row sums in double over 32 strided
+// lanes + a shuffle tree (relative error <= (N/32 + 8) 2^-53 per moment), combined in long double.
+extern "C" int npdrb_surf_radius_from_moments(const double *m0, const double *m1, int64_t N, double sd_frac, double *radius, double *eps) {
+    if (!m0 || !m1 || !radius || N < 3) { npdrb_set_error("npdrb_surf_radius_from_moments: bad arguments"); return NPDRB_EINVAL; }
+    const double num_pair = (double)N * (double)(N - 1) / 2.0;
+    const double mean = m0[0] / (2.0 * num_pair);
+    const double sdv = sqrt(m1[3] / (m1[2] - 1.0));
+    *radius = mean - sd_frac * sdv;
+    if (eps) {
+        const double n2 = (double)N * (double)N;
+        const double rel = 2.0 * n2 * 5.421010862427522e-20 /* 2^-64 */ + ((double)N / 32.0 + 24.0) * 2.220446049250313e-16 /* 2^-52 */;
+        *eps = 1.25 * rel * (fabs(mean) + fabs(sd_frac) * sdv);
+    }
+    return NPDRB_OK;
+}
+
+// number of distances of the owned block inside [lo, hi]
+extern "C" int npdrb_session_surf_band_count(npdrb_session *s, double lo, double hi, int64_t *count) {
+    npdrb_ctx *ctx = s->ctx;
+    if (!s->dD || !count) { npdrb_set_error("surf band count: no distance block"); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long *d_c = nullptr, h_c = 0;
+    NB_CUDA(cudaMalloc(&d_c, sizeof(unsigned long long)));
+    NB_CUDA(cudaMemsetAsync(d_c, 0, sizeof(unsigned long long), ctx->stream));
+    surf_band_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(s->dD, s->ldd, s->N, s->nrows, lo, hi, d_c);
+    NB_LAUNCH_CHECK(ctx);
+    NB_CUDA(cudaMemcpyAsync(&h_c, d_c, sizeof(h_c), cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_c);
+    *count = (int64_t)h_c;
+    return NPDRB_OK;
+}
+
 // Partial SURF moments of the owned rows (see npdr_b200.h).  Each unordered pair {g, j} is counted once,
 // by the owner of row g = min index, through the entries j > g of that row.
 extern "C" int npdrb_session_surf_partial(npdrb_session *s, double centre, double *out4) {
@@ -756,14 +859,20 @@ static int surf_radius(npdrb_session *s, double sd_frac, double *d_rad_scalar) {
         NB_LAUNCH_CHECK(ctx);
         return NPDRB_OK;
     } else {
-        // large N: parallel moments (<= 1 ulp from R's single sequential long-double chain)
-        double m0[4], m1[4];
+        // large N: radius from parallel moments + guard band; exact host replay only if a distance falls inside the band
+        double m0[4], m1[4], eps = 0.0;
         NB_CHECK(npdrb_session_surf_partial(s, 0.0, m0));
         const double mean_u = m0[1] / m0[2];
         NB_CHECK(npdrb_session_surf_partial(s, mean_u, m1));
-        const double num_pair = (double)N * (double)(N - 1) / 2.0;
-        const double sdv = sqrt(m1[3] / (m1[2] - 1.0));
-        radius = m0[0] / (2.0 * num_pair) - sd_frac * sdv;
+        NB_CHECK(npdrb_surf_radius_from_moments(m0, m1, N, sd_frac, &radius, &eps));
+        int64_t in_band = 0;
+        const char *force = getenv("NPDRB_SURF_FORCE_EXACT");           // tests: always take the replay
+        NB_CHECK(npdrb_session_surf_band_count(s, radius - eps, radius + eps, &in_band));
+        if (in_band > 0 || (force && force[0] == '1')) {
+            std::vector<double> hD((size_t)N * (size_t)N);
+            NB_CHECK(npdrb_session_copy_distances(s, hD.data()));
+            NB_CHECK(npdrb_surf_radius_exact_host(hD.data(), N, N, sd_frac, &radius));
+        }
     }
     NB_CUDA(cudaMemcpyAsync(d_rad_scalar, &radius, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -545,7 +545,13 @@ __device__ __forceinline__ double v2_u1_fold(double d, const V2Fold &f, uint32_t
 // predicated row reloads instead of branches keep it one basic block, which is what lets the scheduler interleave them).
 // The running products of u (deviance) are renormalised once per V2_RENORM records: without clamps |eta| < 30, so
 // u < 2^43.3 and 16 factors times a mantissa stay below 2^694.
-constexpr int V2_RENORM = 16;
+#ifndef NB_EXP_FOLD
+#define NB_EXP_FOLD 0
+#endif
+#ifndef NB_EXP_HOIST
+#define NB_EXP_HOIST 1
+#endif
+constexpr int V2_RENORM = NB_EXP_HOIST ? 16 : 4;
 template <int Q, int DIFF, int NSL, bool CHECK>
 __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint32_t sREC_addr, uint32_t sCD_addr,
                                          uint32_t sXI_addr, uint32_t sXJ_addr, uint32_t sT, int diff_type,
@@ -553,7 +559,7 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
                                          double (&acc0)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2],
                                          double (&acc1)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2], unsigned &esum0, unsigned &esum1, int &nren) {
     constexpr int NA = (2 + Q) * (3 + Q) / 2 + (2 + Q) + 2;
-    constexpr bool FOLD = (Q == 0 && !CHECK);
+    constexpr bool FOLD = (Q == 0 && !CHECK && NB_EXP_FOLD);
     // each slice walks a CONTIGUOUS part of the range: records are in list order (grouped by Ri), so the I row
     // repeats for several records in a row and stays in registers (halves the shared-memory tile traffic).
     // m_begin is even and slices are an even number of records long: record pairs are fetched with one 8-byte load.
@@ -624,19 +630,19 @@ __device__ __forceinline__ void v2_range(int m_begin, int m_end, int slice, uint
         v2_renorm(acc1[NA - 2], esum1);
         ++nren;
     };
-    constexpr int RN = CHECK ? 2 : V2_RENORM;                    // checked path: a factor can be 2^52, renormalise per pair
-    while (m + RN <= m_hi) {
-        if (UNR == 2 && !CHECK) {
+    // one loop body for (almost) all records -- a second copy of it for remainders would run them with half the chains in
+    // flight -- with the renormalisation on a counter: every V2_RENORM records, or after every step on the checked path
+    // (a clamped factor can be 2^52)
+    constexpr int STEP = 2 * UNR;                                // records per loop trip
+    constexpr int TRIPS = CHECK ? 1 : (NB_EXP_HOIST ? V2_RENORM / STEP : 1);
+    int trips = 0;
 #pragma unroll 1
-            for (int i = 0; i < RN; i += 4) { two_records(m + i); two_records(m + i + 2); }
-        } else {
-#pragma unroll 1
-            for (int i = 0; i < RN; i += 2) two_records(m + i);
-        }
-        m += RN;
-        renorm();
+    for (; m + STEP <= m_hi; m += STEP) {
+        two_records(m);
+        if (UNR == 2) two_records(m + 2);
+        if (++trips == TRIPS) { renorm(); trips = 0; }
     }
-    for (; m + 1 < m_hi; m += 2) two_records(m);
+    if (UNR == 2 && m + 1 < m_hi) { two_records(m); m += 2; }
     if (m < m_hi) {                                              // odd tail: one record
         uint32_t r;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(sREC_addr + 4u * m));

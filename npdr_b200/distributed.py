@@ -64,6 +64,22 @@ class Engine:
     def set_surf_radius(self, radius):
         raise NotImplementedError
 
+    def surf_radius_from_moments(self, m0, m1, N, sd_frac):
+        """-> (radius, eps): radius from the combined moments and the bound on its distance from the reference's value."""
+        raise NotImplementedError
+
+    def surf_band_count(self, row0, nrows, nbd_metric, lo, hi):
+        """-> number of distances of the owned block inside [lo, hi]."""
+        raise NotImplementedError
+
+    def distance_block(self, row0, nrows, nbd_metric):
+        """-> the owned block of the distance matrix, float64 tensor [nrows, N] on self.device."""
+        raise NotImplementedError
+
+    def surf_radius_exact(self, D, sd_frac):
+        """-> the reference's SURF radius from the full N x N matrix (tensor), replayed in R's summation order."""
+        raise NotImplementedError
+
     def regress_block(self, Ri, NN, attr0, nattr, regression_type, attr_diff_type, covar_diff_type, unique):
         """-> (stats float64 [nattr, 8] numpy, n_unique, n_pairs_used)."""
         raise NotImplementedError
@@ -133,14 +149,25 @@ def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numer
     if world > 1 and hasattr(engine, "balanced_local") and os.environ.get("NPDRB_NO_BALANCED") != "1":
         exchange_balanced(engine, partition_rows(N, world), rank, nbd_metric, group)    # collective: every rank calls it
     if nbd_method == "surf" and world > 1:
-        # one global mean / sd: two scalar all-reduces (R/nearestNeighbors.R:234-241)
+        # one global mean / sd: two scalar all-reduces (R/nearestNeighbors.R:234-241), then the guard band: if no distance
+        # of any block lies within the radius' error bound the moment radius provably selects the reference's pairs;
+        # otherwise the blocks are gathered on rank 0 and R's sequential long-double chains are replayed exactly
         m0 = torch.tensor(engine.surf_partial(row0, nrows, nbd_metric, 0.0) if nrows else [0.0] * 4, dtype=torch.float64, device=dev)
         dist.all_reduce(m0, group=group)
         mean_u = float(m0[1] / m0[2])
         m1 = torch.tensor(engine.surf_partial(row0, nrows, nbd_metric, mean_u) if nrows else [0.0] * 4, dtype=torch.float64, device=dev)
         dist.all_reduce(m1, group=group)
-        num_pair = N * (N - 1) / 2.0
-        radius = float(m0[0]) / (2.0 * num_pair) - msurf_sd_frac * float(torch.sqrt(m1[3] / (m1[2] - 1.0)))
+        radius, eps = engine.surf_radius_from_moments(m0.tolist(), m1.tolist(), N, msurf_sd_frac)
+        band = torch.tensor([engine.surf_band_count(row0, nrows, nbd_metric, radius - eps, radius + eps) if nrows else 0],
+                            dtype=torch.int64, device=dev)
+        dist.all_reduce(band, group=group)
+        if int(band.item()) > 0 or os.environ.get("NPDRB_SURF_FORCE_EXACT") == "1":
+            blk = engine.distance_block(row0, nrows, nbd_metric) if nrows else torch.zeros((0, N), dtype=torch.float64, device=dev)
+            flat, _ = all_gather_varlen(blk.reshape(-1), group)       # rare path: the whole matrix on every rank
+            rad = torch.tensor([engine.surf_radius_exact(flat.reshape(N, N), msurf_sd_frac) if rank == 0 else 0.0],
+                               dtype=torch.float64, device=dev)
+            dist.broadcast(rad, 0, group=group)
+            radius = float(rad.item())
         engine.set_surf_radius(radius)
 
     if nrows > 0:
@@ -234,6 +261,20 @@ class GpuEngine(Engine):
 
     def set_surf_radius(self, radius):
         self.session.set_surf_radius(radius)
+
+    def surf_radius_from_moments(self, m0, m1, N, sd_frac):
+        return self._lib.surf_radius_from_moments(m0, m1, N, sd_frac)
+
+    def surf_band_count(self, row0, nrows, nbd_metric, lo, hi):
+        self._ensure_distances(row0, nrows, nbd_metric)
+        return self.session.surf_band_count(lo, hi)
+
+    def distance_block(self, row0, nrows, nbd_metric):
+        self._ensure_distances(row0, nrows, nbd_metric)
+        return torch.from_numpy(self.session.copy_distances()).to(self.device)
+
+    def surf_radius_exact(self, D, sd_frac):
+        return self._lib.surf_radius_exact_host(D.cpu().numpy(), sd_frac)
 
     def regress_block(self, Ri, NN, attr0, nattr, regression_type, attr_diff_type, covar_diff_type, unique):
         torch.cuda.synchronize(self.device)          # NCCL results complete before the library's stream reads them

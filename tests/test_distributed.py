@@ -55,6 +55,21 @@ class OracleEngine:
     def set_surf_radius(self, r):
         self.surf = r
 
+    def surf_radius_from_moments(self, m0, m1, N, sd_frac):
+        from npdr_b200 import _lib                      # host-only entry points of the library: no GPU needed
+        return _lib.surf_radius_from_moments(m0, m1, N, sd_frac)
+
+    def surf_band_count(self, row0, nrows, nbd_metric, lo, hi):
+        blk = self._dist(nbd_metric)[row0:row0 + nrows]
+        return int(((blk >= lo) & (blk <= hi)).sum())
+
+    def distance_block(self, row0, nrows, nbd_metric):
+        return torch.from_numpy(np.ascontiguousarray(self._dist(nbd_metric)[row0:row0 + nrows]))
+
+    def surf_radius_exact(self, D, sd_frac):
+        from npdr_b200 import _lib
+        return _lib.surf_radius_exact_host(D.numpy(), sd_frac)
+
     def regress_block(self, Ri, NN, attr0, nattr, regression_type, attr_diff_type, covar_diff_type, unique):
         ri, nn = Ri.numpy(), NN.numpy()
         nu, keep = self.O.unique_neighbors(ri, nn, self.X.shape[0])
@@ -222,10 +237,36 @@ def test_sharded_equals_unsharded(world, method, hitmiss, balanced):
     cd = np.column_stack([O.pair_diffs(C[:, 0], ri, nn, "match-mismatch"), O.pair_diffs(C[:, 1], ri, nn, "numeric-abs")])
     exp = O.regress_attrs(X, ri, nn, O.pair_diffs(y, ri, nn, "match-mismatch"), cd)
     assert stats.shape == exp.shape
-    if method == "surf":
-        np.testing.assert_allclose(stats, exp, rtol=1e-9, equal_nan=True)    # radius from combined moments
-    else:
-        assert np.array_equal(stats, exp, equal_nan=True)
+    # surf: the radius comes from combined moments, but no distance lies inside its guard band, so the pair list -- and with
+    # it every statistic -- is the reference's bit for bit
+    assert np.array_equal(stats, exp, equal_nan=True)
+
+
+def test_surf_exact_replay_under_gloo(monkeypatch):
+    """NPDRB_SURF_FORCE_EXACT=1: the ranks gather the matrix and rank 0 replays R's sequential long-double chains."""
+    monkeypatch.setenv("NPDRB_SURF_FORCE_EXACT", "1")
+    test_sharded_equals_unsharded(2, "surf", False, True)
+
+
+def test_surf_exact_host_replay_matches_oracle_and_band_bound():
+    """The library's host replay of R's SURF radius equals the oracle's bit for bit; the moment radius lies inside its own
+    error bound of it (the guarantee the guard band rests on)."""
+    from oracle import oracle as O
+    from npdr_b200 import _lib
+    rng = np.random.default_rng(8)
+    for N in (37, 300, 1500):
+        X = np.asfortranarray(rng.normal(size=(N, 40)))
+        D = O.distances(X, "manhattan")
+        for sd_frac in (0.5, 0.0, 1.3):
+            r_exact = _lib.surf_radius_exact_host(D, sd_frac)
+            assert r_exact == O.radius_surf(D, sd_frac)
+            iu = np.triu_indices(N, 1)
+            up = D[iu]
+            m0 = [D.sum(), up.sum(), float(up.size), float((up ** 2).sum())]
+            mean_u = m0[1] / m0[2]
+            m1 = [m0[0], m0[1], m0[2], float(((up - mean_u) ** 2).sum())]
+            r, eps = _lib.surf_radius_from_moments(m0, m1, N, sd_frac)
+            assert abs(r - r_exact) <= eps and eps < 1e-9 * abs(r_exact)
 
 
 def test_all_gather_varlen_single_process():

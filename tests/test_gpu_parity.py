@@ -22,6 +22,20 @@ def nb():
     return npdr_b200
 
 
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _multi_devices(n, monkeypatch):
+    """Device list for an n-device in-process run: real ordinals when the box has them, otherwise device 0 listed n times
+    (NPDRB_MULTI_ALLOW_DUPLICATES: the workers share the device, every exchange still goes through the peer-copy path)."""
+    if _n_devices() >= n:
+        return list(range(n))
+    monkeypatch.setenv("NPDRB_MULTI_ALLOW_DUPLICATES", "1")
+    return [0] * n
+
+
 def _stats_close(got, exp, rtol, what=""):
     """Columns beta_a, stat_a, beta_0, stat_0, r2|deviance to rtol; df, iters, flags exactly."""
     for col in (0, 1, 2, 3, 5):
@@ -229,14 +243,25 @@ def test_npdr_separate_hitmiss(nb, oracle):
         _stats_close(info["stats"], exp, RTOL_IRLS, f"hitmiss {method}")
 
 
-def test_surf_large_n_close(nb, oracle):
-    """N > 1024: the SURF radius comes from parallel moments (<= 1 ulp-level deviation)."""
+def test_surf_large_n_exact_pair_list(nb, oracle, monkeypatch):
+    """N > 1024: the SURF radius comes from parallel moments with a guard band -- the pair list is the reference's bit for
+    bit either because no distance lies inside the band, or (forced here as well) through the exact host replay of R's
+    sequential long-double chains, which reproduces the radius itself bit for bit; same on two (emulated) devices."""
     rng = np.random.default_rng(12)
     X = np.asfortranarray(rng.normal(size=(1100, 20)))
-    out, info = nb.nearestNeighbors(X, "surf", return_info=True)
     ri, nn, D, r = oracle.nearest_neighbors(X, "surf")
-    assert abs(info["radius"][0] - r[0]) <= 4e-16 * r[0] * 4
+    out, info = nb.nearestNeighbors(X, "surf", return_info=True)
+    assert abs(info["radius"][0] - r[0]) <= 1e-10 * r[0]
     assert np.array_equal(out["Ri_idx"], ri) and np.array_equal(out["NN_idx"], nn)
+    y = (rng.random(1100) < 0.5).astype(float)
+    _, info2 = nb.npdr(y, X, nbd_method="surf", devices=_multi_devices(2, monkeypatch), return_info=True)
+    assert np.array_equal(info2["Ri"], ri) and np.array_equal(info2["NN"], nn)
+    monkeypatch.setenv("NPDRB_SURF_FORCE_EXACT", "1")
+    out, info = nb.nearestNeighbors(X, "surf", return_info=True)
+    assert info["radius"][0] == r[0]
+    assert np.array_equal(out["Ri_idx"], ri) and np.array_equal(out["NN_idx"], nn)
+    _, info2 = nb.npdr(y, X, nbd_method="surf", devices=_multi_devices(2, monkeypatch), return_info=True)
+    assert np.array_equal(info2["Ri"], ri) and np.array_equal(info2["NN"], nn)
 
 
 # ------------------------------------------------------------------ regression
@@ -702,11 +727,6 @@ def test_pipelined_upload_distances_bit_exact(nb, oracle, monkeypatch):
 
 
 # ---------------------------------------------------------------- in-process multi-GPU driver (npdrb_npdr_multi)
-def _n_devices():
-    import torch
-    return torch.cuda.device_count()
-
-
 @pytest.mark.parametrize("name", ["cfg1", "cfg3"])
 def test_npdr_multi_driver_one_device(nb, name):
     """npdrb_npdr_multi with a single device: the threaded driver itself (partition, phases, result assembly)."""
@@ -721,15 +741,6 @@ def test_npdr_multi_driver_one_device(nb, name):
     assert list(out1["att"]) == list(out2["att"])
     for f in ("n_pairs", "n_unique_pairs", "n_pairs_used", "n_empty", "knn_used"):
         assert info1[f] == info2[f], f
-
-
-def _multi_devices(n, monkeypatch):
-    """Device list for an n-device in-process run: real ordinals when the box has them, otherwise device 0 listed n times
-    (NPDRB_MULTI_ALLOW_DUPLICATES: the workers share the device, every exchange still goes through the peer-copy path)."""
-    if _n_devices() >= n:
-        return list(range(n))
-    monkeypatch.setenv("NPDRB_MULTI_ALLOW_DUPLICATES", "1")
-    return [0] * n
 
 
 @pytest.mark.parametrize("method,hitmiss,ndev", [("multisurf", False, 2), ("surf", False, 2), ("relieff", False, 2), ("multisurf", True, 2),
