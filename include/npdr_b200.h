@@ -65,7 +65,8 @@ enum { NPDRB_NBD_MULTISURF = 0, NPDRB_NBD_SURF = 1, NPDRB_NBD_RELIEFF = 2 };
 /* regression.type, R/npdr.R:152 */
 enum { NPDRB_REG_LM = 0, NPDRB_REG_BINOMIAL = 1 };
 
-#define NPDRB_MAX_COVARS 4
+/* R/npdr.R:315-345 has no limit; up to 4 covariates run in the streaming kernels, 5..60 through the wide-design kernel */
+#define NPDRB_MAX_COVARS 60
 
 /* per-attribute statistics, one row per attribute (8 doubles):
  *   [0] beta_a   coefficient of the attribute diff       (coeffs[2,1], R/npdr.R:52)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("NPDRB_LIB_PATH") or os.path.join(_HERE, "libnpdr_b200.so")   # override: A/B runs of two builds
 
 STATS_PER_ATTR = 8
-MAX_COVARS = 4
+MAX_COVARS = 60
 DIFF = {"numeric-abs": 0, "manhattan": 0, "numeric-sqr": 1, "allele-sharing": 2, "match-mismatch": 3, "raw": 4}
 METRIC = {"manhattan": 0, "euclidean": 1, "allele-sharing-manhattan": 2, "relief-scaled-manhattan": 3,
           "relief-scaled-euclidean": 4, "precomputed": 5, "hamming": 6}

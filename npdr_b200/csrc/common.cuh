@@ -47,6 +47,28 @@ cudaError_t nb_cached_free(void *p);
         }                                                                                      \
     } while (0)
 
+// The streaming regression kernels (regress.cu) hold q <= NB_FAST_COVARS covariates in registers; wider designs go through
+// regress_wide.cu (up to NPDRB_MAX_COVARS).
+#define NB_FAST_COVARS 4
+
+// Device buffers that live for one call: everything allocated through a scope is returned to the cache when the scope ends,
+// early error returns included.
+struct nb_scope {
+    std::vector<void *> bufs;
+    nb_scope() = default;
+    nb_scope(const nb_scope &) = delete;
+    nb_scope &operator=(const nb_scope &) = delete;
+    template <typename T>
+    int alloc(T **p, size_t n) {
+        const size_t bytes = sizeof(T) * (n ? n : 1);
+        cudaError_t e = cudaMalloc((void **)p, bytes);
+        if (e != cudaSuccess) { npdrb_set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); *p = nullptr; return NPDRB_ENOMEM; }
+        bufs.push_back((void *)*p);
+        return NPDRB_OK;
+    }
+    ~nb_scope() { for (void *b : bufs) cudaFree(b); }
+};
+
 static inline int64_t nb_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 static inline int64_t nb_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -67,7 +89,7 @@ struct nb_stream {
     double weight = 1.0;          // multiplicity applied to every record's contribution
     uint32_t *rec = nullptr;      // il | jl << 8 | ybit << 16, bucketed by (I-block, J-block) tile
     double *yv = nullptr;         // lm: |y_i - y_j| per record
-    double *cd[NPDRB_MAX_COVARS] = {nullptr, nullptr, nullptr, nullptr};  // covariate diffs per record
+    double *cd[NB_FAST_COVARS] = {nullptr, nullptr, nullptr, nullptr};  // covariate diffs per record
     int32_t n_tiles = 0;          // non-empty tiles
     int64_t *tile_ptr = nullptr;  // [n_tiles + 1] record offsets
     int64_t *tile_mid = nullptr;  // [n_tiles] offset of the first miss (outcome bit 1) record of each tile
@@ -145,6 +167,8 @@ int nb_diff_vectors(npdrb_ctx *ctx, const double *da, const double *db, int64_t 
                     double *dout);
 int nb_measure_fp64_peak(npdrb_ctx *ctx, double *dfma_tflops, double *dadd_tflops);
 void nb_free_streams(npdrb_session *s);
+int nb_regress_wide(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t regression_type, int32_t attr_diff_type,
+                    const int32_t *covar_diff_type, double *stats_out_host, int32_t *irls_passes);
 
 // diff function shared by the pair kernels (npdrDiff, R/nearestNeighbors.R:15-40, norm.fac = 1)
 __device__ __forceinline__ double nb_diff1(double a, double b, int type) {

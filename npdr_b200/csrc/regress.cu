@@ -29,7 +29,7 @@ constexpr int TA = 128;                // attributes per CTA
 constexpr int NSLICE = 4;              // pair slices per attribute
 constexpr int RTHREADS = TA * NSLICE;  // 512
 constexpr int RCHUNK = 1024;           // records staged per step
-constexpr int KMAX = 2 + NPDRB_MAX_COVARS;
+constexpr int KMAX = 2 + NB_FAST_COVARS;
 
 // MODE_LM: moments with the outcome diff from the yv stream; MODE_SIGN: the same moments with the outcome
 // taken as s = +1 (miss) / -1 (hit) from the record bit (closed-form first IRLS pass); MODE_IRLS_FULL: one IRLS pass.
@@ -124,11 +124,11 @@ struct GatherArgs {
     const double *y, *C;
     int64_t M, N;
     int q, reg_type;
-    int cov_type[NPDRB_MAX_COVARS];
+    int cov_type[NB_FAST_COVARS];
     int y_raw;                 // uniReg: outcome of instance Ri itself, no diff
     uint32_t *rec;
     double *yv;
-    double *cd[NPDRB_MAX_COVARS];
+    double *cd[NB_FAST_COVARS];
     unsigned long long *n_miss;
 };
 __global__ void gather_records_kernel(GatherArgs g) {
@@ -191,8 +191,8 @@ __global__ void classify_pairs_kernel(const int32_t *__restrict__ Ri, const int3
 }
 
 // shared (attribute-independent) lm moments of the record stream: M, Sy, Syy, Sc_r, Scy_r, Scc_rs
-constexpr int NSHARED_MAX = 3 + 2 * NPDRB_MAX_COVARS + NPDRB_MAX_COVARS * (NPDRB_MAX_COVARS + 1) / 2;
-struct SharedArgs { const double *yv; const uint32_t *rec; const double *cd[NPDRB_MAX_COVARS]; int64_t n; int q; double *out; };
+constexpr int NSHARED_MAX = 3 + 2 * NB_FAST_COVARS + NB_FAST_COVARS * (NB_FAST_COVARS + 1) / 2;
+struct SharedArgs { const double *yv; const uint32_t *rec; const double *cd[NB_FAST_COVARS]; int64_t n; int q; double *out; };
 __global__ void __launch_bounds__(256)
 shared_moments_kernel(SharedArgs a) {
     __shared__ double red[256];
@@ -201,7 +201,7 @@ shared_moments_kernel(SharedArgs a) {
     for (int s = 0; s < NSHARED_MAX; ++s) acc[s] = 0.0;
     for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < a.n; t += (int64_t)gridDim.x * 256) {
         const double y = a.yv ? a.yv[t] : ((a.rec[t] & 1u) ? 1.0 : -1.0);
-        double c[NPDRB_MAX_COVARS];
+        double c[NB_FAST_COVARS];
         for (int r = 0; r < a.q; ++r) c[r] = a.cd[r][t];
         int s = 0;
         acc[s++] += 1.0; acc[s++] += y; acc[s++] += y * y;
@@ -220,7 +220,7 @@ shared_moments_kernel(SharedArgs a) {
 
 // ------------------------------------------------------------------ the pass kernel
 struct StreamArgs {                // one bucketed pair stream (see nb_stream)
-    const uint32_t *rec; const double *yv; const double *cd[NPDRB_MAX_COVARS];
+    const uint32_t *rec; const double *yv; const double *cd[NB_FAST_COVARS];
     const int64_t *tile_ptr; const int64_t *tile_mid; const int32_t *tile_ib; const int32_t *tile_jb; const int32_t *chunk_tile;
     double *partials;              // [n_chunks][NACC][nattr_pad]
 };
@@ -234,7 +234,7 @@ struct PassArgs {
     const nb_tables *tables;       // device copy of the exp/log tables (v1 kernel)
     const nb_tables1024 *tables1024; // 1024-entry exp table (v2 kernel)
     const double *dmax;            // [nattr_pad] bound on the attribute diff (v2 IRLS pass: clamp pre-check)
-    double cmax[NPDRB_MAX_COVARS]; // bounds on the covariate diffs
+    double cmax[NB_FAST_COVARS]; // bounds on the covariate diffs
     int diff_type;
     int dbg;                       // development switches (NPDRB_V3_DBG)
 };
@@ -1381,7 +1381,7 @@ struct SolveArgs {
     double *dev_old;               // [nattr_pad]
     double *hit_d, *miss_d;        // [nattr_pad] sum of the attribute diff over the hit / miss records (from pass 0)
     const double *dmax;            // [nattr] upper bound of the attribute diff over any pair
-    double cmax[NPDRB_MAX_COVARS]; // upper bounds of the covariate diffs
+    double cmax[NB_FAST_COVARS]; // upper bounds of the covariate diffs
     int speculate;                 // 1: finish without the confirming pass when the predicted deviance change is far below epsilon
     unsigned char *active;         // [nattr_pad]
     unsigned char *tile_active;    // [n attr tiles]
@@ -1694,7 +1694,7 @@ int get_tables(npdrb_ctx *ctx, const nb_tables **out) {
 
 void free_stream(nb_stream &st) {
     cudaFree(st.rec); cudaFree(st.yv);
-    for (int c = 0; c < NPDRB_MAX_COVARS; ++c) cudaFree(st.cd[c]);
+    for (int c = 0; c < NB_FAST_COVARS; ++c) cudaFree(st.cd[c]);
     cudaFree(st.tile_ptr); cudaFree(st.tile_mid); cudaFree(st.tile_ib); cudaFree(st.tile_jb); cudaFree(st.chunk_tile);
     st = nb_stream();
 }
@@ -1737,7 +1737,7 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     for (int c = 0; c < q; ++c) NB_CHECK(dmalloc(&st.cd[c], (size_t)M));
     GatherArgs g;
     g.Ri = dRi; g.NN = dNN; g.perm = perm; g.y = s->dy; g.C = s->dC; g.M = M; g.N = N; g.q = q; g.reg_type = reg_type;
-    for (int c = 0; c < NPDRB_MAX_COVARS; ++c) { g.cov_type[c] = (c < q && cov_type) ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH; g.cd[c] = st.cd[c]; }
+    for (int c = 0; c < NB_FAST_COVARS; ++c) { g.cov_type[c] = (c < q && cov_type) ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH; g.cd[c] = st.cd[c]; }
     g.y_raw = y_raw; g.rec = st.rec; g.yv = st.yv; g.n_miss = d_miss;
     gather_records_kernel<<<grid, 256, 0, ctx->stream>>>(g);
     NB_LAUNCH_CHECK(ctx);
@@ -1879,7 +1879,7 @@ int launch_pass(npdrb_ctx *ctx, int q, const PassArgs &P, int n_at, int n_chunks
     case 3: return launch_pass_q<MODE, 3>(ctx, P, n_at, n_chunks);
     case 4: return launch_pass_q<MODE, 4>(ctx, P, n_at, n_chunks);
     }
-    npdrb_set_error("regress: at most %d covariates are supported", NPDRB_MAX_COVARS);
+    npdrb_set_error("regress: at most %d covariates are supported", NB_FAST_COVARS);
     return NPDRB_EINVAL;
 }
 
@@ -1922,6 +1922,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     if (reg_type != NPDRB_REG_LM && reg_type != NPDRB_REG_BINOMIAL) { npdrb_set_error("regress: bad regression type"); return NPDRB_EINVAL; }
     if (diff_type < 0 || diff_type > NPDRB_DIFF_RAW) { npdrb_set_error("regress: bad attr diff type"); return NPDRB_EINVAL; }
     if (s->M >= (1ll << 31)) { npdrb_set_error("regress: more than 2^31 pairs per device"); return NPDRB_EINVAL; }
+    if (q > NB_FAST_COVARS) return nb_regress_wide(s, attr0, nattr, reg_type, diff_type, cov_type, stats_out_host, irls_passes);
     const int y_raw = (diff_type == NPDRB_DIFF_RAW) ? 1 : 0;
 
     cudaEvent_t e0 = s->ev[0], e1 = s->ev[1];
@@ -2091,14 +2092,14 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         P.beta = d_beta; P.tile_active = tile_active; P.tables = d_tab; P.tables1024 = d_tab1024; P.diff_type = diff_type;
         P.dmax = d_dmax;
         { const char *dbg = getenv("NPDRB_V3_DBG"); P.dbg = dbg ? atoi(dbg) : 0; }
-        for (int c = 0; c < NPDRB_MAX_COVARS; ++c) P.cmax[c] = S.cmax[c];
+        for (int c = 0; c < NB_FAST_COVARS; ++c) P.cmax[c] = S.cmax[c];
         double *pp = d_part;
         int total_chunks = 0;
         for (int i = 0; i < s->n_streams; ++i) {
             const nb_stream &st = s->streams[i];
             StreamArgs &A = P.st[i];
             A.rec = st.rec; A.yv = st.yv;
-            for (int c = 0; c < NPDRB_MAX_COVARS; ++c) A.cd[c] = st.cd[c];
+            for (int c = 0; c < NB_FAST_COVARS; ++c) A.cd[c] = st.cd[c];
             A.tile_ptr = st.tile_ptr; A.tile_mid = st.tile_mid; A.tile_ib = st.tile_ib; A.tile_jb = st.tile_jb;
             A.chunk_tile = st.chunk_tile; A.partials = pp;
             pp += part_stride[i];
@@ -2141,7 +2142,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             SharedArgs a;
             a.yv = lm ? s->streams[i].yv : nullptr; a.rec = s->streams[i].rec;
             a.n = s->streams[i].n_rec; a.q = q; a.out = d_sh;
-            for (int c = 0; c < NPDRB_MAX_COVARS; ++c) a.cd[c] = s->streams[i].cd[c];
+            for (int c = 0; c < NB_FAST_COVARS; ++c) a.cd[c] = s->streams[i].cd[c];
             NB_CUDA(cudaMemsetAsync(d_sh, 0, sizeof(double) * h.size(), ctx->stream));
             shared_moments_kernel<<<nblk, 256, 0, ctx->stream>>>(a);
             NB_LAUNCH_CHECK(ctx);

@@ -41,6 +41,7 @@
 #define ORC_EINVAL 1
 #define ORC_ENOMEM 2
 #define ORC_ESINGLE_LEVEL 3
+#define ORC_MAX_DESIGN 64   /* columns of a regression design: intercept + attribute + covariates (R/npdr.R:404-411) */
 
 /* diff types: npdrDiff's diff.type, R/nearestNeighbors.R:15 */
 enum { ORC_DIFF_NUMERIC_ABS = 0, ORC_DIFF_NUMERIC_SQR = 1, ORC_DIFF_ALLELE_SHARING = 2,
@@ -656,8 +657,8 @@ static void qr_solve(const double *qr, int64_t n, int p, int k, const double *qr
 
 /* chol2inv on the leading k x k upper triangle of qr: diag of (R'R)^-1. Also full inverse if cov != NULL (k x k col-major). */
 static void chol2inv_diag(const double *qr, int64_t n, int k, double *diag, double *cov) {
-    double Rinv[16 * 16];
-    if (k > 16) k = 16;
+    double Rinv[ORC_MAX_DESIGN * ORC_MAX_DESIGN];
+    if (k > ORC_MAX_DESIGN) k = ORC_MAX_DESIGN;
     for (int j = 0; j < k; ++j) {                             /* invert upper-triangular R column by column */
         for (int i = 0; i < k; ++i) Rinv[i + j * k] = 0.0;
         Rinv[j + j * k] = 1.0 / qr[j + (int64_t)j * n];
@@ -703,15 +704,15 @@ typedef struct {
  * Xd: n x p design (column 0 must be the intercept), column-major.  coef/se have p entries in
  * ORIGINAL column order; aliased coefficients are NaN. */
 int orc_lm(const double *Xd, const double *y, int64_t n, int p, double *coef, double *se, orc_fit_info *info) {
-    if (p > 16 || p < 1) return ORC_EINVAL;
+    if (p > ORC_MAX_DESIGN || p < 1) return ORC_EINVAL;
     double *qr = (double *)malloc(sizeof(double) * (size_t)n * (size_t)p);
     double *qty = (double *)malloc(sizeof(double) * (size_t)n);
     double *rsd = (double *)malloc(sizeof(double) * (size_t)n);
     double *fit = (double *)malloc(sizeof(double) * (size_t)n);
     if (!qr || !qty || !rsd || !fit) { free(qr); free(qty); free(rsd); free(fit); return ORC_ENOMEM; }
     memcpy(qr, Xd, sizeof(double) * (size_t)n * (size_t)p);
-    double qraux[16], work[32], b[16], diag[16];
-    int jpvt[16];
+    double qraux[ORC_MAX_DESIGN], work[2 * ORC_MAX_DESIGN], b[ORC_MAX_DESIGN], diag[ORC_MAX_DESIGN];
+    int jpvt[ORC_MAX_DESIGN];
     for (int j = 0; j < p; ++j) jpvt[j] = j;
     int k = dqrdc2(qr, n, p, 1e-7, qraux, jpvt, work);
     qr_solve(qr, n, p, k, qraux, y, qty, b, rsd);
@@ -757,14 +758,14 @@ static inline double binomial_dev_resid(double y, double mu) {   /* weights 1 */
  * summary: dispersion 1, cov.unscaled = chol2inv(R) of the LAST weighted QR.
  * y must be 0/1.  coef/se in original column order; aliased -> NaN. */
 int orc_glm_binomial(const double *Xd, const double *y, int64_t n, int p, double *coef, double *se, orc_fit_info *info) {
-    if (p > 16 || p < 1) return ORC_EINVAL;
+    if (p > ORC_MAX_DESIGN || p < 1) return ORC_EINVAL;
     size_t nn = (size_t)n;
     double *qr = (double *)malloc(sizeof(double) * nn * (size_t)p);
     double *eta = (double *)malloc(sizeof(double) * nn), *mu = (double *)malloc(sizeof(double) * nn);
     double *zw = (double *)malloc(sizeof(double) * nn), *qty = (double *)malloc(sizeof(double) * nn);
     if (!qr || !eta || !mu || !zw || !qty) { free(qr); free(eta); free(mu); free(zw); free(qty); return ORC_ENOMEM; }
-    double qraux[16], work[32], b[16], start[16], coefold[16], diag[16];
-    int jpvt[16], have_old = 0, k = 0, conv = 0, iter;
+    double qraux[ORC_MAX_DESIGN], work[2 * ORC_MAX_DESIGN], b[ORC_MAX_DESIGN], start[ORC_MAX_DESIGN], coefold[ORC_MAX_DESIGN], diag[ORC_MAX_DESIGN];
+    int jpvt[ORC_MAX_DESIGN], have_old = 0, k = 0, conv = 0, iter;
     long double acc = 0.0L;
     for (int64_t i = 0; i < n; ++i) {
         double ms = (y[i] + 0.5) / 2.0;
@@ -844,7 +845,7 @@ int orc_glm_binomial(const double *Xd, const double *y, int64_t n, int p, double
  * nrow(coeffs) < 2 -> NA.  Reproduced here. */
 int orc_diff_regression(const double *design /* M x k, col 0 = 1s */, const double *y, int64_t M, int k,
                         int regression_type, double *out) {
-    double coef[16], se[16];
+    double coef[ORC_MAX_DESIGN], se[ORC_MAX_DESIGN];
     orc_fit_info info;
     int rc = (regression_type == ORC_REG_LM) ? orc_lm(design, y, M, k, coef, se, &info)
                                              : orc_glm_binomial(design, y, M, k, coef, se, &info);

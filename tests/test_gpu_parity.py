@@ -317,6 +317,70 @@ def test_regress_random(nb, oracle, reg, q, diff):
     assert int(info["stats"][7, 7]) & 1                            # the constant attribute is flagged
 
 
+@pytest.mark.parametrize("reg", ["lm", "binomial"])
+@pytest.mark.parametrize("q", [5, 6, 13, 14, 29, 39, 60])
+def test_regress_wide_covariates(nb, oracle, reg, q):
+    """More covariates than the streaming kernels hold (R/npdr.R:315-345 has no limit; mdd.RNAseq.small$covs.short has 39):
+    the wide-design kernel (one CTA fits one attribute, IRLS in-kernel) against the oracle's QR-based lm / glm.fit."""
+    rng = np.random.default_rng(1000 + q + (7 if reg == "lm" else 0))
+    N, p = 120, 37
+    X = rng.normal(size=(N, p))
+    ycls = (rng.random(N) < 0.45).astype(float)
+    X[:, 0] += 1.5 * ycls
+    X[:, 5] = 2.0                                                  # constant attribute -> aliased
+    X = np.asfortranarray(X)
+    kinds = ["match-mismatch", "numeric-abs", "numeric-sqr", "numeric-abs", "allele-sharing"]
+    types = [kinds[c % len(kinds)] for c in range(q)]
+    cols = []
+    for c, t in enumerate(types):
+        if t == "match-mismatch": cols.append(rng.integers(0, 3, N).astype(float))
+        elif t == "allele-sharing": cols.append(rng.integers(0, 3, N).astype(float))
+        elif c % 4 == 1: cols.append(rng.normal(40, 12, N).round())
+        else: cols.append(rng.normal(size=N))
+    C = np.asfortranarray(np.column_stack(cols))
+    y = ycls if reg == "binomial" else rng.normal(size=N) + 0.8 * X[:, 0] + 0.05 * C[:, 1]
+    ri, nn, _, _ = oracle.nearest_neighbors(X)
+    yd = oracle.pair_diffs(y, ri, nn, "numeric-abs" if reg == "lm" else "match-mismatch")
+    cd = np.column_stack([oracle.pair_diffs(C[:, c], ri, nn, types[c]) for c in range(q)])
+    exp = oracle.regress_attrs(X, ri, nn, yd, cd, "numeric-abs", reg)
+    out, info = nb.npdr(y, X, reg, "numeric-abs", covars=C, covar_diff_type=types, return_info=True)
+    assert np.array_equal(info["Ri"], ri) and np.array_equal(info["NN"], nn)
+    _stats_close(info["stats"], exp, RTOL_LM if reg == "lm" else RTOL_IRLS, f"wide {reg} q={q}")
+    assert int(info["stats"][5, 7]) & 1                            # the constant attribute is flagged; its row is the first covariate's
+    # same through the in-process multi-device driver (attribute shards) and with unique sampling
+    _, info2 = nb.npdr(y, X, reg, "numeric-abs", covars=C, covar_diff_type=types, neighbor_sampling="unique", return_info=True)
+    nu, keep = oracle.unique_neighbors(ri, nn, N)
+    k = keep.astype(bool)
+    exp_u = oracle.regress_attrs(X, ri[k], nn[k], yd[k], cd[k], "numeric-abs", reg)
+    _stats_close(info2["stats"], exp_u, RTOL_LM if reg == "lm" else RTOL_IRLS, f"wide unique {reg} q={q}")
+
+
+def test_regress_wide_aliased_covariates(nb, oracle):
+    """Wide path corner cases: a constant covariate (its diff column is all zero -> aliased) and a duplicated covariate
+    (the second copy is aliased): coefficients, residual df (rank drops by two) and flags as lm / glm.fit report them."""
+    from npdr_b200 import _lib
+    rng = np.random.default_rng(77)
+    N, p, q = 100, 12, 7
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    C = rng.normal(size=(N, q))
+    C[:, 2] = 3.0                                                  # constant -> zero diffs
+    C[:, 4] = C[:, 1]                                              # duplicate
+    C = np.asfortranarray(C)
+    ri, nn, _, _ = oracle.nearest_neighbors(X)
+    cd = np.column_stack([oracle.pair_diffs(C[:, c], ri, nn, "numeric-abs") for c in range(q)])
+    cdt = np.zeros(q, dtype=np.int32)
+    for reg in ("binomial", "lm"):
+        y = (rng.random(N) < 0.5).astype(float) if reg == "binomial" else X[:, 3] + rng.normal(size=N)
+        yd = oracle.pair_diffs(y, ri, nn, "match-mismatch" if reg == "binomial" else "numeric-abs")
+        exp = oracle.regress_attrs(X, ri, nn, yd, cd, "numeric-abs", reg)
+        out = np.empty((p, 8))
+        _lib.check(_lib.load().npdrb_regress(_lib.context(0).handle, _lib.dptr(X), N, p, _lib.iptr(ri), _lib.iptr(nn), ri.size,
+                                            _lib.dptr(np.ascontiguousarray(y)), _lib.dptr(C), q, _lib.iptr(cdt), 0,
+                                            1 if reg == "binomial" else 0, _lib.dptr(out)))
+        _stats_close(out, exp, RTOL_LM if reg == "lm" else RTOL_IRLS, f"wide aliased {reg}")
+        assert np.all(out[:, 4] == ri.size - q)                    # rank = 2 + q - 2
+
+
 def test_regress_user_pair_list_any_order(nb, oracle):
     """npdrb_regress with a shuffled pair list (not grouped by Ri) gives the same statistics."""
     from npdr_b200 import _lib

@@ -171,6 +171,34 @@ def test_glm_vs_newton(oracle):
     assert abs(info["deviance"] - dev) < 1e-8 * dev
 
 
+def test_wide_designs_vs_numpy(oracle):
+    """Designs with many covariate columns (up to 64 columns: R/npdr.R:315-345 has no limit): lm against lstsq, glm.fit
+    against Newton-Raphson, and an aliased column in the middle of a wide design."""
+    rng = np.random.default_rng(40)
+    n = 1500
+    for k in (8, 23, 41, 62):
+        Xd = np.asfortranarray(np.column_stack([np.ones(n)] + [rng.normal(size=n) if c % 3 else rng.integers(0, 2, n) for c in range(k - 1)]))
+        bt = rng.normal(scale=0.3, size=k)
+        y = Xd @ bt + rng.normal(size=n)
+        coef, se, info = oracle.lm(Xd, y)
+        b, *_ = np.linalg.lstsq(Xd, y, rcond=None)
+        np.testing.assert_allclose(coef, b, rtol=1e-8, atol=1e-11)
+        res = y - Xd @ b
+        np.testing.assert_allclose(se, np.sqrt(np.diag(np.linalg.inv(Xd.T @ Xd)) * (res @ res / (n - k))), rtol=1e-8)
+        assert info["rank"] == k and info["df_resid"] == n - k
+        yb = (rng.random(n) < 1 / (1 + np.exp(-Xd @ (bt * 0.5)))).astype(float)
+        coef, se, info = oracle.glm_binomial(Xd, yb)
+        bn = np.zeros(k)
+        for _ in range(60):
+            mu = 1 / (1 + np.exp(-Xd @ bn)); W = mu * (1 - mu)
+            bn = bn + np.linalg.solve(Xd.T @ (Xd * W[:, None]), Xd.T @ (yb - mu))
+        np.testing.assert_allclose(coef, bn, rtol=1e-6, atol=1e-8)
+        assert info["converged"] == 1
+        Xa = Xd.copy(); Xa[:, k // 2] = Xa[:, 1]                   # duplicate of an earlier column -> aliased
+        coef, se, info = oracle.lm(Xa, y)
+        assert np.isnan(coef[k // 2]) and info["rank"] == k - 1
+
+
 def test_diff_regression_quirk3(oracle):
     """Constant attribute: NA without covariates; the first covariate's row with covariates."""
     rng = np.random.default_rng(5)
