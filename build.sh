@@ -8,12 +8,12 @@ EXTRA=""
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $EXTRA"
 mkdir -p build
 pids=()
-for f in api distance neighbors regress regress_wide multi; do
+for f in api distance neighbors kgrid regress regress_wide multi; do
     nvcc $FLAGS -c -o build/$f.o npdr_b200/csrc/$f.cu &
     pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o npdr_b200/libnpdr_b200.so build/api.o build/distance.o build/neighbors.o \
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o npdr_b200/libnpdr_b200.so build/api.o build/distance.o build/neighbors.o build/kgrid.o \
      build/regress.o build/regress_wide.o build/multi.o
 make -s -C oracle
 echo "built npdr_b200/libnpdr_b200.so and oracle/libnpdr_oracle.so"

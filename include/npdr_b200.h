@@ -19,6 +19,7 @@
  *                                                    R/npdr.R:256-270, 299-345, 391-430
  *   npdrb_npdr_multi         <- the same on several GPUs from one process (the R session's multi-GPU entry point)
  *   npdrb_unireg             <- uniReg's per-column fits   R/utils.R:66-157
+ *   npdrb_npdr_k_grid        <- vwok's loop of npdr(nbd.method = "relieff", knn = k) over a k grid   R/adaptive.R:73,85-111
  *
  * What stays on the R side (per BASELINE north_star): argument parsing, factor coding,
  * pt()/pnorm() p-values, order(), p.adjust(), data-frame assembly.
@@ -189,6 +190,13 @@ int npdrb_npdr(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const doub
 int npdrb_npdr_multi(int32_t n_devices, const int32_t *devices, const double *X, int64_t N, int64_t p, const double *y,
                      const double *C, const npdrb_opts *opts, npdrb_result *res);
 void npdrb_multi_shutdown(void);                   /* releases the per-device contexts npdrb_npdr_multi keeps between calls */
+/* Batched k (vwok, R/adaptive.R:85-111): npdr(nbd.method = "relieff", knn = k_grid[c]) for every c on ONE resident problem --
+ * one upload, one distance matrix, one stable (d, row) sort of every distance row (a ReliefF list is a prefix of the sorted
+ * row, so each k costs two binary searches per row instead of a selection and a sort), one instance-major attribute copy.
+ * opts->nbd_method must be RELIEFF; opts->knn is ignored.  stats_out: n_k x p x 8 (k-major); n_pairs_out (length n_k) may be
+ * NULL.  Results are identical to n_k separate npdrb_npdr calls. */
+int npdrb_npdr_k_grid(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
+                      const npdrb_opts *opts, const int64_t *k_grid, int32_t n_k, double *stats_out, int64_t *n_pairs_out);
 /* uniReg: univariate lm/glm of y on each raw column (+ covariates C as additional regressors) */
 int npdrb_unireg(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
                  int32_t q, int32_t regression_type, double *stats_out);
@@ -232,6 +240,10 @@ int npdrb_session_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac
 int npdrb_session_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local,
                                     int64_t *n_empty_local);
 int npdrb_session_copy_radius2(npdrb_session *s, double *radius_host);      /* owned rows: miss radius */
+/* k grid: sort the owned distance rows by (d, row) once (_sort_rows), then emit the ReliefF list of any k from the sorted rows
+ * (_neighbors_sorted: the same list, bit for bit, as npdrb_session_neighbors(RELIEFF, k)). */
+int npdrb_session_sort_rows(npdrb_session *s);
+int npdrb_session_neighbors_sorted(npdrb_session *s, int64_t k, int64_t *M_local, int64_t *n_empty_local);
 /* SURF needs one global mean/sd (R/nearestNeighbors.R:234-241).  Partial moments of the owned rows:
  * out4[0] = sum of all owned entries, out4[1] = sum over the owned part of the strict upper triangle,
  * out4[2] = its count, out4[3] = sum over that part of (d - centre)^2.  Multi-rank hosts call it with

@@ -82,6 +82,7 @@ SIGNATURES = {
     "npdrb_npdr_multi": (C.c_int, [_i32, _ip, _dp, _i64, _i64, _dp, _dp, C.POINTER(Opts), C.POINTER(Result)]),
     "npdrb_multi_shutdown": (None, []),
     "npdrb_unireg": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, _i32, _i32, _dp]),
+    "npdrb_npdr_k_grid": (C.c_int, [_vp, _dp, _i64, _i64, _dp, _dp, C.POINTER(Opts), C.POINTER(_i64), _i32, _dp, C.POINTER(_i64)]),
     "npdrb_session_create": (C.c_int, [_vp, _i64, _i64, _i32, C.POINTER(_vp)]),
     "npdrb_session_destroy": (None, [_vp]),
     "npdrb_session_upload": (C.c_int, [_vp, _dp, _dp, _dp]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "npdrb_session_neighbors": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "npdrb_session_neighbors_hitmiss": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "npdrb_session_copy_radius2": (C.c_int, [_vp, _dp]),
+    "npdrb_session_sort_rows": (C.c_int, [_vp]),
+    "npdrb_session_neighbors_sorted": (C.c_int, [_vp, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "npdrb_session_surf_partial": (C.c_int, [_vp, C.c_double, _dp]),
     "npdrb_session_set_surf_radius": (C.c_int, [_vp, C.c_double]),
     "npdrb_surf_radius_from_moments": (C.c_int, [_dp, _dp, _i64, C.c_double, _dp, _dp]),
@@ -308,6 +311,14 @@ class Session:
     def neighbors_hitmiss(self, method="relieff", sd_frac=0.5, k=0):
         M, ne = _i64(), _i64()
         check(load().npdrb_session_neighbors_hitmiss(self.handle, NBD[method], float(sd_frac), int(k), C.byref(M), C.byref(ne)))
+        return M.value, ne.value
+
+    def sort_rows(self):
+        check(load().npdrb_session_sort_rows(self.handle))
+
+    def neighbors_sorted(self, k):
+        M, ne = _i64(), _i64()
+        check(load().npdrb_session_neighbors_sorted(self.handle, int(k), C.byref(M), C.byref(ne)))
         return M.value, ne.value
 
     def copy_radius2(self):

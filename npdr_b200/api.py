@@ -591,35 +591,40 @@ def npdr(outcome, dataset, regression_type="binomial", attr_diff_type="numeric-a
 
 
 def npdr_k_grid(outcome, dataset, k_grid=None, regression_type="binomial", attr_diff_type="numeric-abs",
-                nbd_metric="manhattan", msurf_sd_frac=0.5, separate_hitmiss_nbds=False, padj_method="bonferroni", device=0):
-    """npdr(nbd.method = "relieff", knn = k) for every k of a grid on ONE resident problem: the attribute matrix is
-    uploaded once, the distance matrix and the instance-major attribute copy are computed once and reused for all k
-    (what vwok's foreach loop recomputes per k, R/adaptive.R:85-111).
-    -> dict(att, k_grid, beta_Z [p, len(k_grid)], pval_adj [p, len(k_grid)], beta_raw, pval_att), attributes in input order."""
+                nbd_metric="manhattan", msurf_sd_frac=0.5, separate_hitmiss_nbds=False, padj_method="bonferroni",
+                covars="none", covar_diff_type="match-mismatch", neighbor_sampling="none", device=0):
+    """npdr(nbd.method = "relieff", knn = k) for every k of a grid through ONE C-ABI call (npdrb_npdr_k_grid): the attribute
+    matrix is uploaded once, the distance matrix, the per-row (d, row) sort and the instance-major attribute copy are
+    computed once and reused for all k (what vwok's foreach loop recomputes per k, R/adaptive.R:85-111).
+    -> dict(att, k_grid, beta_Z [p, len(k_grid)], pval_adj, beta_raw, pval_att, n_pairs), attributes in input order."""
     X, att_names, pheno = _split_outcome(outcome, dataset)
     y = _code_outcome(pheno, regression_type)
+    Cm, cdt, _ = _covars_matrix(covars, covar_diff_type)
     N, p = X.shape
     ks = list(range(1, N)) if k_grid is None else [int(k) for k in k_grid]       # seq.int(m - 1), R/adaptive.R:73
-    ctx = context(device)
-    s = _lib.Session(ctx, N, p, 0)
-    try:
-        s.upload(X, y)
-        s.distances(nbd_metric, False, 0, N)
-        bz = np.empty((p, len(ks))); br = np.empty((p, len(ks))); pa = np.empty((p, len(ks))); padj = np.empty((p, len(ks)))
-        for c, k in enumerate(ks):
-            if separate_hitmiss_nbds:
-                s.neighbors_hitmiss("relieff", msurf_sd_frac, k)
-            else:
-                s.neighbors("relieff", msurf_sd_frac, k)
-            a, b, m = s.local_pairs()
-            s.import_pairs(a, b, m)
-            st = s.regress(0, p, regression_type, attr_diff_type, ())
-            pv, _ = _pvalues(st, regression_type)
-            bz[:, c] = st[:, 1]; br[:, c] = st[:, 0]; pa[:, c] = pv
-            padj[:, c] = rstats.p_adjust(pv, padj_method)
-    finally:
-        s.close()
-    return {"att": att_names, "k_grid": ks, "beta_Z": bz, "beta_raw": br, "pval_att": pa, "pval_adj": padj}
+    o = _lib.Opts()
+    L = _lib.load()
+    L.npdrb_opts_default(C.byref(o))
+    o.regression_type = REG[regression_type]; o.attr_diff_type = DIFF[attr_diff_type]; o.nbd_method = _lib.NBD["relieff"]
+    o.nbd_metric = METRIC[nbd_metric]; o.msurf_sd_frac = float(msurf_sd_frac)
+    o.n_covars = len(cdt) if Cm is not None else 0
+    for i, t in enumerate(cdt[:o.n_covars]):
+        o.covar_diff_type[i] = DIFF[t]
+    o.neighbor_sampling_unique = int(neighbor_sampling == "unique")
+    o.separate_hitmiss_nbds = int(bool(separate_hitmiss_nbds))
+    kg = np.asarray(ks, dtype=np.int64)
+    stats = np.empty((len(ks), p, STATS_PER_ATTR))
+    npairs = np.zeros(len(ks), dtype=np.int64)
+    check(L.npdrb_npdr_k_grid(context(device).handle, dptr(X), N, p, dptr(f64(y)), dptr(Cm), C.byref(o),
+                              kg.ctypes.data_as(C.POINTER(C.c_int64)), len(ks), dptr(stats),
+                              npairs.ctypes.data_as(C.POINTER(C.c_int64))))
+    bz = np.empty((p, len(ks))); br = np.empty((p, len(ks))); pa = np.empty((p, len(ks))); padj = np.empty((p, len(ks)))
+    for c in range(len(ks)):
+        pv, _ = _pvalues(stats[c], regression_type)
+        bz[:, c] = stats[c][:, 1]; br[:, c] = stats[c][:, 0]; pa[:, c] = pv
+        padj[:, c] = rstats.p_adjust(pv, padj_method)
+    return {"att": att_names, "k_grid": ks, "beta_Z": bz, "beta_raw": br, "pval_att": pa, "pval_adj": padj,
+            "n_pairs": npairs, "stats": stats}
 
 
 def vwok(dats, k_grid=None, verbose=False, attr_diff_type="numeric-abs", corr_attr_names=None, signal_names=None,
@@ -634,7 +639,8 @@ def vwok(dats, k_grid=None, verbose=False, attr_diff_type="numeric-abs", corr_at
         raise NotImplementedError("vwok(signal.names=...): the PRROC auPRC scoring is outside the accelerated path")
     if pd is None or not isinstance(dats, pd.DataFrame):
         raise TypeError("dats must be a pandas DataFrame that contains the outcome column `label`")
-    g = npdr_k_grid(label, dats, k_grid, "binomial", "numeric-abs", "manhattan", 0.5, separate_hitmiss_nbds, "bonferroni", device)
+    g = npdr_k_grid(label, dats, k_grid, "binomial", "numeric-abs", "manhattan", 0.5, separate_hitmiss_nbds, "bonferroni",
+                    device=device)
     order = sorted(range(len(g["att"])), key=lambda i: g["att"][i])              # arrange(att)
     atts = [g["att"][i] for i in order]
     cols = [f"k.{k}" for k in g["k_grid"]]

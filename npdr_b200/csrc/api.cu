@@ -446,6 +446,7 @@ void npdrb_session_destroy(npdrb_session *s) {
     if (s->own_D) cudaFree(s->dD);
     cudaFree(s->d_sd_vec); cudaFree(s->d_radius); cudaFree(s->d_radius2);
     cudaFree(s->dRiL); cudaFree(s->dNNL); cudaFree(s->d_rowptr);
+    cudaFree(s->d_sortD); cudaFree(s->d_sortJ);
     if (s->own_pairs) { cudaFree(s->dRi); cudaFree(s->dNN); }
     cudaFree(s->dXT);
     nb_free_streams(s);
@@ -542,12 +543,14 @@ int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t 
 
 int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows) {
     NB_CUDA(cudaSetDevice(s->ctx->device));
+    s->sorted_valid = false;
     return nb_distances(s, metric, fast_euclidean, row0, nrows);
 }
 
 int npdrb_session_distances_balanced(npdrb_session *s, int32_t metric, int32_t fast_euclidean, const int64_t *row_starts,
                                      int32_t rank, int32_t world) {
     NB_CUDA(cudaSetDevice(s->ctx->device));
+    s->sorted_valid = false;
     return nb_distances_balanced(s, metric, fast_euclidean, row_starts, rank, world);
 }
 int npdrb_session_balanced_counts(npdrb_session *s, int64_t *send_doubles, int64_t *recv_doubles) {
@@ -559,6 +562,7 @@ int npdrb_session_balanced_pack(npdrb_session *s, double *d_send) {
 }
 int npdrb_session_balanced_unpack(npdrb_session *s, const double *d_recv) {
     NB_CUDA(cudaSetDevice(s->ctx->device));
+    s->sorted_valid = false;
     return nb_balanced_unpack(s, d_recv);
 }
 
@@ -566,6 +570,7 @@ int npdrb_session_set_device_distances(npdrb_session *s, const double *dD, int64
     if (ldd < s->N || row0 < 0 || nrows < 1 || row0 + nrows > s->N) { npdrb_set_error("set_device_distances: bad block"); return NPDRB_EINVAL; }
     if (s->own_D) cudaFree(s->dD);
     s->dD = const_cast<double *>(dD); s->ldd = ldd; s->row0 = row0; s->nrows = nrows; s->own_D = false;
+    s->sorted_valid = false;
     return NPDRB_OK;
 }
 
@@ -588,6 +593,16 @@ int npdrb_session_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double
                                     int64_t *n_empty_local) {
     NB_CUDA(cudaSetDevice(s->ctx->device));
     return nb_neighbors_hitmiss(s, nbd_method, sd_frac, k, M_local, n_empty_local);
+}
+
+int npdrb_session_sort_rows(npdrb_session *s) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_sort_rows(s);
+}
+
+int npdrb_session_neighbors_sorted(npdrb_session *s, int64_t k, int64_t *M_local, int64_t *n_empty_local) {
+    NB_CUDA(cudaSetDevice(s->ctx->device));
+    return nb_neighbors_sorted(s, k, M_local, n_empty_local);
 }
 
 int npdrb_session_copy_radius2(npdrb_session *s, double *radius_host) {
@@ -972,6 +987,38 @@ int npdrb_npdr(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const doub
     }
     npdrb_session_destroy(s);
     cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+    return rc;
+}
+
+int npdrb_npdr_k_grid(npdrb_ctx *ctx, const double *X, int64_t N, int64_t p, const double *y, const double *C,
+                      const npdrb_opts *o, const int64_t *k_grid, int32_t n_k, double *stats_out, int64_t *n_pairs_out) {
+    // vwok's foreach over k (R/adaptive.R:85-111): one upload, one distance matrix, one (d, row) sort of every row and one
+    // instance-major attribute copy serve the whole grid; per k only the list prefix, the pair stream and the fit are redone.
+    if (!ctx) { npdrb_set_error("npdrb_npdr_k_grid: null context (no device)"); return NPDRB_ENODEVICE; }
+    if (!o || !k_grid || n_k < 1 || !stats_out) { npdrb_set_error("npdrb_npdr_k_grid: bad arguments"); return NPDRB_EINVAL; }
+    if (o->nbd_method != NPDRB_NBD_RELIEFF) { npdrb_set_error("npdrb_npdr_k_grid: the k grid is defined for nbd.method = relieff"); return NPDRB_EINVAL; }
+    if (o->nbd_metric == NPDRB_METRIC_PRECOMPUTED) { npdrb_set_error("npdrb_npdr_k_grid: precomputed distances are not supported here"); return NPDRB_EINVAL; }
+    for (int32_t c = 0; c < n_k; ++c)
+        if (k_grid[c] < 1 || k_grid[c] > N - 1) { npdrb_set_error("npdrb_npdr_k_grid: k = %lld outside 1..N-1", (long long)k_grid[c]); return NPDRB_EINVAL; }
+    NB_CUDA(cudaSetDevice(ctx->device));
+    npdrb_session *s = nullptr;
+    int rc = npdrb_session_create(ctx, N, p, o->n_covars, &s);
+    if (rc) return rc;
+    rc = npdrb_session_upload(s, X, y, C);
+    if (!rc) rc = nb_distances(s, o->nbd_metric, o->fast_euclidean, 0, N);
+    if (!rc && !o->separate_hitmiss_nbds) rc = nb_sort_rows(s);
+    for (int32_t c = 0; c < n_k && !rc; ++c) {
+        int64_t M = 0, ne = 0, nu = 0;
+        rc = o->separate_hitmiss_nbds ? nb_neighbors_hitmiss(s, NPDRB_NBD_RELIEFF, o->msurf_sd_frac, k_grid[c], &M, &ne)
+                                      : nb_neighbors_sorted(s, k_grid[c], &M, &ne);
+        if (!rc) rc = npdrb_session_import_pairs(s, s->dRiL, s->dNNL, s->M_local);
+        if (!rc) rc = nb_unique_pairs(s, o->neighbor_sampling_unique, &nu);
+        if (!rc && s->M <= 0) { npdrb_set_error("npdr (k = %lld): no neighbour pairs found", (long long)k_grid[c]); rc = NPDRB_EDATA; }
+        if (!rc) rc = nb_regress(s, 0, p, o->regression_type, o->attr_diff_type, o->covar_diff_type,
+                                 stats_out + (size_t)c * (size_t)p * NPDRB_STATS_PER_ATTR, nullptr);
+        if (!rc && n_pairs_out) n_pairs_out[c] = M;
+    }
+    npdrb_session_destroy(s);
     return rc;
 }
 

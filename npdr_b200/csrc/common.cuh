@@ -125,6 +125,8 @@ struct npdrb_session {
     // local neighbour segment
     int32_t *dRiL = nullptr, *dNNL = nullptr; int64_t M_local = 0; int64_t n_empty_local = 0;
     int64_t *d_rowptr = nullptr;
+    // k grid (kgrid.cu): the owned rows sorted once by (d, row), same leading dimension as the distance block
+    double *d_sortD = nullptr; int32_t *d_sortJ = nullptr; bool sorted_valid = false; double ms_sort = 0;
     // list used by the regression
     int32_t *dRi = nullptr, *dNN = nullptr; int64_t M = 0; bool own_pairs = false;
     // regression workspace
@@ -160,6 +162,8 @@ int nb_distances2(npdrb_ctx *ctx, const double *dX1, int64_t ld1, int64_t m1, co
                   int64_t p, int32_t metric, int32_t fast_euclidean, double *dD, int64_t ldd);
 int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local, int64_t *n_empty);
 int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k, int64_t *M_local, int64_t *n_empty);
+int nb_sort_rows(npdrb_session *s);
+int nb_neighbors_sorted(npdrb_session *s, int64_t k, int64_t *M_local, int64_t *n_empty);
 int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_unique);
 int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t regression_type, int32_t attr_diff_type,
                const int32_t *covar_diff_type, double *stats_out_host, int32_t *irls_passes);

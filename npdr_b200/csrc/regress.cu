@@ -1713,9 +1713,10 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     unsigned *hist = nullptr;
     unsigned long long *d_miss = nullptr;
     void *tmp = nullptr;
-    NB_CHECK(dmalloc(&keys, (size_t)M)); NB_CHECK(dmalloc(&idx, (size_t)M));
-    NB_CHECK(dmalloc(&keys2, (size_t)M)); NB_CHECK(dmalloc(&perm, (size_t)M));
-    NB_CHECK(dmalloc(&hist, (size_t)2 * n_tiles_all)); NB_CHECK(dmalloc(&d_miss, 1));
+    nb_scope scope;                                     // temporaries: released on every return path
+    NB_CHECK(scope.alloc(&keys, (size_t)M)); NB_CHECK(scope.alloc(&idx, (size_t)M));
+    NB_CHECK(scope.alloc(&keys2, (size_t)M)); NB_CHECK(scope.alloc(&perm, (size_t)M));
+    NB_CHECK(scope.alloc(&hist, (size_t)2 * n_tiles_all)); NB_CHECK(scope.alloc(&d_miss, 1));
     NB_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned) * (size_t)2 * n_tiles_all, ctx->stream));
     NB_CUDA(cudaMemsetAsync(d_miss, 0, sizeof(unsigned long long), ctx->stream));
     const unsigned grid = (unsigned)nb_cdiv(M, 256);
@@ -1726,7 +1727,7 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     while ((1ll << end_bit) < 2 * n_tiles_all && end_bit < 32) ++end_bit;
     size_t tmp_bytes = 0;
     NB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, perm, (int)M, 0, end_bit, ctx->stream));
-    NB_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    NB_CHECK(scope.alloc((unsigned char **)&tmp, tmp_bytes ? tmp_bytes : 1));
     NB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, perm, (int)M, 0, end_bit, ctx->stream));
     ctx->launches += 3;
     tile_hist_kernel<<<grid, 256, 0, ctx->stream>>>(keys2, M, hist);
@@ -1795,7 +1796,6 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     }
     NB_CUDA(cudaMemcpyAsync(st.chunk_tile, ctile.data(), sizeof(int32_t) * ctile.size(), cudaMemcpyHostToDevice, ctx->stream));
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(keys); cudaFree(idx); cudaFree(keys2); cudaFree(perm); cudaFree(hist); cudaFree(d_miss); cudaFree(tmp);
     return NPDRB_OK;
 }
 
@@ -1957,8 +1957,9 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             const size_t words = ((size_t)N * (size_t)N + 31) / 32;
             unsigned *d_bits = nullptr; unsigned char *d_f1 = nullptr, *d_f2 = nullptr; unsigned long long *d_cnt = nullptr;
             int32_t *d_sel = nullptr; int *d_nsel = nullptr; void *d_tmp = nullptr;
-            NB_CHECK(dmalloc(&d_bits, words)); NB_CHECK(dmalloc(&d_f1, (size_t)M)); NB_CHECK(dmalloc(&d_f2, (size_t)M));
-            NB_CHECK(dmalloc(&d_cnt, 1)); NB_CHECK(dmalloc(&d_sel, (size_t)4 * M)); NB_CHECK(dmalloc(&d_nsel, 4));
+            nb_scope fold_scope;
+            NB_CHECK(fold_scope.alloc(&d_bits, words)); NB_CHECK(fold_scope.alloc(&d_f1, (size_t)M)); NB_CHECK(fold_scope.alloc(&d_f2, (size_t)M));
+            NB_CHECK(fold_scope.alloc(&d_cnt, 1)); NB_CHECK(fold_scope.alloc(&d_sel, (size_t)4 * M)); NB_CHECK(fold_scope.alloc(&d_nsel, 4));
             NB_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned) * words, ctx->stream));
             NB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
             const unsigned grid = (unsigned)nb_cdiv(M, 256);
@@ -1970,7 +1971,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             NB_LAUNCH_CHECK(ctx);
             size_t tmp_bytes = 0;
             NB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, s->dRi, d_f1, d_sel, d_nsel, (int)M, ctx->stream));
-            NB_CUDA(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+            NB_CHECK(fold_scope.alloc((unsigned char **)&d_tmp, tmp_bytes ? tmp_bytes : 1));
             const int32_t *src[4] = {s->dRi, s->dNN, s->dRi, s->dNN};
             const unsigned char *flg[4] = {d_f1, d_f1, d_f2, d_f2};
             for (int k4 = 0; k4 < 4; ++k4)
@@ -1992,7 +1993,6 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
                 n_miss = miss1 + 2 * miss2;
                 folded = (rc == NPDRB_OK);
             }
-            cudaFree(d_bits); cudaFree(d_f1); cudaFree(d_f2); cudaFree(d_cnt); cudaFree(d_sel); cudaFree(d_nsel); cudaFree(d_tmp);
             if (rc) return rc;
         }
         if (!folded) {
@@ -2026,21 +2026,22 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         part_stride[i] = (int64_t)s->streams[i].n_chunks * mode_na * nattr_pad;
         part_total += part_stride[i];
     }
-    NB_CHECK(dmalloc(&d_part, (size_t)part_total));
-    NB_CHECK(dmalloc(&d_stats, (size_t)nattr * 8));
-    NB_CHECK(dmalloc(&d_beta, (size_t)KMAX * nattr_pad)); NB_CHECK(dmalloc(&d_se, (size_t)KMAX * nattr_pad));
+    nb_scope scope;                                     // per-call buffers: released on every return path
+    NB_CHECK(scope.alloc(&d_part, (size_t)part_total));
+    NB_CHECK(scope.alloc(&d_stats, (size_t)nattr * 8));
+    NB_CHECK(scope.alloc(&d_beta, (size_t)KMAX * nattr_pad)); NB_CHECK(scope.alloc(&d_se, (size_t)KMAX * nattr_pad));
     double *d_hitd = nullptr, *d_missd = nullptr;
-    NB_CHECK(dmalloc(&d_hitd, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_missd, (size_t)nattr_pad));
+    NB_CHECK(scope.alloc(&d_hitd, (size_t)nattr_pad)); NB_CHECK(scope.alloc(&d_missd, (size_t)nattr_pad));
     double *d_dmax = nullptr;
-    NB_CHECK(dmalloc(&d_dmax, (size_t)nattr_pad));
+    NB_CHECK(scope.alloc(&d_dmax, (size_t)nattr_pad));
     NB_CUDA(cudaMemsetAsync(d_dmax, 0, sizeof(double) * nattr_pad, ctx->stream));
     if (!lm) {
         column_dmax_kernel<<<(unsigned)nattr, 256, 0, ctx->stream>>>(s->dX, s->ldx, N, attr0, nattr, diff_type, d_dmax);
         NB_LAUNCH_CHECK(ctx);
     }
-    NB_CHECK(dmalloc(&d_devold, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_active, (size_t)nattr_pad));
-    NB_CHECK(dmalloc(&d_tile_active, (size_t)n_at)); NB_CHECK(dmalloc(&d_iters, (size_t)nattr_pad));
-    NB_CHECK(dmalloc(&d_flags, (size_t)nattr_pad)); NB_CHECK(dmalloc(&d_nactive, 1));
+    NB_CHECK(scope.alloc(&d_devold, (size_t)nattr_pad)); NB_CHECK(scope.alloc(&d_active, (size_t)nattr_pad));
+    NB_CHECK(scope.alloc(&d_tile_active, (size_t)n_at)); NB_CHECK(scope.alloc(&d_iters, (size_t)nattr_pad));
+    NB_CHECK(scope.alloc(&d_flags, (size_t)nattr_pad)); NB_CHECK(scope.alloc(&d_nactive, 1));
     NB_CUDA(cudaMemsetAsync(d_beta, 0, sizeof(double) * KMAX * nattr_pad, ctx->stream));
     NB_CUDA(cudaMemsetAsync(d_se, 0, sizeof(double) * KMAX * nattr_pad, ctx->stream));
     NB_CUDA(cudaMemsetAsync(d_active, 1, (size_t)nattr_pad, ctx->stream));
@@ -2117,7 +2118,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     };
 
     int passes = 0;
-    std::vector<cudaEvent_t> pev;
+    struct EventList : std::vector<cudaEvent_t> { ~EventList() { for (cudaEvent_t e : *this) cudaEventDestroy(e); } } pev;
     auto mark = [&]() -> int {
         cudaEvent_t e;
         NB_CUDA(cudaEventCreate(&e));
@@ -2134,7 +2135,7 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         // outcome diff (lm) or the sign s = +-1 of the hit/miss bit (binomial first pass); weights applied on the host
         const int nblk = 128;
         double *d_sh = nullptr;
-        NB_CHECK(dmalloc(&d_sh, (size_t)nblk * NSHARED_MAX));
+        NB_CHECK(scope.alloc(&d_sh, (size_t)nblk * NSHARED_MAX));
         long double tot[NSHARED_MAX] = {0};
         std::vector<double> h((size_t)nblk * NSHARED_MAX);
         const int ns = 3 + 2 * q + q * (q + 1) / 2;
@@ -2151,7 +2152,6 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             for (int b = 0; b < nblk; ++b)
                 for (int k = 0; k < ns; ++k) tot[k] += (long double)s->streams[i].weight * h[(size_t)b * NSHARED_MAX + k];
         }
-        cudaFree(d_sh);
         for (int k = 0; k < NSHARED_MAX; ++k) S.shared[k] = (double)tot[k];
     }
     if (lm) {
@@ -2202,10 +2202,6 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         else { s->ms_pass_full += pm; s->n_pass_full++; }
     }
     for (double v : pass_evals) s->evals_pass_full += v;
-    for (cudaEvent_t e : pev) cudaEventDestroy(e);
     if (irls_passes) *irls_passes = passes;
-    cudaFree(d_hitd); cudaFree(d_missd); cudaFree(d_dmax);
-    cudaFree(d_part); cudaFree(d_beta); cudaFree(d_se); cudaFree(d_devold); cudaFree(d_stats);
-    cudaFree(d_active); cudaFree(d_tile_active); cudaFree(d_iters); cudaFree(d_flags); cudaFree(d_nactive);
     return NPDRB_OK;
 }

@@ -11,3 +11,10 @@ SEXP Rf_protect(SEXP); void Rf_unprotect(int); void Rf_error(const char *, ...);
 int Rf_isNull(SEXP); SEXP Rf_mkNamed(int, const char **); SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP); SEXP Rf_ScalarReal(double); R_xlen_t XLENGTH(SEXP);
 #define PROTECT(x) Rf_protect(x)
 #define UNPROTECT(n) Rf_unprotect(n)
+typedef void (*R_CFinalizer_t)(SEXP); typedef int Rboolean;
+#ifndef TRUE
+#define TRUE 1
+#define FALSE 0
+#endif
+SEXP R_MakeExternalPtr(void *, SEXP, SEXP); void *R_ExternalPtrAddr(SEXP); void R_ClearExternalPtr(SEXP);
+void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean); char *R_alloc(size_t, int); SEXP Rf_setAttrib(SEXP, SEXP, SEXP);

@@ -43,7 +43,7 @@ int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(npdrb_opts), sizeof(npdrb
     assert _lib.Opts.covar_diff_type.offset == oc and _lib.Result.Ri.offset == ori and _lib.Result.irls_passes.offset == oip
     o = _lib.Opts(); _lib.load().npdrb_opts_default(C.byref(o))
     assert (o.regression_type, o.nbd_method, o.nbd_metric, o.msurf_sd_frac, o.knn) == (1, 0, 0, 0.5, 0)
-    assert list(o.covar_diff_type) == [3, 3, 3, 3]
+    assert list(o.covar_diff_type) == [3] * _lib.MAX_COVARS and _lib.MAX_COVARS == 60
 
 
 def test_knn_surf_matches_reference_formula():
