@@ -57,7 +57,7 @@ def f_bin(q):
 def fp64_instr(q):
     """FP64 instructions the v2 IRLS pass kernel EXECUTES per attribute x record evaluation (SASS count):
     11 (diff 1, range reduction 3, degree-2 exp polynomial 2, 1+t 1, reciprocal 2, weight 1, deviance product 1) +
-    2(k-1) (eta, w*x) + k(k+1)/2 (X'WX) + k (score), k = 2 + q: 18 at q = 0, 31 at q = 2."""
+    2(k-1) (eta, w*x) + k(k+1)/2 (X'WX) + k (score), k = 2 + q: 18 at q = 0, 24 at q = 1, 31 at q = 2."""
     k = 2 + q
     return 11 + 2 * (k - 1) + k * (k + 1) // 2 + k
 
@@ -276,6 +276,7 @@ class Bench:
         stats, info = npdr_sharded(eng, self.N, self.p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, self.cdt,
                                    pair_hash=pair_hash)
         km = eng.session.kernel_ms(); sm = eng.session.stage_ms(); passes = eng.session.irls_passes
+        km.update(eng.session.regress_design())
         eng.close()
         return stats, info, km, sm, passes
 
@@ -310,24 +311,31 @@ class Bench:
             stats, info = nb.npdr_stats(self.hX, self.hy, self.hC, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5,
                                         self.cdt, device=self.local_rank)
             return stats, info
+        from npdr_b200.distributed import gather_columns_pipelined
         dev = self.e2e_dev
-        if self.shard:                                                   # own columns over the own PCIe link, then NVLink all-gather
-            na = p // world
-            mine = dev["dX"][rank * na:(rank + 1) * na]
-            self.ctx.upload_columns(mine.data_ptr(), self.data["ldx"], self.hXs)
-            dist.all_gather_into_tensor(dev["dX"], mine)
-        elif rank == 0:
-            self.ctx.upload_columns(dev["dX"].data_ptr(), self.data["ldx"], self.hX)
         if rank == 0:
             dev["dy"].copy_(torch.from_numpy(self.hy))
             if q:
                 dev["dC"].copy_(torch.from_numpy(np.ascontiguousarray(self.hC.T)))
-        if not self.shard:
-            dist.broadcast(dev["dX"], 0)
         dist.broadcast(dev["dy"], 0)
         if q:
             dist.broadcast(dev["dC"], 0)
-        eng = GpuEngine(device_index=self.local_rank, dX=dev["dX"], ldx=self.data["ldx"], dy=dev["dy"], dC=dev["dC"], N=N, p=p, q=q)
+        slab_events = None
+        if self.shard:                                                   # own columns over the own PCIe link, then over NVLink
+            na = p // world
+            mine = dev["dX"][rank * na:(rank + 1) * na]
+            self.ctx.upload_columns(mine.data_ptr(), self.data["ldx"], self.hXs)
+            if na % 16 == 0 and os.environ.get("NPDRB_NO_PIPELINED_GATHER") != "1":
+                # one broadcast per shard in attribute order; the distance kernel consumes shard g while g+1.. are on the wire
+                slab_events = gather_columns_pipelined(dev["dX"], world, na)
+            else:
+                dist.all_gather_into_tensor(dev["dX"], mine)
+        else:
+            if rank == 0:
+                self.ctx.upload_columns(dev["dX"].data_ptr(), self.data["ldx"], self.hX)
+            dist.broadcast(dev["dX"], 0)
+        eng = GpuEngine(device_index=self.local_rank, dX=dev["dX"], ldx=self.data["ldx"], dy=dev["dy"], dC=dev["dC"], N=N, p=p, q=q,
+                        slab_events=slab_events)
         stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, self.cdt)
         eng.close()
         return stats, info                                               # stats are host numpy on rank 0: D2H done
@@ -469,7 +477,10 @@ class Bench:
         n_full = max(int(km["n_pass_full"]), 1)
         # issue-slot roofline: every FP64 instruction (DADD, DMUL or DFMA) takes one slot of the pipe whose peak the DFMA
         # micro-benchmark measures as 2 flops per slot, so achieved = evaluations x executed FP64 instructions x 2 / time
-        flops = km["evals_pass_full"] * fp64_instr(q) * 2.0
+        # a match-mismatch covariate (diff in {0, 1}) is folded into the intercept stream by stream: the kernels run the design
+        # with q_eff = q - 1 covariates and execute that design's instruction count
+        q_eff = int(km.get("q_eff", q))
+        flops = km["evals_pass_full"] * fp64_instr(q_eff) * 2.0
         achieved = flops / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
         canon = km["evals_pass_full"] * f_bin(q) / (km["pass_full_ms"] * 1e-3) / 1e12 if km["pass_full_ms"] > 0 else 0.0
         hbm_peak = 6553.6
@@ -497,7 +508,8 @@ class Bench:
             "algorithmic_bytes_per_launch": alg_bytes / n_full,
             "peak_source": "measured live by npdrb_measure_fp64_peak (DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
             "launches": n_full, "avg_launch_ms": km["pass_full_ms"] / n_full,
-            "fp64_instr_per_eval": fp64_instr(q), "evals_per_launch_avg": km["evals_pass_full"] / n_full,
+            "fp64_instr_per_eval": fp64_instr(q_eff), "q_eff": q_eff, "pair_streams": int(km.get("n_streams", 0)), "exact_stopping_decisions": int(km.get("n_exact_stops", 0)),
+            "evals_per_launch_avg": km["evals_pass_full"] / n_full,
             "note": "achieved = attribute x record evaluations per launch x FP64 instructions the kernel executes per evaluation "
                     "(SASS count, DESIGN.md 4) x 2 flops per issue slot / CUDA-event launch time, against the measured DFMA peak: frac is "
                     "the FP64 pipe's issue-slot utilisation (ncu sm__pipe_fp64_cycles_active agrees).  records = pairs after folding "

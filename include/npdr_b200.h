@@ -217,6 +217,11 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
 /* or adopt device buffers: dX column-major with leading dimension ldx >= N (ldx % 2 == 0), dy[N], dC N x q (ld N) */
 int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy,
                                     const double *dC);
+/* The adopted device matrix may still be arriving (one NCCL broadcast per rank's attribute shard, a peer copy, ...): column
+ * slab i = attributes [i * slab_cols, (i+1) * slab_cols) is complete once events[i] (cudaEvent_t, owned by the caller, already
+ * recorded on the caller's stream) fires.  The next distance call runs one launch per slab, each waiting for its own event
+ * only, so the transfer of slab i+1 hides behind the kernel of slab i; results are bit-identical.  slab_cols % 16 == 0. */
+int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events);
 /* rows [row0, row0+nrows) of the distance matrix against all N instances (nrows == N: symmetric mode) */
 int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
 /* adopt a precomputed distance block (device, nrows x N row-major = the columns Ri of a symmetric D) */
@@ -288,6 +293,11 @@ int npdrb_session_stage_ms(npdrb_session *s, double *ms_distance, double *ms_nei
  * out[1] summed ms of the full IRLS pass kernels, out[2] their number, out[3] attribute x record evaluations
  * they executed (active attribute tiles x 128 x records), out[4] records in the pair stream. */
 int npdrb_session_kernel_ms(npdrb_session *s, double *out5);
+/* design the pass kernels of the last session_regress call evaluated: *q_eff = covariates per record (q, or q - 1 when a
+ * match-mismatch covariate was folded into the intercept: its diff is 0 / 1, so the pair list is split by its value),
+ * *n_streams = pair streams ({one-directional, mutual pairs} x {covariate value 0, 1}), *n_exact_stops = attributes whose
+ * glm.fit stopping test fell inside the streamed deviance's error band and was decided from exactly re-evaluated deviances */
+int npdrb_session_regress_design(npdrb_session *s, int32_t *q_eff, int32_t *n_streams, int32_t *n_exact_stops);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,7 @@ SIGNATURES = {
     "npdrb_session_set_sd_vec": (C.c_int, [_vp, _dp]),
     "npdrb_session_neighbors": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "npdrb_session_neighbors_hitmiss": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "npdrb_session_set_device_slab_events": (C.c_int, [_vp, _i32, _i64, C.POINTER(_vp)]),
     "npdrb_session_copy_radius2": (C.c_int, [_vp, _dp]),
     "npdrb_session_sort_rows": (C.c_int, [_vp]),
     "npdrb_session_neighbors_sorted": (C.c_int, [_vp, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
@@ -114,6 +115,7 @@ SIGNATURES = {
     "npdrb_session_regress": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _ip, _dp, C.POINTER(_i32)]),
     "npdrb_session_copy_pairs": (C.c_int, [_vp, _ip, _ip]),
     "npdrb_session_stage_ms": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "npdrb_session_regress_design": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "npdrb_session_kernel_ms": (C.c_int, [_vp, _dp]),
 }
 
@@ -273,6 +275,12 @@ class Session:
     def set_device_inputs(self, dX=0, ldx=0, dy=0, dC=0):
         check(load().npdrb_session_set_device_inputs(self.handle, _vp(dX or None), int(ldx), _vp(dy or None), _vp(dC or None)))
 
+    def set_device_slab_events(self, slab_cols, events):
+        """events: raw cudaEvent_t handles (ints), one per column slab of the adopted device matrix (see npdr_b200.h)."""
+        arr = (_vp * len(events))(*[int(e) for e in events])
+        self._slab_events = arr
+        check(load().npdrb_session_set_device_slab_events(self.handle, len(events), int(slab_cols), arr))
+
     def distances(self, metric="manhattan", fast_euclidean=False, row0=0, nrows=None):
         nrows = self.N if nrows is None else nrows
         check(load().npdrb_session_distances(self.handle, METRIC[metric], int(bool(fast_euclidean)), int(row0), int(nrows)))
@@ -386,6 +394,11 @@ class Session:
         if M:
             check(load().npdrb_session_copy_pairs(self.handle, iptr(Ri), iptr(NN)))
         return Ri, NN
+
+    def regress_design(self):
+        qe, ns, nx = _i32(), _i32(), _i32()
+        check(load().npdrb_session_regress_design(self.handle, C.byref(qe), C.byref(ns), C.byref(nx)))
+        return {"q_eff": qe.value, "n_streams": ns.value, "n_exact_stops": nx.value}
 
     def kernel_ms(self):
         out = np.zeros(5)

@@ -252,6 +252,7 @@ int nb_check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what
 
 int nb_issue_slab(npdrb_session *s, int slab) {
     npdrb_ctx *ctx = s->ctx;
+    if (s->slab_ev_external) { if (slab + 1 > s->n_slabs_issued) s->n_slabs_issued = slab + 1; return NPDRB_OK; }   // the caller's copies are already in flight
     for (int i = s->n_slabs_issued; i <= slab && i < s->n_slabs_pending; ++i) {
         const int64_t c0 = (int64_t)i * s->slab_cols, c1 = (c0 + s->slab_cols < s->p) ? c0 + s->slab_cols : s->p;
         if (!s->hX_lazy) { npdrb_set_error("upload: slab %d has no host source", i); return NPDRB_EINVAL; }
@@ -437,7 +438,7 @@ void npdrb_session_destroy(npdrb_session *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     if (s->ctx->copy_stream) cudaStreamSynchronize(s->ctx->copy_stream);
-    for (cudaEvent_t e : s->slab_ev) if (e) cudaEventDestroy(e);
+    if (!s->slab_ev_external) for (cudaEvent_t e : s->slab_ev) if (e) cudaEventDestroy(e);
     cudaStreamSynchronize(s->ctx->stream);
     if (s->own_X) cudaFree(s->dX);
     cudaFree(s->dXs);
@@ -477,7 +478,8 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
                 std::lock_guard<std::mutex> lk(g_ring_mu);
                 if (!ctx->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
             }
-            for (cudaEvent_t e : s->slab_ev) cudaEventDestroy(e);
+            if (!s->slab_ev_external) for (cudaEvent_t e : s->slab_ev) cudaEventDestroy(e);
+            s->slab_ev_external = false;
             s->slab_ev.assign((size_t)n_slabs, nullptr);
             s->slab_cols = nb_round_up(nb_cdiv(p, n_slabs), 16);
             cudaEvent_t ready;                              // the memset / previous users of dX on the main stream come first
@@ -529,7 +531,11 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
 
 int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy, const double *dC) {
     if (dX) {
-        if (s->n_slabs_pending) { cudaStreamSynchronize(s->ctx->copy_stream); s->n_slabs_pending = 0; s->n_slabs_issued = 0; s->hX_lazy = nullptr; }
+        if (s->n_slabs_pending) {
+            if (!s->slab_ev_external && s->ctx->copy_stream) cudaStreamSynchronize(s->ctx->copy_stream);
+            s->n_slabs_pending = 0; s->n_slabs_issued = 0; s->hX_lazy = nullptr;
+        }
+        if (s->slab_ev_external) { s->slab_ev.clear(); s->slab_ev_external = false; }
         if (ldx < s->N || (ldx & 1)) { npdrb_set_error("set_device_inputs: ldx must be even and >= N"); return NPDRB_EINVAL; }
         if (((uintptr_t)dX) & 15) { npdrb_set_error("set_device_inputs: dX must be 16-byte aligned"); return NPDRB_EINVAL; }
         if (s->own_X) cudaFree(s->dX);
@@ -538,6 +544,28 @@ int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t 
     }
     if (dy) { if (s->own_y) cudaFree(s->dy); s->dy = const_cast<double *>(dy); s->own_y = false; s->streams_valid = false; }
     if (dC) { if (s->own_C) cudaFree(s->dC); s->dC = const_cast<double *>(dC); s->own_C = false; s->streams_valid = false; }
+    return NPDRB_OK;
+}
+
+int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events) {
+    // The adopted device matrix is still ARRIVING (e.g. an NCCL broadcast per rank's attribute shard on the caller's
+    // communication stream): column slab i = attributes [i * slab_cols, (i + 1) * slab_cols) is complete once events[i] fires.
+    // The distance stage then runs one launch per slab, each waiting for its own event only (same per-element order
+    // k = 0..p-1, so the result is bit-identical), and the transfer of slab i+1 hides behind the kernel of slab i.
+    if (!s->dX || s->own_X) { npdrb_set_error("set_device_slab_events: adopt the device matrix first (npdrb_session_set_device_inputs)"); return NPDRB_EINVAL; }
+    if (n_slabs < 1 || !events || slab_cols < 1 || (slab_cols % 16) != 0 || (int64_t)(n_slabs - 1) * slab_cols >= s->p ||
+        (int64_t)n_slabs * slab_cols < s->p) {
+        npdrb_set_error("set_device_slab_events: need n_slabs slabs of slab_cols (a multiple of 16) columns covering the p attributes");
+        return NPDRB_EINVAL;
+    }
+    if (!s->slab_ev_external) for (cudaEvent_t e : s->slab_ev) if (e) cudaEventDestroy(e);
+    s->slab_ev.assign((size_t)n_slabs, nullptr);
+    for (int i = 0; i < n_slabs; ++i) {
+        if (!events[i]) { npdrb_set_error("set_device_slab_events: null event %d", i); s->slab_ev.clear(); s->slab_ev_external = false; return NPDRB_EINVAL; }
+        s->slab_ev[(size_t)i] = (cudaEvent_t)events[i];
+    }
+    s->slab_ev_external = true;
+    s->slab_cols = slab_cols; s->n_slabs_pending = n_slabs; s->n_slabs_issued = n_slabs; s->hX_lazy = nullptr;
     return NPDRB_OK;
 }
 
@@ -717,6 +745,13 @@ int npdrb_session_kernel_ms(npdrb_session *s, double *out5) {
 }
 
 // ------------------------------------------------------------------ host-buffer operator API
+int npdrb_session_regress_design(npdrb_session *s, int32_t *q_eff, int32_t *n_streams, int32_t *n_exact_stops) {
+    if (q_eff) *q_eff = s->q_eff;
+    if (n_streams) *n_streams = s->n_streams;
+    if (n_exact_stops) *n_exact_stops = s->n_exact_stops;
+    return NPDRB_OK;
+}
+
 int npdrb_diff(npdrb_ctx *ctx, const double *a, const double *b, int64_t n, int32_t diff_type, double norm_fac, double *out) {
     if (!ctx) { npdrb_set_error("npdrb_diff: null context (no device)"); return NPDRB_ENODEVICE; }
     if (diff_type < 0 || diff_type > NPDRB_DIFF_RAW) { npdrb_set_error("npdrb_diff: unknown diff type %d", diff_type); return NPDRB_EINVAL; }

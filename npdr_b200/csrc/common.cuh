@@ -50,6 +50,8 @@ cudaError_t nb_cached_free(void *p);
 // The streaming regression kernels (regress.cu) hold q <= NB_FAST_COVARS covariates in registers; wider designs go through
 // regress_wide.cu (up to NPDRB_MAX_COVARS).
 #define NB_FAST_COVARS 4
+// pair streams of one regression: {weight 1, weight 2 (folded mutual pairs)} x {binary covariate 0, 1} (regress.cu)
+#define NB_MAX_STREAMS 4
 
 // Device buffers that live for one call: everything allocated through a scope is returned to the cache when the scope ends,
 // early error returns included.
@@ -87,6 +89,7 @@ struct npdrb_ctx {
 struct nb_stream {
     int64_t n_rec = 0;            // records in this stream
     double weight = 1.0;          // multiplicity applied to every record's contribution
+    double fold_val = 0.0;        // value (0 / 1) of the binary covariate folded into the intercept for this stream
     uint32_t *rec = nullptr;      // il | jl << 8 | ybit << 16, bucketed by (I-block, J-block) tile
     double *yv = nullptr;         // lm: |y_i - y_j| per record
     double *cd[NB_FAST_COVARS] = {nullptr, nullptr, nullptr, nullptr};  // covariate diffs per record
@@ -111,6 +114,7 @@ struct npdrb_session {
     // pointer and nb_issue_slab() stages slab i through the context's pinned ring (helper threads memcpy, async H2D) right
     // before the consumer of slab i is launched, so the copy of slab i+1 runs under the distance kernel of slab i.
     std::vector<cudaEvent_t> slab_ev; int64_t slab_cols = 0; int n_slabs_pending = 0;
+    bool slab_ev_external = false;     // slab_ev are the caller's events (npdrb_session_set_device_slab_events): never issued or destroyed here
     const double *hX_lazy = nullptr; int n_slabs_issued = 0;
     double *dy = nullptr; bool own_y = false;
     double *dC = nullptr; bool own_C = false;                            // N x q, ld N
@@ -131,7 +135,7 @@ struct npdrb_session {
     int32_t *dRi = nullptr, *dNN = nullptr; int64_t M = 0; bool own_pairs = false;
     // regression workspace
     double *dXT = nullptr; int64_t ldt = 0; int64_t xt_attr0 = -1, xt_nattr = 0;
-    nb_stream streams[2]; int n_streams = 0;
+    nb_stream streams[NB_MAX_STREAMS]; int n_streams = 0;
     int32_t streams_reg_type = -1; int32_t streams_cov_sig = -1; bool streams_valid = false;
     // timing
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -141,6 +145,8 @@ struct npdrb_session {
     double ms_pass_full = 0;       // binomial: sum over the full IRLS passes
     int n_pass_full = 0;
     double evals_pass_full = 0;    // attribute x record evaluations executed by those passes (active tiles only)
+    int n_exact_stops = 0;         // attributes whose stopping test was decided from exactly re-evaluated deviances (last regress call)
+    int q_eff = 0;                 // covariates of the design the pass kernels evaluated (q, or q - 1 with a folded binary covariate)
 };
 
 // stage implementations (one .cu each)

@@ -123,8 +123,9 @@ struct GatherArgs {
     const uint32_t *perm;
     const double *y, *C;
     int64_t M, N;
-    int q, reg_type;
+    int q, reg_type;           // q: covariates stored per record (the folded binary covariate is not)
     int cov_type[NB_FAST_COVARS];
+    int cov_src[NB_FAST_COVARS];   // column of C behind stored covariate c
     int y_raw;                 // uniReg: outcome of instance Ri itself, no diff
     uint32_t *rec;
     double *yv;
@@ -149,7 +150,7 @@ __global__ void gather_records_kernel(GatherArgs g) {
         }
         g.rec[t] = r;
         for (int c = 0; c < g.q; ++c) {
-            const double *col = g.C + (int64_t)c * g.N;
+            const double *col = g.C + (int64_t)g.cov_src[c] * g.N;
             g.cd[c][t] = g.y_raw ? col[i] : nb_diff1(col[i], col[j], g.cov_type[c]);
         }
     }
@@ -191,8 +192,18 @@ __global__ void classify_pairs_kernel(const int32_t *__restrict__ Ri, const int3
 }
 
 // shared (attribute-independent) lm moments of the record stream: M, Sy, Syy, Sc_r, Scy_r, Scc_rs
+// flags of the pairs whose folded covariate matches (c0) / differs (c1)
+__global__ void cov_flags_kernel(const int32_t *__restrict__ Ri, const int32_t *__restrict__ NN, int64_t M,
+                                 const double *__restrict__ col, unsigned char *__restrict__ c0, unsigned char *__restrict__ c1) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const unsigned char d = (col[Ri[m] - 1] != col[NN[m] - 1]) ? 1 : 0;
+    c1[m] = d; c0[m] = 1 - d;
+}
+
 constexpr int NSHARED_MAX = 3 + 2 * NB_FAST_COVARS + NB_FAST_COVARS * (NB_FAST_COVARS + 1) / 2;
-struct SharedArgs { const double *yv; const uint32_t *rec; const double *cd[NB_FAST_COVARS]; int64_t n; int q; double *out; };
+// cd[r]: diffs of covariate r over the stream's records, or NULL for the covariate that is constant (fold_val) on this stream
+struct SharedArgs { const double *yv; const uint32_t *rec; const double *cd[NB_FAST_COVARS]; double fold_val; int64_t n; int q; double *out; };
 __global__ void __launch_bounds__(256)
 shared_moments_kernel(SharedArgs a) {
     __shared__ double red[256];
@@ -202,7 +213,7 @@ shared_moments_kernel(SharedArgs a) {
     for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < a.n; t += (int64_t)gridDim.x * 256) {
         const double y = a.yv ? a.yv[t] : ((a.rec[t] & 1u) ? 1.0 : -1.0);
         double c[NB_FAST_COVARS];
-        for (int r = 0; r < a.q; ++r) c[r] = a.cd[r][t];
+        for (int r = 0; r < a.q; ++r) c[r] = a.cd[r] ? a.cd[r][t] : a.fold_val;
         int s = 0;
         acc[s++] += 1.0; acc[s++] += y; acc[s++] += y * y;
         for (int r = 0; r < a.q; ++r) acc[s++] += c[r];
@@ -223,13 +234,13 @@ struct StreamArgs {                // one bucketed pair stream (see nb_stream)
     const uint32_t *rec; const double *yv; const double *cd[NB_FAST_COVARS];
     const int64_t *tile_ptr; const int64_t *tile_mid; const int32_t *tile_ib; const int32_t *tile_jb; const int32_t *chunk_tile;
     double *partials;              // [n_chunks][NACC][nattr_pad]
+    const double *beta;            // [2 + Q][nattr_pad] coefficients this stream evaluates with (IRLS_FULL; see fold_beta_kernel)
 };
-// Both weighted streams of a pass go into ONE launch (grid.y = chunks of stream 0 followed by chunks of stream 1), so the
-// pass pays one wave-quantisation tail instead of two.
+// All streams of a pass go into ONE launch (grid.x = the chunks of stream 0, then those of stream 1, ...), so the pass pays
+// one wave-quantisation tail instead of one per stream.
 struct PassArgs {
     const double *XT; int64_t ldt; int64_t N; int nattr; int nattr_pad;
-    StreamArgs st[2]; int n_chunks0;
-    const double *beta;            // [KMAX][nattr_pad] current coefficients (IRLS_FULL)
+    StreamArgs st[NB_MAX_STREAMS]; int chunk_start[NB_MAX_STREAMS + 1];   // first chunk of every stream (unused: the total)
     const unsigned char *tile_active;  // per attribute tile, or NULL
     const nb_tables *tables;       // device copy of the exp/log tables (v1 kernel)
     const nb_tables1024 *tables1024; // 1024-entry exp table (v2 kernel)
@@ -262,8 +273,10 @@ pass_kernel(PassArgs P) {
     // chunk index is the fast grid dimension: the CTAs resident at any moment share a few attribute tiles, whose XT slabs
     // (N x 128 doubles each) then stay in L2 while every chunk of the pair stream sweeps over them
     const int at = blockIdx.y;
-    const int sidx = ((int)blockIdx.x >= P.n_chunks0) ? 1 : 0;
-    const int chunk = (int)blockIdx.x - (sidx ? P.n_chunks0 : 0);
+    int sidx = 0;
+#pragma unroll
+    for (int t = 1; t < NB_MAX_STREAMS; ++t) sidx += ((int)blockIdx.x >= P.chunk_start[t]) ? 1 : 0;
+    const int chunk = (int)blockIdx.x - P.chunk_start[sidx];
     const StreamArgs &A = P.st[sidx];
     if (P.tile_active && !P.tile_active[at]) return;
     const int64_t a0 = (int64_t)at * TA;
@@ -276,7 +289,7 @@ pass_kernel(PassArgs P) {
     double beta[K];
     if (MODE == MODE_IRLS_FULL) {
 #pragma unroll
-        for (int r = 0; r < K; ++r) beta[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + al];
+        for (int r = 0; r < K; ++r) beta[r] = A.beta[(int64_t)r * P.nattr_pad + a0 + al];
     }
     double acc[NA];
 #pragma unroll
@@ -787,8 +800,10 @@ pass2_kernel(PassArgs P) {
     // chunk index is the fast grid dimension: the CTAs resident at any moment share a few attribute tiles, whose XT slabs
     // (N x 128 doubles each) then stay in L2 while every chunk of the pair stream sweeps over them
     const int at = blockIdx.y;
-    const int sidx = ((int)blockIdx.x >= P.n_chunks0) ? 1 : 0;
-    const int chunk = (int)blockIdx.x - (sidx ? P.n_chunks0 : 0);
+    int sidx = 0;
+#pragma unroll
+    for (int t = 1; t < NB_MAX_STREAMS; ++t) sidx += ((int)blockIdx.x >= P.chunk_start[t]) ? 1 : 0;
+    const int chunk = (int)blockIdx.x - P.chunk_start[sidx];
     const StreamArgs &A = P.st[sidx];
     if (MODE == MODE_IRLS_FULL && P.tile_active && !P.tile_active[at]) return;
     const int64_t a0 = (int64_t)at * TA;
@@ -808,8 +823,8 @@ pass2_kernel(PassArgs P) {
     if (MODE == MODE_IRLS_FULL) {
 #pragma unroll
         for (int r = 0; r < K; ++r) {
-            beta0[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl] * c_k[9];         // units of ln2/1024
-            beta1[r] = P.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1] * c_k[9];
+            beta0[r] = A.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl] * c_k[9];         // units of ln2/1024
+            beta1[r] = A.beta[(int64_t)r * P.nattr_pad + a0 + 2 * tl + 1] * c_k[9];
         }
     }
     V2Fold f0 = {0, 0, 0, 0, 0}, f1 = {0, 0, 0, 0, 0};
@@ -1150,8 +1165,10 @@ pass3_kernel(PassArgs P) {
     // chunk index is the fast grid dimension: the CTAs resident at any moment share a few attribute tiles, whose XT slabs
     // (N x 128 doubles each) then stay in L2 while every chunk of the pair stream sweeps over them
     const int at = blockIdx.y;
-    const int sidx = ((int)blockIdx.x >= P.n_chunks0) ? 1 : 0;
-    const int chunk = (int)blockIdx.x - (sidx ? P.n_chunks0 : 0);
+    int sidx = 0;
+#pragma unroll
+    for (int t = 1; t < NB_MAX_STREAMS; ++t) sidx += ((int)blockIdx.x >= P.chunk_start[t]) ? 1 : 0;
+    const int chunk = (int)blockIdx.x - P.chunk_start[sidx];
     const StreamArgs &A = P.st[sidx];
     if (MODE == MODE_IRLS_FULL && P.tile_active && !P.tile_active[at]) return;
     const int64_t a0 = (int64_t)at * TA;
@@ -1174,7 +1191,7 @@ pass3_kernel(PassArgs P) {
 #pragma unroll
         for (int k = 0; k < V3_APT; ++k)
 #pragma unroll
-            for (int r = 0; r < K; ++r) beta[k][r] = P.beta[(int64_t)r * P.nattr_pad + a0 + attr_of(k)] * c_k[9];      // units of ln2/1024
+            for (int r = 0; r < K; ++r) beta[k][r] = A.beta[(int64_t)r * P.nattr_pad + a0 + attr_of(k)] * c_k[9];      // units of ln2/1024
     }
     double acc[V3_APT][NA];
 #pragma unroll
@@ -1354,31 +1371,42 @@ __device__ void chol_solve(const double (&A)[K][K], const double (&b)[K], double
         x[i] = u / L[i][i];
     }
     for (int i = 0; i < K; ++i) x[i] *= s[i];
-    // diag of inverse: columns of L^-1
-    for (int c = 0; c < K; ++c) dinv[c] = 0.0;
-    for (int c = 0; c < K; ++c) {
-        if (aliased[c]) continue;
-        double col[K];                                     // L^-1 e_c
-        for (int i = 0; i < K; ++i) col[i] = 0.0;
-        for (int i = c; i < K; ++i) {
-            if (aliased[i]) continue;
+    // diag of the inverse: (A^-1)_cc = s_c^2 * sum_{i >= c} (L^-1)_{ic}^2, with L^-1 formed once, row by row
+    // (forward substitution on the rows: Li[i][c] = (delta_ic - sum_{t=c}^{i-1} L[i][t] Li[t][c]) / L[i][i])
+    double Li[K][K];
+    for (int i = 0; i < K; ++i)
+        for (int c = 0; c < K; ++c) Li[i][c] = 0.0;
+    for (int i = 0; i < K; ++i) {
+        if (aliased[i]) continue;
+        const double rl = 1.0 / L[i][i];
+        for (int c = 0; c <= i; ++c) {
+            if (aliased[c]) continue;
             double u = (i == c) ? 1.0 : 0.0;
-            for (int t = c; t < i; ++t) if (!aliased[t]) u -= L[i][t] * col[t];
-            col[i] = u / L[i][i];
+            for (int t = c; t < i; ++t) u -= L[i][t] * Li[t][c];      // rows / columns of aliased t are zero
+            Li[i][c] = u * rl;
         }
-        // (A^-1)_{rr} = sum_i (L^-1)_{i r}^2 ; accumulate column c's contribution to row index c only needs
-        // all rows i >= c of column c: (A^-1)_{cc} = sum_{i>=c} col[i]^2
+    }
+    for (int c = 0; c < K; ++c) {
         double d = 0.0;
-        for (int i = c; i < K; ++i) d += col[i] * col[i];
+        for (int i = c; i < K; ++i) d += Li[i][c] * Li[i][c];
         dinv[c] = d * s[c] * s[c];
     }
 }
 
 struct SolveArgs {
-    const double *partials; int n_chunks[2]; double weight[2]; int64_t part_stride[2];  // up to two streams
+    const double *partials; int n_chunks[NB_MAX_STREAMS]; double weight[NB_MAX_STREAMS]; int64_t part_stride[NB_MAX_STREAMS];
+    int fold;                      // covariate (0-based) folded into the intercept stream by stream, or -1 (see nb_regress)
+    double fold_val[NB_MAX_STREAMS];   // its value on every stream
     int nattr, nattr_pad;
     double *beta, *se;             // [KMAX][nattr_pad]
     double *dev_old;               // [nattr_pad]
+    // exact stopping decision (see exact_dev_kernel): coefficients of the previous iteration, attributes whose deviance test is
+    // too close to glm.fit's epsilon to be decided from the streamed deviance, their exactly re-evaluated deviances
+    double *beta_prev;             // [KMAX][nattr_pad]
+    unsigned char *ambig;          // [nattr_pad]
+    unsigned int *n_ambig;
+    const double *dev_exact;       // [2][nattr_pad]: deviance at beta, at beta_prev
+    int resolve;                   // 1: second visit of the ambiguous attributes, with dev_exact
     double *hit_d, *miss_d;        // [nattr_pad] sum of the attribute diff over the hit / miss records (from pass 0)
     const double *dmax;            // [nattr] upper bound of the attribute diff over any pair
     double cmax[NB_FAST_COVARS]; // upper bounds of the covariate diffs
@@ -1394,19 +1422,81 @@ struct SolveArgs {
     double shared[NSHARED_MAX];    // lm shared moments
 };
 
-// sum the per-chunk partials of statistic n for attribute a, fixed order, weights applied per stream
-template <int NA>
-__device__ __forceinline__ void reduce_partials(const SolveArgs &S, int a, double (&out)[NA]) {
+// Binary-covariate folding.  A match-mismatch covariate diff is 0 or 1, so the pair list is split by its value into streams
+// on which that covariate is CONSTANT (c): its design column is c times the intercept column, the streams are evaluated by the
+// kernels of the next smaller design (Q - 1 covariates, intercept shifted by c * beta_f: 24 instead of 31 FP64 instructions
+// per evaluation at q = 2) and the full statistics are rebuilt here:
+//   G[r][s] = cr cs G'[e(r)][e(s)],  b[r] = cr b'[e(r)],  with e(f) = 0 (intercept), cr = c for r = f and 1 otherwise.
+// Exact: the same sums in a different grouping.
+__device__ __forceinline__ int eff_col(int i, int f) {            // full design column (0 intercept, 1 d, 2+u covariates) -> column of the reduced design
+    return (f < 0 || i < 2 + f) ? i : (i == 2 + f ? 0 : i - 1);
+}
+
+// moment statistics (MODE_LM / MODE_SIGN): [S d, S d^2, S d y | S d s, S d c_u ...]
+template <int Q>
+__device__ __forceinline__ void reduce_moments(const SolveArgs &S, int a, double (&out)[3 + Q]) {
+    constexpr int NA = 3 + Q;
     for (int n = 0; n < NA; ++n) out[n] = 0.0;
+    const int f = S.fold, qe = Q - (f >= 0 ? 1 : 0), nae = 3 + qe;
     const double *base = S.partials;
-    for (int st = 0; st < 2; ++st) {
+    for (int st = 0; st < NB_MAX_STREAMS; ++st) {
         if (S.n_chunks[st] == 0) continue;
         double tmp[NA];
         for (int n = 0; n < NA; ++n) tmp[n] = 0.0;
         for (int c = 0; c < S.n_chunks[st]; ++c)
-            for (int n = 0; n < NA; ++n) tmp[n] += base[((int64_t)c * NA + n) * S.nattr_pad + a];
-        for (int n = 0; n < NA; ++n) out[n] += S.weight[st] * tmp[n];
+            for (int n = 0; n < nae; ++n) tmp[n] += base[((int64_t)c * nae + n) * S.nattr_pad + a];
+        const double w = S.weight[st];
+        for (int n = 0; n < 3; ++n) out[n] += w * tmp[n];
+        for (int u = 0; u < Q; ++u)
+            out[3 + u] += w * ((u == f) ? S.fold_val[st] * tmp[0] : tmp[3 + ((f >= 0 && u > f) ? u - 1 : u)]);
         base += S.part_stride[st];
+    }
+}
+
+// IRLS statistics: X'WX upper triangle (row-major), the K score sums, log-product and clamp correction
+template <int Q>
+__device__ __forceinline__ void reduce_irls(const SolveArgs &S, int a, double (&out)[(2 + Q) * (3 + Q) / 2 + (2 + Q) + 2]) {
+    constexpr int K = 2 + Q, NA = K * (K + 1) / 2 + K + 2;
+    for (int n = 0; n < NA; ++n) out[n] = 0.0;
+    const int f = S.fold, ke = K - (f >= 0 ? 1 : 0), nae = ke * (ke + 1) / 2 + ke + 2;
+    const int fc = f >= 0 ? 2 + f : -1;                    // design column of the folded covariate
+    const double *base = S.partials;
+    for (int st = 0; st < NB_MAX_STREAMS; ++st) {
+        if (S.n_chunks[st] == 0) continue;
+        double tmp[NA];
+        for (int n = 0; n < NA; ++n) tmp[n] = 0.0;
+        for (int c = 0; c < S.n_chunks[st]; ++c)
+            for (int n = 0; n < nae; ++n) tmp[n] += base[((int64_t)c * nae + n) * S.nattr_pad + a];
+        const double w = S.weight[st], cv = S.fold_val[st];
+        int n = 0;
+        for (int r = 0; r < K; ++r)
+            for (int c = r; c < K; ++c) {
+                int er = eff_col(r, f), ec = eff_col(c, f);
+                if (er > ec) { const int t = er; er = ec; ec = t; }
+                const int idx = er * ke - er * (er - 1) / 2 + (ec - er);          // upper-triangle position in the reduced design
+                const double sc = ((r == fc) ? cv : 1.0) * ((c == fc) ? cv : 1.0);
+                out[n] += w * sc * tmp[idx];
+                ++n;
+            }
+        const int nge = ke * (ke + 1) / 2;
+        for (int r = 0; r < K; ++r) out[n + r] += w * ((r == fc) ? cv : 1.0) * tmp[nge + eff_col(r, f)];
+        out[NA - 2] += w * tmp[nae - 2];
+        out[NA - 1] += w * tmp[nae - 1];
+        base += S.part_stride[st];
+    }
+}
+
+// coefficients a stream's pass evaluates with: the reduced design's [b0 + c b_f, b1, the other covariates]
+__global__ void fold_beta_kernel(const double *__restrict__ beta, int nattr_pad, int K, int fold, double cval, double *__restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nattr_pad) return;
+    int e = 0;
+    for (int r = 0; r < K; ++r) {
+        if (r == 2 + fold) continue;
+        double v = beta[(int64_t)r * nattr_pad + a];
+        if (r == 0) v += cval * beta[(int64_t)(2 + fold) * nattr_pad + a];
+        out[(int64_t)e * nattr_pad + a] = v;
+        ++e;
     }
 }
 
@@ -1432,7 +1522,7 @@ __global__ void lm_finalize_kernel(SolveArgs S) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= S.nattr) return;
     double m[NA];
-    reduce_partials<NA>(S, a, m);
+    reduce_moments<Q>(S, a, m);
     // shared: [M, Sy, Syy, Sc_r, Scy_r, Scc_rs]
     const double M = S.shared[0], Sy = S.shared[1], Syy = S.shared[2];
     const double *Sc = S.shared + 3, *Scy = S.shared + 3 + Q, *Scc = S.shared + 3 + 2 * Q;
@@ -1504,7 +1594,7 @@ __global__ void irls_init_kernel(SolveArgs S) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= S.nattr) return;
     double m[NA];
-    reduce_partials<NA>(S, a, m);
+    reduce_moments<Q>(S, a, m);
     const double M = S.shared[0], Ss = S.shared[1];
     const double *Sc = S.shared + 3, *Scs = S.shared + 3 + Q, *Scc = S.shared + 3 + 2 * Q;
     const double w0 = 0.1875, z0 = 1.0986122886681098 + 0.25 / 0.1875;
@@ -1551,7 +1641,7 @@ __global__ void irls_step_kernel(SolveArgs S) {
     if (a >= S.nattr) return;
     if (!S.active[a]) return;
     double m[NA];
-    reduce_partials<NA>(S, a, m);
+    reduce_irls<Q>(S, a, m);
     double A[K][K], b[K];                                   // X'WX and the score X'(y - mu)
     int n = 0;
     for (int r = 0; r < K; ++r) for (int c = r; c < K; ++c) { A[r][c] = A[c][r] = m[n]; ++n; }
@@ -1568,11 +1658,29 @@ __global__ void irls_step_kernel(SolveArgs S) {
     // residual deviance = 2 * sum[ log(1 + t) - y * log(t) ], log t = eta = beta . v except for clamped records
     double lin = 0.0;
     for (int r = 0; r < K; ++r) lin += S.beta[(int64_t)r * S.nattr_pad + a] * missv[r];
-    const double dev = 2.0 * (m[NA - 2] - lin - m[NA - 1]);
+    double dev = 2.0 * (m[NA - 2] - lin - m[NA - 1]);
     bool finish = false;
     int flags = 0;
     {
-        const double devold = S.dev_old[a];
+        double devold = S.dev_old[a];
+        // glm.fit stops when |dev - devold| / (|dev| + 0.1) < 1e-8 and reports the standard errors of THAT iteration's
+        // weights, so stopping one iteration early or late moves Z by ~1e-5: the decision has to be R's.  The streamed
+        // deviance carries the exp polynomial's error (<= 1.7e-12 per record, systematic when the diffs take few distinct
+        // values, e.g. SNP data); when the test lands inside that error band the attribute is parked, its two deviances
+        // are re-evaluated record by record with full-accuracy exp / log (exact_dev_kernel) and this kernel visits it again.
+        if (S.resolve) {
+            if (!S.ambig[a]) return;
+            S.ambig[a] = 0;
+            dev = S.dev_exact[a];
+            if (S.pass >= 2) devold = S.dev_exact[S.nattr_pad + a];
+        } else if (isfinite(dev) && S.ambig) {
+            const double thr = 1e-8 * (fabs(dev) + 0.1);
+            if (fabs(fabs(dev - devold) - thr) <= 8e-12 * S.M + 1e-3 * thr * 1e-3) {
+                S.ambig[a] = 1;
+                atomicAdd(S.n_ambig, 1u);
+                return;
+            }
+        }
         if (!isfinite(dev)) { finish = true; flags |= NPDRB_FLAG_NONFINITE; }
         else if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) finish = true;      // glm.control(epsilon = 1e-8)
         else if (S.pass >= 25) { finish = true; flags |= NPDRB_FLAG_NOT_CONVERGED; }   // maxit = 25
@@ -1586,6 +1694,9 @@ __global__ void irls_step_kernel(SolveArgs S) {
             se[r] = S.se[(int64_t)r * S.nattr_pad + a];
             al[r] = !(se[r] == se[r]);                         // NaN se marks an aliased coefficient
         }
+#ifdef NB_DEBUG_SE
+        if (a == 0 && Q == 4) printf("finish pass %d: se %g %g %g %g %g %g\n", S.pass, se[0], se[1], se[2], se[3], se[4], se[5 < K ? 5 : 0]);
+#endif
         int rank = 0;
         for (int r = 0; r < K; ++r) rank += al[r] ? 0 : 1;
         write_stats(S.stats + (int64_t)a * 8, beta, se, al, K, S.M - (double)rank, dev, S.pass, flags);
@@ -1606,6 +1717,13 @@ __global__ void irls_step_kernel(SolveArgs S) {
         S.active[a] = 0;
         return;
     }
+#ifdef NB_DEBUG_SE
+    if (a == 0 && Q == 4) {
+        printf("step pass %d: dinv %g %g %g %g %g %g  al %d%d%d%d%d%d\n", S.pass, dinv[0], dinv[1], dinv[2], dinv[3], dinv[4], dinv[5 < K ? 5 : 0],
+               (int)al[0], (int)al[1], (int)al[2], (int)al[3], (int)al[4], (int)al[5 < K ? 5 : 0]);
+        for (int r = 0; r < K; ++r) printf("   A[%d]: %g %g %g %g %g %g | b %g\n", r, A[r][0], A[r][1], A[r][2], A[r][3], A[r][4], A[r][5 < K ? 5 : 0], b[r]);
+    }
+#endif
     double bnew[K], senew[K];
     for (int r = 0; r < K; ++r) {                           // Newton / IRLS update: beta + (X'WX)^-1 X'(y - mu)
         const double old = S.beta[(int64_t)r * S.nattr_pad + a];
@@ -1642,12 +1760,60 @@ __global__ void irls_step_kernel(SolveArgs S) {
         }
     }
     for (int r = 0; r < K; ++r) {
+        if (S.beta_prev) S.beta_prev[(int64_t)r * S.nattr_pad + a] = S.beta[(int64_t)r * S.nattr_pad + a];
         S.beta[(int64_t)r * S.nattr_pad + a] = bnew[r];
         S.se[(int64_t)r * S.nattr_pad + a] = senew[r];
     }
     S.iters[a] = S.pass + 1;
     S.tile_active[a / TA] = 1;
     atomicAdd(S.n_active, 1u);
+}
+
+// Exact residual deviance of the parked attributes at two coefficient vectors, record by record over the ORIGINAL pair list,
+// with libdevice exp / log and binomial()'s eta clamps -- dev.resids as glm.fit forms them (stats family.c, R/npdr.R:36).
+// One CTA per attribute (exits at once unless parked); fixed-order block reduction.
+struct ExactArgs {
+    const double *X; int64_t ldx; int64_t attr0; int nattr, nattr_pad; int64_t N;
+    const int32_t *Ri, *NN; int64_t M;
+    const double *y, *C; int q, diff_type, y_raw;
+    int cov_type[NB_FAST_COVARS];
+    const double *beta, *beta_prev; const unsigned char *ambig;
+    double *dev_exact;             // [2][nattr_pad]
+};
+__device__ __forceinline__ double exact_dev_term(double eta, bool miss) {
+    const double t = (eta < -30.0) ? 2.220446049250313e-16 : ((eta > 30.0) ? 4503599627370496.0 : exp(eta));
+    const double mu = t / (1.0 + t);
+    return miss ? 2.0 * log(1.0 / mu) : 2.0 * log(1.0 / (1.0 - mu));         // 2 (y log(y/mu) + (1-y) log((1-y)/(1-mu)))
+}
+__global__ void __launch_bounds__(256)
+exact_dev_kernel(ExactArgs E) {
+    const int a = blockIdx.x;
+    if (a >= E.nattr || !E.ambig[a]) return;
+    __shared__ double red0[256], red1[256];
+    const int K = 2 + E.q;
+    double b0[KMAX], b1[KMAX];
+    for (int r = 0; r < K; ++r) { b0[r] = E.beta[(int64_t)r * E.nattr_pad + a]; b1[r] = E.beta_prev[(int64_t)r * E.nattr_pad + a]; }
+    const double *xcol = E.X + (E.attr0 + a) * E.ldx;
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t m = threadIdx.x; m < E.M; m += 256) {
+        const int64_t i = E.Ri[m] - 1, j = E.NN[m] - 1;
+        const double d = nb_diff1(xcol[i], xcol[j], E.diff_type);
+        const bool miss = E.y_raw ? (E.y[i] != 0.0) : (E.y[i] != E.y[j]);
+        double e0 = fma(b0[1], d, b0[0]), e1 = fma(b1[1], d, b1[0]);
+        for (int u = 0; u < E.q; ++u) {
+            const double *col = E.C + (int64_t)u * E.N;
+            const double c = E.y_raw ? col[i] : nb_diff1(col[i], col[j], E.cov_type[u]);
+            e0 = fma(b0[2 + u], c, e0); e1 = fma(b1[2 + u], c, e1);
+        }
+        s0 += exact_dev_term(e0, miss); s1 += exact_dev_term(e1, miss);
+    }
+    red0[threadIdx.x] = s0; red1[threadIdx.x] = s1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { red0[threadIdx.x] += red0[threadIdx.x + o]; red1[threadIdx.x] += red1[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { E.dev_exact[a] = red0[0]; E.dev_exact[E.nattr_pad + a] = red1[0]; }
 }
 
 // ------------------------------------------------------------------ host side
@@ -1700,15 +1866,21 @@ void free_stream(nb_stream &st) {
 }
 
 // Build one bucketed stream from a pair list (device).  y_raw: uniReg mode.
+struct CovPlan {                    // which covariates a stream stores per record (all but the folded one)
+    int q = 0;                      // stored covariates
+    int src[NB_FAST_COVARS] = {0, 0, 0, 0};    // column of C behind stored covariate u
+    int type[NB_FAST_COVARS] = {0, 0, 0, 0};   // its diff type
+    int fold = -1;                  // folded covariate (column of C), or -1
+};
 int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64_t M, int reg_type,
-                 const int32_t *cov_type, int y_raw, double weight, double work_share, nb_stream &st, int64_t *n_miss_out) {
+                 const CovPlan &cp, int y_raw, double weight, double fold_val, double work_share, nb_stream &st, int64_t *n_miss_out) {
     npdrb_ctx *ctx = s->ctx;
     const int64_t N = s->N;
-    const int q = s->q;
+    const int q = cp.q;
     const int n_ib = (int)nb_cdiv(N, BI), n_jb = (int)nb_cdiv(N, BJ);
     const int64_t n_tiles_all = (int64_t)n_ib * n_jb;
     st = nb_stream();
-    st.n_rec = M; st.weight = weight;
+    st.n_rec = M; st.weight = weight; st.fold_val = fold_val;
     uint32_t *keys = nullptr, *idx = nullptr, *keys2 = nullptr, *perm = nullptr;
     unsigned *hist = nullptr;
     unsigned long long *d_miss = nullptr;
@@ -1738,7 +1910,7 @@ int build_stream(npdrb_session *s, const int32_t *dRi, const int32_t *dNN, int64
     for (int c = 0; c < q; ++c) NB_CHECK(dmalloc(&st.cd[c], (size_t)M));
     GatherArgs g;
     g.Ri = dRi; g.NN = dNN; g.perm = perm; g.y = s->dy; g.C = s->dC; g.M = M; g.N = N; g.q = q; g.reg_type = reg_type;
-    for (int c = 0; c < NB_FAST_COVARS; ++c) { g.cov_type[c] = (c < q && cov_type) ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH; g.cd[c] = st.cd[c]; }
+    for (int c = 0; c < NB_FAST_COVARS; ++c) { g.cov_type[c] = cp.type[c]; g.cov_src[c] = cp.src[c]; g.cd[c] = st.cd[c]; }
     g.y_raw = y_raw; g.rec = st.rec; g.yv = st.yv; g.n_miss = d_miss;
     gather_records_kernel<<<grid, 256, 0, ctx->stream>>>(g);
     NB_LAUNCH_CHECK(ctx);
@@ -1904,7 +2076,7 @@ int launch_solve(npdrb_ctx *ctx, int q, int kind, const SolveArgs &S) {
 }  // namespace
 
 void nb_free_streams(npdrb_session *s) {
-    for (int i = 0; i < 2; ++i) free_stream(s->streams[i]);
+    for (int i = 0; i < NB_MAX_STREAMS; ++i) free_stream(s->streams[i]);
     s->n_streams = 0;
     s->streams_valid = false;
 }
@@ -1942,24 +2114,40 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         s->xt_attr0 = attr0; s->xt_nattr = nattr;
         s->streams_valid = false;                       // chunking depends on the attribute tile count
     }
+    // Which covariates the records carry.  The first match-mismatch covariate (diff in {0, 1}) is folded: the pair list is
+    // split by its value and every part runs the kernels of the next smaller design (reduce_irls rebuilds the statistics).
+    CovPlan cp;
+    {
+        const char *ncf = getenv("NPDRB_NO_COVFOLD");
+        if (!y_raw && !(ncf && ncf[0] == '1'))
+            for (int c = 0; c < q && cp.fold < 0; ++c)
+                if ((cov_type ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH) == NPDRB_DIFF_MATCH_MISMATCH) cp.fold = c;
+        for (int c = 0; c < q; ++c) {
+            if (c == cp.fold) continue;
+            cp.src[cp.q] = c; cp.type[cp.q] = cov_type ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH; ++cp.q;
+        }
+    }
+    const int qe = cp.q;                                   // covariates of the design the pass kernels evaluate
+    s->q_eff = qe; s->n_exact_stops = 0;
     // bucketed pair stream(s)
-    int sig = y_raw * 1000003;
+    int sig = y_raw * 1000003 + (cp.fold + 1) * 7919;
     for (int c = 0; c < q; ++c) sig = sig * 31 + (cov_type ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH) + 7;
     if (!s->streams_valid || s->streams_reg_type != reg_type || s->streams_cov_sig != sig) {
         nb_free_streams(s);
-        int64_t n_miss = 0;
-        bool folded = false;
+        struct Seg { const int32_t *Ri, *NN; int64_t n; double w, cval; };
+        std::vector<Seg> segs;
+        nb_scope seg_scope;                                // the split pair lists live until the streams are built
+        const int64_t M = s->M;
         const char *nf = getenv("NPDRB_NO_FOLD");
         // (RAW = uniReg: the row is x[Ri], y[Ri] -- not symmetric in (i, j), so mutual pairs must not be folded)
-        if (!y_raw && !(nf && nf[0] == '1') && s->M >= 2) {
+        if (!y_raw && !(nf && nf[0] == '1') && M >= 2) {
             // classify: one-directional (weight 1) / mutual with i<j (weight 2) / mutual reverse (dropped)
-            const int64_t M = s->M;
             const size_t words = ((size_t)N * (size_t)N + 31) / 32;
             unsigned *d_bits = nullptr; unsigned char *d_f1 = nullptr, *d_f2 = nullptr; unsigned long long *d_cnt = nullptr;
             int32_t *d_sel = nullptr; int *d_nsel = nullptr; void *d_tmp = nullptr;
             nb_scope fold_scope;
             NB_CHECK(fold_scope.alloc(&d_bits, words)); NB_CHECK(fold_scope.alloc(&d_f1, (size_t)M)); NB_CHECK(fold_scope.alloc(&d_f2, (size_t)M));
-            NB_CHECK(fold_scope.alloc(&d_cnt, 1)); NB_CHECK(fold_scope.alloc(&d_sel, (size_t)4 * M)); NB_CHECK(fold_scope.alloc(&d_nsel, 4));
+            NB_CHECK(fold_scope.alloc(&d_cnt, 1)); NB_CHECK(seg_scope.alloc(&d_sel, (size_t)4 * M)); NB_CHECK(fold_scope.alloc(&d_nsel, 4));
             NB_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned) * words, ctx->stream));
             NB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
             const unsigned grid = (unsigned)nb_cdiv(M, 256);
@@ -1982,23 +2170,49 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             NB_CUDA(cudaMemcpyAsync(h_nsel, d_nsel, sizeof(h_nsel), cudaMemcpyDeviceToHost, ctx->stream));
             NB_CUDA(cudaStreamSynchronize(ctx->stream));
             const int64_t n1 = h_nsel[0], n2 = h_nsel[2];
-            int rc = NPDRB_OK;
             if ((int64_t)h_cnt == M && n2 > 0 && n1 + 2 * n2 == M) {       // no repeated ordered pair: folding is exact
-                const double tot = (double)(n1 + n2);
-                int64_t miss1 = 0, miss2 = 0;
-                int ns = 0;
-                if (n1 > 0) { rc = build_stream(s, d_sel, d_sel + M, n1, reg_type, cov_type, y_raw, 1.0, n1 / tot, s->streams[ns], &miss1); ++ns; }
-                if (!rc) { rc = build_stream(s, d_sel + 2 * M, d_sel + 3 * M, n2, reg_type, cov_type, y_raw, 2.0, n2 / tot, s->streams[ns], &miss2); ++ns; }
-                s->n_streams = ns;
-                n_miss = miss1 + 2 * miss2;
-                folded = (rc == NPDRB_OK);
+                if (n1 > 0) segs.push_back({d_sel, d_sel + M, n1, 1.0, 0.0});
+                segs.push_back({d_sel + 2 * M, d_sel + 3 * M, n2, 2.0, 0.0});
             }
-            if (rc) return rc;
         }
-        if (!folded) {
-            nb_free_streams(s);
-            NB_CHECK(build_stream(s, s->dRi, s->dNN, s->M, reg_type, cov_type, y_raw, 1.0, 1.0, s->streams[0], &n_miss));
-            s->n_streams = 1;
+        if (segs.empty()) segs.push_back({s->dRi, s->dNN, M, 1.0, 0.0});
+        if (cp.fold >= 0) {
+            // split every part by the value of the folded covariate's diff (match-mismatch of column cp.fold over the pair)
+            std::vector<Seg> parts;
+            for (const Seg &g : segs) {
+                unsigned char *d_c1 = nullptr, *d_c0 = nullptr; int32_t *d_out = nullptr; int *d_n = nullptr; void *d_tmp = nullptr;
+                nb_scope tmp_scope;
+                NB_CHECK(tmp_scope.alloc(&d_c1, (size_t)g.n)); NB_CHECK(tmp_scope.alloc(&d_c0, (size_t)g.n));
+                NB_CHECK(seg_scope.alloc(&d_out, (size_t)4 * g.n)); NB_CHECK(tmp_scope.alloc(&d_n, 4));
+                cov_flags_kernel<<<(unsigned)nb_cdiv(g.n, 256), 256, 0, ctx->stream>>>(g.Ri, g.NN, g.n, s->dC + (int64_t)cp.fold * N, d_c0, d_c1);
+                NB_LAUNCH_CHECK(ctx);
+                size_t tmp_bytes = 0;
+                NB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, g.Ri, d_c0, d_out, d_n, (int)g.n, ctx->stream));
+                NB_CHECK(tmp_scope.alloc((unsigned char **)&d_tmp, tmp_bytes ? tmp_bytes : 1));
+                const int32_t *src[4] = {g.Ri, g.NN, g.Ri, g.NN};
+                const unsigned char *flg[4] = {d_c0, d_c0, d_c1, d_c1};
+                for (int k4 = 0; k4 < 4; ++k4)
+                    NB_CUDA(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, src[k4], flg[k4], d_out + (size_t)k4 * g.n, d_n + k4, (int)g.n, ctx->stream));
+                ctx->launches += 4;
+                int h_n[4] = {0, 0, 0, 0};
+                NB_CUDA(cudaMemcpyAsync(h_n, d_n, sizeof(h_n), cudaMemcpyDeviceToHost, ctx->stream));
+                NB_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (h_n[0] > 0) parts.push_back({d_out, d_out + g.n, h_n[0], g.w, 0.0});
+                if (h_n[2] > 0) parts.push_back({d_out + 2 * g.n, d_out + 3 * g.n, h_n[2], g.w, 1.0});
+            }
+            segs.swap(parts);
+        }
+        double tot = 0;
+        for (const Seg &g : segs) tot += (double)g.n;
+        int64_t n_miss = 0;
+        int ns = 0;
+        for (const Seg &g : segs) {
+            int64_t miss = 0;
+            int rc = build_stream(s, g.Ri, g.NN, g.n, reg_type, cp, y_raw, g.w, g.cval, (double)g.n / tot, s->streams[ns], &miss);
+            ++ns;
+            s->n_streams = ns;
+            if (rc) { nb_free_streams(s); return rc; }
+            n_miss += (int64_t)(g.w * (double)miss + 0.5);
         }
         s->streams_reg_type = reg_type; s->streams_cov_sig = sig; s->streams_valid = true;
         if (reg_type == NPDRB_REG_BINOMIAL && (n_miss == 0 || n_miss == s->M)) {
@@ -2016,12 +2230,12 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     NB_CUDA(cudaEventRecord(e0, ctx->stream));
 
     const bool lm = reg_type == NPDRB_REG_LM;
-    const int mode_na = nacc_for(lm ? MODE_LM : MODE_IRLS_FULL, q);
+    const int mode_na = nacc_for(lm ? MODE_LM : MODE_IRLS_FULL, qe);
     double *d_part = nullptr, *d_beta = nullptr, *d_se = nullptr, *d_devold = nullptr, *d_stats = nullptr;
     unsigned char *d_active = nullptr, *d_tile_active = nullptr;
     int *d_iters = nullptr, *d_flags = nullptr;
     unsigned int *d_nactive = nullptr;
-    int64_t part_stride[2] = {0, 0}, part_total = 0;
+    int64_t part_stride[NB_MAX_STREAMS] = {0, 0, 0, 0}, part_total = 0;
     for (int i = 0; i < s->n_streams; ++i) {
         part_stride[i] = (int64_t)s->streams[i].n_chunks * mode_na * nattr_pad;
         part_total += part_stride[i];
@@ -2030,6 +2244,16 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     NB_CHECK(scope.alloc(&d_part, (size_t)part_total));
     NB_CHECK(scope.alloc(&d_stats, (size_t)nattr * 8));
     NB_CHECK(scope.alloc(&d_beta, (size_t)KMAX * nattr_pad)); NB_CHECK(scope.alloc(&d_se, (size_t)KMAX * nattr_pad));
+    double *d_beta_prev = nullptr, *d_dev_exact = nullptr; unsigned char *d_ambig = nullptr; unsigned int *d_nambig = nullptr;
+    if (!lm) {
+        NB_CHECK(scope.alloc(&d_beta_prev, (size_t)KMAX * nattr_pad)); NB_CHECK(scope.alloc(&d_dev_exact, (size_t)2 * nattr_pad));
+        NB_CHECK(scope.alloc(&d_ambig, (size_t)nattr_pad)); NB_CHECK(scope.alloc(&d_nambig, 1));
+        NB_CUDA(cudaMemsetAsync(d_beta_prev, 0, sizeof(double) * KMAX * nattr_pad, ctx->stream));
+        NB_CUDA(cudaMemsetAsync(d_ambig, 0, (size_t)nattr_pad, ctx->stream));
+        NB_CUDA(cudaMemsetAsync(d_nambig, 0, sizeof(unsigned int), ctx->stream));
+    }
+    double *d_beta_eff = nullptr;                       // per stream: the reduced design's coefficients (covariate folding)
+    if (cp.fold >= 0 && !lm) NB_CHECK(scope.alloc(&d_beta_eff, (size_t)NB_MAX_STREAMS * KMAX * nattr_pad));
     double *d_hitd = nullptr, *d_missd = nullptr;
     NB_CHECK(scope.alloc(&d_hitd, (size_t)nattr_pad)); NB_CHECK(scope.alloc(&d_missd, (size_t)nattr_pad));
     double *d_dmax = nullptr;
@@ -2077,10 +2301,17 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
     }
     S.beta = d_beta; S.se = d_se; S.dev_old = d_devold; S.active = d_active; S.tile_active = d_tile_active;
     S.iters = d_iters; S.flags = d_flags; S.stats = d_stats; S.n_active = d_nactive;
+    {
+        const char *ne = getenv("NPDRB_NO_EXACT_STOP");        // tests: decide from the streamed deviance alone
+        const bool exact_stop = !(ne && ne[0] == '1');
+        S.beta_prev = d_beta_prev; S.ambig = exact_stop ? d_ambig : nullptr; S.n_ambig = d_nambig; S.dev_exact = d_dev_exact; S.resolve = 0;
+    }
     double Mw = 0;
-    for (int i = 0; i < 2; ++i) {
+    S.fold = cp.fold;
+    for (int i = 0; i < NB_MAX_STREAMS; ++i) {
         S.n_chunks[i] = i < s->n_streams ? s->streams[i].n_chunks : 0;
         S.weight[i] = i < s->n_streams ? s->streams[i].weight : 0.0;
+        S.fold_val[i] = i < s->n_streams ? s->streams[i].fold_val : 0.0;
         S.part_stride[i] = part_stride[i];
         if (i < s->n_streams) Mw += s->streams[i].weight * (double)s->streams[i].n_rec;
     }
@@ -2090,10 +2321,10 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         PassArgs P;
         memset(&P, 0, sizeof(P));
         P.XT = s->dXT; P.ldt = s->ldt; P.N = N; P.nattr = (int)nattr; P.nattr_pad = (int)nattr_pad;
-        P.beta = d_beta; P.tile_active = tile_active; P.tables = d_tab; P.tables1024 = d_tab1024; P.diff_type = diff_type;
+        P.tile_active = tile_active; P.tables = d_tab; P.tables1024 = d_tab1024; P.diff_type = diff_type;
         P.dmax = d_dmax;
         { const char *dbg = getenv("NPDRB_V3_DBG"); P.dbg = dbg ? atoi(dbg) : 0; }
-        for (int c = 0; c < NB_FAST_COVARS; ++c) P.cmax[c] = S.cmax[c];
+        for (int c = 0; c < qe; ++c) P.cmax[c] = S.cmax[cp.src[c]];
         double *pp = d_part;
         int total_chunks = 0;
         for (int i = 0; i < s->n_streams; ++i) {
@@ -2103,18 +2334,27 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             for (int c = 0; c < NB_FAST_COVARS; ++c) A.cd[c] = st.cd[c];
             A.tile_ptr = st.tile_ptr; A.tile_mid = st.tile_mid; A.tile_ib = st.tile_ib; A.tile_jb = st.tile_jb;
             A.chunk_tile = st.chunk_tile; A.partials = pp;
+            A.beta = d_beta;
+            if (d_beta_eff && mode == MODE_IRLS_FULL) {       // this stream's view of the coefficients: [b0 + c b_f, b1, the rest]
+                double *be = d_beta_eff + (size_t)i * KMAX * nattr_pad;
+                fold_beta_kernel<<<(unsigned)nb_cdiv(nattr_pad, 256), 256, 0, ctx->stream>>>(d_beta, (int)nattr_pad, 2 + q, cp.fold,
+                                                                                            st.fold_val, be);
+                NB_LAUNCH_CHECK(ctx);
+                A.beta = be;
+            }
             pp += part_stride[i];
+            P.chunk_start[i] = total_chunks;
             total_chunks += st.n_chunks;
         }
-        P.n_chunks0 = s->streams[0].n_chunks;
-        if (use_v2(q)) {
-            return mode == MODE_LM ? launch_pass2<MODE_LM>(ctx, q, P, (int)n_at, total_chunks)
-                 : mode == MODE_SIGN ? launch_pass2<MODE_SIGN>(ctx, q, P, (int)n_at, total_chunks)
-                                     : launch_pass2<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, total_chunks);
+        for (int i = s->n_streams; i <= NB_MAX_STREAMS; ++i) P.chunk_start[i] = total_chunks;
+        if (use_v2(qe)) {
+            return mode == MODE_LM ? launch_pass2<MODE_LM>(ctx, qe, P, (int)n_at, total_chunks)
+                 : mode == MODE_SIGN ? launch_pass2<MODE_SIGN>(ctx, qe, P, (int)n_at, total_chunks)
+                                     : launch_pass2<MODE_IRLS_FULL>(ctx, qe, P, (int)n_at, total_chunks);
         }
-        return mode == MODE_LM ? launch_pass<MODE_LM>(ctx, q, P, (int)n_at, total_chunks)
-             : mode == MODE_SIGN ? launch_pass<MODE_SIGN>(ctx, q, P, (int)n_at, total_chunks)
-                                 : launch_pass<MODE_IRLS_FULL>(ctx, q, P, (int)n_at, total_chunks);
+        return mode == MODE_LM ? launch_pass<MODE_LM>(ctx, qe, P, (int)n_at, total_chunks)
+             : mode == MODE_SIGN ? launch_pass<MODE_SIGN>(ctx, qe, P, (int)n_at, total_chunks)
+                                 : launch_pass<MODE_IRLS_FULL>(ctx, qe, P, (int)n_at, total_chunks);
     };
 
     int passes = 0;
@@ -2142,8 +2382,9 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
         for (int i = 0; i < s->n_streams; ++i) {
             SharedArgs a;
             a.yv = lm ? s->streams[i].yv : nullptr; a.rec = s->streams[i].rec;
-            a.n = s->streams[i].n_rec; a.q = q; a.out = d_sh;
-            for (int c = 0; c < NB_FAST_COVARS; ++c) a.cd[c] = s->streams[i].cd[c];
+            a.n = s->streams[i].n_rec; a.q = q; a.out = d_sh; a.fold_val = s->streams[i].fold_val;
+            for (int c = 0; c < NB_FAST_COVARS; ++c) a.cd[c] = nullptr;      // full covariate order; NULL = the folded (constant) one
+            for (int u = 0; u < qe; ++u) a.cd[cp.src[u]] = s->streams[i].cd[u];
             NB_CUDA(cudaMemsetAsync(d_sh, 0, sizeof(double) * h.size(), ctx->stream));
             shared_moments_kernel<<<nblk, 256, 0, ctx->stream>>>(a);
             NB_LAUNCH_CHECK(ctx);
@@ -2187,6 +2428,27 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
             NB_CUDA(cudaMemsetAsync(d_nactive, 0, sizeof(unsigned int), ctx->stream));
             S.pass = pass;
             NB_CHECK(launch_solve(ctx, q, SOLVE_IRLS_STEP, S));
+            if (S.ambig) {
+                unsigned int h_ambig = 0;
+                NB_CUDA(cudaMemcpyAsync(&h_ambig, d_nambig, sizeof(h_ambig), cudaMemcpyDeviceToHost, ctx->stream));
+                NB_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (h_ambig > 0) {
+                    // stopping test inside the streamed deviance's error band: exact deviances, then a second visit
+                    ExactArgs E;
+                    memset(&E, 0, sizeof(E));
+                    E.X = s->dX; E.ldx = s->ldx; E.attr0 = attr0; E.nattr = (int)nattr; E.nattr_pad = (int)nattr_pad; E.N = N;
+                    E.Ri = s->dRi; E.NN = s->dNN; E.M = s->M; E.y = s->dy; E.C = s->dC; E.q = q; E.diff_type = diff_type; E.y_raw = y_raw;
+                    for (int c = 0; c < q; ++c) E.cov_type[c] = cov_type ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH;
+                    E.beta = d_beta; E.beta_prev = d_beta_prev; E.ambig = d_ambig; E.dev_exact = d_dev_exact;
+                    exact_dev_kernel<<<(unsigned)nattr, 256, 0, ctx->stream>>>(E);
+                    NB_LAUNCH_CHECK(ctx);
+                    S.resolve = 1;
+                    NB_CHECK(launch_solve(ctx, q, SOLVE_IRLS_STEP, S));
+                    S.resolve = 0;
+                    NB_CUDA(cudaMemsetAsync(d_nambig, 0, sizeof(unsigned int), ctx->stream));
+                    s->n_exact_stops += (int)h_ambig;
+                }
+            }
         }
     }
     NB_CUDA(cudaMemcpyAsync(stats_out_host, d_stats, sizeof(double) * (size_t)nattr * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -446,7 +446,7 @@ int nb_regress_wide(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_
     NB_CUDA(cudaEventSynchronize(e1));
     NB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     s->ms_regress = ms;
-    s->ms_pass_first = ms; s->ms_pass_full = 0; s->n_pass_full = 0; s->evals_pass_full = 0;
+    s->ms_pass_first = ms; s->ms_pass_full = 0; s->n_pass_full = 0; s->evals_pass_full = 0; s->q_eff = q;
     if (irls_passes) *irls_passes = h_passes;
     return NPDRB_OK;
 }

@@ -198,10 +198,29 @@ def npdr_sharded(engine, N, p, regression_type="binomial", attr_diff_type="numer
     return out, info
 
 
+def gather_columns_pipelined(dX, world, ncols, group=None):
+    """Replicate an attribute-sharded matrix without stalling the distance stage.  dX: [p, ldx] device tensor (row a = attribute
+    column a) whose rows [rank * ncols, (rank + 1) * ncols) this rank has already filled.  One asynchronous NCCL broadcast per
+    rank's shard, issued in rank order = attribute order; returns (slab_cols, events) with events[g] firing when shard g has
+    landed here.  Handed to GpuEngine(slab_events=...) the distance kernel consumes shard g while shards g+1.. are still on
+    the wire (npdrb_session_set_device_slab_events) -- bit-identical to gathering first."""
+    side = torch.cuda.Stream(device=dX.device)
+    events = []
+    for g in range(world):
+        work = dist.broadcast(dX[g * ncols:(g + 1) * ncols], src=g, group=group, async_op=True)
+        with torch.cuda.stream(side):
+            work.wait()                                                 # the side stream (not the caller's) waits for the transfer
+            ev = torch.cuda.Event()
+            ev.record(side)
+        events.append(ev)
+    return ncols, events
+
+
 class GpuEngine(Engine):
     """libnpdr_b200 session on this rank's GPU.  Inputs are uploaded once (or adopted from device tensors)."""
 
-    def __init__(self, X=None, y=None, C=None, device_index=0, dX=None, ldx=None, dy=None, dC=None, N=None, p=None, q=None):
+    def __init__(self, X=None, y=None, C=None, device_index=0, dX=None, ldx=None, dy=None, dC=None, N=None, p=None, q=None,
+                 slab_events=None):
         from . import _lib
         self._lib = _lib
         self.device = torch.device("cuda", device_index)
@@ -214,9 +233,14 @@ class GpuEngine(Engine):
         if X is not None:
             self.session.upload(X, y, C)
         else:
-            self._keep = (dX, dy, dC)
-            torch.cuda.synchronize(self.device)      # the producers of the adopted tensors ran on torch's streams, the library has its own
+            self._keep = (dX, dy, dC, slab_events)
+            if slab_events is None:
+                torch.cuda.synchronize(self.device)  # the producers of the adopted tensors ran on torch's streams, the library has its own
+            else:
+                torch.cuda.current_stream(self.device).synchronize()   # y / C only: the column slabs of X are still in flight
             self.session.set_device_inputs(dX.data_ptr(), ldx, dy.data_ptr(), dC.data_ptr() if dC is not None else 0)
+            if slab_events is not None:              # (slab_cols, [torch.cuda.Event]): X arrives slab by slab (gather_columns_pipelined)
+                self.session.set_device_slab_events(slab_events[0], [e.cuda_event for e in slab_events[1]])
         self._metric_done = None
 
     def close(self):
