@@ -42,6 +42,8 @@ WORKLOADS = {
                  desc="synthetic createSimulation2-style interaction data 4,000 x 20,000 per GPU: binomial, multisurf, manhattan"),
     "cfg5": dict(N=20000, p_per_gpu=None, p_total=50000, q=2, pct_signals=0.01, scaling="strong",
                  desc="synthetic 20,000 x 50,000: binomial, multisurf, manhattan, 2 covariates"),
+    "cfg5s": dict(N=4000, p_per_gpu=None, p_total=4096, q=2, pct_signals=0.01, scaling="strong",
+                  desc="the config 5 recipe (2 covariates) at 4,000 x 4,096: profiling size for the q = 2 kernels"),
     "small": dict(N=1024, p_per_gpu=2048, p_total=None, q=0, pct_signals=0.05, scaling="weak",
                   desc="development size 1,024 x 2,048 per GPU"),
 }
@@ -182,7 +184,7 @@ def cpu_oracle_sample(wl_name, N_s, p_s, q, threads=None):
     return float(p_s) * ri.size, dt, O.num_threads(), int(ri.size)
 
 
-CPU_SAMPLE = {"cfg4": (2000, 512), "cfg5": (2000, 512), "small": (512, 128)}      # one sample for cpu_baseline AND --impl reference
+CPU_SAMPLE = {"cfg4": (2000, 512), "cfg5": (2000, 512), "cfg5s": (2000, 512), "small": (512, 128)}      # one sample for cpu_baseline AND --impl reference
 
 
 def workload_config(wl_name, world):
@@ -290,9 +292,19 @@ class Bench:
         if world == 1 or (inproc and rank == 0):
             self.hX = d["dX"][:, :N].cpu().numpy().T                   # (N, p) Fortran-ordered view of a pageable buffer
         if world > 1:
+            self.cyc = None
             if self.shard:
+                from npdr_b200.distributed import cyclic_blocks
                 na = p // world
-                self.hXs = d["dX"][rank * na:(rank + 1) * na, :N].cpu().numpy().T
+                self.cyc = cyclic_blocks(p, world) if os.environ.get("NPDRB_NO_PIPELINED_GATHER") != "1" else None
+                if self.cyc and self.cyc[1] > 1:
+                    # block-cyclic ownership: sub-slab c of rank r = global block c * world + r (upload_gather_pipelined)
+                    nb, n_sub = self.cyc
+                    idx = torch.cat([torch.arange((c * world + rank) * nb, (c * world + rank + 1) * nb) for c in range(n_sub)]).to(self.device)
+                    self.hXs = d["dX"][idx, :N].cpu().numpy().T
+                else:
+                    self.cyc = None
+                    self.hXs = d["dX"][rank * na:(rank + 1) * na, :N].cpu().numpy().T
             elif rank == 0 and self.hX is None:
                 self.hX = d["dX"][:, :N].cpu().numpy().T
             self.e2e_dev = dict(dX=torch.zeros((p, d["ldx"]), dtype=torch.float64, device=self.device),
@@ -321,7 +333,15 @@ class Bench:
         if q:
             dist.broadcast(dev["dC"], 0)
         slab_events = None
-        if self.shard:                                                   # own columns over the own PCIe link, then over NVLink
+        uploader = None
+        if self.shard and self.cyc:
+            # block-cyclic ownership: a helper thread stages + broadcasts sub-slab after sub-slab while the distance kernel
+            # (launched below, at once) consumes the blocks in attribute order as their events fire
+            from npdr_b200.distributed import upload_gather_pipelined
+            nb, n_sub = self.cyc
+            nb_, events, ready, uploader, up_err = upload_gather_pipelined(self.ctx, dev["dX"], self.data["ldx"], self.hXs, rank, world, nb, n_sub)
+            slab_events = (nb_, events, ready)
+        elif self.shard:                                                 # own columns over the own PCIe link, then over NVLink
             na = p // world
             mine = dev["dX"][rank * na:(rank + 1) * na]
             self.ctx.upload_columns(mine.data_ptr(), self.data["ldx"], self.hXs)
@@ -336,7 +356,14 @@ class Bench:
             dist.broadcast(dev["dX"], 0)
         eng = GpuEngine(device_index=self.local_rank, dX=dev["dX"], ldx=self.data["ldx"], dy=dev["dy"], dC=dev["dC"], N=N, p=p, q=q,
                         slab_events=slab_events)
+        # (with the helper thread: the first collective npdr_sharded issues comes after its distance stage, which returns only
+        # once every block's flag is up, i.e. after the helper has issued its last broadcast -- the two threads never issue
+        # NCCL calls concurrently and every rank issues them in the same order)
         stats, info = npdr_sharded(eng, N, p, "binomial", "numeric-abs", "multisurf", "manhattan", 0, 0.5, self.cdt)
+        if uploader is not None:
+            uploader.join()
+            if up_err:
+                raise up_err[0]
         eng.close()
         return stats, info                                               # stats are host numpy on rank 0: D2H done
 

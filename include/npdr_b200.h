@@ -212,7 +212,7 @@ void npdrb_session_destroy(npdrb_session *s);
  * (helper threads memcpy, async H2D), each slab right before the kernel that consumes it is launched, so the staging of
  * slab i+1 runs under the kernel of slab i.  X must therefore stay valid until the first call that consumes it
  * (distances / neighbours / regress) has returned.  NPDRB_NO_PIPELINED_UPLOAD=1 restores one blocking copy;
- * NPDRB_STAGE_THREADS sets the number of copier threads (default 4). */
+ * NPDRB_STAGE_THREADS sets the number of copier threads (default: host cores / GPUs of the box, between 4 and 8). */
 int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, const double *C);
 /* or adopt device buffers: dX column-major with leading dimension ldx >= N (ldx % 2 == 0), dy[N], dC N x q (ld N) */
 int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t ldx, const double *dy,
@@ -220,8 +220,12 @@ int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t 
 /* The adopted device matrix may still be arriving (one NCCL broadcast per rank's attribute shard, a peer copy, ...): column
  * slab i = attributes [i * slab_cols, (i+1) * slab_cols) is complete once events[i] (cudaEvent_t, owned by the caller, already
  * recorded on the caller's stream) fires.  The next distance call runs one launch per slab, each waiting for its own event
- * only, so the transfer of slab i+1 hides behind the kernel of slab i; results are bit-identical.  slab_cols % 16 == 0. */
-int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events);
+ * only, so the transfer of slab i+1 hides behind the kernel of slab i; results are bit-identical.  slab_cols % 16 == 0.
+ * ready (may be NULL): host flags for transfers that ANOTHER host thread is still issuing while the distance call runs --
+ * events[i] is waited for only after ready[i] != 0 (the producer records the event, then sets the flag); the events must
+ * already exist (have been recorded once), and both arrays must stay valid until the distance call has returned. */
+int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events,
+                                         const int32_t *ready);
 /* rows [row0, row0+nrows) of the distance matrix against all N instances (nrows == N: symmetric mode) */
 int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
 /* adopt a precomputed distance block (device, nrows x N row-major = the columns Ri of a symmetric D) */

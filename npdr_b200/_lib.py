@@ -96,7 +96,7 @@ SIGNATURES = {
     "npdrb_session_set_sd_vec": (C.c_int, [_vp, _dp]),
     "npdrb_session_neighbors": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "npdrb_session_neighbors_hitmiss": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
-    "npdrb_session_set_device_slab_events": (C.c_int, [_vp, _i32, _i64, C.POINTER(_vp)]),
+    "npdrb_session_set_device_slab_events": (C.c_int, [_vp, _i32, _i64, C.POINTER(_vp), C.POINTER(_i32)]),
     "npdrb_session_copy_radius2": (C.c_int, [_vp, _dp]),
     "npdrb_session_sort_rows": (C.c_int, [_vp]),
     "npdrb_session_neighbors_sorted": (C.c_int, [_vp, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
@@ -275,11 +275,13 @@ class Session:
     def set_device_inputs(self, dX=0, ldx=0, dy=0, dC=0):
         check(load().npdrb_session_set_device_inputs(self.handle, _vp(dX or None), int(ldx), _vp(dy or None), _vp(dC or None)))
 
-    def set_device_slab_events(self, slab_cols, events):
-        """events: raw cudaEvent_t handles (ints), one per column slab of the adopted device matrix (see npdr_b200.h)."""
+    def set_device_slab_events(self, slab_cols, events, ready=None):
+        """events: raw cudaEvent_t handles (ints), one per column slab of the adopted device matrix; ready: optional int32
+        numpy array of host flags set by the thread that issues the transfers (see npdr_b200.h)."""
         arr = (_vp * len(events))(*[int(e) for e in events])
-        self._slab_events = arr
-        check(load().npdrb_session_set_device_slab_events(self.handle, len(events), int(slab_cols), arr))
+        self._slab_events = (arr, ready)
+        rp = ready.ctypes.data_as(C.POINTER(_i32)) if ready is not None else None
+        check(load().npdrb_session_set_device_slab_events(self.handle, len(events), int(slab_cols), arr, rp))
 
     def distances(self, metric="manhattan", fast_euclidean=False, row0=0, nrows=None):
         nrows = self.N if nrows is None else nrows

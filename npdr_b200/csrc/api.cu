@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <condition_variable>
 #include <map>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -157,10 +158,16 @@ static int get_ring(npdrb_ctx *ctx, nb_stage_ring **out) {
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->done[b], cudaEventDisableTiming);
             if (e != cudaSuccess) { delete r; npdrb_set_error("pinned staging ring: %s", cudaGetErrorString(e)); return NPDRB_ENOMEM; }
         }
-        int want = 3;                                     // + the calling thread = 4 copiers; NPDRB_STAGE_THREADS overrides
+        // copiers (helpers + the calling thread): the host's cores shared out among the box's GPUs (every GPU may be staging at
+        // the same time), between 4 and 8 -- one core moves ~10 GB/s, a PCIe 5 x16 link ~55 GB/s; NPDRB_STAGE_THREADS overrides
+        const unsigned hw = std::thread::hardware_concurrency();
+        int ndev = 1;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
+        int copiers = hw ? (int)hw / ndev : 4;
+        copiers = copiers < 4 ? 4 : (copiers > 8 ? 8 : copiers);
+        int want = copiers - 1;
         const char *e = getenv("NPDRB_STAGE_THREADS");
         if (e && atoi(e) >= 1) want = atoi(e) - 1;
-        const unsigned hw = std::thread::hardware_concurrency();
         if (hw && want > (int)hw - 1) want = (int)hw - 1;
         if (want > 15) want = 15;
         r->start(want < 0 ? 0 : want);
@@ -252,7 +259,24 @@ int nb_check_finite(npdrb_ctx *ctx, const double *d, int64_t n, const char *what
 
 int nb_issue_slab(npdrb_session *s, int slab) {
     npdrb_ctx *ctx = s->ctx;
-    if (s->slab_ev_external) { if (slab + 1 > s->n_slabs_issued) s->n_slabs_issued = slab + 1; return NPDRB_OK; }   // the caller's copies are already in flight
+    if (s->slab_ev_external) {
+        // the caller's transfers are in flight (or, with ready flags, being issued by another host thread right now: an event
+        // must have been recorded before a stream may wait for it, so wait for the producer's flag first)
+        for (int i = s->n_slabs_issued; i <= slab && i < s->n_slabs_pending; ++i) {
+            if (s->slab_ready) {
+                const auto t0 = std::chrono::steady_clock::now();
+                while (__atomic_load_n(&s->slab_ready[i], __ATOMIC_ACQUIRE) == 0) {
+                    std::this_thread::yield();
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+                        npdrb_set_error("column slab %d of the adopted matrix never became ready (producer stalled?)", i);
+                        return NPDRB_ECUDA;
+                    }
+                }
+            }
+            s->n_slabs_issued = i + 1;
+        }
+        return NPDRB_OK;
+    }
     for (int i = s->n_slabs_issued; i <= slab && i < s->n_slabs_pending; ++i) {
         const int64_t c0 = (int64_t)i * s->slab_cols, c1 = (c0 + s->slab_cols < s->p) ? c0 + s->slab_cols : s->p;
         if (!s->hX_lazy) { npdrb_set_error("upload: slab %d has no host source", i); return NPDRB_EINVAL; }
@@ -535,7 +559,7 @@ int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t 
             if (!s->slab_ev_external && s->ctx->copy_stream) cudaStreamSynchronize(s->ctx->copy_stream);
             s->n_slabs_pending = 0; s->n_slabs_issued = 0; s->hX_lazy = nullptr;
         }
-        if (s->slab_ev_external) { s->slab_ev.clear(); s->slab_ev_external = false; }
+        if (s->slab_ev_external) { s->slab_ev.clear(); s->slab_ev_external = false; s->slab_ready = nullptr; }
         if (ldx < s->N || (ldx & 1)) { npdrb_set_error("set_device_inputs: ldx must be even and >= N"); return NPDRB_EINVAL; }
         if (((uintptr_t)dX) & 15) { npdrb_set_error("set_device_inputs: dX must be 16-byte aligned"); return NPDRB_EINVAL; }
         if (s->own_X) cudaFree(s->dX);
@@ -547,7 +571,7 @@ int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t 
     return NPDRB_OK;
 }
 
-int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events) {
+int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events, const int32_t *ready) {
     // The adopted device matrix is still ARRIVING (e.g. an NCCL broadcast per rank's attribute shard on the caller's
     // communication stream): column slab i = attributes [i * slab_cols, (i + 1) * slab_cols) is complete once events[i] fires.
     // The distance stage then runs one launch per slab, each waiting for its own event only (same per-element order
@@ -565,7 +589,8 @@ int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int6
         s->slab_ev[(size_t)i] = (cudaEvent_t)events[i];
     }
     s->slab_ev_external = true;
-    s->slab_cols = slab_cols; s->n_slabs_pending = n_slabs; s->n_slabs_issued = n_slabs; s->hX_lazy = nullptr;
+    s->slab_ready = ready;
+    s->slab_cols = slab_cols; s->n_slabs_pending = n_slabs; s->n_slabs_issued = ready ? 0 : n_slabs; s->hX_lazy = nullptr;
     return NPDRB_OK;
 }
 

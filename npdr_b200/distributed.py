@@ -216,6 +216,62 @@ def gather_columns_pipelined(dX, world, ncols, group=None):
     return ncols, events
 
 
+def cyclic_blocks(p, world, max_sub=8):
+    """Block size nb for the cyclic attribute layout of upload_gather_pipelined: the p // world columns of a rank are cut into
+    n_sub sub-slabs of nb columns (nb % 16 == 0); global block b = c * world + r (sub-slab c of rank r) covers attributes
+    [b * nb, (b + 1) * nb).  -> (nb, n_sub) or None when p does not split that way."""
+    if p % world:
+        return None
+    na = p // world
+    for n_sub in range(max_sub, 0, -1):
+        if na % n_sub == 0 and (na // n_sub) % 16 == 0:
+            return na // n_sub, n_sub
+    return None
+
+
+def upload_gather_pipelined(ctx, dX, ldx, host_cols, rank, world, nb, n_sub, group=None):
+    """Upload AND replicate an attribute-sharded matrix underneath the distance stage.  Ownership is block-cyclic (see
+    cyclic_blocks), so the order in which sub-slabs become available everywhere -- sub-slab 0 of every rank, then sub-slab 1,
+    ... -- IS the attribute order k = 0..p-1 the distance kernel consumes.  A helper thread stages sub-slab c of this rank's
+    host columns (host_cols: N x (n_sub * nb), Fortran order, pageable is fine) through the library's pinned ring, then issues
+    one asynchronous NCCL broadcast per rank for that sub-slab, records an event per block and raises its host flag; the
+    caller passes the result to GpuEngine(slab_events=...) at once and the distance call (npdrb_session_set_device_slab_events
+    with ready flags) starts consuming block 0 while later sub-slabs are still crossing PCIe.
+    -> (nb, events, ready, thread); join the thread after the distance stage."""
+    import threading
+    dev = dX.device
+    n_blocks = n_sub * world
+    side = torch.cuda.Stream(device=dev)
+    issue = torch.cuda.Stream(device=dev)        # the collectives must not queue behind the distance launches of the caller's stream
+    events = [torch.cuda.Event() for _ in range(n_blocks)]
+    for e in events:
+        e.record(side)                           # creates the handles; re-recorded when the block's transfer has been issued
+    ready = np.zeros(n_blocks, dtype=np.int32)
+    err = []
+
+    def work():
+        try:
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(issue):
+                for c in range(n_sub):
+                    b_own = c * world + rank
+                    ctx.upload_columns(dX[b_own * nb:(b_own + 1) * nb].data_ptr(), ldx, host_cols[:, c * nb:(c + 1) * nb])
+                    for r in range(world):
+                        b = c * world + r
+                        work_ = dist.broadcast(dX[b * nb:(b + 1) * nb], src=r, group=group, async_op=True)
+                        with torch.cuda.stream(side):
+                            work_.wait()
+                            events[b].record(side)
+                        ready[b] = 1
+        except Exception as ex:                  # unblock the consumer; it will fail on the data check
+            err.append(ex)
+            ready[:] = 1
+
+    th = threading.Thread(target=work, name="npdr-upload-gather")
+    th.start()
+    return nb, events, ready, th, err
+
+
 class GpuEngine(Engine):
     """libnpdr_b200 session on this rank's GPU.  Inputs are uploaded once (or adopted from device tensors)."""
 
@@ -239,8 +295,9 @@ class GpuEngine(Engine):
             else:
                 torch.cuda.current_stream(self.device).synchronize()   # y / C only: the column slabs of X are still in flight
             self.session.set_device_inputs(dX.data_ptr(), ldx, dy.data_ptr(), dC.data_ptr() if dC is not None else 0)
-            if slab_events is not None:              # (slab_cols, [torch.cuda.Event]): X arrives slab by slab (gather_columns_pipelined)
-                self.session.set_device_slab_events(slab_events[0], [e.cuda_event for e in slab_events[1]])
+            if slab_events is not None:              # (slab_cols, [torch.cuda.Event][, ready flags]): X arrives slab by slab
+                self.session.set_device_slab_events(slab_events[0], [e.cuda_event for e in slab_events[1]],
+                                                    slab_events[2] if len(slab_events) > 2 else None)
         self._metric_done = None
 
     def close(self):

@@ -22,6 +22,8 @@ def main():
         f.write(f"# {title}\n\nsource: `{rep.split('/')[-1]}` (ncu --set full --clock-control none; values are per launch)\n")
         for vals in rows[2:]:
             d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
+            if "nan" in d.get("smsp__inst_executed.sum", ("", ""))[1]:
+                continue                                    # a capture that was cut off mid-replay
             f.write(f"\n## {d.get('Kernel Name', ('', '?'))[1]}\n\n| metric | unit | value |\n|---|---|---|\n")
             for k in KEYS:
                 if k in d:

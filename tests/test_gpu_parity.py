@@ -1000,6 +1000,55 @@ def test_device_slab_events_distances_bit_exact(nb, oracle):
         assert np.array_equal(got, D[row0:row0 + nrows]), (row0, nrows)
 
 
+def test_device_slab_events_with_ready_flags(nb, oracle):
+    """The producer of the column slabs runs on ANOTHER host thread while the distance call is already running (the
+    block-cyclic upload + broadcast pipeline of the multi-GPU end-to-end arm): events are pre-created, the producer records
+    them and raises a host flag per slab, the library waits for the flag before it makes its stream wait for the event."""
+    import threading
+    import time
+    import torch
+    from npdr_b200 import _lib
+    rng = np.random.default_rng(93)
+    N, p, ncols = 600, 5 * 128, 128
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    D = oracle.distances(X, "manhattan")
+    dev = torch.device("cuda", 0)
+    ldx = N + (N % 2)
+    src = torch.zeros((p, ldx), dtype=torch.float64, device=dev)
+    src[:, :N] = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)
+    dX = torch.full((p, ldx), float("nan"), dtype=torch.float64, device=dev)
+    dy = torch.zeros(N, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=dev)
+    n = p // ncols
+    events = [torch.cuda.Event() for _ in range(n)]
+    for e in events:
+        e.record(side)
+    ready = np.zeros(n, dtype=np.int32)
+
+    def producer():
+        torch.cuda.set_device(dev)
+        for g in range(n):
+            time.sleep(0.02)
+            with torch.cuda.stream(side):
+                dX[g * ncols:(g + 1) * ncols].copy_(src[g * ncols:(g + 1) * ncols], non_blocking=True)
+                events[g].record(side)
+            ready[g] = 1
+
+    s = _lib.Session(_lib.context(0), N, p, 0)
+    try:
+        s.set_device_inputs(dX.data_ptr(), ldx, dy.data_ptr(), 0)
+        s.set_device_slab_events(ncols, [e.cuda_event for e in events], ready)
+        th = threading.Thread(target=producer)
+        th.start()
+        s.distances("manhattan", False, 0, N)
+        th.join()
+        got = s.copy_distances()
+    finally:
+        s.close()
+    assert np.array_equal(got, D)
+
+
 # ---------------------------------------------------------------- in-process multi-GPU driver (npdrb_npdr_multi)
 @pytest.mark.parametrize("name", ["cfg1", "cfg3"])
 def test_npdr_multi_driver_one_device(nb, name):
