@@ -314,6 +314,24 @@ class Bench:
             self.hy = d["dy"].cpu().numpy()
             self.hC = np.asfortranarray(d["dC"].cpu().numpy().T) if self.q else None
 
+    def pin_host(self):
+        """Replace the host copies of X by pinned ones (same layout); unpin_host() restores the pageable arrays."""
+        torch = self.torch
+        self._pageable = (self.hX, self.hXs)
+
+        def pinned(a):
+            if a is None:
+                return None
+            t = torch.empty((a.shape[1], a.shape[0]), dtype=torch.float64, pin_memory=True)      # (columns, N) C order = Fortran (N, columns)
+            t.copy_(torch.from_numpy(np.ascontiguousarray(a.T)))
+            self._pinned_keep = getattr(self, "_pinned_keep", []) + [t]
+            return t.numpy().T
+        self.hX, self.hXs = pinned(self.hX), pinned(self.hXs)
+
+    def unpin_host(self):
+        self.hX, self.hXs = self._pageable
+        self._pinned_keep = []
+
     def step_e2e(self):
         import torch.distributed as dist
         import npdr_b200 as nb
@@ -465,7 +483,7 @@ class Bench:
                 out["multi_gpu_check"] = self.multi_gpu_check(stats_h, info_h)
             self.barrier()
 
-        out["e2e"] = out["e2e_inproc"] = None
+        out["e2e"] = out["e2e_inproc"] = out["e2e_pinned"] = None
         if e2e:
             self.prepare_host(inproc and world > 1)
             e_steps = max(1, min(steps, 3))
@@ -480,6 +498,15 @@ class Bench:
                                    ("every rank uploads its attribute columns from pageable memory over its own PCIe link, NCCL all-gather over "
                                     "NVLink; y(/C) from rank 0; statistics read back on rank 0" if self.shard else
                                     "rank 0 uploads pageable X/y(/C) and broadcasts over NVLink (NCCL) every step; statistics read back on rank 0"))}
+            # the same arm from PINNED host buffers (the base contract's wording): the copies are plain DMA, no staging memcpy.
+            # With pageable inputs every byte crosses host DRAM three times (read, staged write, DMA read); on an 8-GPU box
+            # that staging of the whole data set is what bounds the pageable arm, not the GPUs or NVLink.
+            self.pin_host()
+            ms_p, _, _ = self.timed(self.step_e2e, e_steps, 1 if steps > 1 else 0)
+            ms_p /= e_steps
+            out["e2e_pinned"] = {"value": float(p) * M / (ms_p * 1e-3), "unit": "evals/s", "ms_per_step": ms_p, "h2d_bytes_per_step": h2d,
+                                 "d2h_bytes_per_step": int(p * 8 * 8), "host_memory": "pinned (cudaHostAlloc)"}
+            self.unpin_host()
             if inproc and world > 1:
                 ms_i, res_i = self.run_inproc(e_steps, 1 if steps > 1 else 0)
                 if rank == 0:
@@ -628,7 +655,7 @@ def main():
         line = {"metric": "npdr_attr_x_pair_glm_evals_per_s", "value": res["value"], "unit": "evals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": wl["scaling"],
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl_name, world),
-                "pairs_M": res["pairs_M"], "e2e": res["e2e"], "e2e_inproc": res["e2e_inproc"], "gpu_launches": res["gpu_launches"],
+                "pairs_M": res["pairs_M"], "e2e": res["e2e"], "e2e_pinned": res.get("e2e_pinned"), "e2e_inproc": res["e2e_inproc"], "gpu_launches": res["gpu_launches"],
                 "clocks": res["clocks"], "roofline": res["roofline"], "cpu_baseline": res["cpu_baseline"], "stages": res["stages"],
                 "fp64_peak_measured": res["fp64_peak_measured"], "variants": res["variants"], "multi_gpu_check": res["multi_gpu_check"],
                 "target": target,

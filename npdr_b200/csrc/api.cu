@@ -403,9 +403,15 @@ int npdrb_upload_columns(npdrb_ctx *ctx, void *dst_device, int64_t ld_dst, const
     NB_CUDA(cudaSetDevice(ctx->device));
     if (ncols == 0) return NPDRB_OK;
     if (nb_host_pointer_is_pinned(src_host)) {
+        // on the copy stream, never the context's main stream: that one may already hold distance launches waiting for this
+        // very data (block-cyclic upload pipeline, where another host thread calls this function)
+        {
+            std::lock_guard<std::mutex> lk(g_ring_mu);
+            if (!ctx->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        }
         NB_CUDA(cudaMemcpy2DAsync(dst_device, sizeof(double) * (size_t)ld_dst, src_host, sizeof(double) * (size_t)rows,
-                                  sizeof(double) * (size_t)rows, (size_t)ncols, cudaMemcpyHostToDevice, ctx->stream));
-        NB_CUDA(cudaStreamSynchronize(ctx->stream));
+                                  sizeof(double) * (size_t)rows, (size_t)ncols, cudaMemcpyHostToDevice, ctx->copy_stream));
+        NB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
         return NPDRB_OK;
     }
     NB_CHECK(nb_staged_h2d(ctx, (double *)dst_device, ld_dst, src_host, rows, ncols));

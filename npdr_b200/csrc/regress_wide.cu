@@ -143,7 +143,7 @@ __device__ void wide_write_stats(double *st, const double *beta, const double *s
 }
 
 template <int KT>
-__global__ void __launch_bounds__(WT, 1)
+__global__ void __launch_bounds__(WT, KT == 64 ? 1 : 2)      // narrow designs: two CTAs per SM hide the block loads' latency
 wide_fit_kernel(WideArgs P) {
     using S = WideSmem<KT>;
     constexpr int LD = S::LD, NT = S::NT, TPG = S::TPG, NG = S::NG;
