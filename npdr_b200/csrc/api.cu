@@ -582,7 +582,7 @@ int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int6
     // communication stream): column slab i = attributes [i * slab_cols, (i + 1) * slab_cols) is complete once events[i] fires.
     // The distance stage then runs one launch per slab, each waiting for its own event only (same per-element order
     // k = 0..p-1, so the result is bit-identical), and the transfer of slab i+1 hides behind the kernel of slab i.
-    if (!s->dX || s->own_X) { npdrb_set_error("set_device_slab_events: adopt the device matrix first (npdrb_session_set_device_inputs)"); return NPDRB_EINVAL; }
+    if (!s->dX) { npdrb_set_error("set_device_slab_events: the session has no device matrix yet (npdrb_session_set_device_inputs)"); return NPDRB_EINVAL; }
     if (n_slabs < 1 || !events || slab_cols < 1 || (slab_cols % 16) != 0 || (int64_t)(n_slabs - 1) * slab_cols >= s->p ||
         (int64_t)n_slabs * slab_cols < s->p) {
         npdrb_set_error("set_device_slab_events: need n_slabs slabs of slab_cols (a multiple of 16) columns covering the p attributes");

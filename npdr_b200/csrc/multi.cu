@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -50,6 +51,18 @@ struct Worker {
     int64_t surf_band = 0;                           // distances of my block inside the SURF guard band
     int32_t irls_passes = 0;
     double ms_distance = 0, ms_neighbors = 0, ms_prepare = 0, ms_regress = 0;
+    // block-cyclic upload + peer-pull pipeline (run_producer): this device's upload events (one per sub-slab), the events and
+    // host flags the distance call waits for (one per global block), the stream the peer pulls are issued on
+    std::vector<cudaEvent_t> ev_up;
+    std::vector<void *> ev_slab;
+    std::vector<cudaEvent_t> ev_pull;                // the events of ev_slab this worker owns (blocks pulled from peers)
+    std::vector<int32_t> slab_ready;
+    cudaStream_t pull_stream = nullptr;
+    ~Worker() {
+        for (cudaEvent_t e : ev_up) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : ev_pull) if (e) cudaEventDestroy(e);
+        if (pull_stream) cudaStreamDestroy(pull_stream);
+    }
 };
 
 struct Shared {
@@ -65,6 +78,12 @@ struct Shared {
     double *stats = nullptr;                         // p x 8, host
     int64_t k = 0;
     int64_t M_total = 0;
+    // Pipelined replication of X (pipe_nb > 0).  Ownership of the attribute columns is block-cyclic: sub-slab c of device g is
+    // global block c * G + g (pipe_nb columns).  Every device stages its sub-slabs one after the other over its own PCIe
+    // link; as soon as sub-slab c of a peer is on that peer (up_ready), the block is pulled over NVLink; the distance kernel
+    // of every device consumes block after block in attribute order while later sub-slabs are still being staged.
+    int64_t pipe_nb = 0; int pipe_nsub = 0;
+    std::unique_ptr<std::atomic<int>[]> up_ready;    // [G][pipe_nsub]
     std::vector<double> hostD;                       // SURF exact replay: the gathered distance matrix
     double surf_radius_exact = 0.0;
 };
@@ -89,6 +108,45 @@ void fail(Shared &S, Worker &w, int rc) {
 #define STEP(call) do { if (!S.failed.load() && w.rc == NPDRB_OK) { int rc__ = (call); if (rc__ != NPDRB_OK) fail(S, w, rc__); } } while (0)
 #define CU(call) ([&]() -> int { cudaError_t e__ = (call); if (e__ != cudaSuccess) { npdrb_set_error("%s: %s", #call, cudaGetErrorString(e__)); return NPDRB_ECUDA; } return NPDRB_OK; }())
 
+// The upload / pull side of the pipeline for device g (its own host thread; the device's worker thread is inside the
+// distance call meanwhile and waits, block by block, for slab_ready + the block's event).
+void run_producer(Shared &S, int g) {
+    Worker &w = S.w[(size_t)g];
+    const int G = S.G, nsub = S.pipe_nsub;
+    const int64_t nb = S.pipe_nb, ldx = w.s->ldx;
+    int rc = NPDRB_OK;
+    if (cudaSetDevice(w.dev) != cudaSuccess) rc = NPDRB_ECUDA;
+    for (int c = 0; c < nsub && rc == NPDRB_OK && !S.failed.load(); ++c) {
+        const int64_t b_own = (int64_t)c * G + g;
+        rc = npdrb_upload_columns(w.ctx, w.s->dX + b_own * nb * ldx, ldx, S.X + b_own * nb * S.N, S.N, nb);   // pageable: pinned ring
+        if (rc == NPDRB_OK) rc = CU(cudaEventRecord(w.ev_up[(size_t)c], w.ctx->copy_stream));
+        S.up_ready[(size_t)g * nsub + c].store(1, std::memory_order_release);
+        for (int r = 0; r < G && rc == NPDRB_OK; ++r) {
+            const int64_t b = (int64_t)c * G + r;
+            if (r != g) {
+                const Worker &peer = S.w[(size_t)r];
+                const auto t0 = std::chrono::steady_clock::now();
+                while (!S.up_ready[(size_t)r * nsub + c].load(std::memory_order_acquire) && !S.failed.load()) {
+                    std::this_thread::yield();
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) { npdrb_set_error("peer upload stalled"); rc = NPDRB_ECUDA; break; }
+                }
+                if (rc != NPDRB_OK || S.failed.load()) break;
+                rc = CU(cudaStreamWaitEvent(w.pull_stream, peer.ev_up[(size_t)c], 0));
+                if (rc == NPDRB_OK)
+                    rc = CU(cudaMemcpyPeerAsync(w.s->dX + b * nb * ldx, w.dev, peer.s->dX + b * nb * ldx, peer.dev,
+                                                sizeof(double) * (size_t)ldx * (size_t)nb, w.pull_stream));
+                if (rc == NPDRB_OK) rc = CU(cudaEventRecord((cudaEvent_t)w.ev_slab[(size_t)b], w.pull_stream));
+            }
+            if (rc == NPDRB_OK) __atomic_store_n(&w.slab_ready[(size_t)b], 1, __ATOMIC_RELEASE);
+        }
+    }
+    if (rc != NPDRB_OK || S.failed.load()) {             // unblock everybody who waits for this device; the call fails as a whole
+        if (rc != NPDRB_OK) fail(S, w, rc);
+        for (int c = 0; c < nsub; ++c) S.up_ready[(size_t)g * nsub + c].store(1, std::memory_order_release);
+        for (size_t b = 0; b < w.slab_ready.size(); ++b) __atomic_store_n(&w.slab_ready[b], 1, __ATOMIC_RELEASE);
+    }
+}
+
 void run_worker(Shared &S, int g) {
     Worker &w = S.w[(size_t)g];
     const npdrb_opts &o = *S.o;
@@ -111,6 +169,26 @@ void run_worker(Shared &S, int g) {
         double *dX = nullptr;
         STEP(CU(cudaMalloc(&dX, sizeof(double) * (size_t)ldx * (size_t)S.p)));
         if (dX && ldx != S.N) STEP(CU(cudaMemsetAsync(dX, 0, sizeof(double) * (size_t)ldx * (size_t)S.p, w.ctx->stream)));
+        if (S.pipe_nb > 0) {
+            // pipelined replication: events and flags first, the transfers themselves run beside the distance call (phase 1)
+            STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
+            if (w.s && dX) { w.s->dX = dX; w.s->ldx = ldx; w.s->own_X = true; }
+            else if (dX) cudaFree(dX);
+            const size_t n_blocks = (size_t)S.pipe_nsub * (size_t)S.G;
+            w.ev_up.assign((size_t)S.pipe_nsub, nullptr);
+            w.ev_slab.assign(n_blocks, nullptr);
+            w.slab_ready.assign(n_blocks, 0);
+            STEP(CU(cudaStreamCreateWithFlags(&w.pull_stream, cudaStreamNonBlocking)));
+            for (int c = 0; c < S.pipe_nsub; ++c) STEP(CU(cudaEventCreateWithFlags(&w.ev_up[(size_t)c], cudaEventDisableTiming)));
+            for (size_t b = 0; b < n_blocks; ++b) {
+                if ((int)(b % (size_t)S.G) == g) { w.ev_slab[b] = (void *)w.ev_up[b / (size_t)S.G]; continue; }
+                cudaEvent_t e = nullptr;
+                STEP(CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)));
+                w.ev_pull.push_back(e);
+                w.ev_slab[b] = (void *)e;
+            }
+            if (S.bar->wait(S.failed)) return;           // every device's buffer and events exist
+        } else {
         if (dX && w.nattr > 0) {
             if (nb_host_pointer_is_pinned(S.X)) {
                 STEP(CU(cudaMemcpy2DAsync(dX + w.attr0 * ldx, sizeof(double) * (size_t)ldx, S.X + w.attr0 * S.N, sizeof(double) * (size_t)S.N,
@@ -133,8 +211,15 @@ void run_worker(Shared &S, int g) {
         }
         STEP(CU(cudaStreamSynchronize(w.ctx->stream)));
         STEP(nb_check_finite(w.ctx, w.s ? w.s->dX : nullptr, ldx * S.p, "the attribute matrix"));
+        }
     }
     // ---- phase 1: this device's share of the distance matrix, packed halves for the peers
+    std::thread producer;
+    const bool piped = S.pipe_nb > 0 && S.G > 1 && !S.failed.load() && w.rc == NPDRB_OK && w.s;
+    if (piped) {
+        STEP(npdrb_session_set_device_slab_events(w.s, (int32_t)w.ev_slab.size(), S.pipe_nb, w.ev_slab.data(), w.slab_ready.data()));
+        producer = std::thread(run_producer, std::ref(S), g);
+    }
     if (w.live >= 0) {
         if (W == 1) STEP(nb_distances(w.s, o.nbd_metric, o.fast_euclidean, 0, S.N));
         else {
@@ -148,6 +233,7 @@ void run_worker(Shared &S, int g) {
         }
         if (w.s) w.ms_distance = w.s->ms_distance;
     }
+    if (producer.joinable()) producer.join();
     if (S.bar->wait(S.failed)) return;
     // ---- phase 2: pull the halves the peers computed for my rows, unpack
     double *d_recv = nullptr;
@@ -294,6 +380,20 @@ extern "C" int npdrb_npdr_multi(int32_t n_devices, const int32_t *devices, const
         a0 += w.nattr;
     }
     S.row_starts.push_back(N);
+    {
+        // pipelined replication of X: every device owns rows (it consumes the blocks itself) and the columns split into
+        // G x n_sub blocks of a multiple of 16 columns
+        const char *np_ = getenv("NPDRB_NO_PIPELINED_GATHER");
+        if (n_devices > 1 && (int)S.live_devs.size() == n_devices && p % n_devices == 0 && !(np_ && np_[0] == '1')) {
+            const int64_t na = p / n_devices;
+            for (int n_sub = 8; n_sub >= 2 && S.pipe_nb == 0; --n_sub)
+                if (na % n_sub == 0 && (na / n_sub) % 16 == 0) { S.pipe_nb = na / n_sub; S.pipe_nsub = n_sub; }
+            if (S.pipe_nb > 0) {
+                S.up_ready.reset(new std::atomic<int>[(size_t)n_devices * (size_t)S.pipe_nsub]);
+                for (size_t i = 0; i < (size_t)n_devices * (size_t)S.pipe_nsub; ++i) S.up_ready[i].store(0);
+            }
+        }
+    }
     res->stats = (double *)malloc(sizeof(double) * (size_t)p * NPDRB_STATS_PER_ATTR);
     if (!res->stats) { npdrb_set_error("out of host memory"); return NPDRB_ENOMEM; }
     S.stats = res->stats;

@@ -1771,7 +1771,8 @@ __global__ void irls_step_kernel(SolveArgs S) {
 
 // Exact residual deviance of the parked attributes at two coefficient vectors, record by record over the ORIGINAL pair list,
 // with libdevice exp / log and binomial()'s eta clamps -- dev.resids as glm.fit forms them (stats family.c, R/npdr.R:36).
-// One CTA per attribute (exits at once unless parked); fixed-order block reduction.
+// grid = (attributes, splits of the pair list); CTAs of attributes that are not parked exit at once; fixed-order reductions
+// (inside a CTA, then over the splits in exact_dev_reduce_kernel), so the result does not depend on scheduling.
 struct ExactArgs {
     const double *X; int64_t ldx; int64_t attr0; int nattr, nattr_pad; int64_t N;
     const int32_t *Ri, *NN; int64_t M;
@@ -1779,6 +1780,8 @@ struct ExactArgs {
     int cov_type[NB_FAST_COVARS];
     const double *beta, *beta_prev; const unsigned char *ambig;
     double *dev_exact;             // [2][nattr_pad]
+    double *part;                  // [nattr][n_split][2]
+    int n_split;
 };
 __device__ __forceinline__ double exact_dev_term(double eta, bool miss) {
     const double t = (eta < -30.0) ? 2.220446049250313e-16 : ((eta > 30.0) ? 4503599627370496.0 : exp(eta));
@@ -1795,7 +1798,9 @@ exact_dev_kernel(ExactArgs E) {
     for (int r = 0; r < K; ++r) { b0[r] = E.beta[(int64_t)r * E.nattr_pad + a]; b1[r] = E.beta_prev[(int64_t)r * E.nattr_pad + a]; }
     const double *xcol = E.X + (E.attr0 + a) * E.ldx;
     double s0 = 0.0, s1 = 0.0;
-    for (int64_t m = threadIdx.x; m < E.M; m += 256) {
+    const int64_t per = (E.M + E.n_split - 1) / E.n_split;
+    const int64_t m_lo = (int64_t)blockIdx.y * per, m_hi = (m_lo + per < E.M) ? m_lo + per : E.M;
+    for (int64_t m = m_lo + threadIdx.x; m < m_hi; m += 256) {
         const int64_t i = E.Ri[m] - 1, j = E.NN[m] - 1;
         const double d = nb_diff1(xcol[i], xcol[j], E.diff_type);
         const bool miss = E.y_raw ? (E.y[i] != 0.0) : (E.y[i] != E.y[j]);
@@ -1813,7 +1818,17 @@ exact_dev_kernel(ExactArgs E) {
         if ((int)threadIdx.x < o) { red0[threadIdx.x] += red0[threadIdx.x + o]; red1[threadIdx.x] += red1[threadIdx.x + o]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { E.dev_exact[a] = red0[0]; E.dev_exact[E.nattr_pad + a] = red1[0]; }
+    if (threadIdx.x == 0) {
+        double *o = E.part + ((int64_t)a * E.n_split + blockIdx.y) * 2;
+        o[0] = red0[0]; o[1] = red1[0];
+    }
+}
+__global__ void exact_dev_reduce_kernel(ExactArgs E) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= E.nattr || !E.ambig[a]) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int y = 0; y < E.n_split; ++y) { const double *o = E.part + ((int64_t)a * E.n_split + y) * 2; s0 += o[0]; s1 += o[1]; }
+    E.dev_exact[a] = s0; E.dev_exact[E.nattr_pad + a] = s1;
 }
 
 // ------------------------------------------------------------------ host side
@@ -2440,7 +2455,15 @@ int nb_regress(npdrb_session *s, int64_t attr0, int64_t nattr, int32_t reg_type,
                     E.Ri = s->dRi; E.NN = s->dNN; E.M = s->M; E.y = s->dy; E.C = s->dC; E.q = q; E.diff_type = diff_type; E.y_raw = y_raw;
                     for (int c = 0; c < q; ++c) E.cov_type[c] = cov_type ? cov_type[c] : NPDRB_DIFF_MATCH_MISMATCH;
                     E.beta = d_beta; E.beta_prev = d_beta_prev; E.ambig = d_ambig; E.dev_exact = d_dev_exact;
-                    exact_dev_kernel<<<(unsigned)nattr, 256, 0, ctx->stream>>>(E);
+                    int n_split = (int)(s->M >> 20);             // ~1 M pairs per CTA
+                    n_split = n_split < 1 ? 1 : (n_split > 64 ? 64 : n_split);
+                    { const char *xs = getenv("NPDRB_EXACT_SPLIT"); if (xs && atoi(xs) >= 1 && atoi(xs) <= 1024) n_split = atoi(xs); }   // tests
+                    double *d_xpart = nullptr;
+                    NB_CHECK(scope.alloc(&d_xpart, (size_t)nattr * n_split * 2));
+                    E.part = d_xpart; E.n_split = n_split;
+                    exact_dev_kernel<<<dim3((unsigned)nattr, (unsigned)n_split), 256, 0, ctx->stream>>>(E);
+                    NB_LAUNCH_CHECK(ctx);
+                    exact_dev_reduce_kernel<<<(unsigned)nb_cdiv(nattr, 256), 256, 0, ctx->stream>>>(E);
                     NB_LAUNCH_CHECK(ctx);
                     S.resolve = 1;
                     NB_CHECK(launch_solve(ctx, q, SOLVE_IRLS_STEP, S));

@@ -153,9 +153,12 @@ int orc_distances(const double *X, int64_t N, int64_t p, int metric, double *D) 
     return ORC_OK;
 }
 
-/* hamming.binary, R/utils.R:185-188: D <- t(1 - X) %*% X; D + t(D) on the *transposed*
- * input (X there is attributes x instances).  Restated directly: number of attributes
- * on which two 0/1 instances differ. */
+/* hamming.binary, R/utils.R:185-188: D <- t(1 - X) %*% X; D + t(D).  npdrDistances calls it on the m x p
+ * attribute matrix as it stands (R/nearestNeighbors.R:72-73), for which that expression is a p x p
+ * attribute-by-attribute matrix -- it is an instance distance only for an attributes x instances input.
+ * Restated here as the N x N INSTANCE distance the neighbour search needs (the formula applied to t(X)):
+ * the number of attributes on which two 0/1 instances differ.  A documented deviation from the reference
+ * as written (deviation 8). */
 int orc_hamming(const double *X, int64_t N, int64_t p, double *D) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < N; ++i)

@@ -489,6 +489,10 @@ def test_stopping_decision_is_exact_near_epsilon(nb, oracle, monkeypatch):
         st = s.regress(0, p, "binomial", "allele-sharing", ())
         assert s.regress_design()["n_exact_stops"] >= 1
         _stats_close(st, exp, RTOL_IRLS, "exact stopping decision")
+        monkeypatch.setenv("NPDRB_EXACT_SPLIT", "7")                 # the pair list split over several CTAs per attribute (large M)
+        st7 = s.regress(0, p, "binomial", "allele-sharing", ())
+        monkeypatch.delenv("NPDRB_EXACT_SPLIT")
+        _stats_close(st7, exp, RTOL_IRLS, "exact stopping decision, split pair list")
         monkeypatch.setenv("NPDRB_NO_EXACT_STOP", "1")
         st2 = s.regress(0, p, "binomial", "allele-sharing", ())
         assert s.regress_design()["n_exact_stops"] == 0
@@ -1089,6 +1093,28 @@ def test_npdr_multi_driver_two_devices(nb, oracle, method, hitmiss, ndev, monkey
     exp = oracle.regress_attrs(X, ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"), cd)
     _stats_close(info["stats"], exp, RTOL_IRLS, f"multi {method}")
     assert set(out["att"][:4]) == {"1", "2", "3", "4"}
+
+
+@pytest.mark.parametrize("ndev", [2, 3])
+@pytest.mark.parametrize("method", ["multisurf", "relieff"])
+def test_npdr_multi_driver_pipelined_replication(nb, oracle, ndev, method, monkeypatch):
+    """In-process driver with the block-cyclic upload + peer-pull pipeline (p splits into G x n_sub blocks of a multiple of 16
+    columns): every device stages sub-slab after sub-slab of its own columns while its distance kernel consumes the blocks in
+    attribute order.  Same pair list (bit for bit) and statistics as the oracle, and as the driver without the pipeline."""
+    rng = np.random.default_rng(34)
+    N, p = 700, 384                                              # 2 devices: 6 sub-slabs of 32 columns; 3 devices: 8 of 16
+    X = np.asfortranarray(rng.normal(size=(N, p)))
+    y = (rng.random(N) < 0.5).astype(float)
+    X[:, :4] += 0.7 * y[:, None]
+    devs = _multi_devices(ndev, monkeypatch)
+    _, info = nb.npdr(y, X, "binomial", "numeric-abs", method, "manhattan", devices=devs, return_info=True)
+    ri, nn, _, _ = oracle.nearest_neighbors(X, method)
+    assert np.array_equal(info["Ri"], ri) and np.array_equal(info["NN"], nn)
+    exp = oracle.regress_attrs(X, ri, nn, oracle.pair_diffs(y, ri, nn, "match-mismatch"))
+    _stats_close(info["stats"], exp, RTOL_IRLS, f"pipelined multi {method} x{ndev}")
+    monkeypatch.setenv("NPDRB_NO_PIPELINED_GATHER", "1")
+    _, info2 = nb.npdr(y, X, "binomial", "numeric-abs", method, "manhattan", devices=devs, return_info=True)
+    assert np.array_equal(info2["Ri"], ri) and np.array_equal(info["stats"], info2["stats"], equal_nan=True)
 
 
 def test_npdr_multi_driver_error_paths_return(nb, monkeypatch):
