@@ -297,13 +297,13 @@ class Bench:
                 from npdr_b200.distributed import cyclic_blocks
                 na = p // world
                 self.cyc = cyclic_blocks(p, world) if os.environ.get("NPDRB_NO_PIPELINED_GATHER") != "1" else None
-                if self.cyc and self.cyc[1] > 1:
+                if self.cyc:
                     # block-cyclic ownership: sub-slab c of rank r = global block c * world + r (upload_gather_pipelined)
-                    nb, n_sub = self.cyc
-                    idx = torch.cat([torch.arange((c * world + rank) * nb, (c * world + rank + 1) * nb) for c in range(n_sub)]).to(self.device)
+                    st = self.cyc
+                    n_sub = (len(st) - 1) // world
+                    idx = torch.cat([torch.arange(st[c * world + rank], st[c * world + rank + 1]) for c in range(n_sub)]).to(self.device)
                     self.hXs = d["dX"][idx, :N].cpu().numpy().T
                 else:
-                    self.cyc = None
                     self.hXs = d["dX"][rank * na:(rank + 1) * na, :N].cpu().numpy().T
             elif rank == 0 and self.hX is None:
                 self.hX = d["dX"][:, :N].cpu().numpy().T
@@ -356,9 +356,8 @@ class Bench:
             # block-cyclic ownership: a helper thread stages + broadcasts sub-slab after sub-slab while the distance kernel
             # (launched below, at once) consumes the blocks in attribute order as their events fire
             from npdr_b200.distributed import upload_gather_pipelined
-            nb, n_sub = self.cyc
-            nb_, events, ready, uploader, up_err = upload_gather_pipelined(self.ctx, dev["dX"], self.data["ldx"], self.hXs, rank, world, nb, n_sub)
-            slab_events = (nb_, events, ready)
+            st_, events, ready, uploader, up_err = upload_gather_pipelined(self.ctx, dev["dX"], self.data["ldx"], self.hXs, rank, world, self.cyc)
+            slab_events = (st_, events, ready)
         elif self.shard:                                                 # own columns over the own PCIe link, then over NVLink
             na = p // world
             mine = dev["dX"][rank * na:(rank + 1) * na]

@@ -226,6 +226,10 @@ int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t 
  * already exist (have been recorded once), and both arrays must stay valid until the distance call has returned. */
 int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events,
                                          const int32_t *ready);
+/* the same with slabs of different widths: slab i = attributes [slab_starts[i], slab_starts[i+1]), slab_starts[0] = 0,
+ * slab_starts[n_slabs] = p, every bound but the last a multiple of 16 */
+int npdrb_session_set_device_slab_events_v(npdrb_session *s, int32_t n_slabs, const int64_t *slab_starts, void *const *events,
+                                           const int32_t *ready);
 /* rows [row0, row0+nrows) of the distance matrix against all N instances (nrows == N: symmetric mode) */
 int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows);
 /* adopt a precomputed distance block (device, nrows x N row-major = the columns Ri of a symmetric D) */

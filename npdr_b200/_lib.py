@@ -97,6 +97,7 @@ SIGNATURES = {
     "npdrb_session_neighbors": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "npdrb_session_neighbors_hitmiss": (C.c_int, [_vp, _i32, C.c_double, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "npdrb_session_set_device_slab_events": (C.c_int, [_vp, _i32, _i64, C.POINTER(_vp), C.POINTER(_i32)]),
+    "npdrb_session_set_device_slab_events_v": (C.c_int, [_vp, _i32, C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i32)]),
     "npdrb_session_copy_radius2": (C.c_int, [_vp, _dp]),
     "npdrb_session_sort_rows": (C.c_int, [_vp]),
     "npdrb_session_neighbors_sorted": (C.c_int, [_vp, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
@@ -281,7 +282,11 @@ class Session:
         arr = (_vp * len(events))(*[int(e) for e in events])
         self._slab_events = (arr, ready)
         rp = ready.ctypes.data_as(C.POINTER(_i32)) if ready is not None else None
-        check(load().npdrb_session_set_device_slab_events(self.handle, len(events), int(slab_cols), arr, rp))
+        if np.ndim(slab_cols) == 0:
+            check(load().npdrb_session_set_device_slab_events(self.handle, len(events), int(slab_cols), arr, rp))
+        else:                                                  # slab bounds (n + 1 values): slabs of different widths
+            st = (_i64 * len(slab_cols))(*[int(v) for v in slab_cols])
+            check(load().npdrb_session_set_device_slab_events_v(self.handle, len(events), st, arr, rp))
 
     def distances(self, metric="manhattan", fast_euclidean=False, row0=0, nrows=None):
         nrows = self.N if nrows is None else nrows

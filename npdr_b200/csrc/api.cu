@@ -534,6 +534,8 @@ int npdrb_session_upload(npdrb_session *s, const double *X, const double *y, con
                 used = i + 1;
             }
             s->n_slabs_pending = used;
+            s->slab_start.assign((size_t)used + 1, p);
+            for (int i = 0; i < used; ++i) s->slab_start[(size_t)i] = (int64_t)i * s->slab_cols;
             s->n_slabs_issued = pinned ? used : 0;
             s->hX_lazy = pinned ? nullptr : X;
         } else {
@@ -577,27 +579,38 @@ int npdrb_session_set_device_inputs(npdrb_session *s, const double *dX, int64_t 
     return NPDRB_OK;
 }
 
-int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events, const int32_t *ready) {
-    // The adopted device matrix is still ARRIVING (e.g. an NCCL broadcast per rank's attribute shard on the caller's
-    // communication stream): column slab i = attributes [i * slab_cols, (i + 1) * slab_cols) is complete once events[i] fires.
+int npdrb_session_set_device_slab_events_v(npdrb_session *s, int32_t n_slabs, const int64_t *slab_starts, void *const *events,
+                                           const int32_t *ready) {
+    // The adopted device matrix is still ARRIVING (e.g. an NCCL broadcast per rank's attribute block on the caller's
+    // communication stream): column slab i = attributes [slab_starts[i], slab_starts[i + 1]) is complete once events[i] fires.
     // The distance stage then runs one launch per slab, each waiting for its own event only (same per-element order
     // k = 0..p-1, so the result is bit-identical), and the transfer of slab i+1 hides behind the kernel of slab i.
     if (!s->dX) { npdrb_set_error("set_device_slab_events: the session has no device matrix yet (npdrb_session_set_device_inputs)"); return NPDRB_EINVAL; }
-    if (n_slabs < 1 || !events || slab_cols < 1 || (slab_cols % 16) != 0 || (int64_t)(n_slabs - 1) * slab_cols >= s->p ||
-        (int64_t)n_slabs * slab_cols < s->p) {
-        npdrb_set_error("set_device_slab_events: need n_slabs slabs of slab_cols (a multiple of 16) columns covering the p attributes");
+    bool ok = n_slabs >= 1 && events && slab_starts && slab_starts[0] == 0 && slab_starts[n_slabs] == s->p;
+    for (int i = 0; ok && i < n_slabs; ++i)
+        ok = slab_starts[i] < slab_starts[i + 1] && (slab_starts[i] % 16) == 0 && events[i] != nullptr;
+    if (!ok) {
+        npdrb_set_error("set_device_slab_events: need increasing slab bounds 0 = s_0 < ... < s_n = p (multiples of 16 except p) and one event per slab");
         return NPDRB_EINVAL;
     }
     if (!s->slab_ev_external) for (cudaEvent_t e : s->slab_ev) if (e) cudaEventDestroy(e);
     s->slab_ev.assign((size_t)n_slabs, nullptr);
-    for (int i = 0; i < n_slabs; ++i) {
-        if (!events[i]) { npdrb_set_error("set_device_slab_events: null event %d", i); s->slab_ev.clear(); s->slab_ev_external = false; return NPDRB_EINVAL; }
-        s->slab_ev[(size_t)i] = (cudaEvent_t)events[i];
-    }
+    for (int i = 0; i < n_slabs; ++i) s->slab_ev[(size_t)i] = (cudaEvent_t)events[i];
+    s->slab_start.assign(slab_starts, slab_starts + n_slabs + 1);
     s->slab_ev_external = true;
     s->slab_ready = ready;
-    s->slab_cols = slab_cols; s->n_slabs_pending = n_slabs; s->n_slabs_issued = ready ? 0 : n_slabs; s->hX_lazy = nullptr;
+    s->slab_cols = 0; s->n_slabs_pending = n_slabs; s->n_slabs_issued = ready ? 0 : n_slabs; s->hX_lazy = nullptr;
     return NPDRB_OK;
+}
+
+int npdrb_session_set_device_slab_events(npdrb_session *s, int32_t n_slabs, int64_t slab_cols, void *const *events, const int32_t *ready) {
+    if (n_slabs < 1 || slab_cols < 1 || (int64_t)(n_slabs - 1) * slab_cols >= s->p || (int64_t)n_slabs * slab_cols < s->p) {
+        npdrb_set_error("set_device_slab_events: need n_slabs slabs of slab_cols (a multiple of 16) columns covering the p attributes");
+        return NPDRB_EINVAL;
+    }
+    std::vector<int64_t> st((size_t)n_slabs + 1, s->p);
+    for (int i = 0; i < n_slabs; ++i) st[(size_t)i] = (int64_t)i * slab_cols;
+    return npdrb_session_set_device_slab_events_v(s, n_slabs, st.data(), events, ready);
 }
 
 int npdrb_session_distances(npdrb_session *s, int32_t metric, int32_t fast_euclidean, int64_t row0, int64_t nrows) {

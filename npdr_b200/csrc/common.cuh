@@ -114,6 +114,7 @@ struct npdrb_session {
     // pointer and nb_issue_slab() stages slab i through the context's pinned ring (helper threads memcpy, async H2D) right
     // before the consumer of slab i is launched, so the copy of slab i+1 runs under the distance kernel of slab i.
     std::vector<cudaEvent_t> slab_ev; int64_t slab_cols = 0; int n_slabs_pending = 0;
+    std::vector<int64_t> slab_start;   // n_slabs_pending + 1 column bounds of the slabs (multiples of 16 except the last = p)
     const volatile int32_t *slab_ready = nullptr;   // optional host flags: slab_ev[i] may only be waited for once slab_ready[i] != 0
     bool slab_ev_external = false;     // slab_ev are the caller's events (npdrb_session_set_device_slab_events): never issued or destroyed here
     const double *hX_lazy = nullptr; int n_slabs_issued = 0;

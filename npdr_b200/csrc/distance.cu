@@ -365,7 +365,6 @@ int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const 
     // right after its H2D copy has been enqueued (pageable sources are staged by this thread while the previous slab's
     // kernel runs)
     const int n_slabs = slab_s ? slab_s->n_slabs_pending : 0;
-    const int64_t slab_cols = slab_s ? slab_s->slab_cols : 0;
     CUtensorMap mapA, mapB;
     NB_CHECK(make_tensor_map(&mapA, XA, NA, p, ldA));
     NB_CHECK(make_tensor_map(&mapB, XB, NB, p, ldB, plan.tn));
@@ -386,8 +385,8 @@ int launch_tma(npdrb_ctx *ctx, const double *XA, int64_t NA, int64_t ldA, const 
         if (n_launch > 1) {
             NB_CHECK(nb_issue_slab(slab_s, l));
             NB_CUDA(cudaStreamWaitEvent(ctx->stream, slab_s->slab_ev[(size_t)l], 0));
-            c_lo = (int)(l * slab_cols / BK);
-            c_hi = (int)nb_cdiv((l + 1) * slab_cols < p ? (l + 1) * slab_cols : p, BK);
+            c_lo = (int)(slab_s->slab_start[(size_t)l] / BK);
+            c_hi = (int)nb_cdiv(slab_s->slab_start[(size_t)l + 1], BK);
         }
         const int acc = l > 0, fin = l == n_launch - 1;
         if (plan.tn == 64)

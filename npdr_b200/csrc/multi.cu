@@ -82,7 +82,8 @@ struct Shared {
     // global block c * G + g (pipe_nb columns).  Every device stages its sub-slabs one after the other over its own PCIe
     // link; as soon as sub-slab c of a peer is on that peer (up_ready), the block is pulled over NVLink; the distance kernel
     // of every device consumes block after block in attribute order while later sub-slabs are still being staged.
-    int64_t pipe_nb = 0; int pipe_nsub = 0;
+    int64_t pipe_nb = 0; int pipe_nsub = 0;          // pipe_nb > 0: pipeline on (value = width of block 0)
+    std::vector<int64_t> pipe_start;                 // G * pipe_nsub + 1 column bounds of the blocks (multiples of 16 except the last)
     std::unique_ptr<std::atomic<int>[]> up_ready;    // [G][pipe_nsub]
     std::vector<double> hostD;                       // SURF exact replay: the gathered distance matrix
     double surf_radius_exact = 0.0;
@@ -113,12 +114,14 @@ void fail(Shared &S, Worker &w, int rc) {
 void run_producer(Shared &S, int g) {
     Worker &w = S.w[(size_t)g];
     const int G = S.G, nsub = S.pipe_nsub;
-    const int64_t nb = S.pipe_nb, ldx = w.s->ldx;
+    const int64_t ldx = w.s->ldx;
+    const std::vector<int64_t> &st = S.pipe_start;
     int rc = NPDRB_OK;
     if (cudaSetDevice(w.dev) != cudaSuccess) rc = NPDRB_ECUDA;
     for (int c = 0; c < nsub && rc == NPDRB_OK && !S.failed.load(); ++c) {
         const int64_t b_own = (int64_t)c * G + g;
-        rc = npdrb_upload_columns(w.ctx, w.s->dX + b_own * nb * ldx, ldx, S.X + b_own * nb * S.N, S.N, nb);   // pageable: pinned ring
+        rc = npdrb_upload_columns(w.ctx, w.s->dX + st[(size_t)b_own] * ldx, ldx, S.X + st[(size_t)b_own] * S.N, S.N,
+                                  st[(size_t)b_own + 1] - st[(size_t)b_own]);                      // pageable: pinned ring
         if (rc == NPDRB_OK) rc = CU(cudaEventRecord(w.ev_up[(size_t)c], w.ctx->copy_stream));
         S.up_ready[(size_t)g * nsub + c].store(1, std::memory_order_release);
         for (int r = 0; r < G && rc == NPDRB_OK; ++r) {
@@ -133,8 +136,8 @@ void run_producer(Shared &S, int g) {
                 if (rc != NPDRB_OK || S.failed.load()) break;
                 rc = CU(cudaStreamWaitEvent(w.pull_stream, peer.ev_up[(size_t)c], 0));
                 if (rc == NPDRB_OK)
-                    rc = CU(cudaMemcpyPeerAsync(w.s->dX + b * nb * ldx, w.dev, peer.s->dX + b * nb * ldx, peer.dev,
-                                                sizeof(double) * (size_t)ldx * (size_t)nb, w.pull_stream));
+                    rc = CU(cudaMemcpyPeerAsync(w.s->dX + st[(size_t)b] * ldx, w.dev, peer.s->dX + st[(size_t)b] * ldx, peer.dev,
+                                                sizeof(double) * (size_t)ldx * (size_t)(st[(size_t)b + 1] - st[(size_t)b]), w.pull_stream));
                 if (rc == NPDRB_OK) rc = CU(cudaEventRecord((cudaEvent_t)w.ev_slab[(size_t)b], w.pull_stream));
             }
             if (rc == NPDRB_OK) __atomic_store_n(&w.slab_ready[(size_t)b], 1, __ATOMIC_RELEASE);
@@ -217,7 +220,7 @@ void run_worker(Shared &S, int g) {
     std::thread producer;
     const bool piped = S.pipe_nb > 0 && S.G > 1 && !S.failed.load() && w.rc == NPDRB_OK && w.s;
     if (piped) {
-        STEP(npdrb_session_set_device_slab_events(w.s, (int32_t)w.ev_slab.size(), S.pipe_nb, w.ev_slab.data(), w.slab_ready.data()));
+        STEP(npdrb_session_set_device_slab_events_v(w.s, (int32_t)w.ev_slab.size(), S.pipe_start.data(), w.ev_slab.data(), w.slab_ready.data()));
         producer = std::thread(run_producer, std::ref(S), g);
     }
     if (w.live >= 0) {
@@ -384,10 +387,16 @@ extern "C" int npdrb_npdr_multi(int32_t n_devices, const int32_t *devices, const
         // pipelined replication of X: every device owns rows (it consumes the blocks itself) and the columns split into
         // G x n_sub blocks of a multiple of 16 columns
         const char *np_ = getenv("NPDRB_NO_PIPELINED_GATHER");
-        if (n_devices > 1 && (int)S.live_devs.size() == n_devices && p % n_devices == 0 && !(np_ && np_[0] == '1')) {
-            const int64_t na = p / n_devices;
-            for (int n_sub = 8; n_sub >= 2 && S.pipe_nb == 0; --n_sub)
-                if (na % n_sub == 0 && (na / n_sub) % 16 == 0) { S.pipe_nb = na / n_sub; S.pipe_nsub = n_sub; }
+        if (n_devices > 1 && (int)S.live_devs.size() == n_devices && !(np_ && np_[0] == '1')) {
+            // G * n_sub blocks of (nearly) equal width, bounds on multiples of 16 columns (the distance kernel's chunk)
+            const int64_t chunks = p / 16;
+            int n_sub = (int)(chunks / n_devices < 5 ? chunks / n_devices : 5);
+            if (n_sub >= 2) {
+                const int64_t n_blocks = (int64_t)n_devices * n_sub;
+                S.pipe_start.assign((size_t)n_blocks + 1, p);
+                for (int64_t b = 0; b < n_blocks; ++b) S.pipe_start[(size_t)b] = 16 * (b * chunks / n_blocks);
+                S.pipe_nb = S.pipe_start[1]; S.pipe_nsub = n_sub;
+            }
             if (S.pipe_nb > 0) {
                 S.up_ready.reset(new std::atomic<int>[(size_t)n_devices * (size_t)S.pipe_nsub]);
                 for (size_t i = 0; i < (size_t)n_devices * (size_t)S.pipe_nsub; ++i) S.up_ready[i].store(0);

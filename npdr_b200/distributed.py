@@ -216,31 +216,30 @@ def gather_columns_pipelined(dX, world, ncols, group=None):
     return ncols, events
 
 
-def cyclic_blocks(p, world, max_sub=8):
-    """Block size nb for the cyclic attribute layout of upload_gather_pipelined: the p // world columns of a rank are cut into
-    n_sub sub-slabs of nb columns (nb % 16 == 0); global block b = c * world + r (sub-slab c of rank r) covers attributes
-    [b * nb, (b + 1) * nb).  -> (nb, n_sub) or None when p does not split that way."""
-    if p % world:
+def cyclic_blocks(p, world, n_sub=5):
+    """Column bounds of the block-cyclic attribute layout of upload_gather_pipelined: world * n_sub blocks of (nearly) equal
+    width, every bound but the last a multiple of 16 (the distance kernel's attribute chunk); block b = c * world + r is
+    sub-slab c of rank r.  -> list of world * n_sub + 1 bounds, or None when p is too small to give every block 16 columns."""
+    chunks = p // 16
+    n_blocks = world * n_sub
+    if world < 2 or chunks < n_blocks:
         return None
-    na = p // world
-    for n_sub in range(max_sub, 0, -1):
-        if na % n_sub == 0 and (na // n_sub) % 16 == 0:
-            return na // n_sub, n_sub
-    return None
+    return [16 * (b * chunks // n_blocks) for b in range(n_blocks)] + [p]
 
 
-def upload_gather_pipelined(ctx, dX, ldx, host_cols, rank, world, nb, n_sub, group=None):
-    """Upload AND replicate an attribute-sharded matrix underneath the distance stage.  Ownership is block-cyclic (see
-    cyclic_blocks), so the order in which sub-slabs become available everywhere -- sub-slab 0 of every rank, then sub-slab 1,
-    ... -- IS the attribute order k = 0..p-1 the distance kernel consumes.  A helper thread stages sub-slab c of this rank's
-    host columns (host_cols: N x (n_sub * nb), Fortran order, pageable is fine) through the library's pinned ring, then issues
-    one asynchronous NCCL broadcast per rank for that sub-slab, records an event per block and raises its host flag; the
-    caller passes the result to GpuEngine(slab_events=...) at once and the distance call (npdrb_session_set_device_slab_events
-    with ready flags) starts consuming block 0 while later sub-slabs are still crossing PCIe.
-    -> (nb, events, ready, thread); join the thread after the distance stage."""
+def upload_gather_pipelined(ctx, dX, ldx, host_cols, rank, world, starts, group=None):
+    """Upload AND replicate an attribute-sharded matrix underneath the distance stage.  Ownership is block-cyclic (starts =
+    cyclic_blocks(p, world, n_sub)), so the order in which sub-slabs become available everywhere -- sub-slab 0 of every rank,
+    then sub-slab 1, ... -- IS the attribute order k = 0..p-1 the distance kernel consumes.  A helper thread stages sub-slab c
+    of this rank's host columns (host_cols: N x (this rank's columns, blocks in order), Fortran order, pageable is fine)
+    through the library's pinned ring, then issues one asynchronous NCCL broadcast per rank for that sub-slab, records an
+    event per block and raises its host flag; the caller passes the result to GpuEngine(slab_events=...) at once and the
+    distance call (npdrb_session_set_device_slab_events_v with ready flags) starts consuming block 0 while later sub-slabs
+    are still crossing PCIe.  -> (starts, events, ready, thread, errors); join the thread after the distance stage."""
     import threading
     dev = dX.device
-    n_blocks = n_sub * world
+    n_blocks = len(starts) - 1
+    n_sub = n_blocks // world
     side = torch.cuda.Stream(device=dev)
     issue = torch.cuda.Stream(device=dev)        # the collectives must not queue behind the distance launches of the caller's stream
     events = [torch.cuda.Event() for _ in range(n_blocks)]
@@ -253,12 +252,15 @@ def upload_gather_pipelined(ctx, dX, ldx, host_cols, rank, world, nb, n_sub, gro
         try:
             torch.cuda.set_device(dev)
             with torch.cuda.stream(issue):
+                off = 0
                 for c in range(n_sub):
                     b_own = c * world + rank
-                    ctx.upload_columns(dX[b_own * nb:(b_own + 1) * nb].data_ptr(), ldx, host_cols[:, c * nb:(c + 1) * nb])
+                    w_own = starts[b_own + 1] - starts[b_own]
+                    ctx.upload_columns(dX[starts[b_own]:starts[b_own + 1]].data_ptr(), ldx, host_cols[:, off:off + w_own])
+                    off += w_own
                     for r in range(world):
                         b = c * world + r
-                        work_ = dist.broadcast(dX[b * nb:(b + 1) * nb], src=r, group=group, async_op=True)
+                        work_ = dist.broadcast(dX[starts[b]:starts[b + 1]], src=r, group=group, async_op=True)
                         with torch.cuda.stream(side):
                             work_.wait()
                             events[b].record(side)
@@ -269,7 +271,7 @@ def upload_gather_pipelined(ctx, dX, ldx, host_cols, rank, world, nb, n_sub, gro
 
     th = threading.Thread(target=work, name="npdr-upload-gather")
     th.start()
-    return nb, events, ready, th, err
+    return starts, events, ready, th, err
 
 
 class GpuEngine(Engine):

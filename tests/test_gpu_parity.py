@@ -981,22 +981,23 @@ def test_device_slab_events_distances_bit_exact(nb, oracle):
     ldx = N + (N % 2)
     src = torch.zeros((p, ldx), dtype=torch.float64, device=dev)
     src[:, :N] = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)
-    for row0, nrows in ((0, N), (256, 256)):
+    for row0, nrows, bounds in ((0, N, None), (256, 256, None), (0, N, [0, 48, 336, 352, 640])):     # last: slabs of different widths
         dX = torch.full((p, ldx), float("nan"), dtype=torch.float64, device=dev)     # a slab consumed too early would poison D
         dy = torch.zeros(N, dtype=torch.float64, device=dev)
         torch.cuda.synchronize()
         side = torch.cuda.Stream(device=dev)
         events = []
+        st = bounds or list(range(0, p + 1, ncols))
         with torch.cuda.stream(side):
-            for g in range(p // ncols):
+            for g in range(len(st) - 1):
                 torch.cuda._sleep(20_000_000)                     # ~10 ms: the slab is late
-                dX[g * ncols:(g + 1) * ncols].copy_(src[g * ncols:(g + 1) * ncols], non_blocking=True)
+                dX[st[g]:st[g + 1]].copy_(src[st[g]:st[g + 1]], non_blocking=True)
                 ev = torch.cuda.Event(); ev.record(side)
                 events.append(ev)
         s = _lib.Session(_lib.context(0), N, p, 0)
         try:
             s.set_device_inputs(dX.data_ptr(), ldx, dy.data_ptr(), 0)
-            s.set_device_slab_events(ncols, [e.cuda_event for e in events])
+            s.set_device_slab_events(bounds if bounds else ncols, [e.cuda_event for e in events])
             s.distances("manhattan", False, row0, nrows)
             got = s.copy_distances()
         finally:
