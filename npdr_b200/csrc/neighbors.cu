@@ -784,13 +784,13 @@ extern "C" int npdrb_session_surf_band_count(npdrb_session *s, double lo, double
     if (!s->dD || !count) { npdrb_set_error("surf band count: no distance block"); return NPDRB_EINVAL; }
     NB_CUDA(cudaSetDevice(ctx->device));
     unsigned long long *d_c = nullptr, h_c = 0;
-    NB_CUDA(cudaMalloc(&d_c, sizeof(unsigned long long)));
+    nb_scope scope;
+    NB_CHECK(scope.alloc(&d_c, 1));
     NB_CUDA(cudaMemsetAsync(d_c, 0, sizeof(unsigned long long), ctx->stream));
     surf_band_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(s->dD, s->ldd, s->N, s->nrows, lo, hi, d_c);
     NB_LAUNCH_CHECK(ctx);
     NB_CUDA(cudaMemcpyAsync(&h_c, d_c, sizeof(h_c), cudaMemcpyDeviceToHost, ctx->stream));
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_c);
     *count = (int64_t)h_c;
     return NPDRB_OK;
 }
@@ -802,8 +802,9 @@ extern "C" int npdrb_session_surf_partial(npdrb_session *s, double centre, doubl
     if (!s->dD) { npdrb_set_error("surf partial: no distance block"); return NPDRB_EINVAL; }
     const int64_t N = s->N, nrows = s->nrows;
     double *d_out = nullptr, *d_ss = nullptr;
-    NB_CUDA(cudaMalloc(&d_out, sizeof(double) * 3 * (size_t)nrows));
-    NB_CUDA(cudaMalloc(&d_ss, sizeof(double) * (size_t)nrows));
+    nb_scope scope;
+    NB_CHECK(scope.alloc(&d_out, 3 * (size_t)nrows));
+    NB_CHECK(scope.alloc(&d_ss, (size_t)nrows));
     surf_moments_kernel<<<(unsigned)nb_cdiv(nrows, 8), 256, 0, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows, d_out);
     NB_LAUNCH_CHECK(ctx);
     surf_sumsq_kernel<<<(unsigned)nb_cdiv(nrows, 8), 256, 0, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows, centre, d_ss);
@@ -812,7 +813,6 @@ extern "C" int npdrb_session_surf_partial(npdrb_session *s, double centre, doubl
     NB_CUDA(cudaMemcpyAsync(h.data(), d_out, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
     NB_CUDA(cudaMemcpyAsync(hs.data(), d_ss, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_out); cudaFree(d_ss);
     long double sa = 0, su = 0, cu = 0, ss = 0;
     for (int64_t r = 0; r < nrows; ++r) { sa += h[3 * r]; su += h[3 * r + 1]; cu += h[3 * r + 2]; ss += hs[r]; }
     out4[0] = (double)sa; out4[1] = (double)su; out4[2] = (double)cu; out4[3] = (double)ss;
@@ -835,7 +835,8 @@ static int surf_radius(npdrb_session *s, double sd_frac, double *d_rad_scalar) {
         }
         // large blocks: parallel moments (a few ulp from R's sequential long-double chains)
         double *d_m = nullptr;
-        NB_CUDA(cudaMalloc(&d_m, sizeof(double) * (size_t)nrows));
+        nb_scope scope;
+        NB_CHECK(scope.alloc(&d_m, (size_t)nrows));
         std::vector<double> h((size_t)nrows);
         long double tot = 0, ss = 0;
         rect_row_moment_kernel<<<(unsigned)nb_cdiv(nrows, 8), 256, 0, ctx->stream>>>(s->dD, s->ldd, N, nrows, 0, 0.0, d_m);
@@ -849,7 +850,6 @@ static int surf_radius(npdrb_session *s, double sd_frac, double *d_rad_scalar) {
         NB_CUDA(cudaMemcpyAsync(h.data(), d_m, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
         NB_CUDA(cudaStreamSynchronize(ctx->stream));
         for (double v : h) ss += v;
-        cudaFree(d_m);
         radius = mean - sd_frac * sqrt((double)(ss / (long double)(N * nrows - 1)));
     } else if (s->nrows != N) {
         npdrb_set_error("surf on a row block needs npdrb_session_set_surf_radius (combine npdrb_session_surf_partial across ranks)");
@@ -893,15 +893,16 @@ int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k
     if (!s->d_radius) NB_CUDA(cudaMalloc(&s->d_radius, sizeof(double) * (size_t)nmax));
     if (!s->d_rowptr) NB_CUDA(cudaMalloc(&s->d_rowptr, sizeof(int64_t) * (size_t)(nmax + 2)));
     int64_t *d_counts = nullptr, *d_nempty = nullptr;
-    NB_CUDA(cudaMalloc(&d_counts, sizeof(int64_t) * (size_t)nrows));
-    NB_CUDA(cudaMalloc(&d_nempty, sizeof(int64_t)));
+    nb_scope scope;                                     // temporaries: released on every return path
+    NB_CHECK(scope.alloc(&d_counts, (size_t)nrows));
+    NB_CHECK(scope.alloc(&d_nempty, 1));
     int64_t tot[2] = {0, 0};
     const unsigned wgrid = (unsigned)nb_cdiv(nrows, 8);
 
     if (nbd_method == NPDRB_NBD_RELIEFF) {
         if (k <= 0) k = npdrb_knn_surf(N, sd_frac);             // R/nearestNeighbors.R:197-203
         uint64_t *d_cut = nullptr, *d_scratch = nullptr;
-        NB_CUDA(cudaMalloc(&d_cut, sizeof(uint64_t) * (size_t)nrows));
+        NB_CHECK(scope.alloc(&d_cut, (size_t)nrows));
         relieff_select_kernel<<<(unsigned)nrows, 256, 0, ctx->stream>>>(s->dD, s->ldd, N, nrows, k + 1, d_cut, d_counts);
         NB_LAUNCH_CHECK(ctx);
         scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, nrows, s->d_rowptr, d_nempty);
@@ -912,14 +913,13 @@ int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k
         const int64_t M = tot[0];
         NB_CUDA(cudaMalloc(&s->dRiL, sizeof(int32_t) * (size_t)(M > 0 ? M : 1)));
         NB_CUDA(cudaMalloc(&s->dNNL, sizeof(int32_t) * (size_t)(M > 0 ? M : 1)));
-        NB_CUDA(cudaMalloc(&d_scratch, sizeof(uint64_t) * (size_t)(M > 0 ? M : 1)));
+        NB_CHECK(scope.alloc(&d_scratch, (size_t)(M > 0 ? M : 1)));
         const size_t smem = (size_t)SORT_CAP * (sizeof(uint64_t) + sizeof(int32_t));
         NB_CUDA(cudaFuncSetAttribute(relieff_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         relieff_write_kernel<<<(unsigned)nrows, 256, smem, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows, d_cut,
                                                                           s->d_rowptr, d_scratch, s->dRiL, s->dNNL);
         NB_LAUNCH_CHECK(ctx);
         NB_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_cut); cudaFree(d_scratch);
     } else {
         int scalar = 0;
         if (nbd_method == NPDRB_NBD_MULTISURF) {
@@ -957,7 +957,6 @@ int nb_neighbors(npdrb_session *s, int32_t nbd_method, double sd_frac, int64_t k
             NB_CUDA(cudaStreamSynchronize(ctx->stream));
         }
     }
-    cudaFree(d_counts); cudaFree(d_nempty);
     s->M_local = tot[0];
     s->n_empty_local = tot[1];
     if (M_local) *M_local = tot[0];
@@ -1042,7 +1041,8 @@ int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, i
             scalar = 1;
             if (nrows != N) { npdrb_set_error("surf hit/miss radii on a row block are not supported"); return NPDRB_EINVAL; }
             double *d_two = nullptr;
-            NB_CUDA(cudaMalloc(&d_two, sizeof(double) * 2));
+            nb_scope surf_scope;
+            NB_CHECK(surf_scope.alloc(&d_two, 2));
             double two[2];
             if (N <= 1024) {
                 surf_hitmiss_serial_kernel<<<1, 32, 0, ctx->stream>>>(s->dD, s->ldd, N, s->dy, sd_frac, d_two);
@@ -1051,7 +1051,7 @@ int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, i
                 NB_CUDA(cudaStreamSynchronize(ctx->stream));
             } else {                                             // parallel moments (documented deviation, <= few ulp)
                 double *d_m = nullptr;
-                NB_CUDA(cudaMalloc(&d_m, sizeof(double) * 6 * (size_t)nrows));
+                NB_CHECK(surf_scope.alloc(&d_m, 6 * (size_t)nrows));
                 std::vector<double> hm(6 * (size_t)nrows);
                 double centre[2] = {0.0, 0.0};
                 long double acc[6];
@@ -1067,9 +1067,7 @@ int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, i
                 }
                 two[0] = centre[0] - sd_frac * sqrt((double)(acc[2] / (acc[1] - 1)));
                 two[1] = centre[1] - sd_frac * sqrt((double)(acc[5] / (acc[4] - 1)));
-                cudaFree(d_m);
             }
-            cudaFree(d_two);
             std::vector<double> rep((size_t)nrows, two[0]), rep2((size_t)nrows, two[1]);
             NB_CUDA(cudaMemcpyAsync(s->d_radius, rep.data(), sizeof(double) * rep.size(), cudaMemcpyHostToDevice, ctx->stream));
             NB_CUDA(cudaMemcpyAsync(s->d_radius2, rep2.data(), sizeof(double) * rep2.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1077,9 +1075,10 @@ int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, i
             scalar = 0;                                          // radii are replicated per row
         }
         int64_t *d_counts = nullptr, *d_nempty = nullptr; int32_t *d_nh = nullptr;
-        NB_CUDA(cudaMalloc(&d_counts, sizeof(int64_t) * (size_t)nrows));
-        NB_CUDA(cudaMalloc(&d_nempty, sizeof(int64_t)));
-        NB_CUDA(cudaMalloc(&d_nh, sizeof(int32_t) * (size_t)nrows));
+        nb_scope scope;
+        NB_CHECK(scope.alloc(&d_counts, (size_t)nrows));
+        NB_CHECK(scope.alloc(&d_nempty, 1));
+        NB_CHECK(scope.alloc(&d_nh, (size_t)nrows));
         const unsigned wgrid = (unsigned)nb_cdiv(nrows, 8);
         count_hitmiss_kernel<<<wgrid, 256, 0, ctx->stream>>>(s->dD, s->ldd, N, s->row0, nrows, s->dy, s->d_radius, s->d_radius2, scalar,
                                                              d_counts, d_nh);
@@ -1096,7 +1095,6 @@ int nb_neighbors_hitmiss(npdrb_session *s, int32_t nbd_method, double sd_frac, i
                                                              s->d_rowptr, d_nh, s->dRiL, s->dNNL);
         NB_LAUNCH_CHECK(ctx);
         NB_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_counts); cudaFree(d_nempty); cudaFree(d_nh);
     }
     s->M_local = tot[0];
     s->n_empty_local = tot[1];
@@ -1117,9 +1115,10 @@ int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_uniqu
     if (M == 0) { if (n_unique) *n_unique = 0; return NPDRB_OK; }
     const size_t words = ((size_t)N * (size_t)N + 31) / 32;
     unsigned *d_bits = nullptr; uint8_t *d_keep = nullptr; unsigned long long *d_ndup = nullptr;
-    NB_CUDA(cudaMalloc(&d_bits, sizeof(unsigned) * words));
-    NB_CUDA(cudaMalloc(&d_keep, (size_t)M));
-    NB_CUDA(cudaMalloc(&d_ndup, 3 * sizeof(unsigned long long)));      // [0] duplicates, [1] "not grouped by Ri" flag, [2] distinct ordered pairs
+    nb_scope scope;                                     // temporaries: released on every return path
+    NB_CHECK(scope.alloc(&d_bits, words));
+    NB_CHECK(scope.alloc(&d_keep, (size_t)M));
+    NB_CHECK(scope.alloc(&d_ndup, 3));      // [0] duplicates, [1] "not grouped by Ri" flag, [2] distinct ordered pairs
     NB_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned) * words, ctx->stream));
     NB_CUDA(cudaMemsetAsync(d_ndup, 0, 3 * sizeof(unsigned long long), ctx->stream));
     const unsigned grid = (unsigned)nb_cdiv(M, 256);
@@ -1136,7 +1135,6 @@ int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_uniqu
     // only for lists grouped by ascending Ri_idx without repeated ordered pairs -- what nearestNeighbors() emits.  Anything
     // else (a hand-made list through npdrb_session_import_pairs*) is rejected rather than answered differently from R.
     if (h3[1] != 0 || (int64_t)h3[2] != M) {
-        cudaFree(d_bits); cudaFree(d_keep); cudaFree(d_ndup);
         npdrb_set_error("unique_pairs: the pair list must be grouped by ascending Ri_idx and must not repeat an ordered pair "
                         "(%lld rows, %llu distinct pairs%s)", (long long)M, h3[2], h3[1] ? ", Ri_idx decreases somewhere" : "");
         return NPDRB_EINVAL;
@@ -1147,9 +1145,9 @@ int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_uniqu
     if (keep_unique_only && ndup > 0) {
         int64_t *d_bc = nullptr, *d_bp = nullptr, *d_ne = nullptr;
         int32_t *nRi = nullptr, *nNN = nullptr;
-        NB_CUDA(cudaMalloc(&d_bc, sizeof(int64_t) * grid));
-        NB_CUDA(cudaMalloc(&d_bp, sizeof(int64_t) * ((size_t)grid + 1)));
-        NB_CUDA(cudaMalloc(&d_ne, sizeof(int64_t)));
+        NB_CHECK(scope.alloc(&d_bc, (size_t)grid));
+        NB_CHECK(scope.alloc(&d_bp, (size_t)grid + 1));
+        NB_CHECK(scope.alloc(&d_ne, 1));
         NB_CUDA(cudaMalloc(&nRi, sizeof(int32_t) * (size_t)nu));
         NB_CUDA(cudaMalloc(&nNN, sizeof(int32_t) * (size_t)nu));
         block_keep_count_kernel<<<grid, 256, 0, ctx->stream>>>(d_keep, M, d_bc);
@@ -1162,8 +1160,6 @@ int nb_unique_pairs(npdrb_session *s, int32_t keep_unique_only, int64_t *n_uniqu
         if (s->own_pairs) { cudaFree(s->dRi); cudaFree(s->dNN); }
         s->dRi = nRi; s->dNN = nNN; s->M = nu; s->own_pairs = true;
         s->streams_valid = false;
-        cudaFree(d_bc); cudaFree(d_bp); cudaFree(d_ne);
     }
-    cudaFree(d_bits); cudaFree(d_keep); cudaFree(d_ndup);
     return NPDRB_OK;
 }
