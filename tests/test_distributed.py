@@ -273,3 +273,21 @@ def test_all_gather_varlen_single_process():
     from npdr_b200.distributed import partition_attrs, partition_rows
     assert partition_rows(300, 2) == [(0, 256), (256, 44)]
     assert partition_attrs(37, 3) == [(0, 13), (13, 12), (25, 12)]
+
+
+def test_cyclic_blocks_layout():
+    """Block-cyclic attribute layout of the upload pipelines: world * n_sub blocks covering 0..p in order, every bound but the
+    last a multiple of 16 (the distance kernel's attribute chunk), no empty block, nearly equal widths; None when p is too
+    small to give every block a chunk."""
+    from npdr_b200.distributed import cyclic_blocks
+    for p, world in ((50000, 8), (160000, 8), (40000, 2), (300, 2), (4096, 2), (20000 * 4, 4), (1600, 3), (16 * 10, 2)):
+        st = cyclic_blocks(p, world)
+        assert st is not None and st[0] == 0 and st[-1] == p and (len(st) - 1) % world == 0
+        assert all(b % 16 == 0 for b in st[:-1]) and all(st[i] < st[i + 1] for i in range(len(st) - 1))
+        w = [st[i + 1] - st[i] for i in range(len(st) - 1)]
+        assert max(w) - min(w) <= 16 + (p % 16)
+        # every rank owns n_sub blocks, one per round, and the rounds are consumed in attribute order
+        n_sub = (len(st) - 1) // world
+        owned = {r: [c * world + r for c in range(n_sub)] for r in range(world)}
+        assert sorted(b for bl in owned.values() for b in bl) == list(range(world * n_sub))
+    assert cyclic_blocks(100, 8) is None and cyclic_blocks(5000, 1) is None
