@@ -200,7 +200,7 @@ vwok <- function(dats, k.grid = NULL, verbose = FALSE, attr.diff.type = "numeric
   rownames(betas) <- rownames(pvals) <- colnames(X)[ord]
   colnames(betas) <- colnames(pvals) <- paste0("k.", ks)
   best <- apply(betas, 1, which.max)
-  out <- data.frame(att = rownames(betas), best.ks = ks[best], betas = betas[cbind(seq_len(nrow(betas)), best)],
+  out <- data.frame(att = rownames(betas), best.ks = best, betas = betas[cbind(seq_len(nrow(betas)), best)],   # best.ks: the grid INDEX, as apply(betas, 1, which.max) in R/adaptive.R:203
                     pval.att = pvals[cbind(seq_len(nrow(pvals)), best)], stringsAsFactors = FALSE)
   out <- out[order(out$betas, decreasing = TRUE), ]
   list(vwok.out = out, betas = as.data.frame(betas), pvals = as.data.frame(pvals))
