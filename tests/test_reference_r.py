@@ -56,3 +56,31 @@ def test_oracle_matches_the_reference_run_in_r(tmp_path_factory, oracle, name):
     np.testing.assert_allclose(res["beta.raw.att"].to_numpy(), exp["stats"][order, 0], rtol=rtol)
     np.testing.assert_allclose(res["beta.Z.att"].to_numpy(), exp["stats"][order, 1], rtol=rtol)
     np.testing.assert_allclose(res["pval.att"].to_numpy(), pv[order], rtol=max(rtol, 1e-7), atol=1e-300)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _r_available(), reason="no Rscript + dplyr + reference checkout on this machine")
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_gpu_matches_the_reference_run_in_r(tmp_path_factory, name):
+    """The engine itself (through the C ABI) against R's own output -- the north-star bars: pair lists bit-exact, distances
+    1e-12, beta / Z 1e-8 (lm) or 1e-6 (binomial), identical attribute ordering."""
+    import pandas as pd
+    import npdr_b200 as nb
+    out = tmp_path_factory.getbasetemp() / "ref_run"
+    if not (out / "cfg3_npdr.csv").exists():
+        subprocess.check_call(["Rscript", os.path.join(ROOT, "scripts", "ref_run.R"), REF, str(out)])
+    case = load_case(name)
+    D = pd.read_csv(out / f"{name}_dist.csv").to_numpy(dtype=float)
+    got = nb.npdrDistances(case["X"], case["nbd_metric"])
+    assert np.max(np.abs(D - got) / np.maximum(np.abs(D), 1e-300)) <= 1e-12
+    df = pd.DataFrame(case["X"], columns=case["names"])
+    covars = case["C"] if case["C"] is not None else "none"
+    res_gpu, info = nb.npdr(case["y"], df, case["regression_type"], "numeric-abs", case["nbd_method"], case["nbd_metric"], covars=covars,
+                            covar_diff_type=list(case["covar_diff_type"]) or "match-mismatch", return_info=True)
+    pairs = pd.read_csv(out / f"{name}_pairs.csv")
+    assert np.array_equal(pairs["Ri_idx"].to_numpy(), info["Ri"]) and np.array_equal(pairs["NN_idx"].to_numpy(), info["NN"])
+    res = pd.read_csv(out / f"{name}_npdr.csv")
+    assert list(res["att"].astype(str)) == list(res_gpu["att"].astype(str))
+    rtol = 1e-8 if case["regression_type"] == "lm" else 1e-6
+    np.testing.assert_allclose(res_gpu["beta.raw.att"].to_numpy(), res["beta.raw.att"].to_numpy(), rtol=rtol)
+    np.testing.assert_allclose(res_gpu["beta.Z.att"].to_numpy(), res["beta.Z.att"].to_numpy(), rtol=rtol)
