@@ -1274,6 +1274,14 @@ def test_npdr_learner(nb, oracle):
 def test_zz_report_worst_errors():
     """Runs last: prints the worst purely relative error (entries with |value| > 1) seen by every statistics comparison of this
     session, so the GPU test log records how far below the 1e-8 / 1e-6 bars the kernels actually are."""
-    for what, v in sorted(WORST_REL.items(), key=lambda kv: -kv[1])[:40]:
-        print(f"worst relative error |value|>1: {v:.3e}  {what}")
+    lines = [f"worst relative error |value|>1: {v:.3e}  {what}" for what, v in sorted(WORST_REL.items(), key=lambda kv: -kv[1])]
+    for ln in lines[:40]:
+        print(ln)
+    out_dir = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+    try:                                                   # kept with the run's other outputs (copied to profiles/ by hand)
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "worst_rel_errors.txt"), "w") as f:
+            f.write(f"{len(lines)} statistics comparisons of this pytest session; bars: lm {RTOL_LM:g}, binomial {RTOL_IRLS:g}\n" + "\n".join(lines) + "\n")
+    except OSError:
+        pass
     assert all(v <= RTOL_IRLS for v in WORST_REL.values())
